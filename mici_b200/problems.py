@@ -1,0 +1,188 @@
+"""Synthetic benchmark / parity problems (BASELINE.json configs).
+
+Host-side *input generation* only: shapes, seeds, shared metrics and initial states for the
+five configurations C0..C4.  Everything is fp64 and generated with
+``numpy.random.default_rng(BASE_SEED + k)`` so that the CUDA path, the oracle and the
+reference all see identical inputs.  No integrator arithmetic lives here.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+BASE_SEED = 20260924
+
+
+@dataclass
+class Problem:
+    """A fully specified integrator workload.
+
+    Attributes:
+        name: config label (``"C0"`` .. ``"C4"``).
+        integrator: ``"leapfrog"`` | ``"implicit_leapfrog"`` | ``"constrained_leapfrog"``.
+        system: ``"euclidean"`` | ``"softabs_riemannian"`` | ``"dense_riemannian"`` |
+            ``"constrained_euclidean"``.
+        target: target-model name (``mici_b200.targets`` registry key).
+        target_params: constructor kwargs of the target model.
+        metric: ``None`` (identity), 1-D (diagonal) or 2-D (dense SPD) array -- the fixed
+            metric of Euclidean systems.
+        metric_model / metric_params: position-dependent metric (dense Riemannian only).
+        step_size: integrator ``step_size``.
+        pos, mom: ``[n_chains, dim]`` initial states.
+    """
+
+    name: str
+    integrator: str
+    system: str
+    target: str
+    target_params: dict
+    step_size: float
+    pos: np.ndarray
+    mom: np.ndarray
+    metric: np.ndarray | None = None
+    metric_model: str | None = None
+    metric_params: dict = field(default_factory=dict)
+    system_kwargs: dict = field(default_factory=dict)
+    integrator_kwargs: dict = field(default_factory=dict)
+
+    @property
+    def n_chains(self):
+        return self.pos.shape[0]
+
+    @property
+    def dim(self):
+        return self.pos.shape[1]
+
+    @property
+    def algorithmic_bytes_per_chain_step(self):
+        """B_alg = 4 * D * 8: read q, p and write q, p in fp64."""
+        return 32 * self.dim
+
+
+def dense_spd_metric(rng, dim):
+    """M = A A^T / D + I with A_ij ~ N(0, 1): condition number ~5."""
+    a = rng.standard_normal((dim, dim))
+    return a @ a.T / dim + np.identity(dim)
+
+
+def c0_std_gaussian(n_chains=4, dim=10, seed=BASE_SEED + 0):
+    rng = np.random.default_rng(seed)
+    return Problem(
+        name="C0",
+        integrator="leapfrog",
+        system="euclidean",
+        target="std_gaussian",
+        target_params={"dim": dim},
+        step_size=0.1,
+        pos=rng.standard_normal((n_chains, dim)),
+        mom=rng.standard_normal((n_chains, dim)),
+    )
+
+
+def c1_funnel(n_chains=8192, dim=128, seed=BASE_SEED + 1, metric_kind="dense"):
+    rng = np.random.default_rng(seed)
+    metric = dense_spd_metric(rng, dim)
+    pos = 0.1 * rng.standard_normal((n_chains, dim))
+    z = rng.standard_normal((n_chains, dim))
+    if metric_kind == "dense":
+        mom = z @ np.linalg.cholesky(metric).T  # p0 = L z per chain
+    elif metric_kind == "diagonal":
+        metric = np.ascontiguousarray(metric.diagonal())
+        mom = z * np.sqrt(metric)
+    else:
+        metric = None
+        mom = z
+    return Problem(
+        name="C1",
+        integrator="leapfrog",
+        system="euclidean",
+        target="neal_funnel",
+        target_params={"dim": dim},
+        step_size=0.01,
+        pos=pos,
+        mom=mom,
+        metric=metric,
+    )
+
+
+def c2_softabs_banana(n_chains=2048, dim=64, seed=BASE_SEED + 2):
+    rng = np.random.default_rng(seed)
+    return Problem(
+        name="C2",
+        integrator="implicit_leapfrog",
+        system="softabs_riemannian",
+        target="banana",
+        target_params={"dim": dim, "b": 0.5},
+        step_size=0.1,
+        pos=0.5 * rng.standard_normal((n_chains, dim)),
+        mom=rng.standard_normal((n_chains, dim)),
+        system_kwargs={"softabs_coeff": 1.0},
+    )
+
+
+def c3_torus(n_chains=4096, seed=BASE_SEED + 3, R=1.0, r=0.5, alpha=0.9):
+    rng = np.random.default_rng(seed)
+    theta, phi = rng.uniform(0, 2 * np.pi, size=(2, n_chains))
+    pos = np.stack(
+        [
+            (R + r * np.cos(phi)) * np.cos(theta),
+            (R + r * np.cos(phi)) * np.sin(theta),
+            r * np.sin(phi),
+        ],
+        -1,
+    )
+    mom = rng.standard_normal((n_chains, 3))
+    # project the initial momentum onto the cotangent space (identity metric):
+    # p -= J^T (J J^T)^-1 J p with J = [2(rho-R)x/rho, 2(rho-R)y/rho, 2z]
+    rho = np.sqrt(pos[:, 0] ** 2 + pos[:, 1] ** 2)
+    f = 2.0 * (rho - R) / rho
+    jac = np.stack([f * pos[:, 0], f * pos[:, 1], 2.0 * pos[:, 2]], -1)
+    mom = mom - jac * ((jac * mom).sum(-1) / (jac * jac).sum(-1))[:, None]
+    return Problem(
+        name="C3",
+        integrator="constrained_leapfrog",
+        system="constrained_euclidean",
+        target="torus",
+        target_params={"R": R, "r": r, "alpha": alpha},
+        step_size=0.1,
+        pos=pos,
+        mom=mom,
+        integrator_kwargs={"n_inner_step": 1},
+    )
+
+
+def c4_dense_riemannian(n_chains=8192, dim=512, seed=BASE_SEED + 4, coeff=0.1):
+    rng = np.random.default_rng(seed)
+    g = rng.standard_normal((dim, dim))
+    prec = np.identity(dim) + 0.1 * (g @ g.T) / dim
+    base = dense_spd_metric(rng, dim)
+    pos = 0.5 * rng.standard_normal((n_chains, dim))
+    mom = rng.standard_normal((n_chains, dim)) @ np.linalg.cholesky(base).T
+    return Problem(
+        name="C4",
+        integrator="implicit_leapfrog",
+        system="dense_riemannian",
+        target="quadratic",
+        target_params={"prec": prec},
+        step_size=0.05,
+        pos=pos,
+        mom=mom,
+        metric_model="rank1",
+        metric_params={"base": base, "coeff": coeff},
+    )
+
+
+CONFIGS = {
+    "C0": c0_std_gaussian,
+    "C1": c1_funnel,
+    "C2": c2_softabs_banana,
+    "C3": c3_torus,
+    "C4": c4_dense_riemannian,
+}
+
+
+def make_problem(name, **kwargs):
+    """Build config ``name`` (``"C0"``..``"C4"``), optionally overriding sizes/seed."""
+    return CONFIGS[name](**kwargs)

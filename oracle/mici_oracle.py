@@ -1,0 +1,589 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU (NumPy/SciPy) restatement of Mici's ``Integrator.step``.
+
+This module is the *oracle* for the CUDA hot path.  It restates, one chain at a time and
+with the same NumPy/SciPy calls in the same order, the arithmetic that the reference
+performs in
+
+* ``src/mici/integrators.py``  (``LeapfrogIntegrator._step`` :170-173,
+  ``ImplicitLeapfrogIntegrator`` :482-544, ``ConstrainedLeapfrogIntegrator`` :929-984)
+* ``src/mici/systems.py``      (``h1_flow`` :143-152, Euclidean ``h2_flow`` :352-363,
+  Riemannian derivatives :1375-1402, constrained-system methods :786-873, :1006-1031)
+* ``src/mici/solvers.py``      (``solve_fixed_point_direct`` :47-94,
+  ``solve_projection_onto_manifold_newton`` :346-469)
+* ``src/mici/matrices.py``     (dense SPD Cholesky / explicit inverse :1161-1188, :897-912,
+  :1060-1061, LU solve :1311, :1371-1384, SoftAbs :1631-1685)
+
+without the reference's memoising ``ChainState`` cache and ``Matrix`` object model (the
+cache only removes repeated evaluations; it does not change any value).
+
+Pinning: the reference's own tests hold no golden vectors for ``Integrator.step``
+(SURVEY.md section 8c).  The oracle is therefore pinned against *outputs of the reference
+itself*: ``oracle/make_golden.py`` imports the unmodified reference from
+``/root/reference/src``, steps seeded inputs through it, and commits the results under
+``tests/golden/``; ``tests/test_oracle.py`` checks this module against those fixtures
+(and against the live reference when it is importable).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may
+import this module.  Nothing under ``mici_b200/`` does.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import numpy.linalg as nla
+import scipy.linalg as sla
+
+# Per-chain outcome codes shared with the CUDA path (include/mici_b200.h)
+STATUS_OK = 0
+STATUS_CONVERGENCE = 1  # mici.errors.ConvergenceError
+STATUS_NON_REVERSIBLE = 2  # mici.errors.NonReversibleStepError
+STATUS_LINALG = 3  # mici.errors.LinAlgError surfaced as ConvergenceError by the solvers
+
+
+class OracleIntegratorError(RuntimeError):
+    """Stand-in for mici.errors.IntegratorError carrying the per-chain status code."""
+
+    def __init__(self, status, msg=""):
+        super().__init__(msg)
+        self.status = status
+
+
+class _LinAlgError(RuntimeError):
+    """Stand-in for mici.errors.LinAlgError (errors.py:22)."""
+
+
+def maximum_norm(vct):
+    """solvers.py:25-27."""
+    return (abs(vct)).max()
+
+
+# --------------------------------------------------------------------------------------
+# matrices.py arithmetic
+# --------------------------------------------------------------------------------------
+
+
+def _chkfinite(a):
+    """ExplicitArrayMatrix.__init__ (matrices.py:207-215): non-finite -> LinAlgError."""
+    if not np.all(np.isfinite(a)):
+        raise _LinAlgError("Array is not finite.")
+    return a
+
+
+def dense_spd_factor(m):
+    """DenseDefiniteMatrix.factor (matrices.py:1161-1173): lower Cholesky factor."""
+    try:
+        return nla.cholesky(m)
+    except nla.LinAlgError as e:
+        raise _LinAlgError("Cholesky factorisation failed.") from e
+
+
+def dense_spd_inverse(m, chol=None):
+    """Explicit dense inverse exactly as the reference builds it.
+
+    ``DensePositiveDefiniteMatrix._construct_inv`` (matrices.py:1209-1210) ->
+    ``DenseDefiniteMatrix._construct_inv`` (:1183-1188) ->
+    ``_BaseTriangularFactoredDefiniteMatrix._construct_inv`` (:979-980) builds
+    ``TriangularFactoredDefiniteMatrix(factor=L.inv.T)`` whose ``.array`` (:1060-1061) is
+    ``factor @ factor.array.T`` with ``factor = InverseTriangularMatrix(L.T, lower=False)``:
+
+    * ``factor.array = solve_triangular(L.T, I, lower=False)``        (:906-912)
+    * ``factor @ X    = solve_triangular(L.T, X, lower=False)``        (:897-903)
+    """
+    _chkfinite(m)
+    if chol is None:
+        chol = dense_spd_factor(m)
+    lt = chol.T
+    inv_lt = sla.solve_triangular(lt, np.identity(m.shape[0]), lower=False, check_finite=False)
+    inv = sla.solve_triangular(lt, inv_lt.T, lower=False, check_finite=False)
+    return _chkfinite(inv)
+
+
+class IdentityMetric:
+    """matrices.IdentityMatrix (matrices.py:491-554)."""
+
+    kind = "identity"
+
+    def inv_matvec(self, v):
+        return v
+
+    def sqrt_matvec(self, v):
+        return v
+
+
+class DiagonalMetric:
+    """matrices.PositiveDiagonalMatrix (matrices.py:771-792, 709-768)."""
+
+    kind = "diagonal"
+
+    def __init__(self, diagonal):
+        self.diagonal = np.asarray(diagonal, dtype=np.float64)
+        self.inv_diagonal = 1.0 / self.diagonal
+
+    def inv_matvec(self, v):
+        return self.inv_diagonal * v
+
+    def sqrt_matvec(self, v):
+        return self.diagonal**0.5 * v
+
+
+class DenseMetric:
+    """matrices.DensePositiveDefiniteMatrix used as a fixed metric (systems.py:339-340)."""
+
+    kind = "dense"
+
+    def __init__(self, array):
+        self.array = np.asarray(array, dtype=np.float64)
+        self.chol = dense_spd_factor(self.array)
+        self.inv_array = dense_spd_inverse(self.array, self.chol)
+
+    def inv_matvec(self, v):
+        # ExplicitArrayMatrix._left_matrix_multiply (matrices.py:222-223)
+        return self.inv_array @ v
+
+    def sqrt_matvec(self, v):
+        return self.chol @ v
+
+
+def coerce_metric(metric):
+    """EuclideanMetricSystem.__init__ metric coercion (systems.py:332-346)."""
+    if metric is None:
+        return IdentityMetric()
+    if isinstance(metric, (IdentityMetric, DiagonalMetric, DenseMetric)):
+        return metric
+    metric = np.asarray(metric)
+    if metric.ndim == 1:
+        return DiagonalMetric(metric)
+    if metric.ndim == 2:
+        return DenseMetric(metric)
+    raise ValueError("metric must be None, 1D or 2D")
+
+
+# --------------------------------------------------------------------------------------
+# Explicit leapfrog on a Euclidean-metric system
+# --------------------------------------------------------------------------------------
+
+
+def euclidean_h(q, p, target, metric):
+    """System.h = h1 + h2 (systems.py:187-196); h2 = 0.5 p . M^-1 p (:348-350)."""
+    return target.neg_log_dens(q) + 0.5 * (p @ metric.inv_matvec(p))
+
+
+def leapfrog_steps(q, p, time_step, n_steps, target, metric):
+    """``n_steps`` calls of ``LeapfrogIntegrator.step`` (integrators.py:63-80, 170-173).
+
+    ``time_step = state.dir * step_size``.  The reference evaluates the gradient once per
+    step because ``grad_neg_log_dens`` is memoised on ``pos`` (systems.py:109-119,
+    states.py:248-258): the trailing half-step's gradient is reused by the next leading
+    half-step.  The two half-step momentum updates are kept separate (two roundings).
+    """
+    q = np.array(q, dtype=np.float64)
+    p = np.array(p, dtype=np.float64)
+    metric = coerce_metric(metric)
+    grad = target.grad_neg_log_dens(q)
+    for _ in range(n_steps):
+        p -= (0.5 * time_step) * grad  # h1_flow  systems.py:143-152
+        q += time_step * metric.inv_matvec(p)  # h2_flow  systems.py:362-363
+        grad = target.grad_neg_log_dens(q)
+        p -= (0.5 * time_step) * grad
+    return q, p
+
+
+# --------------------------------------------------------------------------------------
+# solve_fixed_point_direct
+# --------------------------------------------------------------------------------------
+
+
+def solve_fixed_point_direct(func, x0, convergence_tol=1e-9, divergence_tol=1e10, max_iters=100):
+    """solvers.py:47-94 with ``norm=maximum_norm``.  Returns ``(x, n_iters)``."""
+    error = np.nan
+    try:
+        for i in range(max_iters):
+            x = func(x0)
+            error = maximum_norm(x - x0)
+            if error > divergence_tol or np.isnan(error):
+                raise OracleIntegratorError(STATUS_CONVERGENCE, f"diverged at iteration {i}")
+            if error < convergence_tol:
+                return x, i + 1
+            x0 = x
+    except (ValueError, _LinAlgError) as e:
+        raise OracleIntegratorError(STATUS_CONVERGENCE, f"{type(e)} in fixed point solver") from e
+    raise OracleIntegratorError(STATUS_CONVERGENCE, f"did not converge, last error {error}")
+
+
+# --------------------------------------------------------------------------------------
+# Riemannian metrics (position dependent)
+# --------------------------------------------------------------------------------------
+
+
+class DenseRiemannianMetricValue:
+    """``DensePositiveDefiniteMatrix(metric_func(q))`` (systems.py:1360-1373, 1727-1734)."""
+
+    def __init__(self, array):
+        self.array = _chkfinite(np.asarray(array))
+        self.chol = dense_spd_factor(self.array)
+        self.inv_array = dense_spd_inverse(self.array, self.chol)
+
+    @property
+    def log_abs_det(self):
+        # _BaseTriangularFactoredDefiniteMatrix.log_abs_det (matrices.py:982-984)
+        return 2 * np.log(np.abs(self.chol.diagonal())).sum()
+
+    def inv_matvec(self, v):
+        return self.inv_array @ v
+
+    def sqrt_matvec(self, v):
+        return self.chol @ v
+
+    @property
+    def grad_log_abs_det(self):
+        # matrices.py:1175-1177
+        return self.inv_array
+
+    def grad_quadratic_form_inv(self, v):
+        # matrices.py:1179-1181
+        w = self.inv_array @ v
+        return -np.outer(w, w)
+
+
+class SoftAbsMetricValue:
+    """``SoftAbsRegularizedPositiveDefiniteMatrix`` (matrices.py:1631-1685)."""
+
+    def __init__(self, symmetric_array, softabs_coeff):
+        self.coeff = softabs_coeff
+        try:
+            self.unreg_eigval, self.eigvec = nla.eigh(symmetric_array)
+        except nla.LinAlgError as e:  # surfaces as ValueError-like failure inside solver
+            raise _LinAlgError("eigh failed") from e
+        self.eigval = self.softabs(self.unreg_eigval)
+        if not np.all(self.eigval > 0):
+            # EigendecomposedPositiveDefiniteMatrix.__init__ (matrices.py:1606-1609); NaN
+            # eigenvalues land here too.  ValueError -> ConvergenceError inside solvers.
+            raise ValueError("Eigenvalues must all be positive.")
+
+    def softabs(self, x):
+        return x / np.tanh(x * self.coeff)  # :1662-1664
+
+    def grad_softabs(self, x):
+        return 1.0 / np.tanh(self.coeff * x) - self.coeff * x / np.sinh(self.coeff * x) ** 2
+
+    @property
+    def log_abs_det(self):
+        # SymmetricMatrix.log_abs_det (matrices.py:456-459)
+        return np.log(np.abs(self.eigval)).sum()
+
+    def inv_matvec(self, v):
+        # EigendecomposedSymmetricMatrix._left_matrix_multiply (:1555-1556) with 1/eigval
+        return self.eigvec @ ((1 / self.eigval) * (self.eigvec.T @ v))
+
+    def sqrt_matvec(self, v):
+        return self.eigvec @ (self.eigval**0.5 * (self.eigvec.T @ v))
+
+    @property
+    def grad_log_abs_det(self):
+        # :1673-1676 -> EigendecomposedSymmetricMatrix._construct_array (:1565-1572)
+        grad_eigval = self.grad_softabs(self.unreg_eigval) / self.eigval
+        d = self.eigvec.shape[0]
+        return self.eigvec @ (grad_eigval[:, None] * (self.eigvec.T @ np.identity(d)))
+
+    def grad_quadratic_form_inv(self, vector):
+        # :1678-1685
+        num_j_mtx = self.eigval[:, None] - self.eigval[None, :]
+        num_j_mtx += np.diag(self.grad_softabs(self.unreg_eigval))
+        den_j_mtx = self.unreg_eigval[:, None] - self.unreg_eigval[None, :]
+        np.fill_diagonal(den_j_mtx, 1)
+        j_mtx = num_j_mtx / den_j_mtx
+        e_vct = self.eigvec.T @ vector / self.eigval
+        return -(self.eigvec @ (np.outer(e_vct, e_vct) * j_mtx) @ self.eigvec.T)
+
+
+class RiemannianSystem:
+    """``RiemannianMetricSystem`` derivative plumbing (systems.py:1360-1402).
+
+    ``kind='dense'``  : DenseRiemannianMetricSystem  -- ``metric_model`` supplies
+                        ``metric_func`` / ``vjp_metric_func``.
+    ``kind='softabs'``: SoftAbsRiemannianMetricSystem -- metric is SoftAbs of the target
+                        Hessian, VJP is the target's matrix-Tressian product (:1846-1920).
+    """
+
+    def __init__(self, target, kind, metric_model=None, softabs_coeff=1.0):
+        self.target = target
+        self.kind = kind
+        self.metric_model = metric_model
+        self.softabs_coeff = softabs_coeff
+        self.n_metric_evals = 0
+
+    def metric(self, q):
+        self.n_metric_evals += 1
+        if self.kind == "dense":
+            return DenseRiemannianMetricValue(self.metric_model.metric_func(q))
+        return SoftAbsMetricValue(self.target.hess_neg_log_dens(q), self.softabs_coeff)
+
+    def vjp(self, q):
+        if self.kind == "dense":
+            return self.metric_model.vjp_metric_func(q)
+        return self.target.mtp_neg_log_dens(q)
+
+    def h(self, q, p):
+        m = self.metric(q)
+        # h1 (:1378-1379) + h2 (:1387-1388)
+        return (self.target.neg_log_dens(q) + 0.5 * m.log_abs_det) + 0.5 * (p @ m.inv_matvec(p))
+
+    def dh1_dpos(self, q, m=None):
+        m = self.metric(q) if m is None else m
+        return self.target.grad_neg_log_dens(q) + 0.5 * self.vjp(q)(m.grad_log_abs_det)
+
+    def dh2_dpos(self, q, p, m=None):
+        m = self.metric(q) if m is None else m
+        return 0.5 * self.vjp(q)(m.grad_quadratic_form_inv(p))
+
+    def dh2_dmom(self, q, p, m=None):
+        m = self.metric(q) if m is None else m
+        return m.inv_matvec(p)
+
+
+def implicit_leapfrog_step(
+    q,
+    p,
+    time_step,
+    system,
+    reverse_check_tol=2e-8,
+    fixed_point_solver_kwargs=None,
+    counts=None,
+):
+    """One ``ImplicitLeapfrogIntegrator.step`` (integrators.py:482-544).
+
+    NB: ``_step`` passes ``time_step`` *unchanged* to all six sub-maps
+    (:538-544), so one call advances time by ``2*time_step``; this is reproduced as is.
+    Raises OracleIntegratorError with the status code on failure.  ``counts`` (dict) collects
+    the fixed-point iteration counts of the four solves.
+    """
+    kw = {} if fixed_point_solver_kwargs is None else fixed_point_solver_kwargs
+    q = np.array(q, dtype=np.float64)
+    p = np.array(p, dtype=np.float64)
+    dt = time_step
+    its = []
+
+    def solve(func, x0):
+        x, n = solve_fixed_point_direct(func, x0, **kw)
+        its.append(n)
+        return x
+
+    def step_b_fwd(q, p, dt):
+        # :496-502 -- fixed point in p at fixed q (metric cached on pos: one build)
+        m = system.metric(q)
+        p_init = p
+        return solve(lambda mom: p_init - dt * system.dh2_dpos(q, mom, m), p_init)
+
+    def step_c_adj(q, p, dt):
+        # :530-536 -- fixed point in q, new metric every iteration
+        q_init = q
+        return solve(lambda pos: q_init + dt * system.dh2_dmom(pos, p), q_init)
+
+    try:
+        # _step_a :493-494
+        p = p - dt * system.dh1_dpos(q)
+        # _step_b_fwd
+        p = step_b_fwd(q, p, dt)
+        # _step_c_fwd :517-528
+        q_init = q.copy()
+        q = q + dt * system.dh2_dmom(q, p)
+        q_back = step_c_adj(q.copy(), p, -dt)
+        rev_diff = maximum_norm(q_back - q_init)
+        if rev_diff > reverse_check_tol:
+            raise OracleIntegratorError(STATUS_NON_REVERSIBLE, f"pos rev diff {rev_diff}")
+        # _step_c_adj
+        q = step_c_adj(q, p, dt)
+        # _step_b_adj :504-515
+        p_init = p.copy()
+        p = p - dt * system.dh2_dpos(q, p)
+        p_back = step_b_fwd(q, p.copy(), -dt)
+        rev_diff = maximum_norm(p_back - p_init)
+        if rev_diff > reverse_check_tol:
+            raise OracleIntegratorError(STATUS_NON_REVERSIBLE, f"mom rev diff {rev_diff}")
+        # _step_a
+        p = p - dt * system.dh1_dpos(q)
+    except (ValueError, _LinAlgError) as e:
+        # Outside the solvers the reference would propagate these as ValueError/LinAlgError
+        # (not IntegratorError); they only occur for non-finite states.
+        raise OracleIntegratorError(STATUS_LINALG, str(e)) from e
+    finally:
+        if counts is not None:
+            counts["fp_iters"] = its
+    return q, p
+
+
+# --------------------------------------------------------------------------------------
+# Constrained leapfrog (RATTLE / geodesic integrator) on a Euclidean-metric system
+# --------------------------------------------------------------------------------------
+
+
+class ConstrainedSystem:
+    """``DenseConstrainedEuclideanMetricSystem`` with ``dens_wrt_hausdorff=True``
+    (systems.py:786-873, 1006-1022)."""
+
+    def __init__(self, target, metric=None):
+        self.target = target
+        self.metric = coerce_metric(metric)
+        self.n_constr_evals = 0
+
+    def constr(self, q):
+        self.n_constr_evals += 1
+        return self.target.constr(q)
+
+    def jacob_constr(self, q):
+        return self.target.jacob_constr(q)
+
+    def inv_metric_mat(self, a):
+        """``metric.inv @ a`` for a [D] vector or [D, K] matrix."""
+        m = self.metric
+        if m.kind == "identity":
+            return a
+        if m.kind == "diagonal":
+            return m.inv_diagonal[:, None] * a if a.ndim == 2 else m.inv_diagonal * a
+        return m.inv_array @ a
+
+    def h(self, q, p):
+        return self.target.neg_log_dens(q) + 0.5 * (p @ self.inv_metric_mat(p))
+
+    def project_onto_cotangent_space(self, mom, q):
+        """systems.py:863-873: p -= J^T (gram^-1 (J (M^-1 p))), gram = J M^-1 J^T as a
+        DensePositiveDefiniteMatrix whose ``.inv @ v`` is the explicit-inverse matvec."""
+        jac = self.jacob_constr(q)
+        gram = jac @ self.inv_metric_mat(jac.T)  # systems.py:1013-1016
+        inv_gram = dense_spd_inverse(gram)
+        mom = mom - jac.T @ (inv_gram @ (jac @ self.inv_metric_mat(mom)))
+        return mom
+
+
+def solve_projection_onto_manifold_newton(
+    q,
+    p,
+    q_prev,
+    time_step,
+    system,
+    constraint_tol=1e-9,
+    position_tol=1e-8,
+    divergence_tol=1e10,
+    max_iters=50,
+    counts=None,
+):
+    """solvers.py:346-469 for a Euclidean metric: ``dh2_flow_dmom = (|dt| M^-1, I)``
+    (systems.py:794-799); residual Jacobian ``J (|dt| M^-1) J_prev^T`` is a
+    ``DenseSquareMatrix`` solved by pivoted LU (systems.py:1020-1022, matrices.py:1311,
+    1371-1384).  Returns ``(q, p)``; raises OracleIntegratorError(STATUS_CONVERGENCE)."""
+    q = q.copy()
+    p = p.copy()
+    mu = np.zeros_like(q)
+    jac_prev = system.jacob_constr(q_prev)
+    adt = abs(time_step)
+    error = np.nan
+    try:
+        for i in range(max_iters):
+            jac = system.jacob_constr(q)
+            c = system.constr(q)
+            error = maximum_norm(c)
+            # dt * metric.inv is a scaled matrix object in the reference:
+            #  identity -> PositiveScaledIdentityMatrix (scalar*J^T),
+            #  diagonal -> PositiveDiagonalMatrix(dt * 1/diag),
+            #  dense    -> DensePositiveDefiniteMatrix(dt * inv_array)
+            res_jac = _chkfinite(jac @ _scaled_inv_metric(system, adt, jac_prev.T))
+            lu_piv = sla.lu_factor(res_jac, check_finite=False)
+            delta_mu = jac_prev.T @ sla.lu_solve(lu_piv, c, 0, check_finite=False)
+            delta_pos = _scaled_inv_metric(system, adt, delta_mu)
+            if error > divergence_tol or np.isnan(error):
+                raise OracleIntegratorError(STATUS_CONVERGENCE, f"Newton diverged at {i}")
+            if error < constraint_tol and maximum_norm(delta_pos) < position_tol:
+                p -= np.sign(time_step) * mu
+                if counts is not None:
+                    counts.setdefault("newton_iters", []).append(i + 1)
+                return q, p
+            mu += delta_mu
+            q -= delta_pos
+    except (ValueError, _LinAlgError) as e:
+        raise OracleIntegratorError(STATUS_CONVERGENCE, f"{type(e)} in Newton solver") from e
+    raise OracleIntegratorError(STATUS_CONVERGENCE, f"Newton did not converge, |c|={error}")
+
+
+def _scaled_inv_metric(system, scale, a):
+    """``(scale * metric.inv) @ a`` with the reference's order of operations."""
+    m = system.metric
+    if m.kind == "identity":
+        return scale * a  # PositiveScaledIdentityMatrix._left_matrix_multiply
+    if m.kind == "diagonal":
+        d = scale * m.inv_diagonal  # _scalar_multiply then diagonal product
+        return d[:, None] * a if a.ndim == 2 else d * a
+    return (scale * m.inv_array) @ a  # DenseDefiniteMatrix._scalar_multiply (:1138-1154)
+
+
+def constrained_leapfrog_step(
+    q,
+    p,
+    time_step,
+    system,
+    n_inner_step=1,
+    reverse_check_tol=2e-8,
+    projection_solver_kwargs=None,
+    counts=None,
+):
+    """One ``ConstrainedLeapfrogIntegrator.step`` (integrators.py:929-984)."""
+    kw = {} if projection_solver_kwargs is None else projection_solver_kwargs
+    q = np.array(q, dtype=np.float64)
+    p = np.array(p, dtype=np.float64)
+    tgt = system.target
+
+    def h2_flow_retraction(q, p, q_prev, dt):
+        # :929-942 ; h2_flow systems.py:362-363
+        q = q + dt * system.inv_metric_mat(p)
+        return solve_projection_onto_manifold_newton(q, p, q_prev, dt, system, counts=counts, **kw)
+
+    try:
+        # _step_a(dt/2) :947-949
+        p = p - (0.5 * time_step) * tgt.grad_neg_log_dens(q)
+        p = system.project_onto_cotangent_space(p, q)
+        # _step_b(dt) :951-979
+        dt_inner = time_step / n_inner_step
+        for _ in range(n_inner_step):
+            q_prev = q.copy()
+            q, p = h2_flow_retraction(q, p, q_prev, dt_inner)
+            p = system.project_onto_cotangent_space(p, q)
+            q_back, _ = h2_flow_retraction(q.copy(), p.copy(), q, -dt_inner)
+            rev_diff = maximum_norm(q_back - q_prev)
+            if rev_diff > reverse_check_tol:
+                raise OracleIntegratorError(STATUS_NON_REVERSIBLE, f"rev diff {rev_diff}")
+        # _step_a(dt/2)
+        p = p - (0.5 * time_step) * tgt.grad_neg_log_dens(q)
+        p = system.project_onto_cotangent_space(p, q)
+    except (ValueError, _LinAlgError) as e:
+        raise OracleIntegratorError(STATUS_LINALG, str(e)) from e
+    return q, p
+
+
+# --------------------------------------------------------------------------------------
+# Batch drivers (loop over chains, convert failures to status codes)
+# --------------------------------------------------------------------------------------
+
+
+def run_batch(step_fn, q, p, dirs, n_steps):
+    """Apply ``step_fn(q_i, p_i, dir_i) -> (q_i, p_i)`` ``n_steps`` times to every chain.
+
+    A chain whose step raises keeps the state it had *before* the failing step and records
+    the status code; it takes no further steps (the reference's transitions terminate the
+    trajectory on ``IntegratorError``: transitions.py:292-295).
+    """
+    q = np.array(q, dtype=np.float64)
+    p = np.array(p, dtype=np.float64)
+    n = q.shape[0]
+    status = np.zeros(n, dtype=np.int32)
+    n_done = np.zeros(n, dtype=np.int32)
+    dirs = np.ones(n, dtype=np.int32) if dirs is None else np.broadcast_to(dirs, (n,))
+    for i in range(n):
+        qi, pi = q[i], p[i]
+        for _ in range(n_steps):
+            try:
+                qi, pi = step_fn(qi, pi, int(dirs[i]))
+            except OracleIntegratorError as e:
+                status[i] = e.status
+                break
+            n_done[i] += 1
+        q[i], p[i] = qi, pi
+    return q, p, status, n_done

@@ -1,0 +1,46 @@
+"""Load the committed reference fixtures (tests/golden/*.npz, made by oracle/make_golden.py)."""
+
+import os
+
+import numpy as np
+
+from mici_b200 import problems as pb
+from oracle.make_golden import CASES, FAILURE_CASES, GOLDEN_DIR, input_checksum
+
+RTOL = 1e-10  # north_star: 1e-10 rtol in fp64
+ATOL = 1e-12
+
+
+def case_names(failures=False):
+    return list(FAILURE_CASES if failures else CASES)
+
+
+def load_case(name):
+    """Return (problem, dirs, overrides, golden npz dict)."""
+    if name in CASES:
+        cfg, kwargs, _, overrides = CASES[name]
+        step_size = None
+    else:
+        cfg, kwargs, step_size, _, overrides = FAILURE_CASES[name]
+    problem = pb.make_problem(cfg, **kwargs)
+    if step_size is not None:
+        problem.step_size = step_size
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    np.testing.assert_allclose(input_checksum(problem), g["input_checksum"], rtol=1e-13)
+    assert float(g["step_size"]) == problem.step_size
+    return problem, g["dirs"], overrides, g
+
+
+def assert_matches_golden(out, g, n_steps, rtol=RTOL, atol=ATOL, label=""):
+    """Compare a run's (pos, mom, status, n_done[, h]) with the reference fixture."""
+    np.testing.assert_array_equal(out["status"], g[f"status_{n_steps}"], err_msg=f"{label} status")
+    np.testing.assert_array_equal(out["n_done"], g[f"n_done_{n_steps}"], err_msg=f"{label} n_done")
+    for key in ("pos", "mom"):
+        np.testing.assert_allclose(
+            out[key], g[f"{key}_{n_steps}"], rtol=rtol, atol=atol, err_msg=f"{label} {key}"
+        )
+    if "h" in out and out["h"] is not None:
+        ok = np.isfinite(g[f"h_{n_steps}"])
+        np.testing.assert_allclose(
+            np.asarray(out["h"])[ok], g[f"h_{n_steps}"][ok], rtol=rtol, atol=1e-9, err_msg=f"{label} h"
+        )
