@@ -1,0 +1,168 @@
+/*
+ * mici_b200.h -- C ABI of libmici_b200.so: batched-chain Hamiltonian integrator steps on
+ * NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for ONE hot path of matt-graham/mici: `Integrator.step`
+ * evaluated over many independent chains.  Each entry point replaces the per-chain Python
+ * call chain named in its comment (paths relative to the reference tree).  The reference is
+ * pure Python with no FFI; a maintainer binds these with `ctypes`.
+ *
+ * Conventions
+ *  - All array pointers are DEVICE pointers (e.g. torch.Tensor.data_ptr()), fp64, row-major
+ *    `[n_chains x dim]`, 16-byte aligned.  `target_params` is a HOST pointer (<= 8 doubles,
+ *    copied by value into the launch).
+ *  - `dir` may be NULL (all chains +1) or int32[n_chains] with entries +-1; the signed time
+ *    step of a chain is `dir * step_size` (integrators.py:79).
+ *  - Out-of-place: `*_out` may alias `*_in` (in-place) or be distinct buffers, so that
+ *    `Integrator.step` keeps its "returns a new state, argument untouched" contract
+ *    (integrators.py:78-80, tests/test_integrators.py:110-124) without an extra copy.
+ *  - Return value: 0 = launched, <0 = argument / launch error (message via
+ *    mb200_last_error()).  Never throws.  Launches are asynchronous on `stream`
+ *    (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *  - Per-chain outcome replaces the reference's exceptions (errors.py:10-27):
+ *    `status[i]` is one of MB200_STATUS_*; a chain whose step fails keeps the state it had
+ *    BEFORE the failing step and takes no further steps in that launch (the reference's
+ *    transitions abort the trajectory on IntegratorError: transitions.py:292-295).
+ *    `n_done[i]` (optional) counts completed steps.
+ *  - Re-entrant: no global mutable state apart from a thread-local error string.
+ */
+#ifndef MICI_B200_H
+#define MICI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB200_VERSION 100
+
+/* per-chain status codes */
+#define MB200_STATUS_OK 0
+#define MB200_STATUS_CONVERGENCE 1    /* mici.errors.ConvergenceError      */
+#define MB200_STATUS_NON_REVERSIBLE 2 /* mici.errors.NonReversibleStepError */
+#define MB200_STATUS_LINALG 3         /* mici.errors.LinAlgError            */
+
+/* error returns */
+#define MB200_ERR_INVALID_ARG (-1)
+#define MB200_ERR_UNSUPPORTED (-2)
+#define MB200_ERR_CUDA (-3)
+
+/* fixed metric of a Euclidean system (systems.py:332-346 coercion) */
+#define MB200_METRIC_IDENTITY 0 /* metric_inv ignored                         */
+#define MB200_METRIC_DIAGONAL 1 /* metric_inv = 1/diag, [dim]                 */
+#define MB200_METRIC_DENSE 2    /* metric_inv = explicit dense M^-1, [dim*dim] */
+
+/* closed registry of target models compiled into the library */
+#define MB200_TARGET_STD_GAUSSIAN 0 /* l = |q|^2/2                      params: -            */
+#define MB200_TARGET_NEAL_FUNNEL 1  /* Neal's funnel                    params: -            */
+#define MB200_TARGET_BANANA 2       /* paired banana                    params: b            */
+#define MB200_TARGET_QUADRATIC 3    /* l = q^T P q / 2                  aux: P [dim*dim]     */
+#define MB200_TARGET_TORUS 4        /* density on torus (README:315-337) params: R, r, alpha */
+#define MB200_TARGET_SPHERE 5       /* tilted density on unit sphere    params: -            */
+
+/* position-dependent metrics of Riemannian systems */
+#define MB200_RMETRIC_SOFTABS 0 /* SoftAbs of target Hessian (matrices.py:1631-1685); params: softabs_coeff */
+#define MB200_RMETRIC_RANK1 1   /* dense M(q) = B + c q q^T;  aux: B [dim*dim], params: c                   */
+
+#define MB200_MAX_PARAMS 8
+
+typedef struct mb200_model {
+  int32_t target_id;                       /* MB200_TARGET_*                              */
+  int32_t n_target_params;
+  double target_params[MB200_MAX_PARAMS];
+  const double* target_aux;                /* device pointer or NULL                      */
+  int32_t rmetric_id;                      /* MB200_RMETRIC_* (Riemannian entry points)   */
+  int32_t n_rmetric_params;
+  double rmetric_params[MB200_MAX_PARAMS];
+  const double* rmetric_aux;               /* device pointer or NULL                      */
+} mb200_model;
+
+int mb200_version(void);
+const char* mb200_last_error(void);
+
+/*
+ * n_steps explicit leapfrog steps on a Euclidean-metric system, fused gradient.
+ * Replaces: LeapfrogIntegrator.step/_step (integrators.py:63-80, 170-173) +
+ *           System.h1_flow/dh1_dpos/grad_neg_log_dens (systems.py:109-152) +
+ *           EuclideanMetricSystem.h2_flow/dh2_dmom (systems.py:352-363) +
+ *           explicit-inverse matvec (matrices.py:222-226, 1183-1188).
+ * h_out (optional, [n_chains]): Hamiltonian of the returned state (systems.py:187-196,348-350).
+ */
+int mb200_leapfrog_euclidean(const double* pos_in, const double* mom_in, double* pos_out,
+                             double* mom_out, const int32_t* dir, int64_t n_chains, int32_t dim,
+                             double step_size, int32_t n_steps, int32_t metric_kind,
+                             const double* metric_inv, const mb200_model* model, double* h_out,
+                             int32_t* status, int32_t* n_done, void* stream);
+
+/* Diagnostic: identical contract, but always through the general-dimension kernel (never the
+ * tensor-core kernel); used by the tests to cross-check the two implementations. */
+int mb200_leapfrog_euclidean_generic(const double* pos_in, const double* mom_in, double* pos_out,
+                                     double* mom_out, const int32_t* dir, int64_t n_chains,
+                                     int32_t dim, double step_size, int32_t n_steps,
+                                     int32_t metric_kind, const double* metric_inv,
+                                     const mb200_model* model, double* h_out, int32_t* status,
+                                     int32_t* n_done, void* stream);
+
+/* Hamiltonian h = l(q) + p.M^-1 p / 2 of a Euclidean-metric system (systems.py:187-196, 348-350). */
+int mb200_hamiltonian_euclidean(const double* pos, const double* mom, int64_t n_chains,
+                                int32_t dim, int32_t metric_kind, const double* metric_inv,
+                                const mb200_model* model, double* h_out, void* stream);
+
+/*
+ * Individual Euclidean-system quantities for callers outside `Integrator.step`
+ * (System.neg_log_dens / grad_neg_log_dens: systems.py:97-119; dh2_dmom / h2: systems.py:348-354).
+ * Any of nld_out [n], grad_out [n*dim], vel_out [n*dim] (= M^-1 p), kin_out [n] (= p.M^-1 p/2)
+ * may be NULL.
+ */
+int mb200_euclidean_eval(const double* pos, const double* mom, int64_t n_chains, int32_t dim,
+                         int32_t metric_kind, const double* metric_inv, const mb200_model* model,
+                         double* nld_out, double* grad_out, double* vel_out, double* kin_out,
+                         void* stream);
+
+/*
+ * n_steps constrained (RATTLE / geodesic) leapfrog steps with Newton projection.
+ * Replaces: ConstrainedLeapfrogIntegrator.step (integrators.py:929-984) +
+ *           solve_projection_onto_manifold_newton (solvers.py:346-469) +
+ *           DenseConstrainedEuclideanMetricSystem methods (systems.py:786-873, 1006-1022),
+ *           dens_wrt_hausdorff=True.
+ * newton_iters (optional, [n_chains]): total Newton iterations used by the chain.
+ */
+int mb200_constrained_leapfrog_euclidean(
+    const double* pos_in, const double* mom_in, double* pos_out, double* mom_out,
+    const int32_t* dir, int64_t n_chains, int32_t dim, double step_size, int32_t n_steps,
+    int32_t n_inner_step, int32_t metric_kind, const double* metric_inv, const mb200_model* model,
+    double constraint_tol, double position_tol, double divergence_tol, int32_t max_iters,
+    double reverse_check_tol, double* h_out, int32_t* status, int32_t* n_done,
+    int32_t* newton_iters, void* stream);
+
+/*
+ * n_steps implicit generalised-leapfrog steps on a Riemannian-metric system, fixed-point
+ * solves by direct iteration.
+ * Replaces: ImplicitLeapfrogIntegrator.step (integrators.py:482-544; NB every sub-map gets the
+ *           full dir*step_size) + solve_fixed_point_direct (solvers.py:47-94) +
+ *           RiemannianMetricSystem derivatives (systems.py:1360-1402) +
+ *           DensePositiveDefiniteMatrix / SoftAbsRegularizedPositiveDefiniteMatrix arithmetic
+ *           (matrices.py:1161-1188, 1631-1685).
+ * fp_iters (optional, [n_chains*4]): iterations of the four fixed-point solves of the LAST
+ *           completed step.  workspace: device scratch of mb200_implicit_workspace_bytes().
+ */
+int mb200_implicit_leapfrog_riemannian(
+    const double* pos_in, const double* mom_in, double* pos_out, double* mom_out,
+    const int32_t* dir, int64_t n_chains, int32_t dim, double step_size, int32_t n_steps,
+    const mb200_model* model, double fp_convergence_tol, double fp_divergence_tol,
+    int32_t fp_max_iters, double reverse_check_tol, double* h_out, int32_t* status,
+    int32_t* n_done, int32_t* fp_iters, void* workspace, int64_t workspace_bytes, void* stream);
+
+int64_t mb200_implicit_workspace_bytes(int64_t n_chains, int32_t dim, const mb200_model* model);
+
+/* Hamiltonian of a Riemannian system: l(q) + log|M(q)|/2 + p.M(q)^-1 p / 2 (systems.py:1375-1390). */
+int mb200_hamiltonian_riemannian(const double* pos, const double* mom, int64_t n_chains,
+                                 int32_t dim, const mb200_model* model, double* h_out,
+                                 int32_t* status, void* workspace, int64_t workspace_bytes,
+                                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MICI_B200_H */

@@ -1,0 +1,46 @@
+// Shared device helpers for libmici_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mici_b200.h"
+
+namespace mb200 {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, o));
+  return v;
+}
+
+// max that propagates NaN (numpy's abs(x).max() returns NaN if any entry is NaN;
+// solvers.py:25-27 + the `np.isnan(error)` checks at :80, :449)
+__device__ __forceinline__ double nanmax(double a, double b) {
+  return (a != a) ? a : ((b != b) ? b : fmax(a, b));
+}
+
+__device__ __forceinline__ double warp_nanmax(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(FULL_MASK, v, o));
+  return v;
+}
+
+// Model parameters passed by value in the kernel argument buffer.
+struct ModelArgs {
+  int target_id;
+  double tp[MB200_MAX_PARAMS];
+  const double* taux;
+  int rmetric_id;
+  double mp[MB200_MAX_PARAMS];
+  const double* maux;
+};
+
+}  // namespace mb200

@@ -1,0 +1,483 @@
+// K6: constrained (RATTLE / geodesic) leapfrog with Newton projection -- one warp per chain.
+//
+// Replaces, per chain (reference paths):
+//   ConstrainedLeapfrogIntegrator._step/_step_a/_step_b            integrators.py:929-984
+//   solve_projection_onto_manifold_newton                          solvers.py:346-469
+//   ConstrainedEuclideanMetricSystem.project_onto_cotangent_space  systems.py:863-873
+//   DenseConstrainedEuclideanMetricSystem.jacob_constr_inner_product systems.py:1006-1022
+//   dh2_flow_dmom = (|dt| M^-1, I)                                 systems.py:794-799
+//
+// One warp owns one chain for the whole launch; vectors are in registers in the pair layout of
+// metric_ops.cuh.  Every branch (Newton convergence, divergence, reversibility failure) is
+// uniform across the warp, so chains in other warps proceed independently: the per-chain
+// convergence mask of the reference's Python loop is the warp's own control flow.  The C x C
+// systems (C = Target::NC <= 4) are solved redundantly in registers by every lane.
+#pragma once
+#include "metric_ops.cuh"
+#include "targets.cuh"
+
+namespace mb200 {
+
+// ---------------------------------------------------------------------------------------------
+// Constrained targets (warp-cooperative interface, pair layout)
+//   grad(lane, dim, q, g)               gradient of l
+//   nld(lane, dim, q)                   l(q), same value on all lanes
+//   constr_jacob(lane, dim, q, c, J)    c(q) [NC] on all lanes; J[NC][NV] columns owned by lane
+// ---------------------------------------------------------------------------------------------
+
+// Torus in R^3 (reference README.md:315-337): rho = sqrt(x^2+y^2), theta = atan2(y, x),
+// phi = atan2(z, rho - R);  l = log1p(r cos(phi)/R) - log1p(alpha sin(4 theta) cos(phi));
+// c = (rho - R)^2 + z^2 - r^2.
+struct TorusTarget {
+  static constexpr int NC = 1;
+  double R, r, alpha;
+  __device__ TorusTarget(const ModelArgs& m, int) : R(m.tp[0]), r(m.tp[1]), alpha(m.tp[2]) {}
+
+  template <int NV>
+  __device__ __forceinline__ void gather(const double (&q)[NV], double& x, double& y,
+                                         double& z) const {
+    x = __shfl_sync(FULL_MASK, q[0], 0);
+    y = __shfl_sync(FULL_MASK, q[1], 0);
+    z = __shfl_sync(FULL_MASK, q[0], 1);
+  }
+
+  template <int NV>
+  __device__ __forceinline__ void grad(int lane, int, const double (&q)[NV],
+                                       double (&g)[NV]) const {
+    double x, y, z;
+    gather(q, x, y, z);
+    const double a = r / R;
+    const double rho2 = x * x + y * y;
+    const double rho = sqrt(rho2);
+    const double u = rho - R;
+    const double theta = atan2(y, x);
+    const double phi = atan2(z, u);
+    double s4, c4, sp, cp;
+    sincos(4.0 * theta, &s4, &c4);
+    sincos(phi, &sp, &cp);
+    const double d1 = 1.0 + a * cp;
+    const double d2 = 1.0 + alpha * s4 * cp;
+    const double dl_dphi = -a * sp / d1 + alpha * s4 * sp / d2;
+    const double dl_dth = -4.0 * alpha * c4 * cp / d2;
+    const double w = u * u + z * z;
+    const double dphi_du = -z / w;
+    const double dphi_dz = u / w;
+    const double gx = dl_dth * (-y / rho2) + dl_dphi * dphi_du * (x / rho);
+    const double gy = dl_dth * (x / rho2) + dl_dphi * dphi_du * (y / rho);
+    const double gz = dl_dphi * dphi_dz;
+#pragma unroll
+    for (int e = 0; e < NV; ++e) g[e] = 0.0;
+    if (lane == 0) g[0] = gx, g[1] = gy;
+    if (lane == 1) g[0] = gz;
+  }
+
+  template <int NV>
+  __device__ __forceinline__ double nld(int, int, const double (&q)[NV]) const {
+    double x, y, z;
+    gather(q, x, y, z);
+    const double rho = sqrt(x * x + y * y);
+    const double theta = atan2(y, x);
+    const double phi = atan2(z, rho - R);
+    return log1p(r * cos(phi) / R) - log1p(sin(4.0 * theta) * cos(phi) * alpha);
+  }
+
+  template <int NV>
+  __device__ __forceinline__ void constr_jacob(int lane, int, const double (&q)[NV],
+                                               double (&c)[NC], double (&J)[NC][NV]) const {
+    double x, y, z;
+    gather(q, x, y, z);
+    const double rho = sqrt(x * x + y * y);
+    const double d = rho - R;
+    c[0] = d * d + z * z - r * r;
+    const double f = 2.0 * d / rho;
+#pragma unroll
+    for (int e = 0; e < NV; ++e) J[0][e] = 0.0;
+    if (lane == 0) J[0][0] = f * x, J[0][1] = f * y;
+    if (lane == 1) J[0][0] = 2.0 * z;
+  }
+};
+
+// Unit sphere in R^D: l = |q|^2/2 + q[0];  c = |q|^2 - 1.
+struct SphereTarget {
+  static constexpr int NC = 1;
+  __device__ SphereTarget(const ModelArgs&, int) {}
+
+  template <int NV>
+  __device__ __forceinline__ void grad(int lane, int dim, const double (&q)[NV],
+                                       double (&g)[NV]) const {
+#pragma unroll
+    for (int e = 0; e < NV; ++e) {
+      const int i = 2 * lane + 64 * (e >> 1) + (e & 1);
+      g[e] = (i < dim) ? q[e] : 0.0;
+      if (i == 0) g[e] += 1.0;
+    }
+  }
+
+  template <int NV>
+  __device__ __forceinline__ double nld(int, int, const double (&q)[NV]) const {
+    double s = 0.0;
+#pragma unroll
+    for (int e = 0; e < NV; ++e) s = fma(q[e], q[e], s);
+    s = warp_sum(s);
+    return 0.5 * s + __shfl_sync(FULL_MASK, q[0], 0);
+  }
+
+  template <int NV>
+  __device__ __forceinline__ void constr_jacob(int, int, const double (&q)[NV], double (&c)[NC],
+                                               double (&J)[NC][NV]) const {
+    double s = 0.0;
+#pragma unroll
+    for (int e = 0; e < NV; ++e) s = fma(q[e], q[e], s);
+    c[0] = warp_sum(s) - 1.0;
+#pragma unroll
+    for (int e = 0; e < NV; ++e) J[0][e] = 2.0 * q[e];
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// small dense C x C algebra in registers (every lane holds the full matrix)
+// ---------------------------------------------------------------------------------------------
+
+// x = G^-1 u via the explicit inverse of the SPD Gram matrix built from its Cholesky factor,
+// as DensePositiveDefiniteMatrix.inv does (matrices.py:1161-1188): inv = L^-T (L^-1).
+template <int C>
+__device__ __forceinline__ void spd_inverse_apply(const double (&G)[C][C], const double (&u)[C],
+                                                  double (&x)[C]) {
+  double L[C][C];
+#pragma unroll
+  for (int i = 0; i < C; ++i)
+#pragma unroll
+    for (int j = 0; j < C; ++j) L[i][j] = 0.0;
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    double d = G[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+    d = sqrt(d);
+    L[j][j] = d;
+#pragma unroll
+    for (int i = j + 1; i < C; ++i) {
+      double s = G[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+      L[i][j] = s / d;
+    }
+  }
+  // Linv = L^-1 (lower), then inv = Linv^T Linv
+  double Li[C][C];
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+      if (i < j) {
+        Li[i][j] = 0.0;
+      } else {
+        double s = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+          if (k >= j && k < i) s -= L[i][k] * Li[k][j];
+        Li[i][j] = s / L[i][i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < C; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      double a = 0.0;
+#pragma unroll
+      for (int k = 0; k < C; ++k) a = fma(Li[k][i], Li[k][j], a);
+      s = fma(a, u[j], s);
+    }
+    x[i] = s;
+  }
+}
+
+// x = R^-1 c by LU with partial pivoting (scipy.linalg.lu_factor / lu_solve:
+// matrices.py:1311, 1371-1384)
+template <int C>
+__device__ __forceinline__ void lu_solve(double (&R)[C][C], const double (&c)[C],
+                                         double (&x)[C]) {
+  double b[C];
+#pragma unroll
+  for (int i = 0; i < C; ++i) b[i] = c[i];
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    int piv = k;
+    double best = fabs(R[k][k]);
+#pragma unroll
+    for (int i = k + 1; i < C; ++i) {
+      const double a = fabs(R[i][k]);
+      if (a > best) best = a, piv = i;
+    }
+#pragma unroll
+    for (int i = k + 1; i < C; ++i) {
+      if (i == piv) {
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+          const double t = R[k][j];
+          R[k][j] = R[i][j];
+          R[i][j] = t;
+        }
+        const double t = b[k];
+        b[k] = b[i];
+        b[i] = t;
+      }
+    }
+#pragma unroll
+    for (int i = k + 1; i < C; ++i) {
+      const double f = R[i][k] / R[k][k];
+#pragma unroll
+      for (int j = k + 1; j < C; ++j) R[i][j] -= f * R[k][j];
+      b[i] -= f * b[k];
+    }
+  }
+#pragma unroll
+  for (int i = C - 1; i >= 0; --i) {
+    double s = b[i];
+#pragma unroll
+    for (int j = i + 1; j < C; ++j) s -= R[i][j] * x[j];
+    x[i] = s / R[i][i];
+  }
+}
+
+template <class Target, int KP>
+struct ConstrainedOps {
+  static constexpr int NV = 2 * KP;
+  static constexpr int C = Target::NC;
+
+  const Target& t;
+  int metric_kind;
+  const double* minv;
+  int dim, lane;
+  double* psm;
+
+  __device__ __forceinline__ void inv_metric_rows(const double (&a)[C][NV],
+                                                  double (&out)[C][NV]) const {
+    inv_metric_apply<KP, C>(metric_kind, minv, dim, lane, psm, a, out);
+  }
+  __device__ __forceinline__ void inv_metric_vec(const double (&a)[NV], double (&out)[NV]) const {
+    double ai[1][NV], oi[1][NV];
+#pragma unroll
+    for (int e = 0; e < NV; ++e) ai[0][e] = a[e];
+    inv_metric_apply<KP, 1>(metric_kind, minv, dim, lane, psm, ai, oi);
+#pragma unroll
+    for (int e = 0; e < NV; ++e) out[e] = oi[0][e];
+  }
+  static __device__ __forceinline__ double dot(const double (&a)[NV], const double (&b)[NV]) {
+    double s = 0.0;
+#pragma unroll
+    for (int e = 0; e < NV; ++e) s = fma(a[e], b[e], s);
+    return warp_sum(s);
+  }
+  static __device__ __forceinline__ double maxabs(const double (&a)[NV]) {
+    double m = 0.0;
+#pragma unroll
+    for (int e = 0; e < NV; ++e) m = nanmax(m, fabs(a[e]));
+    return warp_nanmax(m);
+  }
+
+  // p <- p - J^T (J M^-1 J^T)^-1 J M^-1 p     (systems.py:863-873)
+  __device__ __forceinline__ void project(double (&p)[NV], const double (&q)[NV]) const {
+    double c[C], J[C][NV], W[C][NV], G[C][C], u[C], w[C], v[NV];
+    t.constr_jacob(lane, dim, q, c, J);
+    inv_metric_rows(J, W);  // W_d = M^-1 J_d^T
+#pragma unroll
+    for (int a = 0; a < C; ++a)
+#pragma unroll
+      for (int b = 0; b < C; ++b) G[a][b] = dot(J[a], W[b]);
+    inv_metric_vec(p, v);
+#pragma unroll
+    for (int a = 0; a < C; ++a) u[a] = dot(J[a], v);
+    spd_inverse_apply<C>(G, u, w);
+#pragma unroll
+    for (int e = 0; e < NV; ++e) {
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < C; ++a) s = fma(J[a][e], w[a], s);
+      p[e] = __dsub_rn(p[e], s);
+    }
+  }
+
+  // h2_flow then Newton retraction onto the manifold (integrators.py:929-942,
+  // solvers.py:346-469).  Returns false on ConvergenceError.
+  __device__ __forceinline__ bool retract(double (&q)[NV], double (&p)[NV],
+                                          const double (&q_prev)[NV], double dt,
+                                          double constraint_tol, double position_tol,
+                                          double divergence_tol, int max_iters,
+                                          int& iters) const {
+    double v[NV];
+    inv_metric_vec(p, v);
+#pragma unroll
+    for (int e = 0; e < NV; ++e) q[e] = __dadd_rn(q[e], __dmul_rn(dt, v[e]));
+    double mu[NV];
+#pragma unroll
+    for (int e = 0; e < NV; ++e) mu[e] = 0.0;
+    double cp[C], Jp[C][NV], S[C][NV];
+    t.constr_jacob(lane, dim, q_prev, cp, Jp);
+    const double adt = fabs(dt);
+    inv_metric_rows(Jp, S);
+#pragma unroll
+    for (int a = 0; a < C; ++a)
+#pragma unroll
+      for (int e = 0; e < NV; ++e) S[a][e] = adt * S[a][e];  // S_a = |dt| M^-1 Jp_a^T
+    for (int i = 0; i < max_iters; ++i) {
+      double c[C], J[C][NV], R[C][C], x[C];
+      t.constr_jacob(lane, dim, q, c, J);
+      double err = 0.0;
+#pragma unroll
+      for (int a = 0; a < C; ++a) err = nanmax(err, fabs(c[a]));
+#pragma unroll
+      for (int a = 0; a < C; ++a)
+#pragma unroll
+        for (int b = 0; b < C; ++b) R[a][b] = dot(J[a], S[b]);
+      lu_solve<C>(R, c, x);
+      double dmu[NV], dpos[NV];
+#pragma unroll
+      for (int e = 0; e < NV; ++e) {
+        double s = 0.0, d = 0.0;
+#pragma unroll
+        for (int a = 0; a < C; ++a) s = fma(Jp[a][e], x[a], s), d = fma(S[a][e], x[a], d);
+        dmu[e] = s;
+        dpos[e] = d;
+      }
+      ++iters;
+      if (err > divergence_tol || err != err) return false;
+      if (err < constraint_tol && maxabs(dpos) < position_tol) {
+        const double sgn = (dt > 0.0) ? 1.0 : ((dt < 0.0) ? -1.0 : 0.0);
+#pragma unroll
+        for (int e = 0; e < NV; ++e) p[e] = __dsub_rn(p[e], sgn * mu[e]);
+        return true;
+      }
+#pragma unroll
+      for (int e = 0; e < NV; ++e) {
+        mu[e] = __dadd_rn(mu[e], dmu[e]);
+        q[e] = __dsub_rn(q[e], dpos[e]);
+      }
+    }
+    return false;
+  }
+};
+
+template <class Target, int KP>
+__global__ void __launch_bounds__(128)
+    constrained_leapfrog_kernel(const double* q_in, const double* p_in, double* q_out,
+                                double* p_out, const int32_t* __restrict__ dir, int64_t n_chains,
+                                int dim, double step_size, int n_steps, int n_inner,
+                                int metric_kind, const double* __restrict__ minv, ModelArgs model,
+                                double constraint_tol, double position_tol, double divergence_tol,
+                                int max_iters, double rev_tol, double* __restrict__ h_out,
+                                int32_t* __restrict__ status, int32_t* __restrict__ n_done,
+                                int32_t* __restrict__ newton_iters) {
+  constexpr int NV = 2 * KP;
+  constexpr int C = Target::NC;
+  constexpr int SM_PER_WARP = (C > 1 ? C : 1) * 64 * KP;
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const Target target(model, dim);
+  const ConstrainedOps<Target, KP> ops{target, metric_kind, minv, dim, lane,
+                                       smem + (size_t)warp * SM_PER_WARP};
+  const bool even = (dim & 1) == 0;
+
+  for (int64_t ch = (int64_t)blockIdx.x * wpb + warp; ch < n_chains;
+       ch += (int64_t)gridDim.x * wpb) {
+    double q[NV], p[NV], g[NV];
+    const double dt = (dir != nullptr) ? (double)dir[ch] * step_size : step_size;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int i = 2 * lane + 64 * k;
+      double q0 = 0, q1 = 0, p0 = 0, p1 = 0;
+      if (i < dim) {
+        const size_t o = (size_t)ch * dim + i;
+        if (even) {
+          const double2 a = *reinterpret_cast<const double2*>(q_in + o);
+          const double2 b = *reinterpret_cast<const double2*>(p_in + o);
+          q0 = a.x, q1 = a.y, p0 = b.x, p1 = b.y;
+        } else {
+          q0 = q_in[o], p0 = p_in[o];
+          if (i + 1 < dim) q1 = q_in[o + 1], p1 = p_in[o + 1];
+        }
+      }
+      q[2 * k] = q0, q[2 * k + 1] = q1, p[2 * k] = p0, p[2 * k + 1] = p1;
+    }
+    target.grad(lane, dim, q, g);
+    int st = MB200_STATUS_OK, done = 0, iters = 0;
+    const double dt_inner = dt / n_inner;
+    for (int s = 0; s < n_steps && st == MB200_STATUS_OK; ++s) {
+      double qs[NV], ps[NV];
+#pragma unroll
+      for (int e = 0; e < NV; ++e) qs[e] = q[e], ps[e] = p[e];
+      // _step_a(dt/2)
+#pragma unroll
+      for (int e = 0; e < NV; ++e) p[e] = __dsub_rn(p[e], __dmul_rn(0.5 * dt, g[e]));
+      ops.project(p, q);
+      // _step_b(dt)
+      for (int i = 0; i < n_inner && st == MB200_STATUS_OK; ++i) {
+        double qprev[NV];
+#pragma unroll
+        for (int e = 0; e < NV; ++e) qprev[e] = q[e];
+        if (!ops.retract(q, p, qprev, dt_inner, constraint_tol, position_tol, divergence_tol,
+                         max_iters, iters)) {
+          st = MB200_STATUS_CONVERGENCE;
+          break;
+        }
+        ops.project(p, q);
+        double qb[NV], pb[NV];
+#pragma unroll
+        for (int e = 0; e < NV; ++e) qb[e] = q[e], pb[e] = p[e];
+        if (!ops.retract(qb, pb, q, -dt_inner, constraint_tol, position_tol, divergence_tol,
+                         max_iters, iters)) {
+          st = MB200_STATUS_CONVERGENCE;
+          break;
+        }
+        double diff[NV];
+#pragma unroll
+        for (int e = 0; e < NV; ++e) diff[e] = qb[e] - qprev[e];
+        const double rev = ConstrainedOps<Target, KP>::maxabs(diff);
+        if (rev > rev_tol) st = MB200_STATUS_NON_REVERSIBLE;
+      }
+      if (st == MB200_STATUS_OK) {
+        // _step_a(dt/2)
+        target.grad(lane, dim, q, g);
+#pragma unroll
+        for (int e = 0; e < NV; ++e) p[e] = __dsub_rn(p[e], __dmul_rn(0.5 * dt, g[e]));
+        ops.project(p, q);
+        ++done;
+      } else {
+#pragma unroll
+        for (int e = 0; e < NV; ++e) q[e] = qs[e], p[e] = ps[e];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int i = 2 * lane + 64 * k;
+      if (i < dim) {
+        const size_t o = (size_t)ch * dim + i;
+        if (even) {
+          *reinterpret_cast<double2*>(q_out + o) = make_double2(q[2 * k], q[2 * k + 1]);
+          *reinterpret_cast<double2*>(p_out + o) = make_double2(p[2 * k], p[2 * k + 1]);
+        } else {
+          q_out[o] = q[2 * k], p_out[o] = p[2 * k];
+          if (i + 1 < dim) q_out[o + 1] = q[2 * k + 1], p_out[o + 1] = p[2 * k + 1];
+        }
+      }
+    }
+    if (h_out != nullptr) {
+      double v[NV];
+      ops.inv_metric_vec(p, v);
+      const double kin = ConstrainedOps<Target, KP>::dot(p, v);
+      const double l = target.nld(lane, dim, q);
+      if (lane == 0) h_out[ch] = l + 0.5 * kin;
+    }
+    if (lane == 0) {
+      if (status != nullptr) status[ch] = st;
+      if (n_done != nullptr) n_done[ch] = done;
+      if (newton_iters != nullptr) newton_iters[ch] = iters;
+    }
+  }
+}
+
+}  // namespace mb200

@@ -1,0 +1,316 @@
+// libmici_b200.so -- C-ABI entry points (include/mici_b200.h).  Host-side argument checking and
+// kernel dispatch only; all arithmetic is in the .cuh kernels.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "leapfrog_generic.cuh"
+#ifndef MB200_NO_DMMA
+#include "leapfrog_dmma.cuh"
+#endif
+#ifndef MB200_NO_CONSTRAINED
+#include "constrained.cuh"
+#endif
+#ifndef MB200_NO_RIEMANNIAN
+#include "riemannian.cuh"
+#endif
+
+namespace mb200 {
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MB200_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+static ModelArgs to_args(const mb200_model* m) {
+  ModelArgs a;
+  memset(&a, 0, sizeof(a));
+  a.target_id = m->target_id;
+  for (int i = 0; i < MB200_MAX_PARAMS; ++i) a.tp[i] = m->target_params[i];
+  a.taux = m->target_aux;
+  a.rmetric_id = m->rmetric_id;
+  for (int i = 0; i < MB200_MAX_PARAMS; ++i) a.mp[i] = m->rmetric_params[i];
+  a.maux = m->rmetric_aux;
+  return a;
+}
+
+static int num_sms() {
+  static thread_local int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+template <class Target, int KP, int CPW>
+static int launch_generic(const double* q_in, const double* p_in, double* q_out, double* p_out,
+                          const int32_t* dir, int64_t n, int dim, double eps, int n_steps,
+                          int metric_kind, const double* minv, const ModelArgs& m, double* h_out,
+                          int32_t* status, int32_t* n_done, cudaStream_t st) {
+  constexpr int WARPS = 4;
+  auto kern = leapfrog_generic_kernel<Target, KP, CPW>;
+  const size_t smem = (size_t)WARPS * CPW * 64 * KP * sizeof(double);
+  if (smem > 48 * 1024) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(MB200_ERR_CUDA, "smem attr: %s", cudaGetErrorString(e));
+  }
+  const int64_t groups = (n + CPW - 1) / CPW;
+  int64_t blocks = (groups + WARPS - 1) / WARPS;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(q_in, p_in, q_out, p_out, dir, n, dim, eps,
+                                                   n_steps, metric_kind, minv, m, h_out, status,
+                                                   n_done);
+  return check_launch("leapfrog_generic_kernel");
+}
+
+template <class Target>
+static int dispatch_generic_dim(const double* q_in, const double* p_in, double* q_out,
+                                double* p_out, const int32_t* dir, int64_t n, int dim, double eps,
+                                int n_steps, int metric_kind, const double* minv,
+                                const ModelArgs& m, double* h_out, int32_t* status,
+                                int32_t* n_done, cudaStream_t st) {
+#define MB200_GEN(KP, CPW)                                                                    \
+  return launch_generic<Target, KP, CPW>(q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, \
+                                         metric_kind, minv, m, h_out, status, n_done, st)
+  if (dim <= 64) MB200_GEN(1, 4);
+  if (dim <= 128) MB200_GEN(2, 4);
+  if (dim <= 256) MB200_GEN(4, 2);
+  if (dim <= 512) MB200_GEN(8, 1);
+  if (dim <= 1024) MB200_GEN(16, 1);
+#undef MB200_GEN
+  return fail(MB200_ERR_UNSUPPORTED, "dim %d > 1024 not supported by the Euclidean leapfrog", dim);
+}
+
+static int leapfrog_euclidean_impl(const double* q_in, const double* p_in, double* q_out,
+                                   double* p_out, const int32_t* dir, int64_t n, int dim,
+                                   double eps, int n_steps, int metric_kind, const double* minv,
+                                   const mb200_model* model, double* h_out, int32_t* status,
+                                   int32_t* n_done, cudaStream_t st, bool allow_dmma) {
+  if (!q_in || !p_in || !q_out || !p_out || !model)
+    return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
+  if (n < 0 || dim < 1 || n_steps < 0) return fail(MB200_ERR_INVALID_ARG, "bad sizes");
+  if (metric_kind < 0 || metric_kind > 2) return fail(MB200_ERR_INVALID_ARG, "bad metric_kind");
+  if (metric_kind != MB200_METRIC_IDENTITY && !minv)
+    return fail(MB200_ERR_INVALID_ARG, "metric_inv is NULL");
+  if (n == 0) return 0;
+  const ModelArgs m = to_args(model);
+  if (m.target_id == MB200_TARGET_BANANA && (dim & 1))
+    return fail(MB200_ERR_INVALID_ARG, "banana target needs even dim");
+#ifndef MB200_NO_DMMA
+  if (allow_dmma && metric_kind == MB200_METRIC_DENSE && n_steps > 0) {
+    int rc = leapfrog_dmma_dispatch(q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, minv, m,
+                                    h_out, status, n_done, st);
+    if (rc == 0) return check_launch("leapfrog_dmma_kernel");
+    if (rc != MB200_ERR_UNSUPPORTED) return fail(rc, "leapfrog_dmma launch failed");
+  }
+#endif
+#define MB200_ARGS                                                                            \
+  q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, metric_kind, minv, m, h_out, status, \
+      n_done, st
+  switch (m.target_id) {
+    case MB200_TARGET_STD_GAUSSIAN:
+      return dispatch_generic_dim<StdGaussianTarget>(MB200_ARGS);
+    case MB200_TARGET_NEAL_FUNNEL:
+      return dispatch_generic_dim<NealFunnelTarget>(MB200_ARGS);
+    case MB200_TARGET_BANANA:
+      return dispatch_generic_dim<BananaTarget>(MB200_ARGS);
+    default:
+      return fail(MB200_ERR_UNSUPPORTED, "target %d not available for Euclidean leapfrog",
+                  m.target_id);
+  }
+#undef MB200_ARGS
+}
+
+
+template <class Target, int KP>
+static int launch_eval(const double* q, const double* p, int64_t n, int dim, int metric_kind,
+                       const double* minv, const ModelArgs& m, double* nld, double* grad,
+                       double* vel, double* kin, cudaStream_t st) {
+  constexpr int WARPS = 4;
+  auto kern = euclidean_eval_kernel<Target, KP>;
+  const size_t smem = (size_t)WARPS * 64 * KP * sizeof(double);
+  int64_t blocks = (n + WARPS - 1) / WARPS;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(q, p, n, dim, metric_kind, minv, m, nld, grad,
+                                                   vel, kin);
+  return check_launch("euclidean_eval_kernel");
+}
+
+template <class Target>
+static int dispatch_eval_dim(const double* q, const double* p, int64_t n, int dim,
+                             int metric_kind, const double* minv, const ModelArgs& m, double* nld,
+                             double* grad, double* vel, double* kin, cudaStream_t st) {
+#define MB200_EV(KP) \
+  return launch_eval<Target, KP>(q, p, n, dim, metric_kind, minv, m, nld, grad, vel, kin, st)
+  if (dim <= 64) MB200_EV(1);
+  if (dim <= 128) MB200_EV(2);
+  if (dim <= 256) MB200_EV(4);
+  if (dim <= 512) MB200_EV(8);
+  if (dim <= 1024) MB200_EV(16);
+#undef MB200_EV
+  return fail(MB200_ERR_UNSUPPORTED, "dim %d > 1024 not supported", dim);
+}
+
+#ifndef MB200_NO_CONSTRAINED
+template <class Target, int KP>
+static int launch_constrained(const double* q_in, const double* p_in, double* q_out,
+                              double* p_out, const int32_t* dir, int64_t n, int dim, double eps,
+                              int n_steps, int n_inner, int metric_kind, const double* minv,
+                              const ModelArgs& m, double ctol, double ptol, double dtol,
+                              int max_iters, double rev_tol, double* h_out, int32_t* status,
+                              int32_t* n_done, int32_t* iters, cudaStream_t st) {
+  constexpr int WARPS = 4;
+  auto kern = constrained_leapfrog_kernel<Target, KP>;
+  const size_t smem = (size_t)WARPS * (Target::NC > 1 ? Target::NC : 1) * 64 * KP * sizeof(double);
+  int64_t blocks = (n + WARPS - 1) / WARPS;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(q_in, p_in, q_out, p_out, dir, n, dim, eps,
+                                                   n_steps, n_inner, metric_kind, minv, m, ctol,
+                                                   ptol, dtol, max_iters, rev_tol, h_out, status,
+                                                   n_done, iters);
+  return check_launch("constrained_leapfrog_kernel");
+}
+#endif
+
+}  // namespace mb200
+
+using namespace mb200;
+
+extern "C" {
+
+int mb200_version(void) { return MB200_VERSION; }
+
+const char* mb200_last_error(void) { return g_err; }
+
+int mb200_leapfrog_euclidean(const double* pos_in, const double* mom_in, double* pos_out,
+                             double* mom_out, const int32_t* dir, int64_t n_chains, int32_t dim,
+                             double step_size, int32_t n_steps, int32_t metric_kind,
+                             const double* metric_inv, const mb200_model* model, double* h_out,
+                             int32_t* status, int32_t* n_done, void* stream) {
+  return leapfrog_euclidean_impl(pos_in, mom_in, pos_out, mom_out, dir, n_chains, dim, step_size,
+                                 n_steps, metric_kind, metric_inv, model, h_out, status, n_done,
+                                 (cudaStream_t)stream, true);
+}
+
+// Same arithmetic through the general-dimension kernel only (used by tests to cross-check the
+// tensor-core kernel; not part of the reference-facing surface).
+int mb200_leapfrog_euclidean_generic(const double* pos_in, const double* mom_in, double* pos_out,
+                                     double* mom_out, const int32_t* dir, int64_t n_chains,
+                                     int32_t dim, double step_size, int32_t n_steps,
+                                     int32_t metric_kind, const double* metric_inv,
+                                     const mb200_model* model, double* h_out, int32_t* status,
+                                     int32_t* n_done, void* stream) {
+  return leapfrog_euclidean_impl(pos_in, mom_in, pos_out, mom_out, dir, n_chains, dim, step_size,
+                                 n_steps, metric_kind, metric_inv, model, h_out, status, n_done,
+                                 (cudaStream_t)stream, false);
+}
+
+int mb200_hamiltonian_euclidean(const double* pos, const double* mom, int64_t n_chains,
+                                int32_t dim, int32_t metric_kind, const double* metric_inv,
+                                const mb200_model* model, double* h_out, void* stream) {
+  if (!h_out) return fail(MB200_ERR_INVALID_ARG, "h_out is NULL");
+  // zero leapfrog steps: loads the state, evaluates h, writes the (unchanged) state back in place
+  return leapfrog_euclidean_impl(pos, mom, const_cast<double*>(pos), const_cast<double*>(mom),
+                                 nullptr, n_chains, dim, 0.0, 0, metric_kind, metric_inv, model,
+                                 h_out, nullptr, nullptr, (cudaStream_t)stream, false);
+}
+
+int mb200_euclidean_eval(const double* pos, const double* mom, int64_t n_chains, int32_t dim,
+                         int32_t metric_kind, const double* metric_inv, const mb200_model* model,
+                         double* nld_out, double* grad_out, double* vel_out, double* kin_out,
+                         void* stream) {
+  if (!pos || !mom || !model) return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
+  if (n_chains < 0 || dim < 1) return fail(MB200_ERR_INVALID_ARG, "bad sizes");
+  if (metric_kind < 0 || metric_kind > 2) return fail(MB200_ERR_INVALID_ARG, "bad metric_kind");
+  if (metric_kind != MB200_METRIC_IDENTITY && !metric_inv)
+    return fail(MB200_ERR_INVALID_ARG, "metric_inv is NULL");
+  if (n_chains == 0) return 0;
+  const ModelArgs m = to_args(model);
+  cudaStream_t st = (cudaStream_t)stream;
+#define MB200_ARGS pos, mom, n_chains, dim, metric_kind, metric_inv, m, nld_out, grad_out, vel_out, kin_out, st
+  switch (m.target_id) {
+    case MB200_TARGET_STD_GAUSSIAN: return dispatch_eval_dim<StdGaussianTarget>(MB200_ARGS);
+    case MB200_TARGET_NEAL_FUNNEL: return dispatch_eval_dim<NealFunnelTarget>(MB200_ARGS);
+    case MB200_TARGET_BANANA: return dispatch_eval_dim<BananaTarget>(MB200_ARGS);
+    default:
+      return fail(MB200_ERR_UNSUPPORTED, "target %d not available for Euclidean eval", m.target_id);
+  }
+#undef MB200_ARGS
+}
+
+int mb200_constrained_leapfrog_euclidean(
+    const double* pos_in, const double* mom_in, double* pos_out, double* mom_out,
+    const int32_t* dir, int64_t n_chains, int32_t dim, double step_size, int32_t n_steps,
+    int32_t n_inner_step, int32_t metric_kind, const double* metric_inv, const mb200_model* model,
+    double constraint_tol, double position_tol, double divergence_tol, int32_t max_iters,
+    double reverse_check_tol, double* h_out, int32_t* status, int32_t* n_done,
+    int32_t* newton_iters, void* stream) {
+#ifdef MB200_NO_CONSTRAINED
+  return fail(MB200_ERR_UNSUPPORTED, "constrained leapfrog not compiled in");
+#else
+  if (!pos_in || !mom_in || !pos_out || !mom_out || !model)
+    return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
+  if (n_chains < 0 || dim < 1 || n_steps < 0 || n_inner_step < 1 || max_iters < 0)
+    return fail(MB200_ERR_INVALID_ARG, "bad sizes");
+  if (metric_kind < 0 || metric_kind > 2) return fail(MB200_ERR_INVALID_ARG, "bad metric_kind");
+  if (metric_kind != MB200_METRIC_IDENTITY && !metric_inv)
+    return fail(MB200_ERR_INVALID_ARG, "metric_inv is NULL");
+  if (n_chains == 0) return 0;
+  const ModelArgs m = to_args(model);
+  cudaStream_t st = (cudaStream_t)stream;
+#define MB200_ARGS                                                                              \
+  pos_in, mom_in, pos_out, mom_out, dir, n_chains, dim, step_size, n_steps, n_inner_step,       \
+      metric_kind, metric_inv, m, constraint_tol, position_tol, divergence_tol, max_iters,      \
+      reverse_check_tol, h_out, status, n_done, newton_iters, st
+  switch (m.target_id) {
+    case MB200_TARGET_TORUS:
+      if (dim != 3) return fail(MB200_ERR_INVALID_ARG, "torus target needs dim == 3");
+      return launch_constrained<TorusTarget, 1>(MB200_ARGS);
+    case MB200_TARGET_SPHERE:
+      if (dim <= 64) return launch_constrained<SphereTarget, 1>(MB200_ARGS);
+      if (dim <= 128) return launch_constrained<SphereTarget, 2>(MB200_ARGS);
+      if (dim <= 256) return launch_constrained<SphereTarget, 4>(MB200_ARGS);
+      return fail(MB200_ERR_UNSUPPORTED, "sphere target: dim %d > 256 not supported", dim);
+    default:
+      return fail(MB200_ERR_UNSUPPORTED, "target %d defines no constraint", m.target_id);
+  }
+#undef MB200_ARGS
+#endif
+}
+
+#ifdef MB200_NO_RIEMANNIAN
+int mb200_implicit_leapfrog_riemannian(const double*, const double*, double*, double*,
+                                       const int32_t*, int64_t, int32_t, double, int32_t,
+                                       const mb200_model*, double, double, int32_t, double,
+                                       double*, int32_t*, int32_t*, int32_t*, void*, int64_t,
+                                       void*) {
+  return fail(MB200_ERR_UNSUPPORTED, "implicit leapfrog not compiled in");
+}
+int64_t mb200_implicit_workspace_bytes(int64_t, int32_t, const mb200_model*) { return 0; }
+int mb200_hamiltonian_riemannian(const double*, const double*, int64_t, int32_t,
+                                 const mb200_model*, double*, int32_t*, void*, int64_t, void*) {
+  return fail(MB200_ERR_UNSUPPORTED, "riemannian hamiltonian not compiled in");
+}
+#endif
+
+}  // extern "C"

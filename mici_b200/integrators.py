@@ -1,0 +1,238 @@
+"""Batched symplectic integrators -- drop-in for the three ``mici.integrators`` classes on the
+hot path (reference ``src/mici/integrators.py``):
+
+* ``LeapfrogIntegrator``             integrators.py:134-173
+* ``ImplicitLeapfrogIntegrator``     integrators.py:381-544
+* ``ConstrainedLeapfrogIntegrator``  integrators.py:684-984
+
+Same constructor signatures, keyword names and defaults; ``step(state)`` returns a NEW state and
+leaves its argument untouched (integrators.py:63-80).  A state holds ``[n_chains, dim]`` tensors:
+one call advances every chain by one step in a single kernel launch.  ``step_n(state, n)`` fuses
+``n`` steps per launch (the loop ``for _ in range(n_step): state = integrator.step(state)`` of
+transitions.py:289-291).
+
+Failures: the reference raises ``IntegratorError`` subclasses from ``step``.  For a batched
+state the per-chain outcome is returned in ``new_state.status`` (0 ok, 1 ConvergenceError,
+2 NonReversibleStepError, 3 LinAlgError) and failed chains keep their pre-step state; for a
+single-chain state (1-D ``pos``) the matching exception is raised, as in the reference.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from abc import ABC, abstractmethod
+
+import torch
+
+from . import _lib
+from .errors import AdaptationError, raise_for_status
+from .solvers import (
+    maximum_norm,
+    solve_fixed_point_direct,
+    solve_projection_onto_manifold_newton,
+)
+from .states import ChainState
+from .systems import (
+    ConstrainedEuclideanMetricSystem,
+    EuclideanMetricSystem,
+    RiemannianMetricSystem,
+    _batched,
+    _dir_tensor,
+)
+
+
+class Integrator(ABC):
+    """Base class for integrators (integrators.py:30-89)."""
+
+    def __init__(self, system, step_size=None):
+        self.system = system
+        self.step_size = step_size
+
+    def step(self, state):
+        """Perform a single integrator step from a supplied state; returns a new state."""
+        return self.step_n(state, 1)
+
+    def step_n(self, state, n_steps, *, return_h=False):
+        """``n_steps`` integrator steps fused in one launch; returns a new state.
+
+        With ``return_h=True`` the Hamiltonian of the new state is evaluated in the same launch
+        and stored as ``new_state.h`` (callers evaluate ``system.h`` after every trajectory:
+        transitions.py:300-301).
+        """
+        if self.step_size is None:
+            msg = (
+                "Integrator `step_size` is `None`. This value should only be used if a "
+                "step size adapter is being used to set the step size."
+            )
+            raise AdaptationError(msg)
+        pos, mom, d, single = _batched(state)
+        n, dim = pos.shape
+        dev = pos.device
+        pos = pos.contiguous()
+        mom = mom.contiguous()
+        pos_out = torch.empty_like(pos)
+        mom_out = torch.empty_like(mom)
+        status = torch.empty(n, dtype=torch.int32, device=dev)
+        n_done = torch.empty(n, dtype=torch.int32, device=dev)
+        h = torch.empty(n, dtype=torch.float64, device=dev) if return_h else None
+        aux = self._launch(pos, mom, pos_out, mom_out, _dir_tensor(d, n, dev), int(n_steps), h,
+                           status, n_done)
+        new = _new_state_like(state, pos_out[0] if single else pos_out,
+                              mom_out[0] if single else mom_out)
+        new.status = status
+        new.n_done = n_done
+        if return_h:
+            new.h = h[0] if single else h
+        if aux is not None:
+            new.solver_iters = aux
+        if single:
+            raise_for_status(int(status.item()), type(self).__name__ + ".step")
+        return new
+
+    def _step(self, state, time_step):
+        """In-place single step with an explicit signed time step (integrators.py:82-89)."""
+        saved = self.step_size
+        try:
+            self.step_size = abs(float(time_step))
+            tmp = state.copy()
+            if "dir" in tmp:
+                tmp.dir = 1 if time_step >= 0 else -1
+            new = self.step_n(tmp, 1)
+        finally:
+            self.step_size = saved
+        state.pos, state.mom = new.pos, new.mom
+        state.status, state.n_done = new.status, new.n_done
+
+    @abstractmethod
+    def _launch(self, pos, mom, pos_out, mom_out, dirs, n_steps, h, status, n_done):
+        """Enqueue the kernel(s); may return a tensor of solver iteration counts."""
+
+
+def _new_state_like(state, pos, mom):
+    if isinstance(state, ChainState):
+        extra = {k: v for k, v in state._variables.items() if k not in ("pos", "mom")}
+        extra = {k: (v.clone() if hasattr(v, "clone") else v) for k, v in extra.items()}
+        return ChainState(pos=pos, mom=mom, **extra)
+    new = state.copy()  # duck-typed foreign state object
+    new.pos, new.mom = pos, mom
+    return new
+
+
+class TractableFlowIntegrator(Integrator):
+    """integrators.py:92-131."""
+
+    def __init__(self, system, step_size=None):
+        if not hasattr(system, "h1_flow") or not hasattr(system, "h2_flow"):
+            msg = (
+                f"{type(self)} can only be used for systems with explicit `h1_flow` "
+                f"and `h2_flow` Hamiltonian component flow maps. For systems in which "
+                f"only `h1_flow` is available the `ImplicitLeapfrogIntegrator` class "
+                f"may be used instead."
+            )
+            raise ValueError(msg)
+        super().__init__(system, step_size)
+
+
+class LeapfrogIntegrator(TractableFlowIntegrator):
+    """Explicit leapfrog Psi(t) = Phi_1(t/2) o Phi_2(t) o Phi_1(t/2) (integrators.py:134-173)
+    for ``EuclideanMetricSystem`` s, target gradient and metric product fused in one kernel."""
+
+    def __init__(self, system, step_size=None):
+        super().__init__(system, step_size)
+        if not isinstance(system, EuclideanMetricSystem) or isinstance(
+            system, ConstrainedEuclideanMetricSystem
+        ):
+            raise TypeError("LeapfrogIntegrator needs an (unconstrained) EuclideanMetricSystem.")
+
+    def _launch(self, pos, mom, pos_out, mom_out, dirs, n_steps, h, status, n_done):
+        n, dim = pos.shape
+        dev = pos.device
+        sysm = self.system
+        model = sysm._model(dev)
+        rc = _lib.load().mb200_leapfrog_euclidean(
+            _lib.ptr(pos), _lib.ptr(mom), _lib.ptr(pos_out), _lib.ptr(mom_out), _lib.ptr(dirs),
+            n, dim, float(self.step_size), n_steps, sysm.metric.kind,
+            _lib.ptr(sysm.metric.inv_device(dev)), ctypes.byref(model), _lib.ptr(h),
+            _lib.ptr(status), _lib.ptr(n_done), _lib.current_stream_ptr(dev),
+        )
+        _lib.check(rc, "mb200_leapfrog_euclidean")
+
+
+class ImplicitLeapfrogIntegrator(Integrator):
+    """Implicit generalised leapfrog for non-separable Hamiltonians (integrators.py:381-544),
+    for ``RiemannianMetricSystem`` s.  Fixed-point solves and reversibility checks run inside
+    the kernel.  NB: as in the reference at this commit every sub-map receives the full
+    ``dir * step_size`` (integrators.py:538-544)."""
+
+    def __init__(self, system, step_size=None, reverse_check_tol=2e-8,
+                 reverse_check_norm=maximum_norm, fixed_point_solver=solve_fixed_point_direct,
+                 fixed_point_solver_kwargs=None):
+        super().__init__(system, step_size)
+        if not isinstance(system, RiemannianMetricSystem):
+            raise TypeError("ImplicitLeapfrogIntegrator needs a RiemannianMetricSystem.")
+        if reverse_check_norm is not maximum_norm:
+            raise ValueError("Only `maximum_norm` is available for the reversibility check.")
+        if fixed_point_solver is not solve_fixed_point_direct:
+            raise ValueError("Only `solve_fixed_point_direct` is fused into the kernels.")
+        self.reverse_check_tol = reverse_check_tol
+        self.reverse_check_norm = reverse_check_norm
+        self.fixed_point_solver = fixed_point_solver
+        self.fixed_point_solver_kwargs = dict(fixed_point_solver_kwargs or {})
+
+    def _launch(self, pos, mom, pos_out, mom_out, dirs, n_steps, h, status, n_done):
+        n, dim = pos.shape
+        dev = pos.device
+        sysm = self.system
+        kw = self.fixed_point_solver.resolve_kwargs(self.fixed_point_solver_kwargs)
+        model = sysm._model(dev)
+        ws = sysm._workspace(n, dim, dev)
+        iters = torch.zeros((n, 4), dtype=torch.int32, device=dev)
+        rc = _lib.load().mb200_implicit_leapfrog_riemannian(
+            _lib.ptr(pos), _lib.ptr(mom), _lib.ptr(pos_out), _lib.ptr(mom_out), _lib.ptr(dirs),
+            n, dim, float(self.step_size), n_steps, ctypes.byref(model),
+            float(kw["convergence_tol"]), float(kw["divergence_tol"]), int(kw["max_iters"]),
+            float(self.reverse_check_tol), _lib.ptr(h), _lib.ptr(status), _lib.ptr(n_done),
+            _lib.ptr(iters), _lib.ptr(ws), ws.numel(), _lib.current_stream_ptr(dev),
+        )
+        _lib.check(rc, "mb200_implicit_leapfrog_riemannian")
+        return iters
+
+
+class ConstrainedLeapfrogIntegrator(TractableFlowIntegrator):
+    """Leapfrog for constrained systems: RATTLE / geodesic integrator with Newton projection
+    and reversibility check (integrators.py:684-984)."""
+
+    def __init__(self, system, step_size=None, n_inner_step=1, reverse_check_tol=2e-8,
+                 reverse_check_norm=maximum_norm,
+                 projection_solver=solve_projection_onto_manifold_newton,
+                 projection_solver_kwargs=None):
+        super().__init__(system, step_size)
+        if not isinstance(system, ConstrainedEuclideanMetricSystem):
+            raise TypeError("ConstrainedLeapfrogIntegrator needs a constrained Euclidean system.")
+        if reverse_check_norm is not maximum_norm:
+            raise ValueError("Only `maximum_norm` is available for the reversibility check.")
+        if projection_solver is not solve_projection_onto_manifold_newton:
+            raise ValueError("Only `solve_projection_onto_manifold_newton` is fused into the kernels.")
+        self.n_inner_step = n_inner_step
+        self.reverse_check_tol = reverse_check_tol
+        self.reverse_check_norm = reverse_check_norm
+        self.projection_solver = projection_solver
+        self.projection_solver_kwargs = dict(projection_solver_kwargs or {})
+
+    def _launch(self, pos, mom, pos_out, mom_out, dirs, n_steps, h, status, n_done):
+        n, dim = pos.shape
+        dev = pos.device
+        sysm = self.system
+        kw = self.projection_solver.resolve_kwargs(self.projection_solver_kwargs)
+        model = sysm._model(dev)
+        iters = torch.zeros(n, dtype=torch.int32, device=dev)
+        rc = _lib.load().mb200_constrained_leapfrog_euclidean(
+            _lib.ptr(pos), _lib.ptr(mom), _lib.ptr(pos_out), _lib.ptr(mom_out), _lib.ptr(dirs),
+            n, dim, float(self.step_size), n_steps, int(self.n_inner_step), sysm.metric.kind,
+            _lib.ptr(sysm.metric.inv_device(dev)), ctypes.byref(model),
+            float(kw["constraint_tol"]), float(kw["position_tol"]), float(kw["divergence_tol"]),
+            int(kw["max_iters"]), float(self.reverse_check_tol), _lib.ptr(h), _lib.ptr(status),
+            _lib.ptr(n_done), _lib.ptr(iters), _lib.current_stream_ptr(dev),
+        )
+        _lib.check(rc, "mb200_constrained_leapfrog_euclidean")
+        return iters

@@ -1,0 +1,129 @@
+"""Target-model registry of the CUDA path.
+
+The reference accepts arbitrary Python callables for ``neg_log_dens`` and its derivatives
+(``src/mici/systems.py:88-95``).  A fused GPU gradient cannot, so the engine ships a closed
+registry of models compiled into ``libmici_b200.so`` (``mici_b200/csrc/targets.cuh``); an
+instance of one of these classes is what is passed as ``neg_log_dens=`` to the systems in
+``mici_b200.systems``.  Instances only carry ids and parameters -- no host arithmetic.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+TARGET_STD_GAUSSIAN = 0
+TARGET_NEAL_FUNNEL = 1
+TARGET_BANANA = 2
+TARGET_QUADRATIC = 3
+TARGET_TORUS = 4
+TARGET_SPHERE = 5
+
+RMETRIC_SOFTABS = 0
+RMETRIC_RANK1 = 1
+
+
+class Target:
+    """Base class: ``target_id``, scalar ``params`` and an optional dense ``aux`` array."""
+
+    target_id: int = -1
+    name: str = ""
+    n_constr: int = 0
+
+    def __init__(self, dim, params=(), aux=None):
+        self.dim = int(dim)
+        self.params = tuple(float(x) for x in params)
+        self.aux = None if aux is None else np.ascontiguousarray(aux, dtype=np.float64)
+
+    def __repr__(self):
+        return f"{type(self).__name__}(dim={self.dim}, params={self.params})"
+
+
+class StdGaussian(Target):
+    """l(q) = |q|^2 / 2."""
+
+    target_id = TARGET_STD_GAUSSIAN
+    name = "std_gaussian"
+
+    def __init__(self, dim):
+        super().__init__(dim)
+
+
+class NealFunnel(Target):
+    """v = q[0], x = q[1:]; l = v^2/18 + (D-1) v/2 + exp(-v) |x|^2 / 2."""
+
+    target_id = TARGET_NEAL_FUNNEL
+    name = "neal_funnel"
+
+    def __init__(self, dim):
+        super().__init__(dim)
+
+
+class Banana(Target):
+    """Pairs (x, y): l = sum x^2/8 + (y - b x^2)^2 / 2."""
+
+    target_id = TARGET_BANANA
+    name = "banana"
+
+    def __init__(self, dim, b=0.5):
+        if dim % 2:
+            raise ValueError("Banana target needs an even dimension.")
+        super().__init__(dim, (b,))
+
+
+class Quadratic(Target):
+    """l(q) = q^T P q / 2 with dense SPD ``prec``."""
+
+    target_id = TARGET_QUADRATIC
+    name = "quadratic"
+
+    def __init__(self, prec):
+        prec = np.asarray(prec, dtype=np.float64)
+        super().__init__(prec.shape[0], (), prec)
+
+
+class Torus(Target):
+    """Density on a torus in R^3 with constraint c(q) = (rho - R)^2 + z^2 - r^2
+    (reference README.md:315-337)."""
+
+    target_id = TARGET_TORUS
+    name = "torus"
+    n_constr = 1
+
+    def __init__(self, R=1.0, r=0.5, alpha=0.9):
+        super().__init__(3, (R, r, alpha))
+
+
+class Sphere(Target):
+    """l = |q|^2/2 + q[0] on the unit sphere c(q) = |q|^2 - 1."""
+
+    target_id = TARGET_SPHERE
+    name = "sphere"
+    n_constr = 1
+
+    def __init__(self, dim):
+        super().__init__(dim)
+
+
+class Rank1Metric:
+    """Position-dependent dense metric M(q) = B + c q q^T."""
+
+    rmetric_id = RMETRIC_RANK1
+    name = "rank1"
+
+    def __init__(self, base, coeff):
+        self.aux = np.ascontiguousarray(base, dtype=np.float64)
+        self.params = (float(coeff),)
+
+
+REGISTRY = {
+    cls.name: cls for cls in (StdGaussian, NealFunnel, Banana, Quadratic, Torus, Sphere)
+}
+METRIC_REGISTRY = {"rank1": Rank1Metric}
+
+
+def make_target(name, **params):
+    return REGISTRY[name](**params)
+
+
+def make_metric_model(name, **params):
+    return METRIC_REGISTRY[name](**params)

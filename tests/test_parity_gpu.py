@@ -1,0 +1,174 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the reference fixtures
+(tests/golden, generated from the unmodified reference) and against the oracle port on the
+same seeded inputs.  Tolerance: rtol 1e-10 (north_star), atol 1e-12."""
+
+import numpy as np
+import pytest
+import torch
+
+from mici_b200 import engine, problems
+from oracle import drivers as dr
+
+from golden_util import ATOL, RTOL, assert_matches_golden, case_names, load_case
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def run_cuda(problem, n_steps, dirs=None, overrides=None, chains=None, return_h=True):
+    integ = engine.build_integrator(problem, **(overrides or {}))
+    state = engine.build_state(problem, DEV, dirs=dirs, chains=chains)
+    pos0, mom0 = state.pos.clone(), state.mom.clone()
+    new = integ.step_n(state, n_steps, return_h=return_h)
+    torch.cuda.synchronize()
+    # Integrator.step must not mutate its argument (reference tests/test_integrators.py:110-124)
+    assert torch.equal(state.pos, pos0) and torch.equal(state.mom, mom0)
+    assert new.pos.data_ptr() != state.pos.data_ptr()
+    return {
+        "pos": new.pos.cpu().numpy(),
+        "mom": new.mom.cpu().numpy(),
+        "status": new.status.cpu().numpy(),
+        "n_done": new.n_done.cpu().numpy(),
+        "h": new.h.cpu().numpy() if return_h else None,
+        "iters": None if new.solver_iters is None else new.solver_iters.cpu().numpy(),
+    }
+
+
+@pytest.mark.parametrize("name", case_names() + case_names(failures=True))
+def test_cuda_matches_reference_fixture(name):
+    problem, dirs, overrides, g = load_case(name)
+    for n_steps in g["step_counts"]:
+        out = run_cuda(problem, int(n_steps), dirs=dirs, overrides=overrides)
+        ok = out["status"] == 0
+        out["h"] = np.where(ok, out["h"], np.nan)
+        gg = dict(g)
+        gg[f"h_{n_steps}"] = np.where(ok, g[f"h_{n_steps}"], np.nan)
+        assert_matches_golden(out, gg, int(n_steps), label=f"{name}[{n_steps}]")
+
+
+@pytest.mark.parametrize("cfg,kwargs", [
+    ("C0", {"n_chains": 37, "dim": 10}),
+    ("C1", {"n_chains": 64}),
+    ("C1", {"n_chains": 33, "dim": 9}),
+    ("C1", {"n_chains": 19, "dim": 130}),
+    ("C1", {"n_chains": 5, "dim": 300}),
+    ("C1", {"n_chains": 40, "dim": 96, "metric_kind": "diagonal"}),
+    ("C3", {"n_chains": 64}),
+])
+def test_cuda_matches_oracle_port(cfg, kwargs):
+    problem = problems.make_problem(cfg, **kwargs)
+    dirs = np.where(np.arange(problem.n_chains) % 2 == 0, 1, -1).astype(np.int32)
+    for n_steps in (1, 5, 20):
+        ref = dr.oracle_run(problem, n_steps, dirs=dirs)
+        out = run_cuda(problem, n_steps, dirs=dirs)
+        np.testing.assert_array_equal(out["status"], ref["status"])
+        np.testing.assert_allclose(out["pos"], ref["pos"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(out["mom"], ref["mom"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(out["h"], ref["h"], rtol=RTOL, atol=1e-9)
+
+
+@pytest.mark.parametrize("cfg,kwargs", [("C1", {"n_chains": 48}), ("C3", {"n_chains": 48})])
+def test_step_n_equals_repeated_step(cfg, kwargs):
+    problem = problems.make_problem(cfg, **kwargs)
+    integ = engine.build_integrator(problem)
+    state = engine.build_state(problem, DEV)
+    fused = integ.step_n(state, 7)
+    s = state
+    for _ in range(7):
+        s = integ.step(s)
+    torch.cuda.synchronize()
+    assert torch.equal(fused.pos, s.pos) and torch.equal(fused.mom, s.mom)
+
+
+def test_dmma_and_generic_kernels_agree():
+    """The tensor-core leapfrog kernel against the general-dimension kernel (same C ABI)."""
+    import ctypes
+
+    from mici_b200 import _lib
+
+    problem = problems.make_problem("C1", n_chains=500)
+    integ = engine.build_integrator(problem)
+    state = engine.build_state(problem, DEV)
+    fast = integ.step_n(state, 10, return_h=True)
+    sysm = integ.system
+    n, dim = state.pos.shape
+    model = sysm._model(state.pos.device)
+    q, p = torch.empty_like(state.pos), torch.empty_like(state.mom)
+    h = torch.empty(n, dtype=torch.float64, device=DEV)
+    rc = _lib.load().mb200_leapfrog_euclidean_generic(
+        _lib.ptr(state.pos), _lib.ptr(state.mom), _lib.ptr(q), _lib.ptr(p), None, n, dim,
+        problem.step_size, 10, sysm.metric.kind, _lib.ptr(sysm.metric.inv_device(state.pos.device)),
+        ctypes.byref(model), _lib.ptr(h), None, None, _lib.current_stream_ptr(state.pos.device))
+    assert rc == 0
+    torch.cuda.synchronize()
+    torch.testing.assert_close(fast.pos, q, rtol=1e-11, atol=1e-13)
+    torch.testing.assert_close(fast.mom, p, rtol=1e-11, atol=1e-13)
+    torch.testing.assert_close(fast.h, h, rtol=1e-11, atol=1e-10)
+
+
+def test_reversibility_full_size_c1():
+    """Size-independent property at BASELINE's full C1 size (reference
+    tests/test_integrators.py:75-91): n steps forward, flip dir, n steps back."""
+    problem = problems.make_problem("C1")
+    integ = engine.build_integrator(problem)
+    state = engine.build_state(problem, DEV)
+    fwd = integ.step_n(state, 20)
+    fwd.dir = -1
+    back = integ.step_n(fwd, 20)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(back.pos, state.pos, rtol=0, atol=1e-9)
+    torch.testing.assert_close(back.mom, state.mom, rtol=0, atol=1e-8)
+
+
+def test_energy_conservation_full_size_c1():
+    """tests/test_integrators.py:93-108 style check on all 8192 chains."""
+    problem = problems.make_problem("C1")
+    integ = engine.build_integrator(problem)
+    state = engine.build_state(problem, DEV)
+    h0 = integ.system.h(state)
+    new = integ.step_n(state, 200, return_h=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(new.h).all()
+    assert (new.h - h0).abs().max().item() < 5e-2
+
+
+def test_constraint_satisfaction_full_size_c3():
+    """tests/test_integrators.py:159-197: |c(q)| < 1e-8 and J M^-1 p = 0 after steps."""
+    problem = problems.make_problem("C3")
+    integ = engine.build_integrator(problem)
+    state = engine.build_state(problem, DEV)
+    new = integ.step_n(state, 10)
+    torch.cuda.synchronize()
+    ok = new.status == 0
+    assert ok.float().mean().item() > 0.9
+    q, p = new.pos[ok], new.mom[ok]
+    rho = torch.sqrt(q[:, 0] ** 2 + q[:, 1] ** 2)
+    c = (rho - 1.0) ** 2 + q[:, 2] ** 2 - 0.25
+    assert c.abs().max().item() < 1e-8
+    f = 2.0 * (rho - 1.0) / rho
+    jac = torch.stack([f * q[:, 0], f * q[:, 1], 2.0 * q[:, 2]], -1)
+    assert (jac * p).sum(-1).abs().max().item() < 1e-8
+
+
+def test_single_chain_state_raises_like_reference():
+    from mici_b200 import ChainState
+    from mici_b200.errors import IntegratorError
+
+    problem = problems.make_problem("C3", n_chains=64)
+    problem.step_size = 0.4
+    ref = dr.oracle_run(problem, 1)
+    bad = int(np.nonzero(ref["status"])[0][0])
+    good = int(np.nonzero(ref["status"] == 0)[0][0])
+    integ = engine.build_integrator(problem)
+    for idx, should_raise in ((bad, True), (good, False)):
+        st = ChainState(
+            pos=torch.as_tensor(problem.pos[idx], device=DEV),
+            mom=torch.as_tensor(problem.mom[idx], device=DEV),
+            dir=1,
+        )
+        if should_raise:
+            with pytest.raises(IntegratorError):
+                integ.step(st)
+        else:
+            new = integ.step(st)
+            np.testing.assert_allclose(new.pos.cpu().numpy(), ref["pos"][idx], rtol=RTOL, atol=ATOL)
