@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched ``Integrator.step`` on B200.
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU reference arm
+
+Workload (BASELINE.json configs[1], "C1"): dense-mass Euclidean leapfrog on Neal's funnel,
+D = 128, 8192 chains per GPU, step size 0.01.  One bench "step" = one launch of
+``LEAPFROG_PER_LAUNCH`` fused leapfrog steps over the whole batch (the trajectory loop of
+``transitions.py:289-291``).  Metric: aggregate leapfrog steps / s = chains x leapfrog steps /
+time.  Prints ONE JSON line (rank 0).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "leapfrog steps/sec (aggregate over chains)"
+UNIT = "leapfrog steps/s"
+WORKLOAD = "C1: dense-mass Euclidean leapfrog, Neal's funnel D=128, 8192 chains per GPU"
+N_CHAINS = 8192
+DIM = 128
+LEAPFROG_PER_LAUNCH = 50
+FP64_PEAK_TFLOPS = 37.1  # measured DMMA peak on this pool's B200 (profiles/r01_fp64_peak.txt)
+HBM_FALLBACK_GBS = 6650.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--leapfrog-per-launch", type=int, default=LEAPFROG_PER_LAUNCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:  # noqa: BLE001
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    QUERY = (
+        "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+        "clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                     "--format=csv,noheader,nounits"],
+                    capture_output=True, text=True, timeout=5,
+                ).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.splitlines()[0].split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=10)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for name, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": sm[len(sm) // 2] if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "reasons": sorted(reasons),
+            "samples": len(self.rows),
+        }
+
+
+def cpu_baseline(kind_note=""):
+    from oracle import cpu_baseline as cb
+
+    cores = os.cpu_count() or 1
+    res = cb.run("C1", {"n_chains": N_CHAINS, "dim": DIM}, chains_per_worker=8,
+                 n_steps=LEAPFROG_PER_LAUNCH, reps=150, n_workers=cores)
+    return {
+        "value": res["value"],
+        "unit": UNIT,
+        "cores": res["cores"],
+        "kind": "port",
+        "sample": res["sample"] + kind_note,
+        "seconds": res["seconds"],
+    }
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU algorithm (oracle port; the Python reference cannot
+    travel to the GPU box) on all host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import cpu_baseline as cb
+
+    cores = os.cpu_count() or 1
+    pool = cb.Pool(cores)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        if i == args.warmup:
+            t0 = time.perf_counter()
+        res = cb.run("C1", {"n_chains": N_CHAINS, "dim": DIM}, chains_per_worker=8,
+                     n_steps=args.leapfrog_per_launch, reps=10, pool=pool)
+        if i >= args.warmup:
+            vals.append(res["value"])
+    wall = time.perf_counter() - t0
+    pool.close()
+    value = sum(vals) / len(vals)
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "leapfrog_steps_per_launch": args.leapfrog_per_launch,
+                   "integrator": "LeapfrogIntegrator", "metric": "dense"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": res["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_cuda(args, rank, local_rank, world):
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline()  # before CUDA is initialised in this process
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from mici_b200 import engine, parallel, problems
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    L = args.leapfrog_per_launch
+    prob = problems.make_problem("C1", n_chains=N_CHAINS, dim=DIM,
+                                 seed=problems.BASE_SEED + 1 + 1000 * rank)
+    integ = engine.build_integrator(prob)
+    state = engine.build_state(prob, dev)
+    n, dim = state.pos.shape
+
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident throughput (value) + per-launch kernel time
+    for _ in range(args.warmup):
+        integ.step_n(state, L)
+    sync_all()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        sync_all()
+        out = state
+        for i in range(args.steps):
+            flush.fill_(float(i))  # evict q, p, M^-1 from L2 between timed launches
+            ev[i][0].record()
+            out = integ.step_n(state, L)
+            ev[i][1].record()
+        sync_all()
+    times_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(times_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    assert int((out.status != 0).sum().item()) == 0 and bool(torch.isfinite(out.pos).all())
+
+    # ---------------- end-to-end through the public API with HOST buffers
+    pos_h = torch.as_tensor(prob.pos).pin_memory()
+    mom_h = torch.as_tensor(prob.mom).pin_memory()
+    pos_o = torch.empty_like(pos_h).pin_memory()
+    mom_o = torch.empty_like(mom_h).pin_memory()
+    st_o = torch.empty(n, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        from mici_b200 import ChainState
+
+        s = ChainState(pos=pos_h.to(dev, non_blocking=True), mom=mom_h.to(dev, non_blocking=True),
+                       dir=1)
+        new = integ.step_n(s, L)
+        pos_o.copy_(new.pos, non_blocking=True)
+        mom_o.copy_(new.mom, non_blocking=True)
+        st_o.copy_(new.status, non_blocking=True)
+
+    for _ in range(args.warmup):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    sync_all()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms.item())
+    _ = time.perf_counter() - t0
+
+    # ---------------- write-out: the one collective (outside the timed step path)
+    if world > 1:
+        gathered = parallel.gather_state(out, n * world, dst=0)
+        if rank == 0:
+            assert gathered["pos"].shape[0] == n * world
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    chain_steps_per_launch = n * L
+    value = world * chain_steps_per_launch * args.steps / (total_ms * 1e-3)
+    e2e_value = world * chain_steps_per_launch * args.steps / (e2e_ms * 1e-3)
+    b_alg = prob.algorithmic_bytes_per_chain_step  # 32 * D = 4096 B
+    avg_launch_s = (sum(times_ms) / len(times_ms)) * 1e-3
+    hbm_peak, peak_src = measured_hbm_peak()
+    achieved_gbs = b_alg * chain_steps_per_launch / avg_launch_s / 1e9
+    flops = (2.0 * dim * dim) * chain_steps_per_launch / avg_launch_s
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {
+            "workload": WORKLOAD,
+            "chains_per_gpu": n,
+            "dim": dim,
+            "leapfrog_steps_per_launch": L,
+            "integrator": "LeapfrogIntegrator",
+            "metric": "dense (explicit M^-1, shared)",
+            "step_size": prob.step_size,
+            "l2": "flushed between timed launches (256 MB fill)",
+            "parallelism": f"chains sharded over {world} GPU(s), no collective on the step path",
+        },
+        "roofline": {
+            "bound": "hbm",
+            "achieved": achieved_gbs,
+            "peak": hbm_peak,
+            "unit": "GB/s",
+            "frac": achieved_gbs / hbm_peak,
+            "traffic": None,
+            "peak_source": peak_src,
+            "kernel": "leapfrog_dmma_kernel<NealFunnelTarget,128>",
+            "algorithmic_bytes_per_chain_step": b_alg,
+            "fp64_tflops": flops / 1e12,
+            "fp64_peak_tflops": FP64_PEAK_TFLOPS,
+            "fp64_frac": flops / 1e12 / FP64_PEAK_TFLOPS,
+        },
+        "e2e": {
+            "value": e2e_value,
+            "unit": UNIT,
+            "h2d_bytes_per_step": int(2 * n * dim * 8),
+            "d2h_bytes_per_step": int(2 * n * dim * 8 + n * 4),
+        },
+        "gpu_launches": args.steps,
+        "clocks": clocks.summary(),
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_cuda(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,404 @@
+// K1: explicit leapfrog, dense shared metric, fused target gradient, n_steps per launch --
+// FP64 tensor-core kernel (DMMA m8n8k4) for dim <= 128.
+//
+// Replaces, for every chain at once (reference paths):
+//   LeapfrogIntegrator._step          integrators.py:170-173
+//   System.h1_flow                    systems.py:143-152      p -= (dt/2) grad l(q)
+//   EuclideanMetricSystem.h2_flow     systems.py:362-363      q += dt * (M^-1 p)
+//   explicit-inverse mat-vec          matrices.py:222-223 (ExplicitArrayMatrix @ vector)
+//
+// The one genuine contraction on the path is V = P * A  ([chains x D] . [D x D], A = M^-1
+// explicit and symmetric): 2 D^2 flop per chain-step against 32 D bytes of state, i.e. above the
+// B200 fp64 ridge, so the kernel is organised around the FP64 tensor pipe (tcgen05 has no fp64
+// kind; DMMA.8x8x4 is the native sm_100a instruction, 37.1 TFLOP/s measured:
+// profiles/r01_fp64_peak.txt).
+//
+// Work decomposition (one CTA per SM, 8 warps, 2 groups x 4 warps):
+//   * a CTA owns up to 56 chains = 7 row tiles of 8 chains; group 0 takes tiles 0-3, group 1
+//     tiles 4-6 -- 7 tile-quarters per SM sub-partition, which balances 8192 chains over
+//     148 SMs x 4 sub-partitions (8192 / 148 = 55.4 chains per SM);
+//   * warp w of a group computes output columns [w*DP/4, (w+1)*DP/4) for all the group's tiles:
+//     accumulators, positions and momenta of that slice stay in registers in the DMMA
+//     C-fragment layout for the whole launch (HBM is touched once on entry and once on exit);
+//   * A lives in shared memory for the whole launch (staged by TMA bulk copies, row stride
+//     padded by 4 doubles so A/B fragment loads are bank-conflict free); B fragments are read
+//     through the symmetry A[k][n] = A[n][k] as 8 rows x 4 consecutive doubles;
+//   * momenta are exchanged through a shared-memory tile once per step (A fragments), and the
+//     per-chain reductions of the target gradient through per-warp partial sums; the two groups
+//     synchronise only internally (named barriers), so one group's gradient/update phase
+//     overlaps the other's DMMA phase.
+#pragma once
+#include "targets.cuh"
+
+namespace mb200 {
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+constexpr int DMMA_TILES_PER_CTA = 7;
+constexpr int DMMA_ROWS_PER_CTA = 8 * DMMA_TILES_PER_CTA;  // 56 chains
+constexpr int DMMA_MAX_RED = 4;
+
+template <int DP>
+struct DmmaSmem {
+  static constexpr int LDA = DP + 4;  // row stride (doubles): rows shift by 32 B mod 128 B
+  double A[DP * LDA];
+  double P[DMMA_ROWS_PER_CTA * LDA];
+  double part[DMMA_ROWS_PER_CTA][4][DMMA_MAX_RED];
+  unsigned long long mbar;
+};
+
+// One group's work: MT row tiles starting at CTA-local row `row0`.
+template <class Target, int DP, int MT>
+__device__ __forceinline__ void leapfrog_dmma_group(
+    DmmaSmem<DP>& sm, const Target& target, const double* q_in, const double* p_in,
+    double* q_out, double* p_out, const int32_t* __restrict__ dir, int64_t n_chains, int dim,
+    double step_size, int n_steps, double* __restrict__ h_out, int32_t* __restrict__ status,
+    int32_t* __restrict__ n_done, int64_t chain0, int row0, int w, int lane, int bar_id) {
+  constexpr int LDA = DmmaSmem<DP>::LDA;
+  constexpr int NT = DP / 32;  // 8-column tiles per warp
+  constexpr int KS = DP / 4;   // k steps
+  constexpr int NRED = Target::NRED;
+  static_assert(NRED + 2 <= DMMA_MAX_RED, "too many reductions");
+  const int r = lane >> 2, c = lane & 3;
+  const int col0 = w * (DP / 4);  // first column of this warp's slice
+
+  double q[MT][NT][2], p[MT][NT][2], acc[MT][NT][2], dt[MT];
+  bool live[MT];
+
+  // ---- load the register slices (C-fragment layout: row 8mt + r, cols col0 + 8nt + 2c + {0,1})
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int64_t ch = chain0 + row0 + 8 * mt + r;
+    live[mt] = ch < n_chains;
+    dt[mt] = (live[mt] && dir != nullptr) ? (double)dir[ch] * step_size : step_size;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int i = col0 + 8 * nt + 2 * c;
+      double2 a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
+      if (live[mt] && i < dim) {  // dim is even on this path
+        a = *reinterpret_cast<const double2*>(q_in + (size_t)ch * dim + i);
+        b = *reinterpret_cast<const double2*>(p_in + (size_t)ch * dim + i);
+      }
+      q[mt][nt][0] = a.x, q[mt][nt][1] = a.y, p[mt][nt][0] = b.x, p[mt][nt][1] = b.y;
+    }
+  }
+
+  // gradient of the target on the slices; per-chain reductions across the 4 warps of the group
+  auto gradient = [&](double (&g)[MT][NT][2]) {
+    double red[MT][NRED + 1];
+    if (NRED > 0) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int k = 0; k < NRED; ++k) red[mt][k] = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+          target.accumulate(col0 + 8 * nt + 2 * c, q[mt][nt][0], q[mt][nt][1], red[mt]);
+#pragma unroll
+        for (int k = 0; k < NRED; ++k) {
+          double v = red[mt][k];
+          v += __shfl_xor_sync(FULL_MASK, v, 1);
+          v += __shfl_xor_sync(FULL_MASK, v, 2);
+          if (c == 0) sm.part[row0 + 8 * mt + r][w][k] = v;
+        }
+      }
+    }
+    named_barrier_sync(bar_id, 128);  // partials visible; everyone is done reading sm.P
+    if (NRED > 0) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int k = 0; k < NRED; ++k) {
+          const double* pp = &sm.part[row0 + 8 * mt + r][0][k];
+          red[mt][k] = ((pp[0] + pp[DMMA_MAX_RED]) + pp[2 * DMMA_MAX_RED]) + pp[3 * DMMA_MAX_RED];
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int i = col0 + 8 * nt + 2 * c;
+        target.grad_pair(i, q[mt][nt][0], q[mt][nt][1], red[mt], g[mt][nt][0], g[mt][nt][1]);
+        if (i >= dim) g[mt][nt][0] = 0.0, g[mt][nt][1] = 0.0;
+      }
+  };
+
+  auto half_kick = [&](const double (&g)[MT][NT][2]) {
+    // p -= (dt/2) * g with product and difference rounded separately (systems.py:152)
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          p[mt][nt][e] = __dsub_rn(p[mt][nt][e], __dmul_rn(0.5 * dt[mt], g[mt][nt][e]));
+  };
+
+  auto publish_p = [&]() {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+        *reinterpret_cast<double2*>(&sm.P[(row0 + 8 * mt + r) * LDA + col0 + 8 * nt + 2 * c]) =
+            make_double2(p[mt][nt][0], p[mt][nt][1]);
+    named_barrier_sync(bar_id, 128);
+  };
+
+  // V = P * A on the tensor pipe
+  auto matvec = [&]() {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = 0.0, acc[mt][nt][1] = 0.0;
+    const double* a_base = &sm.P[(row0 + r) * LDA + c];
+    const double* b_base = &sm.A[(col0 + r) * LDA + c];
+#pragma unroll 4
+    for (int j = 0; j < KS; ++j) {
+      double a[MT], b[NT];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) a[mt] = a_base[mt * 8 * LDA + 4 * j];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) b[nt] = b_base[nt * 8 * LDA + 4 * j];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    }
+  };
+
+  {
+    double g[MT][NT][2];
+    gradient(g);
+    if (n_steps > 0) half_kick(g);
+    publish_p();
+    for (int s = 0; s < n_steps; ++s) {
+      matvec();
+      // h2_flow: q += dt * v, product and sum rounded separately (systems.py:363)
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            q[mt][nt][e] = __dadd_rn(q[mt][nt][e], __dmul_rn(dt[mt], acc[mt][nt][e]));
+      gradient(g);
+      half_kick(g);                      // closes step s
+      if (s + 1 < n_steps) half_kick(g);  // opens step s+1 with the cached gradient
+      publish_p();
+    }
+  }
+
+  // ---- store
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int64_t ch = chain0 + row0 + 8 * mt + r;
+    if (!live[mt]) continue;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int i = col0 + 8 * nt + 2 * c;
+      if (i < dim) {
+        *reinterpret_cast<double2*>(q_out + (size_t)ch * dim + i) =
+            make_double2(q[mt][nt][0], q[mt][nt][1]);
+        *reinterpret_cast<double2*>(p_out + (size_t)ch * dim + i) =
+            make_double2(p[mt][nt][0], p[mt][nt][1]);
+      }
+    }
+    if (w == 0 && c == 0) {
+      if (status != nullptr) status[ch] = MB200_STATUS_OK;
+      if (n_done != nullptr) n_done[ch] = n_steps;
+    }
+  }
+
+  // ---- Hamiltonian of the final state: l(q) + p . (A p) / 2   (systems.py:187-196, 348-350)
+  if (h_out != nullptr) {
+    matvec();  // sm.P holds the final momenta (published after the last kick)
+    double red[MT][NRED + 1];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      // the gradient() call of the last step left the reduced values of the final q in
+      // sm.part; recompute them here to keep this block self-contained
+#pragma unroll
+      for (int k = 0; k < NRED; ++k) {
+        const double* pp = &sm.part[row0 + 8 * mt + r][0][k];
+        red[mt][k] = ((pp[0] + pp[DMMA_MAX_RED]) + pp[2 * DMMA_MAX_RED]) + pp[3 * DMMA_MAX_RED];
+      }
+    }
+    named_barrier_sync(bar_id, 128);  // all reads of sm.part done before it is overwritten
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      double kin = 0.0, l = 0.0;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int i = col0 + 8 * nt + 2 * c;
+        kin = fma(p[mt][nt][0], acc[mt][nt][0], kin);
+        kin = fma(p[mt][nt][1], acc[mt][nt][1], kin);
+        if (i < dim) l += target.nld_pair(i, q[mt][nt][0], q[mt][nt][1], red[mt]);
+      }
+      kin += __shfl_xor_sync(FULL_MASK, kin, 1);
+      kin += __shfl_xor_sync(FULL_MASK, kin, 2);
+      l += __shfl_xor_sync(FULL_MASK, l, 1);
+      l += __shfl_xor_sync(FULL_MASK, l, 2);
+      if (c == 0) {
+        sm.part[row0 + 8 * mt + r][w][0] = kin;
+        sm.part[row0 + 8 * mt + r][w][1] = l;
+      }
+    }
+    named_barrier_sync(bar_id, 128);
+    if (w == 0 && c == 0) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        if (!live[mt]) continue;
+        const double* pk = &sm.part[row0 + 8 * mt + r][0][0];
+        const double kin = ((pk[0] + pk[DMMA_MAX_RED]) + pk[2 * DMMA_MAX_RED]) + pk[3 * DMMA_MAX_RED];
+        const double l = ((pk[1] + pk[DMMA_MAX_RED + 1]) + pk[2 * DMMA_MAX_RED + 1]) +
+                         pk[3 * DMMA_MAX_RED + 1];
+        h_out[chain0 + row0 + 8 * mt + r] = l + 0.5 * kin;
+      }
+    }
+  }
+}
+
+template <class Target, int DP>
+__global__ void __launch_bounds__(256, 1)
+    leapfrog_dmma_kernel(const double* q_in, const double* p_in, double* q_out, double* p_out,
+                         const int32_t* __restrict__ dir, int64_t n_chains, int dim,
+                         double step_size, int n_steps, const double* __restrict__ minv,
+                         ModelArgs model, double* __restrict__ h_out,
+                         int32_t* __restrict__ status, int32_t* __restrict__ n_done) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  DmmaSmem<DP>& sm = *reinterpret_cast<DmmaSmem<DP>*>(smem_raw);
+  constexpr int LDA = DmmaSmem<DP>::LDA;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int group = warp >> 2;  // 0: tiles 0-3, 1: tiles 4-6
+  const int w = warp & 3;
+  const Target target(model, dim);
+
+  // ---- stage A = M^-1 into shared memory: one TMA bulk copy per row, one mbarrier
+  const uint32_t mbar = smem_u32(&sm.mbar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // zero the padding (rows >= dim, columns >= dim) -- disjoint from the TMA destinations
+  for (int idx = tid; idx < DP * LDA; idx += blockDim.x) {
+    const int row = idx / LDA, col = idx - row * LDA;
+    if (row >= dim || col >= dim) sm.A[idx] = 0.0;
+  }
+  for (int idx = tid; idx < DMMA_ROWS_PER_CTA * LDA; idx += blockDim.x) sm.P[idx] = 0.0;
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t row_bytes = (uint32_t)dim * 8u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar),
+                 "r"(row_bytes * (uint32_t)dim)
+                 : "memory");
+    for (int row = 0; row < dim; ++row) {
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+          ::"r"(smem_u32(&sm.A[row * LDA])),
+          "l"(minv + (size_t)row * dim), "r"(row_bytes), "r"(mbar)
+          : "memory");
+    }
+  }
+  // wait for the bytes to land (phase 0)
+  {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+          " selp.u32 %0, 1, 0, p;\n}"
+          : "=r"(done)
+          : "r"(mbar)
+          : "memory");
+    }
+  }
+
+  for (int64_t blk = blockIdx.x; blk * DMMA_ROWS_PER_CTA < n_chains; blk += gridDim.x) {
+    const int64_t chain0 = blk * DMMA_ROWS_PER_CTA;
+    const int64_t left = n_chains - chain0;
+    const int tiles = (int)((left >= DMMA_ROWS_PER_CTA) ? DMMA_TILES_PER_CTA : (left + 7) / 8);
+    const int row0 = group * 32;
+    const int mt = group == 0 ? (tiles < 4 ? tiles : 4) : (tiles - 4);
+#define MB200_GROUP(MT)                                                                       \
+  leapfrog_dmma_group<Target, DP, MT>(sm, target, q_in, p_in, q_out, p_out, dir, n_chains,    \
+                                      dim, step_size, n_steps, h_out, status, n_done, chain0, \
+                                      row0, w, lane, 1 + group)
+    if (mt == 4) MB200_GROUP(4);
+    else if (mt == 3) MB200_GROUP(3);
+    else if (mt == 2) MB200_GROUP(2);
+    else if (mt == 1) MB200_GROUP(1);
+#undef MB200_GROUP
+    __syncthreads();  // next block of chains reuses sm.P / sm.part
+  }
+}
+
+template <class Target, int DP>
+static int launch_dmma(const double* q_in, const double* p_in, double* q_out, double* p_out,
+                       const int32_t* dir, int64_t n, int dim, double eps, int n_steps,
+                       const double* minv, const ModelArgs& m, double* h_out, int32_t* status,
+                       int32_t* n_done, cudaStream_t st, int sms) {
+  auto kern = leapfrog_dmma_kernel<Target, DP>;
+  const size_t smem = sizeof(DmmaSmem<DP>);
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+      cudaSuccess)
+    return MB200_ERR_CUDA;
+  int64_t blocks = (n + DMMA_ROWS_PER_CTA - 1) / DMMA_ROWS_PER_CTA;
+  if (blocks > sms) blocks = sms;  // persistent: CTAs loop over blocks of 56 chains
+  kern<<<(unsigned)blocks, 256, smem, st>>>(q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps,
+                                            minv, m, h_out, status, n_done);
+  return 0;
+}
+
+template <class Target>
+static int dispatch_dmma_dim(const double* q_in, const double* p_in, double* q_out, double* p_out,
+                             const int32_t* dir, int64_t n, int dim, double eps, int n_steps,
+                             const double* minv, const ModelArgs& m, double* h_out,
+                             int32_t* status, int32_t* n_done, cudaStream_t st, int sms) {
+#define MB200_DM(DP)                                                                           \
+  return launch_dmma<Target, DP>(q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, minv, m, \
+                                 h_out, status, n_done, st, sms)
+  if (dim <= 32) MB200_DM(32);
+  if (dim <= 64) MB200_DM(64);
+  if (dim <= 96) MB200_DM(96);
+  MB200_DM(128);
+#undef MB200_DM
+}
+
+// Returns MB200_ERR_UNSUPPORTED when the shape is outside this kernel's domain (the caller
+// then uses the general-dimension kernel).
+static int leapfrog_dmma_dispatch(const double* q_in, const double* p_in, double* q_out,
+                                  double* p_out, const int32_t* dir, int64_t n, int dim,
+                                  double eps, int n_steps, const double* minv, const ModelArgs& m,
+                                  double* h_out, int32_t* status, int32_t* n_done,
+                                  cudaStream_t st) {
+  if (dim > 128 || (dim & 1) || dim < 8) return MB200_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(minv) & 15) != 0) return MB200_ERR_UNSUPPORTED;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#define MB200_ARGS \
+  q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, minv, m, h_out, status, n_done, st, sms
+  switch (m.target_id) {
+    case MB200_TARGET_STD_GAUSSIAN: return dispatch_dmma_dim<StdGaussianTarget>(MB200_ARGS);
+    case MB200_TARGET_NEAL_FUNNEL: return dispatch_dmma_dim<NealFunnelTarget>(MB200_ARGS);
+    case MB200_TARGET_BANANA: return dispatch_dmma_dim<BananaTarget>(MB200_ARGS);
+    default: return MB200_ERR_UNSUPPORTED;
+  }
+#undef MB200_ARGS
+}
+
+}  // namespace mb200
