@@ -16,7 +16,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -56,33 +55,46 @@ def measured_hbm_peak():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clock / clock-event reasons during the timed region through NVML (no
+    subprocesses: forking from the benchmark process would stall the launch thread)."""
 
-    QUERY = (
-        "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-        "clocks_event_reasons.sw_power_cap"
-    )
+    REASONS = {
+        "hw_slowdown": 0x8,
+        "sw_power_cap": 0x4,
+        "sw_thermal_slowdown": 0x20,
+        "hw_thermal_slowdown": 0x40,
+    }
 
     def __init__(self, index):
         self.index = index
         self.rows = []
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:  # initialise NVML here, outside any timed region
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._max = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+            self._nvml = pynvml
+        except Exception:  # noqa: BLE001
+            pass
 
     def _run(self):
+        pynvml, h, mx = self._nvml, getattr(self, "_h", None), getattr(self, "_max", None)
+        if pynvml is None:
+            return
         while not self._stop.is_set():
             try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                     "--format=csv,noheader,nounits"],
-                    capture_output=True, text=True, timeout=5,
-                ).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.splitlines()[0].split(",")])
+                self.rows.append((
+                    pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), mx,
+                    pynvml.nvmlDeviceGetCurrentClocksEventReasons(h),
+                    pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                ))
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.002)
 
     def __enter__(self):
         self._thread.start()
@@ -93,19 +105,14 @@ class ClockSampler:
         self._thread.join(timeout=10)
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for name, v in zip(names, r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted(k for k, bit in self.REASONS.items() if any(r[2] & bit for r in self.rows))
         return {
             "sm_mhz": sm[len(sm) // 2] if sm else None,
-            "sm_max_mhz": max(mx) if mx else None,
-            "reasons": sorted(reasons),
+            "sm_max_mhz": self.rows[0][1] if self.rows else None,
+            "reasons": reasons,
             "samples": len(self.rows),
+            "power_w_max": max((r[3] for r in self.rows), default=None),
         }
 
 
@@ -204,7 +211,10 @@ def run_cuda(args, rank, local_rank, world):
     sync_all()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
-    with ClockSampler(local_rank) as clocks:
+    sampler = ClockSampler(local_rank)
+    with sampler as clocks:
+        for _ in range(2):  # sampler thread is running: absorb its start-up before timing
+            integ.step_n(state, L)
         sync_all()
         out = state
         for i in range(args.steps):
@@ -280,6 +290,8 @@ def run_cuda(args, rank, local_rank, world):
         "steps": args.steps,
         "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps,
+        "ms_per_step_min_median_max": [min(times_ms), sorted(times_ms)[len(times_ms) // 2],
+                                       max(times_ms)],
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,

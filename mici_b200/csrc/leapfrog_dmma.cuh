@@ -13,20 +13,23 @@
 // kind; DMMA.8x8x4 is the native sm_100a instruction, 37.1 TFLOP/s measured:
 // profiles/r01_fp64_peak.txt).
 //
-// Work decomposition (one CTA per SM, 8 warps, 2 groups x 4 warps):
-//   * a CTA owns up to 56 chains = 7 row tiles of 8 chains; group 0 takes tiles 0-3, group 1
-//     tiles 4-6 -- 7 tile-quarters per SM sub-partition, which balances 8192 chains over
+// Work decomposition (one CTA per SM, 16 warps, 4 groups x 4 warps):
+//   * a CTA owns up to 56 chains = 7 row tiles of 8 chains; groups 0-2 take two tiles each,
+//     group 3 one -- 7 tile-quarters per SM sub-partition, which balances 8192 chains over
 //     148 SMs x 4 sub-partitions (8192 / 148 = 55.4 chains per SM);
-//   * warp w of a group computes output columns [w*DP/4, (w+1)*DP/4) for all the group's tiles:
-//     accumulators, positions and momenta of that slice stay in registers in the DMMA
-//     C-fragment layout for the whole launch (HBM is touched once on entry and once on exit);
+//   * warp w of a group (one per sub-partition) computes output columns [w*DP/4, (w+1)*DP/4) for
+//     the group's tiles: accumulators and positions of that slice stay in registers in the DMMA
+//     C-fragment layout for the whole launch, momenta in a shared-memory tile (HBM is touched
+//     once on entry and once on exit);
 //   * A lives in shared memory for the whole launch (staged by TMA bulk copies, row stride
 //     padded by 4 doubles so A/B fragment loads are bank-conflict free); B fragments are read
 //     through the symmetry A[k][n] = A[n][k] as 8 rows x 4 consecutive doubles;
-//   * momenta are exchanged through a shared-memory tile once per step (A fragments), and the
-//     per-chain reductions of the target gradient through per-warp partial sums; the two groups
-//     synchronise only internally (named barriers), so one group's gradient/update phase
-//     overlaps the other's DMMA phase.
+//   * momenta are exchanged through the shared-memory tile once per step (A fragments), and the
+//     per-chain reductions of the target gradient through per-warp partial sums; the groups
+//     synchronise only internally (named barriers), so while one group is in its gradient /
+//     update phase the other three keep the sub-partition's DMMA pipe fed (ptxas spaces
+//     back-to-back DMMAs of one warp with NOPs, so >= 2 warps per sub-partition must be in the
+//     DMMA phase to saturate it).
 #pragma once
 #include "targets.cuh"
 
@@ -48,6 +51,8 @@ __device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
 }
 
 constexpr int DMMA_TILES_PER_CTA = 7;
+constexpr int DMMA_GROUPS = 4;           // 4 warps each; tiles per group 2,2,2,1
+constexpr int DMMA_THREADS = 32 * 4 * DMMA_GROUPS;
 constexpr int DMMA_ROWS_PER_CTA = 8 * DMMA_TILES_PER_CTA;  // 56 chains
 constexpr int DMMA_MAX_RED = 4;
 
@@ -56,11 +61,11 @@ struct DmmaSmem {
   static constexpr int LDA = DP + 4;  // row stride (doubles): rows shift by 32 B mod 128 B
   double A[DP * LDA];
   double P[DMMA_ROWS_PER_CTA * LDA];
-  double part[DMMA_ROWS_PER_CTA][4][DMMA_MAX_RED];
+  double part[4][DMMA_MAX_RED][DMMA_ROWS_PER_CTA];  // [warp-in-group][reduction][row]
   unsigned long long mbar;
 };
 
-// One group's work: MT row tiles starting at CTA-local row `row0`.
+// One group's work: MT (1 or 2) row tiles starting at CTA-local row `row0`.
 template <class Target, int DP, int MT>
 __device__ __forceinline__ void leapfrog_dmma_group(
     DmmaSmem<DP>& sm, const Target& target, const double* q_in, const double* p_in,
@@ -75,15 +80,18 @@ __device__ __forceinline__ void leapfrog_dmma_group(
   const int r = lane >> 2, c = lane & 3;
   const int col0 = w * (DP / 4);  // first column of this warp's slice
 
-  double q[MT][NT][2], p[MT][NT][2], acc[MT][NT][2], dt[MT];
+  // registers: positions and accumulators of the slice in C-fragment layout
+  // (row 8mt + r, columns col0 + 8nt + 2c + {0,1}); momenta live in sm.P (same ownership)
+  double q[MT][NT][2], acc[MT][NT][2], dt[MT];
   bool live[MT];
+  double2* pslot[MT];  // &sm.P[row][col0 + 2c]; + 4*nt double2 per column tile
 
-  // ---- load the register slices (C-fragment layout: row 8mt + r, cols col0 + 8nt + 2c + {0,1})
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
     const int64_t ch = chain0 + row0 + 8 * mt + r;
     live[mt] = ch < n_chains;
     dt[mt] = (live[mt] && dir != nullptr) ? (double)dir[ch] * step_size : step_size;
+    pslot[mt] = reinterpret_cast<double2*>(&sm.P[(row0 + 8 * mt + r) * LDA + col0 + 2 * c]);
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       const int i = col0 + 8 * nt + 2 * c;
@@ -92,13 +100,17 @@ __device__ __forceinline__ void leapfrog_dmma_group(
         a = *reinterpret_cast<const double2*>(q_in + (size_t)ch * dim + i);
         b = *reinterpret_cast<const double2*>(p_in + (size_t)ch * dim + i);
       }
-      q[mt][nt][0] = a.x, q[mt][nt][1] = a.y, p[mt][nt][0] = b.x, p[mt][nt][1] = b.y;
+      q[mt][nt][0] = a.x, q[mt][nt][1] = a.y;
+      pslot[mt][4 * nt] = b;
     }
   }
 
-  // gradient of the target on the slices; per-chain reductions across the 4 warps of the group
-  auto gradient = [&](double (&g)[MT][NT][2]) {
-    double red[MT][NRED + 1];
+  double red[MT][NRED + 1];
+
+  // per-chain sum reductions of the target over the full row: partial over this warp's slice,
+  // exchanged through shared memory.  The barrier also orders "all A-fragment reads of sm.P
+  // done" before the in-place momentum update that follows.
+  auto reduce_rows = [&]() {
     if (NRED > 0) {
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
@@ -112,48 +124,40 @@ __device__ __forceinline__ void leapfrog_dmma_group(
           double v = red[mt][k];
           v += __shfl_xor_sync(FULL_MASK, v, 1);
           v += __shfl_xor_sync(FULL_MASK, v, 2);
-          if (c == 0) sm.part[row0 + 8 * mt + r][w][k] = v;
+          if (c == 0) sm.part[w][k][row0 + 8 * mt + r] = v;
         }
       }
     }
-    named_barrier_sync(bar_id, 128);  // partials visible; everyone is done reading sm.P
+    named_barrier_sync(bar_id, 128);
     if (NRED > 0) {
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int k = 0; k < NRED; ++k) {
-          const double* pp = &sm.part[row0 + 8 * mt + r][0][k];
-          red[mt][k] = ((pp[0] + pp[DMMA_MAX_RED]) + pp[2 * DMMA_MAX_RED]) + pp[3 * DMMA_MAX_RED];
+          const int row = row0 + 8 * mt + r;
+          red[mt][k] = ((sm.part[0][k][row] + sm.part[1][k][row]) + sm.part[2][k][row]) +
+                       sm.part[3][k][row];
         }
     }
+  };
+
+  // p -= (dt/2) * grad l(q), `kicks` times (1 or 2), each with product and difference rounded
+  // separately (systems.py:152); then make the new momenta visible to the group.
+  auto kick_and_publish = [&](int kicks) {
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int i = col0 + 8 * nt + 2 * c;
-        target.grad_pair(i, q[mt][nt][0], q[mt][nt][1], red[mt], g[mt][nt][0], g[mt][nt][1]);
-        if (i >= dim) g[mt][nt][0] = 0.0, g[mt][nt][1] = 0.0;
+        double g0, g1;
+        target.grad_pair(i, q[mt][nt][0], q[mt][nt][1], red[mt], g0, g1);
+        if (i >= dim) g0 = 0.0, g1 = 0.0;
+        const double h0 = __dmul_rn(0.5 * dt[mt], g0), h1 = __dmul_rn(0.5 * dt[mt], g1);
+        double2 pv = pslot[mt][4 * nt];
+        if (kicks >= 1) pv.x = __dsub_rn(pv.x, h0), pv.y = __dsub_rn(pv.y, h1);
+        if (kicks >= 2) pv.x = __dsub_rn(pv.x, h0), pv.y = __dsub_rn(pv.y, h1);
+        pslot[mt][4 * nt] = pv;
       }
-  };
-
-  auto half_kick = [&](const double (&g)[MT][NT][2]) {
-    // p -= (dt/2) * g with product and difference rounded separately (systems.py:152)
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e)
-          p[mt][nt][e] = __dsub_rn(p[mt][nt][e], __dmul_rn(0.5 * dt[mt], g[mt][nt][e]));
-  };
-
-  auto publish_p = [&]() {
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-        *reinterpret_cast<double2*>(&sm.P[(row0 + 8 * mt + r) * LDA + col0 + 8 * nt + 2 * c]) =
-            make_double2(p[mt][nt][0], p[mt][nt][1]);
     named_barrier_sync(bar_id, 128);
   };
 
@@ -165,7 +169,7 @@ __device__ __forceinline__ void leapfrog_dmma_group(
       for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = 0.0, acc[mt][nt][1] = 0.0;
     const double* a_base = &sm.P[(row0 + r) * LDA + c];
     const double* b_base = &sm.A[(col0 + r) * LDA + c];
-#pragma unroll 4
+#pragma unroll 8
     for (int j = 0; j < KS; ++j) {
       double a[MT], b[NT];
 #pragma unroll
@@ -179,26 +183,21 @@ __device__ __forceinline__ void leapfrog_dmma_group(
     }
   };
 
-  {
-    double g[MT][NT][2];
-    gradient(g);
-    if (n_steps > 0) half_kick(g);
-    publish_p();
-    for (int s = 0; s < n_steps; ++s) {
-      matvec();
-      // h2_flow: q += dt * v, product and sum rounded separately (systems.py:363)
+  reduce_rows();
+  kick_and_publish(n_steps > 0 ? 1 : 0);
+  for (int s = 0; s < n_steps; ++s) {
+    matvec();
+    // h2_flow: q += dt * v, product and sum rounded separately (systems.py:363)
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
+      for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-          for (int e = 0; e < 2; ++e)
-            q[mt][nt][e] = __dadd_rn(q[mt][nt][e], __dmul_rn(dt[mt], acc[mt][nt][e]));
-      gradient(g);
-      half_kick(g);                      // closes step s
-      if (s + 1 < n_steps) half_kick(g);  // opens step s+1 with the cached gradient
-      publish_p();
-    }
+        for (int e = 0; e < 2; ++e)
+          q[mt][nt][e] = __dadd_rn(q[mt][nt][e], __dmul_rn(dt[mt], acc[mt][nt][e]));
+    reduce_rows();
+    // closes step s and (cached gradient) opens step s+1
+    kick_and_publish(s + 1 < n_steps ? 2 : 1);
   }
 
   // ---- store
@@ -212,8 +211,7 @@ __device__ __forceinline__ void leapfrog_dmma_group(
       if (i < dim) {
         *reinterpret_cast<double2*>(q_out + (size_t)ch * dim + i) =
             make_double2(q[mt][nt][0], q[mt][nt][1]);
-        *reinterpret_cast<double2*>(p_out + (size_t)ch * dim + i) =
-            make_double2(p[mt][nt][0], p[mt][nt][1]);
+        *reinterpret_cast<double2*>(p_out + (size_t)ch * dim + i) = pslot[mt][4 * nt];
       }
     }
     if (w == 0 && c == 0) {
@@ -224,55 +222,49 @@ __device__ __forceinline__ void leapfrog_dmma_group(
 
   // ---- Hamiltonian of the final state: l(q) + p . (A p) / 2   (systems.py:187-196, 348-350)
   if (h_out != nullptr) {
-    matvec();  // sm.P holds the final momenta (published after the last kick)
-    double red[MT][NRED + 1];
+    matvec();  // sm.P holds the final momenta; red[] the reductions of the final positions
+    double kin[MT], l[MT];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      // the gradient() call of the last step left the reduced values of the final q in
-      // sm.part; recompute them here to keep this block self-contained
-#pragma unroll
-      for (int k = 0; k < NRED; ++k) {
-        const double* pp = &sm.part[row0 + 8 * mt + r][0][k];
-        red[mt][k] = ((pp[0] + pp[DMMA_MAX_RED]) + pp[2 * DMMA_MAX_RED]) + pp[3 * DMMA_MAX_RED];
-      }
-    }
-    named_barrier_sync(bar_id, 128);  // all reads of sm.part done before it is overwritten
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      double kin = 0.0, l = 0.0;
+      kin[mt] = 0.0, l[mt] = 0.0;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int i = col0 + 8 * nt + 2 * c;
-        kin = fma(p[mt][nt][0], acc[mt][nt][0], kin);
-        kin = fma(p[mt][nt][1], acc[mt][nt][1], kin);
-        if (i < dim) l += target.nld_pair(i, q[mt][nt][0], q[mt][nt][1], red[mt]);
+        const double2 pv = pslot[mt][4 * nt];
+        kin[mt] = fma(pv.x, acc[mt][nt][0], kin[mt]);
+        kin[mt] = fma(pv.y, acc[mt][nt][1], kin[mt]);
+        if (i < dim) l[mt] += target.nld_pair(i, q[mt][nt][0], q[mt][nt][1], red[mt]);
       }
-      kin += __shfl_xor_sync(FULL_MASK, kin, 1);
-      kin += __shfl_xor_sync(FULL_MASK, kin, 2);
-      l += __shfl_xor_sync(FULL_MASK, l, 1);
-      l += __shfl_xor_sync(FULL_MASK, l, 2);
-      if (c == 0) {
-        sm.part[row0 + 8 * mt + r][w][0] = kin;
-        sm.part[row0 + 8 * mt + r][w][1] = l;
-      }
+      kin[mt] += __shfl_xor_sync(FULL_MASK, kin[mt], 1);
+      kin[mt] += __shfl_xor_sync(FULL_MASK, kin[mt], 2);
+      l[mt] += __shfl_xor_sync(FULL_MASK, l[mt], 1);
+      l[mt] += __shfl_xor_sync(FULL_MASK, l[mt], 2);
     }
+    named_barrier_sync(bar_id, 128);  // every warp has consumed the gradient partials
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+      if (c == 0) {
+        sm.part[w][0][row0 + 8 * mt + r] = kin[mt];
+        sm.part[w][1][row0 + 8 * mt + r] = l[mt];
+      }
     named_barrier_sync(bar_id, 128);
     if (w == 0 && c == 0) {
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         if (!live[mt]) continue;
-        const double* pk = &sm.part[row0 + 8 * mt + r][0][0];
-        const double kin = ((pk[0] + pk[DMMA_MAX_RED]) + pk[2 * DMMA_MAX_RED]) + pk[3 * DMMA_MAX_RED];
-        const double l = ((pk[1] + pk[DMMA_MAX_RED + 1]) + pk[2 * DMMA_MAX_RED + 1]) +
-                         pk[3 * DMMA_MAX_RED + 1];
-        h_out[chain0 + row0 + 8 * mt + r] = l + 0.5 * kin;
+        const int row = row0 + 8 * mt + r;
+        const double ks = ((sm.part[0][0][row] + sm.part[1][0][row]) + sm.part[2][0][row]) +
+                          sm.part[3][0][row];
+        const double ls = ((sm.part[0][1][row] + sm.part[1][1][row]) + sm.part[2][1][row]) +
+                          sm.part[3][1][row];
+        h_out[chain0 + row] = ls + 0.5 * ks;
       }
     }
   }
 }
 
 template <class Target, int DP>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(DMMA_THREADS, 1)
     leapfrog_dmma_kernel(const double* q_in, const double* p_in, double* q_out, double* p_out,
                          const int32_t* __restrict__ dir, int64_t n_chains, int dim,
                          double step_size, int n_steps, const double* __restrict__ minv,
@@ -284,8 +276,8 @@ __global__ void __launch_bounds__(256, 1)
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const int group = warp >> 2;  // 0: tiles 0-3, 1: tiles 4-6
-  const int w = warp & 3;
+  const int group = warp >> 2;  // tiles {0,1}, {2,3}, {4,5}, {6}
+  const int w = warp & 3;       // == SM sub-partition of the warp
   const Target target(model, dim);
 
   // ---- stage A = M^-1 into shared memory: one TMA bulk copy per row, one mbarrier
@@ -331,15 +323,14 @@ __global__ void __launch_bounds__(256, 1)
     const int64_t chain0 = blk * DMMA_ROWS_PER_CTA;
     const int64_t left = n_chains - chain0;
     const int tiles = (int)((left >= DMMA_ROWS_PER_CTA) ? DMMA_TILES_PER_CTA : (left + 7) / 8);
-    const int row0 = group * 32;
-    const int mt = group == 0 ? (tiles < 4 ? tiles : 4) : (tiles - 4);
+    const int row0 = group * 16;
+    int mt = tiles - 2 * group;
+    mt = mt > 2 ? 2 : mt;
 #define MB200_GROUP(MT)                                                                       \
   leapfrog_dmma_group<Target, DP, MT>(sm, target, q_in, p_in, q_out, p_out, dir, n_chains,    \
                                       dim, step_size, n_steps, h_out, status, n_done, chain0, \
                                       row0, w, lane, 1 + group)
-    if (mt == 4) MB200_GROUP(4);
-    else if (mt == 3) MB200_GROUP(3);
-    else if (mt == 2) MB200_GROUP(2);
+    if (mt == 2) MB200_GROUP(2);
     else if (mt == 1) MB200_GROUP(1);
 #undef MB200_GROUP
     __syncthreads();  // next block of chains reuses sm.P / sm.part
@@ -358,7 +349,7 @@ static int launch_dmma(const double* q_in, const double* p_in, double* q_out, do
     return MB200_ERR_CUDA;
   int64_t blocks = (n + DMMA_ROWS_PER_CTA - 1) / DMMA_ROWS_PER_CTA;
   if (blocks > sms) blocks = sms;  // persistent: CTAs loop over blocks of 56 chains
-  kern<<<(unsigned)blocks, 256, smem, st>>>(q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps,
+  kern<<<(unsigned)blocks, DMMA_THREADS, smem, st>>>(q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps,
                                             minv, m, h_out, status, n_done);
   return 0;
 }
