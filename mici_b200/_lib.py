@@ -16,7 +16,10 @@ from .errors import Error, ExtensionNotBuiltError
 
 MAX_PARAMS = 8
 LIB_NAME = "libmici_b200.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+# MICI_B200_LIB lets profiling experiments load an alternative build of the same C ABI
+LIB_PATH = os.environ.get(
+    "MICI_B200_LIB", os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+)
 
 c_double_p = ctypes.c_void_p  # device pointers travel as integers
 c_int32_p = ctypes.c_void_p

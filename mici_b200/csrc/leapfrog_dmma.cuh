@@ -27,9 +27,8 @@
 //   * momenta are exchanged through the shared-memory tile once per step (A fragments), and the
 //     per-chain reductions of the target gradient through per-warp partial sums; the groups
 //     synchronise only internally (named barriers), so while one group is in its gradient /
-//     update phase the other three keep the sub-partition's DMMA pipe fed (ptxas spaces
-//     back-to-back DMMAs of one warp with NOPs, so >= 2 warps per sub-partition must be in the
-//     DMMA phase to saturate it).
+//     update phase the other three keep the sub-partition's DMMA pipe fed (one warp alone
+//     reaches 80 % of the pipe, two 96 %: profiles/r01_notes.md).
 #pragma once
 #include "targets.cuh"
 
@@ -47,7 +46,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 __device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
+#if defined(MB200_EXP) && MB200_EXP == 4  // experiment: no group barriers (racy, results invalid)
+  __syncwarp();
+#else
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
 }
 
 constexpr int DMMA_TILES_PER_CTA = 7;
@@ -66,6 +69,16 @@ struct DmmaSmem {
 };
 
 // One group's work: MT (1 or 2) row tiles starting at CTA-local row `row0`.
+//
+// Formulation used inside the kernel (exact re-parametrisation of integrators.py:170-173):
+//   s = dir * p   (signed momentum; the sign flip is exact)
+//   kick:  s -= (eps/2) * grad l(q)          == dir * (p - (dir*eps/2) * grad)
+//   drift: q += s . (eps * A)                == q + (dir*eps) * (A p)
+// so the per-chain direction only appears in the load and the store, sm.A holds eps*A (scaled
+// once after the TMA lands), and the drift is a DMMA whose accumulator operand IS q: positions
+// never leave the accumulator registers and the only fp64-ALU work per coordinate and step is
+// one FMA for the target's reduction and one per half-kick.  (Every fp64-ALU instruction costs
+// DMMA issue slots on the shared pipe -- measured ~8 cycles each, profiles/r01_notes.md.)
 template <class Target, int DP, int MT>
 __device__ __forceinline__ void leapfrog_dmma_group(
     DmmaSmem<DP>& sm, const Target& target, const double* q_in, const double* p_in,
@@ -79,10 +92,11 @@ __device__ __forceinline__ void leapfrog_dmma_group(
   static_assert(NRED + 2 <= DMMA_MAX_RED, "too many reductions");
   const int r = lane >> 2, c = lane & 3;
   const int col0 = w * (DP / 4);  // first column of this warp's slice
+  const double mh = -0.5 * step_size;
 
-  // registers: positions and accumulators of the slice in C-fragment layout
-  // (row 8mt + r, columns col0 + 8nt + 2c + {0,1}); momenta live in sm.P (same ownership)
-  double q[MT][NT][2], acc[MT][NT][2], dt[MT];
+  // registers: positions of the slice in C-fragment layout (row 8mt + r, columns
+  // col0 + 8nt + 2c + {0,1}); signed momenta live in sm.P with the same ownership
+  double q[MT][NT][2], sgn[MT];
   bool live[MT];
   double2* pslot[MT];  // &sm.P[row][col0 + 2c]; + 4*nt double2 per column tile
 
@@ -90,7 +104,7 @@ __device__ __forceinline__ void leapfrog_dmma_group(
   for (int mt = 0; mt < MT; ++mt) {
     const int64_t ch = chain0 + row0 + 8 * mt + r;
     live[mt] = ch < n_chains;
-    dt[mt] = (live[mt] && dir != nullptr) ? (double)dir[ch] * step_size : step_size;
+    sgn[mt] = (live[mt] && dir != nullptr && dir[ch] < 0) ? -1.0 : 1.0;
     pslot[mt] = reinterpret_cast<double2*>(&sm.P[(row0 + 8 * mt + r) * LDA + col0 + 2 * c]);
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
@@ -101,7 +115,7 @@ __device__ __forceinline__ void leapfrog_dmma_group(
         b = *reinterpret_cast<const double2*>(p_in + (size_t)ch * dim + i);
       }
       q[mt][nt][0] = a.x, q[mt][nt][1] = a.y;
-      pslot[mt][4 * nt] = b;
+      pslot[mt][4 * nt] = make_double2(sgn[mt] * b.x, sgn[mt] * b.y);
     }
   }
 
@@ -114,11 +128,22 @@ __device__ __forceinline__ void leapfrog_dmma_group(
     if (NRED > 0) {
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
+        // independent per-tile terms, then a pairwise tree: keeps the dependent fp64 chain short
+        // (every dependent op queues behind other warps' DMMAs on the shared pipe)
+        double term[NT][NRED + 1];
 #pragma unroll
-        for (int k = 0; k < NRED; ++k) red[mt][k] = 0.0;
+        for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-          target.accumulate(col0 + 8 * nt + 2 * c, q[mt][nt][0], q[mt][nt][1], red[mt]);
+          for (int k = 0; k < NRED; ++k) term[nt][k] = 0.0;
+          target.accumulate(col0 + 8 * nt + 2 * c, q[mt][nt][0], q[mt][nt][1], term[nt]);
+        }
+#pragma unroll
+        for (int k = 0; k < NRED; ++k) {
+          if (NT == 4) red[mt][k] = (term[0][k] + term[1][k]) + (term[2 % NT][k] + term[3 % NT][k]);
+          else if (NT == 3) red[mt][k] = (term[0][k] + term[1][k]) + term[2 % NT][k];
+          else if (NT == 2) red[mt][k] = term[0][k] + term[1 % NT][k];
+          else red[mt][k] = term[0][k];
+        }
 #pragma unroll
         for (int k = 0; k < NRED; ++k) {
           double v = red[mt][k];
@@ -141,32 +166,29 @@ __device__ __forceinline__ void leapfrog_dmma_group(
     }
   };
 
-  // p -= (dt/2) * grad l(q), `kicks` times (1 or 2), each with product and difference rounded
-  // separately (systems.py:152); then make the new momenta visible to the group.
+  // s -= (eps/2) * grad l(q), `kicks` times (1 or 2: the two half-steps either side of a step
+  // boundary stay two separately rounded updates, systems.py:152), one FMA per coordinate and
+  // kick; then make the new momenta visible to the group.
   auto kick_and_publish = [&](int kicks) {
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
+    for (int mt = 0; mt < MT; ++mt) {
+      const double ks = target.kick_scalar(red[mt], mh);
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int i = col0 + 8 * nt + 2 * c;
-        double g0, g1;
-        target.grad_pair(i, q[mt][nt][0], q[mt][nt][1], red[mt], g0, g1);
-        if (i >= dim) g0 = 0.0, g1 = 0.0;
-        const double h0 = __dmul_rn(0.5 * dt[mt], g0), h1 = __dmul_rn(0.5 * dt[mt], g1);
         double2 pv = pslot[mt][4 * nt];
-        if (kicks >= 1) pv.x = __dsub_rn(pv.x, h0), pv.y = __dsub_rn(pv.y, h1);
-        if (kicks >= 2) pv.x = __dsub_rn(pv.x, h0), pv.y = __dsub_rn(pv.y, h1);
+        if (i < dim) {
+          if (kicks >= 1) target.kick_pair(i, q[mt][nt][0], q[mt][nt][1], red[mt], mh, ks, pv.x, pv.y);
+          if (kicks >= 2) target.kick_pair(i, q[mt][nt][0], q[mt][nt][1], red[mt], mh, ks, pv.x, pv.y);
+        }
         pslot[mt][4 * nt] = pv;
       }
+    }
     named_barrier_sync(bar_id, 128);
   };
 
-  // V = P * A on the tensor pipe
-  auto matvec = [&]() {
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = 0.0, acc[mt][nt][1] = 0.0;
+  // acc += S * (eps A) on the tensor pipe (acc = q for the drift, acc = 0 for the energy)
+  auto drift = [&](double (&acc)[MT][NT][2]) {
     const double* a_base = &sm.P[(row0 + r) * LDA + c];
     const double* b_base = &sm.A[(col0 + r) * LDA + c];
 #pragma unroll 8
@@ -185,22 +207,23 @@ __device__ __forceinline__ void leapfrog_dmma_group(
 
   reduce_rows();
   kick_and_publish(n_steps > 0 ? 1 : 0);
+#ifndef MB200_EXP
+#define MB200_EXP 0
+#endif
   for (int s = 0; s < n_steps; ++s) {
-    matvec();
-    // h2_flow: q += dt * v, product and sum rounded separately (systems.py:363)
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e)
-          q[mt][nt][e] = __dadd_rn(q[mt][nt][e], __dmul_rn(dt[mt], acc[mt][nt][e]));
+    drift(q);  // h2_flow (systems.py:363): q += dir*eps * (A p)
+#if MB200_EXP == 2 || MB200_EXP == 5 || MB200_EXP == 6  // experiment: drift only (results invalid)
+    continue;
+#endif
     reduce_rows();
+#if MB200_EXP == 3  // experiment: one barrier per step (results invalid)
+    continue;
+#endif
     // closes step s and (cached gradient) opens step s+1
     kick_and_publish(s + 1 < n_steps ? 2 : 1);
   }
 
-  // ---- store
+  // ---- store (p = dir * s)
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
     const int64_t ch = chain0 + row0 + 8 * mt + r;
@@ -211,7 +234,9 @@ __device__ __forceinline__ void leapfrog_dmma_group(
       if (i < dim) {
         *reinterpret_cast<double2*>(q_out + (size_t)ch * dim + i) =
             make_double2(q[mt][nt][0], q[mt][nt][1]);
-        *reinterpret_cast<double2*>(p_out + (size_t)ch * dim + i) = pslot[mt][4 * nt];
+        const double2 sv = pslot[mt][4 * nt];
+        *reinterpret_cast<double2*>(p_out + (size_t)ch * dim + i) =
+            make_double2(sgn[mt] * sv.x, sgn[mt] * sv.y);
       }
     }
     if (w == 0 && c == 0) {
@@ -222,18 +247,26 @@ __device__ __forceinline__ void leapfrog_dmma_group(
 
   // ---- Hamiltonian of the final state: l(q) + p . (A p) / 2   (systems.py:187-196, 348-350)
   if (h_out != nullptr) {
-    matvec();  // sm.P holds the final momenta; red[] the reductions of the final positions
-    double kin[MT], l[MT];
+    double l[MT], kin[MT], u[MT][NT][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      kin[mt] = 0.0, l[mt] = 0.0;
+      l[mt] = 0.0;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int i = col0 + 8 * nt + 2 * c;
-        const double2 pv = pslot[mt][4 * nt];
-        kin[mt] = fma(pv.x, acc[mt][nt][0], kin[mt]);
-        kin[mt] = fma(pv.y, acc[mt][nt][1], kin[mt]);
         if (i < dim) l[mt] += target.nld_pair(i, q[mt][nt][0], q[mt][nt][1], red[mt]);
+        u[mt][nt][0] = 0.0, u[mt][nt][1] = 0.0;
+      }
+    }
+    drift(u);  // u = s . (eps A); sm.P holds the final momenta
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      kin[mt] = 0.0;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const double2 sv = pslot[mt][4 * nt];
+        kin[mt] = fma(sv.x, u[mt][nt][0], kin[mt]);
+        kin[mt] = fma(sv.y, u[mt][nt][1], kin[mt]);
       }
       kin[mt] += __shfl_xor_sync(FULL_MASK, kin[mt], 1);
       kin[mt] += __shfl_xor_sync(FULL_MASK, kin[mt], 2);
@@ -257,7 +290,7 @@ __device__ __forceinline__ void leapfrog_dmma_group(
                           sm.part[3][0][row];
         const double ls = ((sm.part[0][1][row] + sm.part[1][1][row]) + sm.part[2][1][row]) +
                           sm.part[3][1][row];
-        h_out[chain0 + row] = ls + 0.5 * ks;
+        h_out[chain0 + row] = ls + 0.5 * (ks / step_size);
       }
     }
   }
@@ -277,7 +310,11 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   const int lane = tid & 31;
   const int warp = tid >> 5;
   const int group = warp >> 2;  // tiles {0,1}, {2,3}, {4,5}, {6}
-  const int w = warp & 3;       // == SM sub-partition of the warp
+  // Column quarter owned by this warp.  warp & 3 is its SM sub-partition; rotating the quarters by
+  // the group index puts each group's "coordinate 0" warp (which carries the target's per-chain
+  // special work, e.g. exp(-v) of the funnel) on a different sub-partition -- otherwise one
+  // sub-partition is systematically slower and the other three idle at the group barriers.
+  const int w = ((warp & 3) + group) & 3;
   const Target target(model, dim);
 
   // ---- stage A = M^-1 into shared memory: one TMA bulk copy per row, one mbarrier
@@ -306,7 +343,7 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
           : "memory");
     }
   }
-  // wait for the bytes to land (phase 0)
+  // wait for the bytes to land (phase 0), then scale the staged metric: sm.A = eps * A
   {
     uint32_t done = 0;
     while (!done) {
@@ -318,6 +355,8 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
           : "memory");
     }
   }
+  for (int idx = tid; idx < DP * LDA; idx += blockDim.x) sm.A[idx] = step_size * sm.A[idx];
+  __syncthreads();
 
   for (int64_t blk = blockIdx.x; blk * DMMA_ROWS_PER_CTA < n_chains; blk += gridDim.x) {
     const int64_t chain0 = blk * DMMA_ROWS_PER_CTA;
@@ -330,6 +369,12 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   leapfrog_dmma_group<Target, DP, MT>(sm, target, q_in, p_in, q_out, p_out, dir, n_chains,    \
                                       dim, step_size, n_steps, h_out, status, n_done, chain0, \
                                       row0, w, lane, 1 + group)
+#if defined(MB200_EXP) && MB200_EXP == 5  // experiment: 2 warps per sub-partition
+    if (group >= 2) mt = 0;
+#endif
+#if defined(MB200_EXP) && MB200_EXP == 6  // experiment: 1 warp per sub-partition
+    if (group >= 1) mt = 0;
+#endif
     if (mt == 2) MB200_GROUP(2);
     else if (mt == 1) MB200_GROUP(1);
 #undef MB200_GROUP
@@ -377,6 +422,7 @@ static int leapfrog_dmma_dispatch(const double* q_in, const double* p_in, double
                                   double* h_out, int32_t* status, int32_t* n_done,
                                   cudaStream_t st) {
   if (dim > 128 || (dim & 1) || dim < 8) return MB200_ERR_UNSUPPORTED;
+  if (!(eps != 0.0) || !isfinite(eps)) return MB200_ERR_UNSUPPORTED;  // eps*A formulation
   if ((reinterpret_cast<uintptr_t>(minv) & 15) != 0) return MB200_ERR_UNSUPPORTED;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -28,31 +28,54 @@ struct StdGaussianTarget {
   __device__ __forceinline__ double nld_pair(int, double q0, double q1, const double*) const {
     return 0.5 * (q0 * q0 + q1 * q1);
   }
+  // fused momentum kick p += mh * grad (mh = -step/2): per-row scalar prepared once, then one
+  // fused multiply-add per coordinate (used by the tensor-core kernel)
+  __device__ __forceinline__ double kick_scalar(const double*, double mh) const { return mh; }
+  __device__ __forceinline__ void kick_pair(int, double q0, double q1, const double*, double mh,
+                                            double, double& p0, double& p1) const {
+    p0 = fma(mh, q0, p0);
+    p1 = fma(mh, q1, p1);
+  }
 };
 
 // v = q[0], x = q[1:]:  l = v^2/18 + (D-1) v/2 + exp(-v) |x|^2 / 2
 struct NealFunnelTarget {
-  static constexpr int NRED = 2;  // red[0] = |x|^2, red[1] = v
+  // red[0] = |x|^2, red[1] = exp(-v).  exp(-v) is "reduced" with a single contributor (the
+  // owner of coordinate 0), so it is evaluated once per chain instead of once per thread.
+  static constexpr int NRED = 2;
   int dim;
   __device__ NealFunnelTarget(const ModelArgs&, int d) : dim(d) {}
   __device__ __forceinline__ void accumulate(int i, double q0, double q1, double* red) const {
     if (i == 0) {
       red[0] += q1 * q1;
-      red[1] += q0;
+      red[1] += exp(-q0);
     } else {
       red[0] += q0 * q0 + q1 * q1;
     }
   }
   __device__ __forceinline__ void grad_pair(int i, double q0, double q1, const double* red,
                                             double& g0, double& g1) const {
-    const double e = exp(-red[1]);
-    g0 = (i == 0) ? (red[1] / 9.0 + 0.5 * (dim - 1) - 0.5 * e * red[0]) : e * q0;
+    const double e = red[1];
+    g0 = (i == 0) ? (q0 / 9.0 + 0.5 * (dim - 1) - 0.5 * e * red[0]) : e * q0;
     g1 = e * q1;
   }
-  __device__ __forceinline__ double nld_pair(int i, double, double, const double* red) const {
+  __device__ __forceinline__ double nld_pair(int i, double q0, double, const double* red) const {
     if (i != 0) return 0.0;
-    const double v = red[1];
-    return v * v / 18.0 + 0.5 * (dim - 1) * v + 0.5 * exp(-v) * red[0];
+    return q0 * q0 / 18.0 + 0.5 * (dim - 1) * q0 + 0.5 * red[1] * red[0];
+  }
+  // grad = exp(-v) * x for every coordinate but the first: fold exp(-v) into the kick scalar
+  __device__ __forceinline__ double kick_scalar(const double* red, double mh) const {
+    return mh * red[1];
+  }
+  __device__ __forceinline__ void kick_pair(int i, double q0, double q1, const double* red,
+                                            double mh, double mhe, double& p0, double& p1) const {
+    if (i == 0) {
+      const double g0 = q0 / 9.0 + 0.5 * (dim - 1) - 0.5 * red[1] * red[0];
+      p0 = fma(mh, g0, p0);
+    } else {
+      p0 = fma(mhe, q0, p0);
+    }
+    p1 = fma(mhe, q1, p1);
   }
 };
 
@@ -71,6 +94,14 @@ struct BananaTarget {
   __device__ __forceinline__ double nld_pair(int, double x, double y, const double*) const {
     const double r = y - b * x * x;
     return x * x / 8.0 + 0.5 * r * r;
+  }
+  __device__ __forceinline__ double kick_scalar(const double*, double mh) const { return mh; }
+  __device__ __forceinline__ void kick_pair(int i, double x, double y, const double* red,
+                                            double mh, double, double& p0, double& p1) const {
+    double g0, g1;
+    grad_pair(i, x, y, red, g0, g1);
+    p0 = fma(mh, g0, p0);
+    p1 = fma(mh, g1, p1);
   }
 };
 
