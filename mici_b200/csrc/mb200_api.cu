@@ -192,6 +192,71 @@ static int launch_constrained(const double* q_in, const double* p_in, double* q_
 }
 #endif
 
+#ifndef MB200_NO_RIEMANNIAN
+template <class Target, template <class> class MetricT>
+static int launch_implicit(const double* q_in, const double* p_in, double* q_out, double* p_out,
+                           const int32_t* dir, int64_t n, int dim, double eps, int n_steps,
+                           const ModelArgs& m, double fp_tol, double fp_div, int fp_max,
+                           double rev_tol, double* h_out, int32_t* status, int32_t* n_done,
+                           int32_t* fp_iters, cudaStream_t st) {
+  auto kern = implicit_leapfrog_kernel<Target, MetricT>;
+  const size_t smem = rm_smem_doubles(dim, MetricT<Target>::SOFTABS) * sizeof(double);
+  if (smem > 227 * 1024)
+    return fail(MB200_ERR_UNSUPPORTED,
+                "dim %d: per-chain metric (%zu bytes) exceeds shared memory; not supported yet",
+                dim, smem);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(MB200_ERR_CUDA, "smem attr: %s", cudaGetErrorString(e));
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RM_THREADS, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t blocks = (int64_t)num_sms() * per_sm;
+  if (blocks > n) blocks = n;
+  kern<<<(unsigned)blocks, RM_THREADS, smem, st>>>(q_in, p_in, q_out, p_out, dir, n, dim, eps,
+                                                   n_steps, m, fp_tol, fp_div, fp_max, rev_tol,
+                                                   h_out, status, n_done, fp_iters);
+  return check_launch("implicit_leapfrog_kernel");
+}
+
+static int implicit_dispatch(const double* q_in, const double* p_in, double* q_out, double* p_out,
+                             const int32_t* dir, int64_t n, int dim, double eps, int n_steps,
+                             const ModelArgs& m, double fp_tol, double fp_div, int fp_max,
+                             double rev_tol, double* h_out, int32_t* status, int32_t* n_done,
+                             int32_t* fp_iters, cudaStream_t st) {
+#define MB200_ARGS                                                                           \
+  q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, m, fp_tol, fp_div, fp_max, rev_tol,   \
+      h_out, status, n_done, fp_iters, st
+  if (m.rmetric_id == MB200_RMETRIC_SOFTABS) {
+    if (!(m.mp[0] > 0.0)) return fail(MB200_ERR_INVALID_ARG, "softabs_coeff must be positive");
+    switch (m.target_id) {
+      case MB200_TARGET_BANANA:
+        if (dim & 1) return fail(MB200_ERR_INVALID_ARG, "banana target needs even dim");
+        return launch_implicit<BananaRTarget, SoftAbsMetric>(MB200_ARGS);
+      default:
+        return fail(MB200_ERR_UNSUPPORTED, "target %d has no device Hessian / MTP (SoftAbs metric)",
+                    m.target_id);
+    }
+  }
+  if (m.rmetric_id == MB200_RMETRIC_RANK1) {
+    if (!m.maux) return fail(MB200_ERR_INVALID_ARG, "rank-1 metric needs its base matrix (rmetric_aux)");
+    switch (m.target_id) {
+      case MB200_TARGET_QUADRATIC:
+        if (!m.taux) return fail(MB200_ERR_INVALID_ARG, "quadratic target needs its precision matrix");
+        return launch_implicit<QuadraticRTarget, Rank1DenseMetric>(MB200_ARGS);
+      case MB200_TARGET_STD_GAUSSIAN:
+        return launch_implicit<StdGaussianRTarget, Rank1DenseMetric>(MB200_ARGS);
+      case MB200_TARGET_BANANA:
+        if (dim & 1) return fail(MB200_ERR_INVALID_ARG, "banana target needs even dim");
+        return launch_implicit<BananaRTarget, Rank1DenseMetric>(MB200_ARGS);
+      default:
+        return fail(MB200_ERR_UNSUPPORTED, "target %d not available for Riemannian systems", m.target_id);
+    }
+  }
+#undef MB200_ARGS
+  return fail(MB200_ERR_INVALID_ARG, "unknown rmetric_id %d", m.rmetric_id);
+}
+#endif
+
 }  // namespace mb200
 
 using namespace mb200;
@@ -310,6 +375,45 @@ int64_t mb200_implicit_workspace_bytes(int64_t, int32_t, const mb200_model*) { r
 int mb200_hamiltonian_riemannian(const double*, const double*, int64_t, int32_t,
                                  const mb200_model*, double*, int32_t*, void*, int64_t, void*) {
   return fail(MB200_ERR_UNSUPPORTED, "riemannian hamiltonian not compiled in");
+}
+#endif
+
+#ifndef MB200_NO_RIEMANNIAN
+int mb200_implicit_leapfrog_riemannian(
+    const double* pos_in, const double* mom_in, double* pos_out, double* mom_out,
+    const int32_t* dir, int64_t n_chains, int32_t dim, double step_size, int32_t n_steps,
+    const mb200_model* model, double fp_convergence_tol, double fp_divergence_tol,
+    int32_t fp_max_iters, double reverse_check_tol, double* h_out, int32_t* status,
+    int32_t* n_done, int32_t* fp_iters, void* workspace, int64_t workspace_bytes, void* stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  if (!pos_in || !mom_in || !pos_out || !mom_out || !model)
+    return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
+  if (n_chains < 0 || dim < 1 || n_steps < 0 || fp_max_iters < 0)
+    return fail(MB200_ERR_INVALID_ARG, "bad sizes");
+  if (n_chains == 0) return 0;
+  return implicit_dispatch(pos_in, mom_in, pos_out, mom_out, dir, n_chains, dim, step_size,
+                           n_steps, to_args(model), fp_convergence_tol, fp_divergence_tol,
+                           fp_max_iters, reverse_check_tol, h_out, status, n_done, fp_iters,
+                           (cudaStream_t)stream);
+}
+
+// every per-chain buffer of the implicit kernels lives in shared memory for the supported sizes
+int64_t mb200_implicit_workspace_bytes(int64_t, int32_t, const mb200_model*) { return 0; }
+
+int mb200_hamiltonian_riemannian(const double* pos, const double* mom, int64_t n_chains,
+                                 int32_t dim, const mb200_model* model, double* h_out,
+                                 int32_t* status, void* workspace, int64_t workspace_bytes,
+                                 void* stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  if (!pos || !mom || !model || !h_out) return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
+  if (n_chains < 0 || dim < 1) return fail(MB200_ERR_INVALID_ARG, "bad sizes");
+  if (n_chains == 0) return 0;
+  // zero steps: state written back unchanged in place, h evaluated
+  return implicit_dispatch(pos, mom, const_cast<double*>(pos), const_cast<double*>(mom), nullptr,
+                           n_chains, dim, 0.0, 0, to_args(model), 1e-9, 1e10, 100, 2e-8, h_out,
+                           status, nullptr, nullptr, (cudaStream_t)stream);
 }
 #endif
 

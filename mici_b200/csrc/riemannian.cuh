@@ -1,0 +1,763 @@
+// K2 / K3 / K4 / K5: implicit generalised leapfrog on a Riemannian-metric system --
+// one CTA per chain, everything for the chain resident in shared memory.
+//
+// Replaces, per chain (reference paths):
+//   ImplicitLeapfrogIntegrator._step and sub-steps          integrators.py:482-544
+//   solve_fixed_point_direct                                solvers.py:47-94
+//   RiemannianMetricSystem.{metric,h1,dh1_dpos,h2,dh2_dpos,dh2_dmom}   systems.py:1360-1402
+//   DensePositiveDefiniteMatrix (Cholesky, solves, logdet, gradients)  matrices.py:1161-1188
+//   SoftAbsRegularizedPositiveDefiniteMatrix (eigh, softabs, gradients) matrices.py:1631-1685
+//
+// Per-chain control flow (fixed-point convergence / divergence, reversibility failure) is the
+// CTA's own uniform control flow: chains that converge early simply retire their CTA and the
+// next chain is scheduled, so divergent iteration counts cost no idle lanes.
+//
+// K3 (symmetric eigensolver) is a parallel cyclic two-sided Jacobi iteration: D/2 disjoint
+// rotations per round (round-robin ordering), each round applied as R^T A R on 2x2 blocks, the
+// eigenvectors accumulated as U R.  Jacobi is used because it is the most accurate dense
+// symmetric eigensolver (relative accuracy of eigenvectors), which the divided differences in
+// grad_quadratic_form_inv (matrices.py:1679-1685) need, and because it parallelises over a CTA
+// without any serial tridiagonal phase.
+#pragma once
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace mb200 {
+
+constexpr int RM_THREADS = 256;
+constexpr int RM_MAX_SWEEPS = 40;
+
+struct Blk {
+  int tid, nthr, lane, warp, nwarp;
+  double* red;  // [34] reduction scratch
+};
+
+__device__ __forceinline__ double block_sum(const Blk& b, double v) {
+  v = warp_sum(v);
+  __syncthreads();
+  if (b.lane == 0) b.red[b.warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < b.nwarp; ++w) t += b.red[w];
+  return t;
+}
+
+__device__ __forceinline__ double block_nanmax(const Blk& b, double v) {
+  v = warp_nanmax(v);
+  __syncthreads();
+  if (b.lane == 0) b.red[b.warp] = v;
+  __syncthreads();
+  double t = b.red[0];
+  for (int w = 1; w < b.nwarp; ++w) t = nanmax(t, b.red[w]);
+  return t;
+}
+
+// true on all threads iff `flag` is true on any thread
+__device__ __forceinline__ bool block_any(const Blk&, bool flag) {
+  return __syncthreads_or(flag ? 1 : 0) != 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Targets (block-cooperative interface; vectors in shared memory)
+// ---------------------------------------------------------------------------------------------
+
+struct BananaRTarget {
+  static constexpr bool HAS_HESSIAN = true;
+  static constexpr int NEED = 2;  // entries of a D x D gradient matrix needed per row by mtp
+  double b;
+  int dim;
+  __device__ BananaRTarget(const ModelArgs& m, int d) : b(m.tp[0]), dim(d) {}
+
+  __device__ double nld(const Blk& k, const double* q) const {
+    double s = 0.0;
+    for (int i = 2 * k.tid; i < dim; i += 2 * k.nthr) {
+      const double x = q[i], y = q[i + 1], r = y - b * x * x;
+      s += x * x / 8.0 + 0.5 * r * r;
+    }
+    return block_sum(k, s);
+  }
+  __device__ void grad(const Blk& k, const double* q, double* g) const {
+    for (int i = 2 * k.tid; i < dim; i += 2 * k.nthr) {
+      const double x = q[i], y = q[i + 1], r = y - b * x * x;
+      g[i] = x / 4.0 - 2.0 * b * x * r;
+      g[i + 1] = r;
+    }
+  }
+  // dense Hessian (block diagonal for this model, but produced and consumed as a dense matrix)
+  __device__ void hess(const Blk& k, const double* q, double* A, int ld) const {
+    for (int idx = k.tid; idx < dim * dim; idx += k.nthr) {
+      const int i = idx / dim, j = idx - i * dim;
+      const int pi = i & ~1;
+      double v = 0.0;
+      if ((j & ~1) == pi) {
+        const double x = q[pi], y = q[pi + 1];
+        if (i == pi && j == pi) v = 0.25 - 2.0 * b * y + 6.0 * b * b * x * x;
+        else if (i == pi + 1 && j == pi + 1) v = 1.0;
+        else v = -2.0 * b * x;
+      }
+      A[i * ld + j] = v;
+    }
+  }
+  // columns of row `a` of the matrix argument that the matrix-Tressian product reads
+  __device__ __forceinline__ int need_col(int a, int j) const {
+    if ((a & 1) == 0) return a + j;  // (x,x), (x,y)
+    return j == 0 ? a - 1 : -1;      // (y,x)
+  }
+  // mtp(V)_k = sum_ij V_ij d^3 l / dq_i dq_j dq_k  from the needed entries Vn[a][j]
+  __device__ void mtp_entries(const Blk& k, const double* q, const double* Vn, double* out) const {
+    for (int i = 2 * k.tid; i < dim; i += 2 * k.nthr) {
+      const double x = q[i];
+      const double vxx = Vn[i * NEED + 0], vxy = Vn[i * NEED + 1], vyx = Vn[(i + 1) * NEED + 0];
+      out[i] = vxx * (12.0 * b * b * x) - 2.0 * b * (vxy + vyx);
+      out[i + 1] = -2.0 * b * vxx;
+    }
+  }
+};
+
+struct QuadraticRTarget {
+  static constexpr bool HAS_HESSIAN = false;
+  static constexpr int NEED = 1;
+  const double* P;
+  int dim;
+  __device__ QuadraticRTarget(const ModelArgs& m, int d) : P(m.taux), dim(d) {}
+  __device__ void grad(const Blk& k, const double* q, double* g) const {
+    for (int i = k.tid; i < dim; i += k.nthr) {
+      const double* row = P + (size_t)i * dim;
+      double s = 0.0;
+      for (int j = 0; j < dim; ++j) s = fma(row[j], q[j], s);
+      g[i] = s;
+    }
+  }
+  __device__ double nld(const Blk& k, const double* q) const {
+    double s = 0.0;
+    for (int i = k.tid; i < dim; i += k.nthr) {
+      const double* row = P + (size_t)i * dim;
+      double t = 0.0;
+      for (int j = 0; j < dim; ++j) t = fma(row[j], q[j], t);
+      s = fma(q[i], t, s);
+    }
+    return 0.5 * block_sum(k, s);
+  }
+  __device__ void hess(const Blk&, const double*, double*, int) const {}
+  __device__ __forceinline__ int need_col(int, int) const { return -1; }
+  __device__ void mtp_entries(const Blk&, const double*, const double*, double*) const {}
+};
+
+struct StdGaussianRTarget {
+  static constexpr bool HAS_HESSIAN = false;
+  static constexpr int NEED = 1;
+  int dim;
+  __device__ StdGaussianRTarget(const ModelArgs&, int d) : dim(d) {}
+  __device__ void grad(const Blk& k, const double* q, double* g) const {
+    for (int i = k.tid; i < dim; i += k.nthr) g[i] = q[i];
+  }
+  __device__ double nld(const Blk& k, const double* q) const {
+    double s = 0.0;
+    for (int i = k.tid; i < dim; i += k.nthr) s = fma(q[i], q[i], s);
+    return 0.5 * block_sum(k, s);
+  }
+  __device__ void hess(const Blk&, const double*, double*, int) const {}
+  __device__ __forceinline__ int need_col(int, int) const { return -1; }
+  __device__ void mtp_entries(const Blk&, const double*, const double*, double*) const {}
+};
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory workspace of one chain
+// ---------------------------------------------------------------------------------------------
+struct RmWork {
+  int dim, ld;
+  double *M1, *M2;  // [dim*ld] each (M2 only for SoftAbs)
+  double *q, *p, *qs, *ps, *x0, *x1, *base, *v1, *v2, *v3, *lam, *sa, *gsa, *ev, *Vn;
+  double *rc, *rs;  // rotation cos / sin [dim/2 + 1]
+  int *top, *bot;   // round-robin index arrays [dim/2 + 1]
+};
+
+__host__ __device__ inline size_t rm_smem_doubles(int dim, bool softabs) {
+  const int ld = dim + 1;
+  const int dpad = (dim + 1) & ~1;
+  size_t n = (size_t)dim * ld * (softabs ? 2 : 1);
+  n += (size_t)15 * dpad;      // vectors (Vn counts double: NEED <= 2)
+  n += (size_t)dpad;           // second half of Vn
+  n += 2 * (size_t)(dpad / 2 + 2);  // rc, rs
+  n += (size_t)(dpad / 2 + 2);      // top, bot (ints, 2 per double)
+  n += 40;                     // reduction scratch
+  return n;
+}
+
+__device__ inline void rm_carve(RmWork& w, double* s, int dim, bool softabs, Blk& blk) {
+  const int ld = dim + 1;
+  const int dpad = (dim + 1) & ~1;
+  w.dim = dim;
+  w.ld = ld;
+  w.M1 = s;
+  s += (size_t)dim * ld;
+  w.M2 = softabs ? s : nullptr;
+  if (softabs) s += (size_t)dim * ld;
+  double** vecs[] = {&w.q, &w.p, &w.qs, &w.ps, &w.x0, &w.x1, &w.base, &w.v1,
+                     &w.v2, &w.v3, &w.lam, &w.sa, &w.gsa, &w.ev};
+  for (auto v : vecs) {
+    *v = s;
+    s += dpad;
+  }
+  w.Vn = s;
+  s += 2 * dpad;
+  w.rc = s;
+  s += dpad / 2 + 2;
+  w.rs = s;
+  s += dpad / 2 + 2;
+  w.top = reinterpret_cast<int*>(s);
+  w.bot = w.top + (dpad / 2 + 2);
+  s += dpad / 2 + 2;
+  blk.red = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: symmetric eigendecomposition A = U diag(lam) U^T by parallel cyclic Jacobi.
+// A [dim x dim, stride ld] is destroyed (its diagonal becomes lam); U receives the eigenvectors
+// as columns.  Returns false if not converged / non-finite (-> LinAlgError, matrices.py:437).
+// ---------------------------------------------------------------------------------------------
+__device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U) {
+  const int n = w.dim, ld = w.ld;
+  const int m = (n + 1) / 2;  // pairs per round (odd n: one index idles each round)
+  const int np = 2 * m;       // padded player count; index n (if odd) is a bye
+  for (int idx = k.tid; idx < n * n; idx += k.nthr) {
+    const int i = idx / n, j = idx - i * n;
+    U[i * ld + j] = (i == j) ? 1.0 : 0.0;
+  }
+  for (int i = k.tid; i < m; i += k.nthr) {
+    w.top[i] = 2 * i;
+    w.bot[i] = 2 * i + 1;
+  }
+  // scale for the convergence test
+  double dmax = 0.0;
+  for (int idx = k.tid; idx < n * n; idx += k.nthr) {
+    const int i = idx / n, j = idx - i * n;
+    dmax = nanmax(dmax, fabs(A[i * ld + j]));
+  }
+  const double scale = block_nanmax(k, dmax);
+  if (!(scale == scale) || isinf(scale)) return false;
+  if (scale == 0.0) return true;
+  const double tol = 1e-15 * scale;
+
+  for (int sweep = 0; sweep < RM_MAX_SWEEPS; ++sweep) {
+    double off = 0.0;
+    for (int round = 0; round < np - 1; ++round) {
+      // --- rotation parameters for the m disjoint pairs of this round
+      for (int t = k.tid; t < m; t += k.nthr) {
+        int p = w.top[t], q = w.bot[t];
+        double c = 1.0, s = 0.0;
+        if (p < n && q < n) {
+          if (p > q) {
+            const int tmp = p;
+            p = q;
+            q = tmp;
+          }
+          const double apq = A[p * ld + q];
+          off = fmax(off, fabs(apq));
+          if (fabs(apq) > 1e-300 && fabs(apq) > 1e-18 * scale) {
+            const double app = A[p * ld + p], aqq = A[q * ld + q];
+            const double tau = (aqq - app) / (2.0 * apq);
+            const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            c = 1.0 / sqrt(1.0 + tt * tt);
+            s = tt * c;
+          }
+        }
+        w.rc[t] = c;
+        w.rs[t] = s;
+      }
+      __syncthreads();
+      // --- A <- R^T A R on 2x2 blocks (pair a rows, pair b cols), U <- U R
+      for (int idx = k.tid; idx < m * m; idx += k.nthr) {
+        const int a = idx / m, b = idx - a * m;
+        int pa = w.top[a], qa = w.bot[a], pb = w.top[b], qb = w.bot[b];
+        if (pa > qa) { const int t2 = pa; pa = qa; qa = t2; }
+        if (pb > qb) { const int t2 = pb; pb = qb; qb = t2; }
+        const bool va = qa < n, vb = qb < n;  // pair contains the bye index?
+        const double ca = w.rc[a], sa = w.rs[a], cb = w.rc[b], sb = w.rs[b];
+        if (va && vb) {
+          const double a00 = A[pa * ld + pb], a01 = A[pa * ld + qb];
+          const double a10 = A[qa * ld + pb], a11 = A[qa * ld + qb];
+          // rows: (r0, r1) = (ca*x0 - sa*x1, sa*x0 + ca*x1)
+          const double r00 = ca * a00 - sa * a10, r01 = ca * a01 - sa * a11;
+          const double r10 = sa * a00 + ca * a10, r11 = sa * a01 + ca * a11;
+          // cols
+          A[pa * ld + pb] = cb * r00 - sb * r01;
+          A[pa * ld + qb] = sb * r00 + cb * r01;
+          A[qa * ld + pb] = cb * r10 - sb * r11;
+          A[qa * ld + qb] = sb * r10 + cb * r11;
+        } else if (va && !vb) {  // single column pb (< n), rotated rows only
+          if (pb < n) {
+            const double a0 = A[pa * ld + pb], a1 = A[qa * ld + pb];
+            A[pa * ld + pb] = ca * a0 - sa * a1;
+            A[qa * ld + pb] = sa * a0 + ca * a1;
+          }
+        } else if (!va && vb) {  // single row pa (< n), rotated cols only
+          if (pa < n) {
+            const double a0 = A[pa * ld + pb], a1 = A[pa * ld + qb];
+            A[pa * ld + pb] = cb * a0 - sb * a1;
+            A[pa * ld + qb] = sb * a0 + cb * a1;
+          }
+        }
+      }
+      for (int idx = k.tid; idx < n * m; idx += k.nthr) {
+        const int i = idx / m, b = idx - i * m;
+        int pb = w.top[b], qb = w.bot[b];
+        if (pb > qb) { const int t2 = pb; pb = qb; qb = t2; }
+        if (qb < n) {
+          const double cb = w.rc[b], sb = w.rs[b];
+          const double u0 = U[i * ld + pb], u1 = U[i * ld + qb];
+          U[i * ld + pb] = cb * u0 - sb * u1;
+          U[i * ld + qb] = sb * u0 + cb * u1;
+        }
+      }
+      __syncthreads();
+      // --- rotate the round-robin schedule (top[0] fixed)
+      if (k.tid == 0 && m > 1) {
+        const int last_top = w.top[m - 1];
+        const int first_bot = w.bot[0];
+        for (int i = m - 1; i > 1; --i) w.top[i] = w.top[i - 1];
+        w.top[1] = first_bot;
+        for (int i = 0; i < m - 1; ++i) w.bot[i] = w.bot[i + 1];
+        w.bot[m - 1] = last_top;
+      }
+      __syncthreads();
+    }
+    const double offmax = block_nanmax(k, off);
+    if (!(offmax == offmax)) return false;
+    if (offmax <= tol) return true;  // the sweep just done squares this again
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: in-place lower Cholesky factor of the SPD matrix M [dim x dim, stride ld]
+// (numpy.linalg.cholesky, matrices.py:1165-1169).  Returns false on a non-positive / non-finite
+// pivot (-> LinAlgError "Cholesky factorisation failed", matrices.py:1170-1172).
+// ---------------------------------------------------------------------------------------------
+__device__ inline bool cholesky_inplace(const Blk& k, double* M, int n, int ld) {
+  for (int j = 0; j < n; ++j) {
+    __syncthreads();
+    const double d = M[j * ld + j];
+    const bool bad = !(d > 0.0) || isinf(d);
+    if (bad) return false;  // uniform: every thread reads the same value
+    const double l = sqrt(d);
+    __syncthreads();
+    for (int i = j + k.tid; i < n; i += k.nthr) M[i * ld + j] = (i == j) ? l : M[i * ld + j] / l;
+    __syncthreads();
+    // trailing update of the lower triangle: M[i][c] -= L[i][j] * L[c][j], j < c <= i
+    const int rem = n - j - 1;
+    for (int idx = k.tid; idx < rem * rem; idx += k.nthr) {
+      const int i = j + 1 + idx / rem, c = j + 1 + idx % rem;
+      if (c <= i) M[i * ld + c] -= M[i * ld + j] * M[c * ld + j];
+    }
+  }
+  __syncthreads();
+  return true;
+}
+
+// x = (L L^T)^-1 b by forward / back substitution (scipy solve_triangular, matrices.py:897-912).
+// Column-oriented so that each elimination step is parallel over rows.  x may alias b.
+__device__ inline void cholesky_solve(const Blk& k, const double* L, int n, int ld,
+                                      const double* b, double* x) {
+  for (int i = k.tid; i < n; i += k.nthr) x[i] = b[i];
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {  // L y = b
+    if (k.tid == 0) x[j] /= L[j * ld + j];
+    __syncthreads();
+    const double xj = x[j];
+    for (int i = j + 1 + k.tid; i < n; i += k.nthr) x[i] -= L[i * ld + j] * xj;
+    __syncthreads();
+  }
+  for (int j = n - 1; j >= 0; --j) {  // L^T x = y
+    if (k.tid == 0) x[j] /= L[j * ld + j];
+    __syncthreads();
+    const double xj = x[j];
+    for (int i = k.tid; i < j; i += k.nthr) x[i] -= L[j * ld + i] * xj;
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Metric policies.  build(q) -> 0 ok, else status of the failure kind; methods mirror
+// RiemannianMetricSystem's use of the matrix object (systems.py:1375-1402).
+// ---------------------------------------------------------------------------------------------
+
+// SoftAbs of the target Hessian (matrices.py:1631-1685)
+template <class Target>
+struct SoftAbsMetric {
+  static constexpr bool SOFTABS = true;
+  const Target& t;
+  double alpha;
+  bool have_j;  // divided-difference matrix J built in w.M2 for the current metric?
+
+  __device__ SoftAbsMetric(const Target& tt, const ModelArgs& m) : t(tt), alpha(m.mp[0]), have_j(false) {}
+
+  // returns 0, or MB200_STATUS_LINALG (eigh failure) / -1 (ValueError: non-positive eigenvalues)
+  __device__ int build(const Blk& k, RmWork& w, const double* q) {
+    have_j = false;
+    t.hess(k, q, w.M2, w.ld);
+    __syncthreads();
+    if (!jacobi_eigh(k, w, w.M2, w.M1)) return MB200_STATUS_LINALG;
+    bool bad = false;
+    for (int i = k.tid; i < w.dim; i += k.nthr) {
+      const double x = w.M2[i * w.ld + i];
+      const double ax = alpha * x;
+      const double s = x / tanh(x * alpha);                            // :1662-1664
+      const double sh = sinh(ax);
+      w.lam[i] = x;
+      w.sa[i] = s;
+      w.gsa[i] = 1.0 / tanh(ax) - ax / (sh * sh);                      // :1666-1671
+      if (!(s > 0.0)) bad = true;  // EigendecomposedPositiveDefiniteMatrix: ValueError (:1606-1609)
+    }
+    if (block_any(k, bad)) return -1;
+    return 0;
+  }
+  __device__ double log_abs_det(const Blk& k, RmWork& w) const {
+    double s = 0.0;
+    for (int i = k.tid; i < w.dim; i += k.nthr) s += log(fabs(w.sa[i]));
+    return block_sum(k, s);
+  }
+  // out = M^-1 v = U ((U^T v) / s)   (matrices.py:1555-1556 with 1/eigval); out must not alias v
+  __device__ void inv_matvec(const Blk& k, RmWork& w, const double* v, double* out) const {
+    const int n = w.dim, ld = w.ld;
+    for (int j = k.tid; j < n; j += k.nthr) {
+      double s = 0.0;
+      for (int i = 0; i < n; ++i) s = fma(w.M1[i * ld + j], v[i], s);
+      w.ev[j] = s / w.sa[j];
+    }
+    __syncthreads();
+    for (int i = k.tid; i < n; i += k.nthr) {
+      double s = 0.0;
+      for (int j = 0; j < n; ++j) s = fma(w.M1[i * ld + j], w.ev[j], s);
+      out[i] = s;
+    }
+    __syncthreads();
+  }
+  // out = vjp(grad_log_abs_det), grad_log_abs_det = U diag(gs/s) U^T   (:1673-1676)
+  __device__ void vjp_grad_log_abs_det(const Blk& k, RmWork& w, const double* q, double* out) const {
+    const int n = w.dim, ld = w.ld;
+    for (int idx = k.tid; idx < n * Target::NEED; idx += k.nthr) {
+      const int a = idx / Target::NEED, j = idx - a * Target::NEED;
+      const int b = t.need_col(a, j);
+      double s = 0.0;
+      if (b >= 0)
+        for (int i = 0; i < n; ++i)
+          s = fma(w.M1[a * ld + i] * (w.gsa[i] / w.sa[i]), w.M1[b * ld + i], s);
+      w.Vn[idx] = s;
+    }
+    __syncthreads();
+    t.mtp_entries(k, q, w.Vn, out);
+    __syncthreads();
+  }
+  // out = vjp(grad_quadratic_form_inv(p)) = vjp(-U ((e e^T) o J) U^T), e = U^T p / s  (:1678-1685)
+  __device__ void vjp_grad_quad_inv(const Blk& k, RmWork& w, const double* q, const double* p,
+                                    double* out) {
+    const int n = w.dim, ld = w.ld;
+    if (!have_j) {  // J depends on the metric only: build once per metric, reuse per iteration
+      for (int idx = k.tid; idx < n * n; idx += k.nthr) {
+        const int i = idx / n, j = idx - i * n;
+        w.M2[i * ld + j] = (i == j) ? w.gsa[i] : (w.sa[i] - w.sa[j]) / (w.lam[i] - w.lam[j]);
+      }
+      have_j = true;
+    }
+    for (int j = k.tid; j < n; j += k.nthr) {
+      double s = 0.0;
+      for (int i = 0; i < n; ++i) s = fma(w.M1[i * ld + j], p[i], s);
+      w.ev[j] = s / w.sa[j];
+    }
+    __syncthreads();
+    // one warp per row a: t_j = sum_i (U_ai e_i) J_ij, then V(a,b) = -sum_j t_j e_j U_bj
+    double* trow = w.v3;  // reused per warp below via registers; v3 holds (U_a o e) of the row
+    (void)trow;
+    for (int a = k.warp; a < n; a += k.nwarp) {
+      double acc[Target::NEED];
+#pragma unroll
+      for (int jn = 0; jn < Target::NEED; ++jn) acc[jn] = 0.0;
+      for (int j = k.lane; j < n; j += 32) {
+        double tj = 0.0;
+        for (int i = 0; i < n; ++i) tj = fma(w.M1[a * ld + i] * w.ev[i], w.M2[i * ld + j], tj);
+        tj *= w.ev[j];
+#pragma unroll
+        for (int jn = 0; jn < Target::NEED; ++jn) {
+          const int b = t.need_col(a, jn);
+          if (b >= 0) acc[jn] = fma(tj, w.M1[b * ld + j], acc[jn]);
+        }
+      }
+#pragma unroll
+      for (int jn = 0; jn < Target::NEED; ++jn) {
+        const double s = warp_sum(acc[jn]);
+        if (k.lane == 0) w.Vn[a * Target::NEED + jn] = -s;
+      }
+    }
+    __syncthreads();
+    t.mtp_entries(k, q, w.Vn, out);
+    __syncthreads();
+  }
+};
+
+// Dense metric M(q) = B + c q q^T (DenseRiemannianMetricSystem, systems.py:1710-1760) with
+// DensePositiveDefiniteMatrix arithmetic (matrices.py:1161-1188).  The two gradient matrices are
+// never formed: vjp(V) = c (V + V^T) q needs only V q, i.e. M^-1 q for grad_log_abs_det = M^-1
+// (:1175-1177) and -w (w.q) for grad_quadratic_form_inv = -w w^T, w = M^-1 p (:1179-1181).
+template <class Target>
+struct Rank1DenseMetric {
+  static constexpr bool SOFTABS = false;
+  const Target& t;
+  const double* B;
+  double c;
+  __device__ Rank1DenseMetric(const Target& tt, const ModelArgs& m) : t(tt), B(m.maux), c(m.mp[0]) {}
+
+  __device__ int build(const Blk& k, RmWork& w, const double* q) {
+    const int n = w.dim, ld = w.ld;
+    bool bad = false;
+    for (int idx = k.tid; idx < n * n; idx += k.nthr) {
+      const int i = idx / n, j = idx - i * n;
+      const double v = B[idx] + c * (q[i] * q[j]);
+      if (!isfinite(v)) bad = true;
+      w.M1[i * ld + j] = v;
+    }
+    if (block_any(k, bad)) return MB200_STATUS_LINALG;  // "Array is not finite" (:211-215)
+    if (!cholesky_inplace(k, w.M1, n, ld)) return MB200_STATUS_LINALG;
+    return 0;
+  }
+  __device__ double log_abs_det(const Blk& k, RmWork& w) const {
+    double s = 0.0;
+    for (int i = k.tid; i < w.dim; i += k.nthr) s += log(fabs(w.M1[i * w.ld + i]));
+    return 2.0 * block_sum(k, s);  // matrices.py:982-984
+  }
+  __device__ void inv_matvec(const Blk& k, RmWork& w, const double* v, double* out) const {
+    cholesky_solve(k, w.M1, w.dim, w.ld, v, out);
+  }
+  __device__ void vjp_grad_log_abs_det(const Blk& k, RmWork& w, const double* q, double* out) const {
+    cholesky_solve(k, w.M1, w.dim, w.ld, q, w.ev);  // M^-1 q
+    for (int i = k.tid; i < w.dim; i += k.nthr) out[i] = c * (w.ev[i] + w.ev[i]);
+    __syncthreads();
+  }
+  __device__ void vjp_grad_quad_inv(const Blk& k, RmWork& w, const double* q, const double* p,
+                                    double* out) {
+    cholesky_solve(k, w.M1, w.dim, w.ld, p, w.ev);  // w = M^-1 p
+    double s = 0.0;
+    for (int i = k.tid; i < w.dim; i += k.nthr) s = fma(w.ev[i], q[i], s);
+    const double wq = block_sum(k, s);
+    // V q = -(w w^T) q = -w (w.q);  c (V + V^T) q = 2 c V q
+    for (int i = k.tid; i < w.dim; i += k.nthr) {
+      const double vq = -(w.ev[i] * wq);
+      out[i] = c * (vq + vq);
+    }
+    __syncthreads();
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// K4 + K5: the integrator
+// ---------------------------------------------------------------------------------------------
+template <class Target, class Metric>
+struct ImplicitLeapfrog {
+  const Blk& k;
+  RmWork& w;
+  const Target& t;
+  Metric& m;
+  double fp_tol, fp_div, rev_tol;
+  int fp_max;
+
+  // K4: solve_fixed_point_direct (solvers.py:47-94).  `func(x_in, x_out)` returns 0 or a failure
+  // code (any failure inside the solver is a ConvergenceError, :89-92).  Iterates alternate
+  // between w.x0 and w.x1; on success the solution is in *result.
+  template <class F>
+  __device__ int fixed_point(F func, double** result, int& iters) {
+    double* xin = w.x0;
+    double* xout = w.x1;
+    for (int i = 0; i < fp_max; ++i) {
+      if (func(xin, xout) != 0) return MB200_STATUS_CONVERGENCE;
+      double e = 0.0;
+      for (int j = k.tid; j < w.dim; j += k.nthr) e = nanmax(e, fabs(xout[j] - xin[j]));
+      const double err = block_nanmax(k, e);
+      ++iters;
+      if (err > fp_div || err != err) return MB200_STATUS_CONVERGENCE;
+      if (err < fp_tol) {
+        *result = xout;
+        return 0;
+      }
+      double* tmp = xin;
+      xin = xout;
+      xout = tmp;
+    }
+    return MB200_STATUS_CONVERGENCE;
+  }
+
+  // dh1_dpos = grad l + vjp(grad_log_abs_det) / 2   (systems.py:1381-1385); metric of q current
+  __device__ void kick_h1(double dt) {
+    t.grad(k, w.q, w.v1);
+    m.vjp_grad_log_abs_det(k, w, w.q, w.v2);
+    for (int i = k.tid; i < w.dim; i += k.nthr)
+      w.p[i] = __dsub_rn(w.p[i], __dmul_rn(dt, __dadd_rn(w.v1[i], __dmul_rn(0.5, w.v2[i]))));
+    __syncthreads();
+  }
+
+  // one step; q, p in w.q / w.p updated in place; returns status
+  __device__ int step(double dt, int* iters4) {
+    const int n = w.dim;
+    int st;
+    int it_b = 0, it_crev = 0, it_c = 0, it_brev = 0;
+    // ---- _step_a (:493-494)
+    st = m.build(k, w, w.q);
+    if (st != 0) return MB200_STATUS_LINALG;
+    kick_h1(dt);
+    // ---- _step_b_fwd (:496-502): p = p0 - dt * dh2_dpos(q, p), metric fixed
+    for (int i = k.tid; i < n; i += k.nthr) w.base[i] = w.p[i], w.x0[i] = w.p[i];
+    __syncthreads();
+    double* sol;
+    auto fb = [&](double sdt) {
+      return [&, sdt](const double* xin, double* xout) {
+        m.vjp_grad_quad_inv(k, w, w.q, xin, w.v1);
+        for (int i = k.tid; i < n; i += k.nthr)
+          xout[i] = __dsub_rn(w.base[i], __dmul_rn(sdt, __dmul_rn(0.5, w.v1[i])));
+        __syncthreads();
+        return 0;
+      };
+    };
+    st = fixed_point(fb(dt), &sol, it_b);
+    iters4[0] = it_b;
+    if (st != 0) return st;
+    for (int i = k.tid; i < n; i += k.nthr) w.p[i] = sol[i];
+    __syncthreads();
+    // ---- _step_c_fwd (:517-528): q += dt * M(q)^-1 p, then reverse check with _step_c_adj(-dt)
+    for (int i = k.tid; i < n; i += k.nthr) w.v3[i] = w.q[i];  // pos_init
+    __syncthreads();
+    m.inv_matvec(k, w, w.p, w.v1);
+    for (int i = k.tid; i < n; i += k.nthr) w.q[i] = __dadd_rn(w.q[i], __dmul_rn(dt, w.v1[i]));
+    __syncthreads();
+    // fixed point in q: x = base + sdt * M(x)^-1 p, new metric every iteration (:530-536)
+    auto fc = [&](double sdt) {
+      return [&, sdt](const double* xin, double* xout) {
+        const int bs = m.build(k, w, xin);
+        if (bs != 0) return 1;
+        m.inv_matvec(k, w, w.p, w.v1);
+        for (int i = k.tid; i < n; i += k.nthr)
+          xout[i] = __dadd_rn(w.base[i], __dmul_rn(sdt, w.v1[i]));
+        __syncthreads();
+        return 0;
+      };
+    };
+    for (int i = k.tid; i < n; i += k.nthr) w.base[i] = w.q[i], w.x0[i] = w.q[i];
+    __syncthreads();
+    st = fixed_point(fc(-dt), &sol, it_crev);
+    iters4[1] = it_crev;
+    if (st != 0) return st;
+    {
+      double e = 0.0;
+      for (int i = k.tid; i < n; i += k.nthr) e = nanmax(e, fabs(sol[i] - w.v3[i]));
+      const double rev = block_nanmax(k, e);
+      if (rev > rev_tol) return MB200_STATUS_NON_REVERSIBLE;
+    }
+    // ---- _step_c_adj (:530-536)
+    for (int i = k.tid; i < n; i += k.nthr) w.base[i] = w.q[i], w.x0[i] = w.q[i];
+    __syncthreads();
+    st = fixed_point(fc(dt), &sol, it_c);
+    iters4[2] = it_c;
+    if (st != 0) return st;
+    for (int i = k.tid; i < n; i += k.nthr) w.q[i] = sol[i];
+    __syncthreads();
+    // ---- _step_b_adj (:504-515): p -= dt * dh2_dpos(q, p) at the new metric, then reverse check
+    st = m.build(k, w, w.q);
+    if (st != 0) return MB200_STATUS_LINALG;
+    for (int i = k.tid; i < n; i += k.nthr) w.v3[i] = w.p[i];  // mom_init
+    __syncthreads();
+    m.vjp_grad_quad_inv(k, w, w.q, w.p, w.v1);
+    for (int i = k.tid; i < n; i += k.nthr)
+      w.p[i] = __dsub_rn(w.p[i], __dmul_rn(dt, __dmul_rn(0.5, w.v1[i])));
+    __syncthreads();
+    for (int i = k.tid; i < n; i += k.nthr) w.base[i] = w.p[i], w.x0[i] = w.p[i];
+    __syncthreads();
+    st = fixed_point(fb(-dt), &sol, it_brev);
+    iters4[3] = it_brev;
+    if (st != 0) return st;
+    {
+      double e = 0.0;
+      for (int i = k.tid; i < n; i += k.nthr) e = nanmax(e, fabs(sol[i] - w.v3[i]));
+      const double rev = block_nanmax(k, e);
+      if (rev > rev_tol) return MB200_STATUS_NON_REVERSIBLE;
+    }
+    // ---- _step_a
+    kick_h1(dt);
+    return MB200_STATUS_OK;
+  }
+
+  // h = l(q) + log|M|/2 + p.M^-1 p/2   (systems.py:1375-1390); NaN if the metric cannot be built
+  __device__ double hamiltonian() {
+    if (m.build(k, w, w.q) != 0) return nan("");
+    m.inv_matvec(k, w, w.p, w.v1);
+    double s = 0.0;
+    for (int i = k.tid; i < w.dim; i += k.nthr) s = fma(w.p[i], w.v1[i], s);
+    const double kin = block_sum(k, s);
+    const double lad = m.log_abs_det(k, w);
+    const double l = t.nld(k, w.q);
+    return (l + 0.5 * lad) + 0.5 * kin;
+  }
+};
+
+template <class Target, template <class> class MetricT>
+__global__ void __launch_bounds__(RM_THREADS)
+    implicit_leapfrog_kernel(const double* q_in, const double* p_in, double* q_out, double* p_out,
+                             const int32_t* __restrict__ dir, int64_t n_chains, int dim,
+                             double step_size, int n_steps, ModelArgs model, double fp_tol,
+                             double fp_div, int fp_max, double rev_tol,
+                             double* __restrict__ h_out, int32_t* __restrict__ status,
+                             int32_t* __restrict__ n_done, int32_t* __restrict__ fp_iters) {
+  extern __shared__ double smem[];
+  Blk blk;
+  blk.tid = threadIdx.x;
+  blk.nthr = blockDim.x;
+  blk.lane = threadIdx.x & 31;
+  blk.warp = threadIdx.x >> 5;
+  blk.nwarp = blockDim.x >> 5;
+  RmWork w;
+  rm_carve(w, smem, dim, MetricT<Target>::SOFTABS, blk);
+  const Target target(model, dim);
+  MetricT<Target> metric(target, model);
+  ImplicitLeapfrog<Target, MetricT<Target>> integ{blk, w, target, metric, fp_tol, fp_div, rev_tol, fp_max};
+
+  for (int64_t ch = blockIdx.x; ch < n_chains; ch += gridDim.x) {
+    __syncthreads();
+    for (int i = blk.tid; i < dim; i += blk.nthr) {
+      w.q[i] = q_in[(size_t)ch * dim + i];
+      w.p[i] = p_in[(size_t)ch * dim + i];
+    }
+    __syncthreads();
+    const double dt = (dir != nullptr) ? (double)dir[ch] * step_size : step_size;
+    int st = MB200_STATUS_OK, done = 0;
+    int it4[4] = {0, 0, 0, 0};
+    for (int s = 0; s < n_steps && st == MB200_STATUS_OK; ++s) {
+      for (int i = blk.tid; i < dim; i += blk.nthr) w.qs[i] = w.q[i], w.ps[i] = w.p[i];
+      __syncthreads();
+      int it_step[4] = {0, 0, 0, 0};
+      st = integ.step(dt, it_step);
+      if (st == MB200_STATUS_OK) {
+        ++done;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) it4[j] = it_step[j];
+      } else {
+        __syncthreads();
+        for (int i = blk.tid; i < dim; i += blk.nthr) w.q[i] = w.qs[i], w.p[i] = w.ps[i];
+        __syncthreads();
+      }
+    }
+    for (int i = blk.tid; i < dim; i += blk.nthr) {
+      q_out[(size_t)ch * dim + i] = w.q[i];
+      p_out[(size_t)ch * dim + i] = w.p[i];
+    }
+    if (h_out != nullptr) {
+      const double h = integ.hamiltonian();
+      if (blk.tid == 0) h_out[ch] = h;
+    }
+    if (blk.tid == 0) {
+      if (status != nullptr) status[ch] = st;
+      if (n_done != nullptr) n_done[ch] = done;
+      if (fp_iters != nullptr)
+        for (int j = 0; j < 4; ++j) fp_iters[ch * 4 + j] = it4[j];
+    }
+  }
+}
+
+}  // namespace mb200
