@@ -63,7 +63,7 @@ extern "C" {
 
 /* position-dependent metrics of Riemannian systems */
 #define MB200_RMETRIC_SOFTABS 0 /* SoftAbs of target Hessian (matrices.py:1631-1685); params: softabs_coeff */
-#define MB200_RMETRIC_RANK1 1   /* dense M(q) = B + c q q^T;  aux: B [dim*dim], params: c                   */
+#define MB200_RMETRIC_RANK1 1   /* dense M(q) = B + c q q^T;  aux: [B | B^-1] (2*dim*dim), params: c, log|B|, force_woodbury */
 
 #define MB200_MAX_PARAMS 8
 

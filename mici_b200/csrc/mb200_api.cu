@@ -200,7 +200,7 @@ static int launch_implicit(const double* q_in, const double* p_in, double* q_out
                            double rev_tol, double* h_out, int32_t* status, int32_t* n_done,
                            int32_t* fp_iters, cudaStream_t st) {
   auto kern = implicit_leapfrog_kernel<Target, MetricT>;
-  const size_t smem = rm_smem_doubles(dim, MetricT<Target>::SOFTABS) * sizeof(double);
+  const size_t smem = rm_smem_doubles(dim, MetricT<Target>::N_MATS) * sizeof(double);
   if (smem > 227 * 1024)
     return fail(MB200_ERR_UNSUPPORTED,
                 "dim %d: per-chain metric (%zu bytes) exceeds shared memory; not supported yet",
@@ -239,15 +239,24 @@ static int implicit_dispatch(const double* q_in, const double* p_in, double* q_o
   }
   if (m.rmetric_id == MB200_RMETRIC_RANK1) {
     if (!m.maux) return fail(MB200_ERR_INVALID_ARG, "rank-1 metric needs its base matrix (rmetric_aux)");
+    if (m.target_id == MB200_TARGET_QUADRATIC && !m.taux)
+      return fail(MB200_ERR_INVALID_ARG, "quadratic target needs its precision matrix");
+    if (m.target_id == MB200_TARGET_BANANA && (dim & 1))
+      return fail(MB200_ERR_INVALID_ARG, "banana target needs even dim");
+    // per-chain Cholesky factor in shared memory when it fits (or when forced), else the
+    // Sherman-Morrison form that never materialises M(q); mp[2] != 0 forces the latter
+    const bool fits = rm_smem_doubles(dim, 1) * sizeof(double) <= 227 * 1024;
+    const bool woodbury = !fits || m.mp[2] != 0.0;
     switch (m.target_id) {
       case MB200_TARGET_QUADRATIC:
-        if (!m.taux) return fail(MB200_ERR_INVALID_ARG, "quadratic target needs its precision matrix");
-        return launch_implicit<QuadraticRTarget, Rank1DenseMetric>(MB200_ARGS);
+        return woodbury ? launch_implicit<QuadraticRTarget, Rank1WoodburyMetric>(MB200_ARGS)
+                        : launch_implicit<QuadraticRTarget, Rank1DenseMetric>(MB200_ARGS);
       case MB200_TARGET_STD_GAUSSIAN:
-        return launch_implicit<StdGaussianRTarget, Rank1DenseMetric>(MB200_ARGS);
+        return woodbury ? launch_implicit<StdGaussianRTarget, Rank1WoodburyMetric>(MB200_ARGS)
+                        : launch_implicit<StdGaussianRTarget, Rank1DenseMetric>(MB200_ARGS);
       case MB200_TARGET_BANANA:
-        if (dim & 1) return fail(MB200_ERR_INVALID_ARG, "banana target needs even dim");
-        return launch_implicit<BananaRTarget, Rank1DenseMetric>(MB200_ARGS);
+        return woodbury ? launch_implicit<BananaRTarget, Rank1WoodburyMetric>(MB200_ARGS)
+                        : launch_implicit<BananaRTarget, Rank1DenseMetric>(MB200_ARGS);
       default:
         return fail(MB200_ERR_UNSUPPORTED, "target %d not available for Riemannian systems", m.target_id);
     }

@@ -173,10 +173,11 @@ struct RmWork {
   int *top, *bot;   // round-robin index arrays [dim/2 + 1]
 };
 
-__host__ __device__ inline size_t rm_smem_doubles(int dim, bool softabs) {
+// n_mats: per-chain D x D matrices kept in shared memory (2 SoftAbs, 1 dense Cholesky, 0 Woodbury)
+__host__ __device__ inline size_t rm_smem_doubles(int dim, int n_mats) {
   const int ld = dim + 1;
   const int dpad = (dim + 1) & ~1;
-  size_t n = (size_t)dim * ld * (softabs ? 2 : 1);
+  size_t n = (size_t)dim * ld * n_mats;
   n += (size_t)15 * dpad;      // vectors (Vn counts double: NEED <= 2)
   n += (size_t)dpad;           // second half of Vn
   n += 2 * (size_t)(dpad / 2 + 2);  // rc, rs
@@ -185,15 +186,15 @@ __host__ __device__ inline size_t rm_smem_doubles(int dim, bool softabs) {
   return n;
 }
 
-__device__ inline void rm_carve(RmWork& w, double* s, int dim, bool softabs, Blk& blk) {
+__device__ inline void rm_carve(RmWork& w, double* s, int dim, int n_mats, Blk& blk) {
   const int ld = dim + 1;
   const int dpad = (dim + 1) & ~1;
   w.dim = dim;
   w.ld = ld;
-  w.M1 = s;
-  s += (size_t)dim * ld;
-  w.M2 = softabs ? s : nullptr;
-  if (softabs) s += (size_t)dim * ld;
+  w.M1 = n_mats >= 1 ? s : nullptr;
+  if (n_mats >= 1) s += (size_t)dim * ld;
+  w.M2 = n_mats >= 2 ? s : nullptr;
+  if (n_mats >= 2) s += (size_t)dim * ld;
   double** vecs[] = {&w.q, &w.p, &w.qs, &w.ps, &w.x0, &w.x1, &w.base, &w.v1,
                      &w.v2, &w.v3, &w.lam, &w.sa, &w.gsa, &w.ev};
   for (auto v : vecs) {
@@ -387,6 +388,7 @@ __device__ inline void cholesky_solve(const Blk& k, const double* L, int n, int 
 template <class Target>
 struct SoftAbsMetric {
   static constexpr bool SOFTABS = true;
+  static constexpr int N_MATS = 2;
   const Target& t;
   double alpha;
   bool have_j;  // divided-difference matrix J built in w.M2 for the current metric?
@@ -503,6 +505,7 @@ struct SoftAbsMetric {
 template <class Target>
 struct Rank1DenseMetric {
   static constexpr bool SOFTABS = false;
+  static constexpr int N_MATS = 1;
   const Target& t;
   const double* B;
   double c;
@@ -541,6 +544,80 @@ struct Rank1DenseMetric {
     for (int i = k.tid; i < w.dim; i += k.nthr) s = fma(w.ev[i], q[i], s);
     const double wq = block_sum(k, s);
     // V q = -(w w^T) q = -w (w.q);  c (V + V^T) q = 2 c V q
+    for (int i = k.tid; i < w.dim; i += k.nthr) {
+      const double vq = -(w.ev[i] * wq);
+      out[i] = c * (vq + vq);
+    }
+    __syncthreads();
+  }
+};
+
+// The same metric M(q) = B + c q q^T for dimensions whose D x D factor does not fit in shared
+// memory (config C4, D = 512): the matrix is never formed.  With the shared explicit inverse
+// B^-1 (built on the host exactly like a fixed dense metric, matrices.py:1183-1188) and
+// u = B^-1 q, the matrix-determinant and Sherman-Morrison identities give
+//   log|M|  = log|B| + log(1 + c q.u)
+//   M^-1 v  = B^-1 v - u (c (u.v) / (1 + c q.u))
+//   M^-1 q  = u / (1 + c q.u)
+// -- O(D^2) per metric instead of the reference's O(D^3) Cholesky (matrices.py:1161-1173);
+// equal to it up to rounding (checked against the D = 512 reference fixture).
+template <class Target>
+struct Rank1WoodburyMetric {
+  static constexpr bool SOFTABS = false;
+  static constexpr int N_MATS = 0;
+  const Target& t;
+  const double* Binv;
+  double c, logdet_b, denom;
+  __device__ Rank1WoodburyMetric(const Target& tt, const ModelArgs& m)
+      : t(tt), Binv(m.maux + (size_t)tt.dim * tt.dim), c(m.mp[0]), logdet_b(m.mp[1]), denom(1.0) {}
+
+  // out = B^-1 v (B^-1 symmetric: column-wise reads are coalesced across threads)
+  __device__ void binv_matvec(const Blk& k, int n, const double* v, double* out) const {
+    for (int i = k.tid; i < n; i += k.nthr) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int j = 0;
+      for (; j + 3 < n; j += 4) {
+        s0 = fma(Binv[(size_t)j * n + i], v[j], s0);
+        s1 = fma(Binv[(size_t)(j + 1) * n + i], v[j + 1], s1);
+        s2 = fma(Binv[(size_t)(j + 2) * n + i], v[j + 2], s2);
+        s3 = fma(Binv[(size_t)(j + 3) * n + i], v[j + 3], s3);
+      }
+      for (; j < n; ++j) s0 = fma(Binv[(size_t)j * n + i], v[j], s0);
+      out[i] = (s0 + s1) + (s2 + s3);
+    }
+    __syncthreads();
+  }
+  // u = B^-1 q kept in w.lam (unused by dense metrics)
+  __device__ int build(const Blk& k, RmWork& w, const double* q) {
+    binv_matvec(k, w.dim, q, w.lam);
+    double s = 0.0;
+    for (int i = k.tid; i < w.dim; i += k.nthr) s = fma(q[i], w.lam[i], s);
+    denom = 1.0 + c * block_sum(k, s);
+    if (!(denom > 0.0) || isinf(denom)) return MB200_STATUS_LINALG;  // M not SPD / not finite
+    return 0;
+  }
+  __device__ double log_abs_det(const Blk&, RmWork&) const { return logdet_b + log(denom); }
+  __device__ void inv_matvec(const Blk& k, RmWork& w, const double* v, double* out) const {
+    binv_matvec(k, w.dim, v, out);
+    double s = 0.0;
+    for (int i = k.tid; i < w.dim; i += k.nthr) s = fma(w.lam[i], v[i], s);
+    const double f = c * block_sum(k, s) / denom;
+    for (int i = k.tid; i < w.dim; i += k.nthr) out[i] -= w.lam[i] * f;
+    __syncthreads();
+  }
+  __device__ void vjp_grad_log_abs_det(const Blk& k, RmWork& w, const double*, double* out) const {
+    for (int i = k.tid; i < w.dim; i += k.nthr) {
+      const double mq = w.lam[i] / denom;  // (M^-1 q)_i
+      out[i] = c * (mq + mq);
+    }
+    __syncthreads();
+  }
+  __device__ void vjp_grad_quad_inv(const Blk& k, RmWork& w, const double* q, const double* p,
+                                    double* out) {
+    inv_matvec(k, w, p, w.ev);  // w = M^-1 p
+    double s = 0.0;
+    for (int i = k.tid; i < w.dim; i += k.nthr) s = fma(w.ev[i], q[i], s);
+    const double wq = block_sum(k, s);
     for (int i = k.tid; i < w.dim; i += k.nthr) {
       const double vq = -(w.ev[i] * wq);
       out[i] = c * (vq + vq);
@@ -713,7 +790,7 @@ __global__ void __launch_bounds__(RM_THREADS)
   blk.warp = threadIdx.x >> 5;
   blk.nwarp = blockDim.x >> 5;
   RmWork w;
-  rm_carve(w, smem, dim, MetricT<Target>::SOFTABS, blk);
+  rm_carve(w, smem, dim, MetricT<Target>::N_MATS, blk);
   const Target target(model, dim);
   MetricT<Target> metric(target, model);
   ImplicitLeapfrog<Target, MetricT<Target>> integ{blk, w, target, metric, fp_tol, fp_div, rev_tol, fp_max};

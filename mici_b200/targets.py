@@ -110,9 +110,22 @@ class Rank1Metric:
     rmetric_id = RMETRIC_RANK1
     name = "rank1"
 
-    def __init__(self, base, coeff):
-        self.aux = np.ascontiguousarray(base, dtype=np.float64)
-        self.params = (float(coeff),)
+    def __init__(self, base, coeff, force_low_rank_form=False):
+        base = np.ascontiguousarray(base, dtype=np.float64)
+        # shared explicit inverse and log-determinant of B, built once on the host the way the
+        # reference builds a fixed dense metric's inverse (matrices.py:1161-1188, 982-984)
+        import scipy.linalg as sla  # noqa: PLC0415
+
+        chol = np.linalg.cholesky(base)
+        inv_lt = sla.solve_triangular(chol.T, np.identity(base.shape[0]), lower=False)
+        inv = sla.solve_triangular(chol.T, inv_lt.T, lower=False)
+        self.base = base
+        self.aux = np.ascontiguousarray(np.concatenate([base.ravel(), inv.ravel()]))
+        self.params = (
+            float(coeff),
+            float(2.0 * np.log(np.abs(chol.diagonal())).sum()),
+            1.0 if force_low_rank_form else 0.0,
+        )
 
 
 REGISTRY = {

@@ -1,0 +1,175 @@
+"""CPU tests of the host-side mirror of the reference interface (no kernels are launched)."""
+
+import copy
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+import mici_b200 as mb
+from mici_b200 import engine, integrators, problems, solvers, systems, targets
+from mici_b200.errors import (
+    AdaptationError,
+    ConvergenceError,
+    IntegratorError,
+    LinAlgError,
+    NonReversibleStepError,
+    ReadOnlyStateError,
+    raise_for_status,
+)
+
+
+def test_chain_state_semantics():
+    """reference tests/test_states.py: construct / attribute access / copy / read-only."""
+    pos, mom = torch.zeros(4, 3, dtype=torch.float64), torch.ones(4, 3, dtype=torch.float64)
+    s = mb.ChainState(pos=pos, mom=mom, dir=1)
+    assert "pos" in s and "mom" in s and "dir" in s and "foo" not in s
+    assert s.n_chains == 4 and s.dim == 3
+    c = s.copy()
+    c.pos[0, 0] = 5.0
+    assert s.pos[0, 0] == 0.0  # deep copy of variables (states.py:263-279)
+    r = s.copy(read_only=True)
+    with pytest.raises(ReadOnlyStateError):
+        r.pos = pos
+    with pytest.raises(AttributeError):
+        _ = s.nonexistent
+    with pytest.raises(ValueError):
+        mb.ChainState(_bad=1, pos=pos)
+    s.status = torch.zeros(4, dtype=torch.int32)
+    s.mom = mom * 2  # setting a variable drops derived per-call outputs
+    assert s.status is None
+    s2 = pickle.loads(pickle.dumps(s))
+    assert torch.equal(s2.mom, s.mom)
+
+
+def test_error_hierarchy_and_status_mapping():
+    assert issubclass(ConvergenceError, IntegratorError)
+    assert issubclass(NonReversibleStepError, IntegratorError)
+    assert not issubclass(LinAlgError, IntegratorError)
+    raise_for_status(0)
+    with pytest.raises(ConvergenceError):
+        raise_for_status(1)
+    with pytest.raises(NonReversibleStepError):
+        raise_for_status(2)
+    with pytest.raises(LinAlgError):
+        raise_for_status(3)
+
+
+def test_metric_coercion_matches_reference_rules():
+    """systems.py:332-346: None -> identity, 1-D -> diagonal, 2-D -> dense, else ValueError."""
+    t = targets.StdGaussian(4)
+    assert systems.EuclideanMetricSystem(t).metric.kind == systems.METRIC_IDENTITY
+    d = systems.EuclideanMetricSystem(t, metric=np.array([1.0, 2.0, 3.0, 4.0]))
+    assert d.metric.kind == systems.METRIC_DIAGONAL
+    np.testing.assert_allclose(d.metric.inv, [1.0, 0.5, 1 / 3, 0.25])
+    rng = np.random.default_rng(0)
+    m = problems.dense_spd_metric(rng, 4)
+    e = systems.EuclideanMetricSystem(t, metric=m)
+    assert e.metric.kind == systems.METRIC_DENSE
+    np.testing.assert_allclose(e.metric.inv @ m, np.identity(4), atol=1e-13)
+    np.testing.assert_allclose(e.metric.sqrt @ e.metric.sqrt.T, m, atol=1e-13)
+    with pytest.raises(ValueError):
+        systems.EuclideanMetricSystem(t, metric=np.zeros((2, 2, 2)))
+    with pytest.raises(ValueError):
+        systems.EuclideanMetricSystem(t, metric=np.array([1.0, -1.0, 1.0, 1.0]))
+    with pytest.raises(LinAlgError):
+        systems.EuclideanMetricSystem(t, metric=-np.identity(4))
+    e.metric = None  # assignable, as adapters do (adapters.py:513, 642)
+    assert e.metric.kind == systems.METRIC_IDENTITY
+
+
+def test_explicit_inverse_is_built_like_the_reference():
+    from oracle import mici_oracle as mo
+
+    rng = np.random.default_rng(1)
+    m = problems.dense_spd_metric(rng, 24)
+    _, inv = systems._explicit_spd_inverse(m)
+    np.testing.assert_array_equal(inv, mo.DenseMetric(m).inv_array)
+
+
+def test_system_rejects_python_callables_and_foreign_derivatives():
+    with pytest.raises(TypeError):
+        systems.EuclideanMetricSystem(lambda q: 0.0)
+    with pytest.raises(ValueError):
+        systems.EuclideanMetricSystem(targets.StdGaussian(3), grad_neg_log_dens=lambda q: q)
+    with pytest.raises(ValueError):
+        systems.DenseConstrainedEuclideanMetricSystem(targets.StdGaussian(3))
+    with pytest.raises(NotImplementedError):
+        systems.DenseConstrainedEuclideanMetricSystem(targets.Torus(), dens_wrt_hausdorff=False)
+    with pytest.raises(ValueError):
+        systems.SoftAbsRiemannianMetricSystem(targets.Banana(4), softabs_coeff=0.0)
+
+
+def test_integrator_constructor_contracts():
+    """integrators.py:52-80, 121-130, 438-446, 855-864: names, defaults, rejections."""
+    eu = systems.EuclideanMetricSystem(targets.NealFunnel(8))
+    lf = integrators.LeapfrogIntegrator(eu)
+    assert lf.step_size is None and lf.system is eu
+    s = mb.ChainState(pos=torch.zeros(2, 8, dtype=torch.float64),
+                      mom=torch.zeros(2, 8, dtype=torch.float64), dir=1)
+    with pytest.raises(AdaptationError):
+        lf.step(s)  # step_size None (integrators.py:72-77)
+    lf.step_size = 0.25  # adapters assign it (adapters.py:322-340)
+    rm = systems.SoftAbsRiemannianMetricSystem(targets.Banana(4))
+    with pytest.raises(ValueError):
+        integrators.LeapfrogIntegrator(rm)  # no h1_flow / h2_flow (integrators.py:121-130)
+    il = integrators.ImplicitLeapfrogIntegrator(rm, 0.1)
+    assert il.reverse_check_tol == 2e-8 and il.fixed_point_solver is solvers.solve_fixed_point_direct
+    assert il.fixed_point_solver.resolve_kwargs({"convergence_tol": 1e-12}) == {
+        "convergence_tol": 1e-12, "divergence_tol": 1e10, "max_iters": 100}
+    with pytest.raises(TypeError):
+        il.fixed_point_solver.resolve_kwargs({"bogus": 1})
+    with pytest.raises(ValueError):
+        integrators.ImplicitLeapfrogIntegrator(rm, 0.1, fixed_point_solver=lambda f, x: x)
+    cs = systems.DenseConstrainedEuclideanMetricSystem(targets.Torus())
+    cl = integrators.ConstrainedLeapfrogIntegrator(cs, 0.1, n_inner_step=3)
+    assert cl.n_inner_step == 3
+    assert cl.projection_solver.defaults == {
+        "constraint_tol": 1e-9, "position_tol": 1e-8, "divergence_tol": 1e10, "max_iters": 50}
+    with pytest.raises(TypeError):
+        integrators.ConstrainedLeapfrogIntegrator(eu, 0.1)
+
+
+def test_integrators_survive_deepcopy_and_pickle():
+    """samplers.py:1124-1129 deep-copies the integrator per chain; multiprocess pickles it."""
+    for cfg, kw in (("C1", {"n_chains": 4, "dim": 8}), ("C2", {"n_chains": 4, "dim": 4}),
+                    ("C3", {"n_chains": 4}), ("C4", {"n_chains": 2, "dim": 8})):
+        integ = engine.build_integrator(problems.make_problem(cfg, **kw))
+        for clone in (copy.deepcopy(integ), pickle.loads(pickle.dumps(integ))):
+            assert type(clone) is type(integ)
+            assert clone.step_size == integ.step_size
+            assert clone.system.target.target_id == integ.system.target.target_id
+
+
+def test_solver_markers_are_not_host_callables():
+    from mici_b200.errors import Error
+
+    with pytest.raises(Error):
+        solvers.solve_fixed_point_direct(np.cos, np.array([1.0]))
+    x = torch.tensor([[1.0, -3.0], [0.5, 0.25]])
+    assert torch.equal(solvers.maximum_norm(x), torch.tensor([3.0, 0.5]))
+
+
+def test_problem_configs_match_baseline_shapes():
+    shapes = {"C0": (4, 10), "C1": (8192, 128), "C2": (2048, 64), "C3": (4096, 3)}
+    for name, shp in shapes.items():
+        p = problems.make_problem(name)
+        assert p.pos.shape == shp and p.mom.shape == shp and p.pos.dtype == np.float64
+        assert p.algorithmic_bytes_per_chain_step == 32 * shp[1]
+    p = problems.make_problem("C4", n_chains=8)
+    assert p.dim == 512
+    # seeded: identical on every call
+    a, b = problems.make_problem("C1", n_chains=8), problems.make_problem("C1", n_chains=8)
+    np.testing.assert_array_equal(a.pos, b.pos)
+    np.testing.assert_array_equal(a.metric, b.metric)
+
+
+def test_compute_call_without_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    prob = problems.make_problem("C1", n_chains=4, dim=8)
+    integ = engine.build_integrator(prob)
+    state = engine.build_state(prob, "cpu")
+    with pytest.raises(Exception):  # noqa: B017 - no CPU fallback exists
+        integ.step(state)

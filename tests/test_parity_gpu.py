@@ -172,3 +172,60 @@ def test_single_chain_state_raises_like_reference():
         else:
             new = integ.step(st)
             np.testing.assert_allclose(new.pos.cpu().numpy(), ref["pos"][idx], rtol=RTOL, atol=ATOL)
+
+
+def test_rank1_low_rank_form_matches_cholesky_form_and_fixture():
+    """The Sherman-Morrison metric policy (used when the per-chain factor does not fit in shared
+    memory) against the per-chain Cholesky policy and the reference fixture at D = 64."""
+    problem, dirs, overrides, g = load_case("c4_dense_riemannian_d64")
+    chol = run_cuda(problem, 5, dirs=dirs, overrides=overrides)
+    problem.metric_params = dict(problem.metric_params, force_low_rank_form=True)
+    low = run_cuda(problem, 5, dirs=dirs, overrides=overrides)
+    assert_matches_golden(low, g, 5, label="low-rank form")
+    np.testing.assert_array_equal(low["status"], chol["status"])
+    np.testing.assert_allclose(low["pos"], chol["pos"], rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(low["mom"], chol["mom"], rtol=1e-11, atol=1e-13)
+    np.testing.assert_array_equal(low["iters"], chol["iters"])
+
+
+def test_implicit_solver_iteration_counts_match_oracle():
+    """H2: the fused fixed-point solves stop on the same iterate as
+    solve_fixed_point_direct (solvers.py:77-88) -- compare per-chain iteration counts."""
+    for cfg, kwargs in (("C2", {"n_chains": 24, "dim": 8}), ("C4", {"n_chains": 6, "dim": 16})):
+        problem = problems.make_problem(cfg, **kwargs)
+        counts = {}
+        ref = dr.oracle_run(problem, 1, counts=counts)
+        out = run_cuda(problem, 1)
+        np.testing.assert_array_equal(out["status"], ref["status"])
+        ok = ref["status"] == 0
+        ref_iters = np.array([c for c in counts["all_fp_iters"]])
+        np.testing.assert_array_equal(out["iters"][ok], ref_iters[ok])
+
+
+def test_riemannian_hamiltonian_matches_oracle():
+    for cfg, kwargs in (("C2", {"n_chains": 16, "dim": 8}), ("C4", {"n_chains": 4, "dim": 32})):
+        problem = problems.make_problem(cfg, **kwargs)
+        integ = engine.build_integrator(problem)
+        state = engine.build_state(problem, DEV)
+        h = integ.system.h(state).cpu().numpy()
+        ref = dr.oracle_run(problem, 0)
+        np.testing.assert_allclose(h, ref["h_init"], rtol=RTOL, atol=1e-10)
+
+
+def test_softabs_full_size_c2_reversibility_and_energy():
+    """Full BASELINE size C2 (2048 chains, D = 64): size-independent properties
+    (tests/test_integrators.py:75-108)."""
+    problem = problems.make_problem("C2")
+    integ = engine.build_integrator(problem)
+    state = engine.build_state(problem, DEV)
+    h0 = integ.system.h(state)
+    fwd = integ.step_n(state, 3, return_h=True)
+    ok = fwd.status == 0
+    assert ok.float().mean().item() > 0.95
+    dh = (fwd.h - h0)[ok].abs()
+    assert dh.median().item() < 0.1 and dh.max().item() < 2.0  # step 2*eps = 0.2 (H3), D = 64
+    fwd.dir = -1
+    back = integ.step_n(fwd, 3)
+    torch.cuda.synchronize()
+    both = ok & (back.status == 0)
+    torch.testing.assert_close(back.pos[both], state.pos[both], rtol=0, atol=1e-6)
