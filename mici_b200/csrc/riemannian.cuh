@@ -218,6 +218,25 @@ __device__ inline void rm_carve(RmWork& w, double* s, int dim, int n_mats, Blk& 
 // A [dim x dim, stride ld] is destroyed (its diagonal becomes lam); U receives the eigenvectors
 // as columns.  Returns false if not converged / non-finite (-> LinAlgError, matrices.py:437).
 // ---------------------------------------------------------------------------------------------
+// Round-robin (circle method) schedule: in round r of np-1, pair t couples
+//   t == 0 : (np-1, r)          t > 0 : ((r+t) mod (np-1), (r-t) mod (np-1))
+// every unordered pair of the np players meets exactly once per sweep; no schedule arrays.
+__device__ __forceinline__ void rr_pair(int np, int r, int t, int& p, int& q) {
+  const int m1 = np - 1;
+  int a, b;
+  if (t == 0) {
+    a = m1;
+    b = r;
+  } else {
+    a = r + t;
+    if (a >= m1) a -= m1;
+    b = r - t;
+    if (b < 0) b += m1;
+  }
+  p = a < b ? a : b;
+  q = a < b ? b : a;
+}
+
 __device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U) {
   const int n = w.dim, ld = w.ld;
   const int m = (n + 1) / 2;  // pairs per round (odd n: one index idles each round)
@@ -225,10 +244,6 @@ __device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U
   for (int idx = k.tid; idx < n * n; idx += k.nthr) {
     const int i = idx / n, j = idx - i * n;
     U[i * ld + j] = (i == j) ? 1.0 : 0.0;
-  }
-  for (int i = k.tid; i < m; i += k.nthr) {
-    w.top[i] = 2 * i;
-    w.bot[i] = 2 * i + 1;
   }
   // scale for the convergence test
   double dmax = 0.0;
@@ -246,14 +261,10 @@ __device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U
     for (int round = 0; round < np - 1; ++round) {
       // --- rotation parameters for the m disjoint pairs of this round
       for (int t = k.tid; t < m; t += k.nthr) {
-        int p = w.top[t], q = w.bot[t];
+        int p, q;
+        rr_pair(np, round, t, p, q);
         double c = 1.0, s = 0.0;
-        if (p < n && q < n) {
-          if (p > q) {
-            const int tmp = p;
-            p = q;
-            q = tmp;
-          }
+        if (q < n) {
           const double apq = A[p * ld + q];
           off = fmax(off, fabs(apq));
           if (fabs(apq) > 1e-300 && fabs(apq) > 1e-18 * scale) {
@@ -271,9 +282,9 @@ __device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U
       // --- A <- R^T A R on 2x2 blocks (pair a rows, pair b cols), U <- U R
       for (int idx = k.tid; idx < m * m; idx += k.nthr) {
         const int a = idx / m, b = idx - a * m;
-        int pa = w.top[a], qa = w.bot[a], pb = w.top[b], qb = w.bot[b];
-        if (pa > qa) { const int t2 = pa; pa = qa; qa = t2; }
-        if (pb > qb) { const int t2 = pb; pb = qb; qb = t2; }
+        int pa, qa, pb, qb;
+        rr_pair(np, round, a, pa, qa);
+        rr_pair(np, round, b, pb, qb);
         const bool va = qa < n, vb = qb < n;  // pair contains the bye index?
         const double ca = w.rc[a], sa = w.rs[a], cb = w.rc[b], sb = w.rs[b];
         if (va && vb) {
@@ -288,39 +299,25 @@ __device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U
           A[qa * ld + pb] = cb * r10 - sb * r11;
           A[qa * ld + qb] = sb * r10 + cb * r11;
         } else if (va && !vb) {  // single column pb (< n), rotated rows only
-          if (pb < n) {
-            const double a0 = A[pa * ld + pb], a1 = A[qa * ld + pb];
-            A[pa * ld + pb] = ca * a0 - sa * a1;
-            A[qa * ld + pb] = sa * a0 + ca * a1;
-          }
+          const double a0 = A[pa * ld + pb], a1 = A[qa * ld + pb];
+          A[pa * ld + pb] = ca * a0 - sa * a1;
+          A[qa * ld + pb] = sa * a0 + ca * a1;
         } else if (!va && vb) {  // single row pa (< n), rotated cols only
-          if (pa < n) {
-            const double a0 = A[pa * ld + pb], a1 = A[pa * ld + qb];
-            A[pa * ld + pb] = cb * a0 - sb * a1;
-            A[pa * ld + qb] = sb * a0 + cb * a1;
-          }
+          const double a0 = A[pa * ld + pb], a1 = A[pa * ld + qb];
+          A[pa * ld + pb] = cb * a0 - sb * a1;
+          A[pa * ld + qb] = sb * a0 + cb * a1;
         }
       }
       for (int idx = k.tid; idx < n * m; idx += k.nthr) {
         const int i = idx / m, b = idx - i * m;
-        int pb = w.top[b], qb = w.bot[b];
-        if (pb > qb) { const int t2 = pb; pb = qb; qb = t2; }
+        int pb, qb;
+        rr_pair(np, round, b, pb, qb);
         if (qb < n) {
           const double cb = w.rc[b], sb = w.rs[b];
           const double u0 = U[i * ld + pb], u1 = U[i * ld + qb];
           U[i * ld + pb] = cb * u0 - sb * u1;
           U[i * ld + qb] = sb * u0 + cb * u1;
         }
-      }
-      __syncthreads();
-      // --- rotate the round-robin schedule (top[0] fixed)
-      if (k.tid == 0 && m > 1) {
-        const int last_top = w.top[m - 1];
-        const int first_bot = w.bot[0];
-        for (int i = m - 1; i > 1; --i) w.top[i] = w.top[i - 1];
-        w.top[1] = first_bot;
-        for (int i = 0; i < m - 1; ++i) w.bot[i] = w.bot[i + 1];
-        w.bot[m - 1] = last_top;
       }
       __syncthreads();
     }
