@@ -89,6 +89,46 @@ class Integrator(ABC):
             raise_for_status(int(status.item()), type(self).__name__ + ".step")
         return new
 
+    def step_n_host(self, pos, mom, n_steps, *, dir=1, out_pos=None, out_mom=None,  # noqa: A002
+                    out_status=None, device="cuda", n_chunks=4):
+        """``step_n`` for states that live in HOST memory (the reference's ``ChainState`` arrays
+        are NumPy: states.py:160-305).  ``pos`` / ``mom`` are CPU tensors ``[n_chains, dim]``
+        (pinned memory makes the copies asynchronous); the batch is cut into ``n_chunks`` row
+        blocks, each on its own stream, so that the host->device copy of block ``k+1`` and the
+        device->host copy of block ``k-1`` overlap the kernel of block ``k`` (chains are
+        independent, so chunking changes no result).  Returns ``(pos, mom, status)`` CPU tensors
+        (written into ``out_*`` when given) after synchronising the streams.
+        """
+        dev = torch.device(device)
+        pos = torch.as_tensor(pos)
+        mom = torch.as_tensor(mom)
+        n = pos.shape[0]
+        out_pos = torch.empty_like(pos) if out_pos is None else out_pos
+        out_mom = torch.empty_like(mom) if out_mom is None else out_mom
+        out_status = torch.empty(n, dtype=torch.int32) if out_status is None else out_status
+        n_chunks = max(1, min(int(n_chunks), n))
+        streams = _host_streams(dev, n_chunks)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        bounds = [(n * c) // n_chunks for c in range(n_chunks + 1)]
+        for c in range(n_chunks):
+            lo, hi = bounds[c], bounds[c + 1]
+            if hi == lo:
+                continue
+            st = streams[c]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                d = dir[lo:hi] if isinstance(dir, torch.Tensor) else dir
+                blk = ChainState(pos=pos[lo:hi].to(dev, non_blocking=True),
+                                 mom=mom[lo:hi].to(dev, non_blocking=True), dir=d)
+                new = self.step_n(blk, n_steps)
+                out_pos[lo:hi].copy_(new.pos, non_blocking=True)
+                out_mom[lo:hi].copy_(new.mom, non_blocking=True)
+                out_status[lo:hi].copy_(new.status, non_blocking=True)
+        for st in streams:
+            st.synchronize()
+        return out_pos, out_mom, out_status
+
     def _step(self, state, time_step):
         """In-place single step with an explicit signed time step (integrators.py:82-89)."""
         saved = self.step_size
@@ -106,6 +146,18 @@ class Integrator(ABC):
     @abstractmethod
     def _launch(self, pos, mom, pos_out, mom_out, dirs, n_steps, h, status, n_done):
         """Enqueue the kernel(s); may return a tensor of solver iteration counts."""
+
+
+_STREAMS = {}
+
+
+def _host_streams(dev, n):
+    """Per-device pool of side streams for the chunked host-buffer path."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    pool = _STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
 
 
 def _new_state_like(state, pos, mom):

@@ -229,3 +229,18 @@ def test_softabs_full_size_c2_reversibility_and_energy():
     torch.cuda.synchronize()
     both = ok & (back.status == 0)
     torch.testing.assert_close(back.pos[both], state.pos[both], rtol=0, atol=1e-6)
+
+
+def test_host_buffer_path_equals_device_path():
+    """`step_n_host` (pinned host buffers, chunked over streams) returns exactly what the
+    device-resident `step_n` returns: chunking the independent chains changes no result."""
+    problem = problems.make_problem("C1", n_chains=777)
+    integ = engine.build_integrator(problem)
+    state = engine.build_state(problem, DEV)
+    ref = integ.step_n(state, 6)
+    pos_h = torch.as_tensor(problem.pos).pin_memory()
+    mom_h = torch.as_tensor(problem.mom).pin_memory()
+    pos, mom, status = integ.step_n_host(pos_h, mom_h, 6, device=DEV, n_chunks=4)
+    torch.cuda.synchronize()
+    assert torch.equal(pos, ref.pos.cpu()) and torch.equal(mom, ref.mom.cpu())
+    assert torch.equal(status, ref.status.cpu())
