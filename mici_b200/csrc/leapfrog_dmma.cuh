@@ -223,6 +223,30 @@ __device__ __forceinline__ void leapfrog_dmma_group(
     kick_and_publish(s + 1 < n_steps ? 2 : 1);
   }
 
+#if MB200_EXP == 8  // experiment 8: re-run the loop with per-phase cycle counters (CTA 0 only)
+  if (h_out != nullptr && blockIdx.x == 0) {
+    long long t_drift = 0, t_red = 0, t_kick = 0;
+    for (int s = 0; s < n_steps; ++s) {
+      const long long t0 = clock64();
+      drift(q);
+      const long long t1 = clock64();
+      reduce_rows();
+      const long long t2 = clock64();
+      kick_and_publish(2);
+      const long long t3 = clock64();
+      t_drift += t1 - t0, t_red += t2 - t1, t_kick += t3 - t2;
+    }
+    if (lane == 0) {
+      const int wid = (bar_id - 1) * 4 + w;
+      double* dbg = h_out + 4096;  // debug area in the h buffer (read by profiles/tools/phase_c1.py)
+      dbg[wid * 4 + 0] = (double)t_drift / n_steps;
+      dbg[wid * 4 + 1] = (double)t_red / n_steps;
+      dbg[wid * 4 + 2] = (double)t_kick / n_steps;
+      dbg[wid * 4 + 3] = (double)MT;
+    }
+    return;
+  }
+#endif
   // ---- store (p = dir * s)
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {

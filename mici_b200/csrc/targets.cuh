@@ -70,7 +70,11 @@ struct NealFunnelTarget {
   __device__ __forceinline__ void kick_pair(int i, double q0, double q1, const double* red,
                                             double mh, double mhe, double& p0, double& p1) const {
     if (i == 0) {
-      const double g0 = q0 / 9.0 + 0.5 * (dim - 1) - 0.5 * red[1] * red[0];
+      // v/9 as a multiplication by the rounded reciprocal and the sum as two FMAs: the fp64
+      // division is a ~15-deep dependent chain that sits on the critical path of the whole
+      // 4-warp group in the tensor-core kernel (profiles/r01_notes.md); differs from
+      // grad_pair's `q0 / 9.0` by at most 1 ulp.
+      const double g0 = fma(-0.5 * red[1], red[0], fma(q0, 1.0 / 9.0, 0.5 * (dim - 1)));
       p0 = fma(mh, g0, p0);
     } else {
       p0 = fma(mhe, q0, p0);
