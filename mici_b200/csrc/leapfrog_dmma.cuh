@@ -354,16 +354,21 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   }
   for (int idx = tid; idx < DMMA_ROWS_PER_CTA * LDA; idx += blockDim.x) sm.P[idx] = 0.0;
   __syncthreads();
-  if (tid == 0) {
+  if (warp == 0) {  // the 32 lanes of warp 0 issue the row copies (one TMA bulk copy per row)
     const uint32_t row_bytes = (uint32_t)dim * 8u;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar),
-                 "r"(row_bytes * (uint32_t)dim)
-                 : "memory");
-    for (int row = 0; row < dim; ++row) {
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar),
+                   "r"(row_bytes * (uint32_t)dim)
+                   : "memory");
+    __syncwarp();
+#pragma unroll 1
+    for (int row = lane; row < dim; row += 32) {
+      const unsigned long long src =
+          reinterpret_cast<unsigned long long>(minv) + (unsigned long long)row * row_bytes;
       asm volatile(
           "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
           ::"r"(smem_u32(&sm.A[row * LDA])),
-          "l"(minv + (size_t)row * dim), "r"(row_bytes), "r"(mbar)
+          "l"(src), "r"(row_bytes), "r"(mbar)
           : "memory");
     }
   }

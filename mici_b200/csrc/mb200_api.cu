@@ -8,6 +8,9 @@
 #include "leapfrog_generic.cuh"
 #ifndef MB200_NO_DMMA
 #include "leapfrog_dmma.cuh"
+#ifdef MB200_DMMA_V2  // experimental second-generation kernel (slower: profiles/r01_notes.md)
+#include "leapfrog_dmma2.cuh"
+#endif
 #endif
 #ifndef MB200_NO_CONSTRAINED
 #include "constrained.cuh"
@@ -116,8 +119,13 @@ static int leapfrog_euclidean_impl(const double* q_in, const double* p_in, doubl
     return fail(MB200_ERR_INVALID_ARG, "banana target needs even dim");
 #ifndef MB200_NO_DMMA
   if (allow_dmma && metric_kind == MB200_METRIC_DENSE && n_steps > 0) {
+#ifdef MB200_DMMA_V2
+    int rc = leapfrog_dmma2_dispatch(q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, minv, m,
+                                     h_out, status, n_done, st);
+#else
     int rc = leapfrog_dmma_dispatch(q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, minv, m,
                                     h_out, status, n_done, st);
+#endif
     if (rc == 0) return check_launch("leapfrog_dmma_kernel");
     if (rc != MB200_ERR_UNSUPPORTED) return fail(rc, "leapfrog_dmma launch failed");
   }
