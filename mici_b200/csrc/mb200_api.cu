@@ -208,7 +208,10 @@ static int launch_implicit(const double* q_in, const double* p_in, double* q_out
                            double rev_tol, double* h_out, int32_t* status, int32_t* n_done,
                            int32_t* fp_iters, cudaStream_t st) {
   auto kern = implicit_leapfrog_kernel<Target, MetricT>;
-  const size_t smem = rm_smem_doubles(dim, MetricT<Target>::N_MATS) * sizeof(double);
+  int n_mats = MetricT<Target>::N_MATS;
+  // SoftAbs: a third matrix enables warm-started eigensolves; use it when two CTAs still fit
+  if (MetricT<Target>::SOFTABS && rm_smem_doubles(dim, 3) * sizeof(double) <= 113 * 1024) n_mats = 3;
+  const size_t smem = rm_smem_doubles(dim, n_mats) * sizeof(double);
   if (smem > 227 * 1024)
     return fail(MB200_ERR_UNSUPPORTED,
                 "dim %d: per-chain metric (%zu bytes) exceeds shared memory; not supported yet",
@@ -222,7 +225,7 @@ static int launch_implicit(const double* q_in, const double* p_in, double* q_out
   if (blocks > n) blocks = n;
   kern<<<(unsigned)blocks, RM_THREADS, smem, st>>>(q_in, p_in, q_out, p_out, dir, n, dim, eps,
                                                    n_steps, m, fp_tol, fp_div, fp_max, rev_tol,
-                                                   h_out, status, n_done, fp_iters);
+                                                   h_out, status, n_done, fp_iters, n_mats);
   return check_launch("implicit_leapfrog_kernel");
 }
 

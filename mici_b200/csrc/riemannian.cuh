@@ -167,13 +167,14 @@ struct StdGaussianRTarget {
 // ---------------------------------------------------------------------------------------------
 struct RmWork {
   int dim, ld;
-  double *M1, *M2;  // [dim*ld] each (M2 only for SoftAbs)
+  double *M1, *M2, *M3;  // [dim*ld] each (M2: SoftAbs; M3: SoftAbs warm start, when it fits)
   double *q, *p, *qs, *ps, *x0, *x1, *base, *v1, *v2, *v3, *lam, *sa, *gsa, *ev, *Vn;
   double *rc, *rs;  // rotation cos / sin [dim/2 + 1]
   int *top, *bot;   // round-robin index arrays [dim/2 + 1]
 };
 
-// n_mats: per-chain D x D matrices kept in shared memory (2 SoftAbs, 1 dense Cholesky, 0 Woodbury)
+// n_mats: per-chain D x D matrices kept in shared memory (SoftAbs 2, or 3 with warm-started
+// eigensolves; dense Cholesky 1; Sherman-Morrison 0)
 __host__ __device__ inline size_t rm_smem_doubles(int dim, int n_mats) {
   const int ld = dim + 1;
   const int dpad = (dim + 1) & ~1;
@@ -195,6 +196,8 @@ __device__ inline void rm_carve(RmWork& w, double* s, int dim, int n_mats, Blk& 
   if (n_mats >= 1) s += (size_t)dim * ld;
   w.M2 = n_mats >= 2 ? s : nullptr;
   if (n_mats >= 2) s += (size_t)dim * ld;
+  w.M3 = n_mats >= 3 ? s : nullptr;
+  if (n_mats >= 3) s += (size_t)dim * ld;
   double** vecs[] = {&w.q, &w.p, &w.qs, &w.ps, &w.x0, &w.x1, &w.base, &w.v1,
                      &w.v2, &w.v3, &w.lam, &w.sa, &w.gsa, &w.ev};
   for (auto v : vecs) {
@@ -237,14 +240,17 @@ __device__ __forceinline__ void rr_pair(int np, int r, int t, int& p, int& q) {
   q = a < b ? b : a;
 }
 
-__device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U) {
+// `warm`: U already holds an orthogonal basis V and A holds V^T H V (nearly diagonal); the
+// rotations are accumulated onto V, so that on return U holds the eigenvectors of H.
+__device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U, bool warm = false) {
   const int n = w.dim, ld = w.ld;
   const int m = (n + 1) / 2;  // pairs per round (odd n: one index idles each round)
   const int np = 2 * m;       // padded player count; index n (if odd) is a bye
-  for (int idx = k.tid; idx < n * n; idx += k.nthr) {
-    const int i = idx / n, j = idx - i * n;
-    U[i * ld + j] = (i == j) ? 1.0 : 0.0;
-  }
+  if (!warm)
+    for (int idx = k.tid; idx < n * n; idx += k.nthr) {
+      const int i = idx / n, j = idx - i * n;
+      U[i * ld + j] = (i == j) ? 1.0 : 0.0;
+    }
   // scale for the convergence test
   double dmax = 0.0;
   for (int idx = k.tid; idx < n * n; idx += k.nthr) {
@@ -287,36 +293,38 @@ __device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U
         rr_pair(np, round, b, pb, qb);
         const bool va = qa < n, vb = qb < n;  // pair contains the bye index?
         const double ca = w.rc[a], sa = w.rs[a], cb = w.rc[b], sb = w.rs[b];
+        if (sa == 0.0 && sb == 0.0) continue;  // both rotations are the identity
         if (va && vb) {
           const double a00 = A[pa * ld + pb], a01 = A[pa * ld + qb];
           const double a10 = A[qa * ld + pb], a11 = A[qa * ld + qb];
           // rows: (r0, r1) = (ca*x0 - sa*x1, sa*x0 + ca*x1)
-          const double r00 = ca * a00 - sa * a10, r01 = ca * a01 - sa * a11;
-          const double r10 = sa * a00 + ca * a10, r11 = sa * a01 + ca * a11;
+          const double r00 = fma(ca, a00, -(sa * a10)), r01 = fma(ca, a01, -(sa * a11));
+          const double r10 = fma(sa, a00, ca * a10), r11 = fma(sa, a01, ca * a11);
           // cols
-          A[pa * ld + pb] = cb * r00 - sb * r01;
-          A[pa * ld + qb] = sb * r00 + cb * r01;
-          A[qa * ld + pb] = cb * r10 - sb * r11;
-          A[qa * ld + qb] = sb * r10 + cb * r11;
+          A[pa * ld + pb] = fma(cb, r00, -(sb * r01));
+          A[pa * ld + qb] = fma(sb, r00, cb * r01);
+          A[qa * ld + pb] = fma(cb, r10, -(sb * r11));
+          A[qa * ld + qb] = fma(sb, r10, cb * r11);
         } else if (va && !vb) {  // single column pb (< n), rotated rows only
           const double a0 = A[pa * ld + pb], a1 = A[qa * ld + pb];
-          A[pa * ld + pb] = ca * a0 - sa * a1;
-          A[qa * ld + pb] = sa * a0 + ca * a1;
+          A[pa * ld + pb] = fma(ca, a0, -(sa * a1));
+          A[qa * ld + pb] = fma(sa, a0, ca * a1);
         } else if (!va && vb) {  // single row pa (< n), rotated cols only
           const double a0 = A[pa * ld + pb], a1 = A[pa * ld + qb];
-          A[pa * ld + pb] = cb * a0 - sb * a1;
-          A[pa * ld + qb] = sb * a0 + cb * a1;
+          A[pa * ld + pb] = fma(cb, a0, -(sb * a1));
+          A[pa * ld + qb] = fma(sb, a0, cb * a1);
         }
       }
       for (int idx = k.tid; idx < n * m; idx += k.nthr) {
         const int i = idx / m, b = idx - i * m;
         int pb, qb;
         rr_pair(np, round, b, pb, qb);
-        if (qb < n) {
-          const double cb = w.rc[b], sb = w.rs[b];
+        const double sb = w.rs[b];
+        if (qb < n && sb != 0.0) {
+          const double cb = w.rc[b];
           const double u0 = U[i * ld + pb], u1 = U[i * ld + qb];
-          U[i * ld + pb] = cb * u0 - sb * u1;
-          U[i * ld + qb] = sb * u0 + cb * u1;
+          U[i * ld + pb] = fma(cb, u0, -(sb * u1));
+          U[i * ld + qb] = fma(sb, u0, cb * u1);
         }
       }
       __syncthreads();
@@ -326,6 +334,42 @@ __device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U
     if (offmax <= tol) return true;  // the sweep just done squares this again
   }
   return false;
+}
+
+// C = op(X) * Y for n x n shared-memory matrices (stride ld), op = transpose if XT.  4x4 register
+// tiles, one per thread.  C must not alias X or Y.
+template <bool XT>
+__device__ inline void smem_matmul(const Blk& k, int n, int ld, const double* X, const double* Y,
+                                   double* C) {
+  const int tn = (n + 3) / 4;
+  for (int t = k.tid; t < tn * tn; t += k.nthr) {
+    const int i0 = 4 * (t / tn), j0 = 4 * (t % tn);
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int kk = 0; kk < n; ++kk) {
+      double x[4], y[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int i = i0 + a;
+        x[a] = (i < n) ? (XT ? X[kk * ld + i] : X[i * ld + kk]) : 0.0;
+        const int j = j0 + a;
+        y[a] = (j < n) ? Y[kk * ld + j] : 0.0;
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fma(x[a], y[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (i0 + a < n && j0 + b < n) C[(i0 + a) * ld + j0 + b] = acc[a][b];
+  }
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -388,16 +432,41 @@ struct SoftAbsMetric {
   static constexpr int N_MATS = 2;
   const Target& t;
   double alpha;
-  bool have_j;  // divided-difference matrix J built in w.M2 for the current metric?
+  bool have_j;     // divided-difference matrix J built in w.M2 for the current metric?
+  bool have_prev;  // w.M1 holds the eigenvectors of the previous build (warm start available)
 
-  __device__ SoftAbsMetric(const Target& tt, const ModelArgs& m) : t(tt), alpha(m.mp[0]), have_j(false) {}
+  __device__ SoftAbsMetric(const Target& tt, const ModelArgs& m)
+      : t(tt), alpha(m.mp[0]), have_j(false), have_prev(false) {}
+  // forget the previous eigenvectors (start of every integrator step: bounds the loss of
+  // orthogonality from accumulating rotations over many warm-started solves)
+  __device__ void reset() { have_prev = false; }
 
   // returns 0, or MB200_STATUS_LINALG (eigh failure) / -1 (ValueError: non-positive eigenvalues)
   __device__ int build(const Blk& k, RmWork& w, const double* q) {
     have_j = false;
     t.hess(k, q, w.M2, w.ld);
     __syncthreads();
-    if (!jacobi_eigh(k, w, w.M2, w.M1)) return MB200_STATUS_LINALG;
+    // Warm start: successive fixed-point iterates move q only slightly, so the previous
+    // eigenvectors V almost diagonalise the new Hessian: iterate on V^T H V (2 products of
+    // D^3 flop) and accumulate the rotations onto V -- 3-4 sweeps instead of 8-9.
+    const bool warm = have_prev && w.M3 != nullptr;
+    if (warm) {
+      smem_matmul<false>(k, w.dim, w.ld, w.M2, w.M1, w.M3);  // T = H V
+      smem_matmul<true>(k, w.dim, w.ld, w.M1, w.M3, w.M2);   // A = V^T T
+      // symmetrise (the two products round differently above and below the diagonal)
+      for (int idx = k.tid; idx < w.dim * w.dim; idx += k.nthr) {
+        const int i = idx / w.dim, j = idx - i * w.dim;
+        if (i < j) {
+          const double v = 0.5 * (w.M2[i * w.ld + j] + w.M2[j * w.ld + i]);
+          w.M2[i * w.ld + j] = v;
+          w.M2[j * w.ld + i] = v;
+        }
+      }
+      __syncthreads();
+    }
+    have_prev = false;
+    if (!jacobi_eigh(k, w, w.M2, w.M1, warm)) return MB200_STATUS_LINALG;
+    have_prev = true;
     bool bad = false;
     for (int i = k.tid; i < w.dim; i += k.nthr) {
       const double x = w.M2[i * w.ld + i];
@@ -507,6 +576,7 @@ struct Rank1DenseMetric {
   const double* B;
   double c;
   __device__ Rank1DenseMetric(const Target& tt, const ModelArgs& m) : t(tt), B(m.maux), c(m.mp[0]) {}
+  __device__ void reset() {}
 
   __device__ int build(const Blk& k, RmWork& w, const double* q) {
     const int n = w.dim, ld = w.ld;
@@ -567,6 +637,7 @@ struct Rank1WoodburyMetric {
   double c, logdet_b, denom;
   __device__ Rank1WoodburyMetric(const Target& tt, const ModelArgs& m)
       : t(tt), Binv(m.maux + (size_t)tt.dim * tt.dim), c(m.mp[0]), logdet_b(m.mp[1]), denom(1.0) {}
+  __device__ void reset() {}
 
   // out = B^-1 v (B^-1 symmetric: column-wise reads are coalesced across threads)
   __device__ void binv_matvec(const Blk& k, int n, const double* v, double* out) const {
@@ -675,6 +746,7 @@ struct ImplicitLeapfrog {
     int st;
     int it_b = 0, it_crev = 0, it_c = 0, it_brev = 0;
     // ---- _step_a (:493-494)
+    m.reset();
     st = m.build(k, w, w.q);
     if (st != 0) return MB200_STATUS_LINALG;
     kick_h1(dt);
@@ -760,6 +832,7 @@ struct ImplicitLeapfrog {
 
   // h = l(q) + log|M|/2 + p.M^-1 p/2   (systems.py:1375-1390); NaN if the metric cannot be built
   __device__ double hamiltonian() {
+    m.reset();
     if (m.build(k, w, w.q) != 0) return nan("");
     m.inv_matvec(k, w, w.p, w.v1);
     double s = 0.0;
@@ -778,7 +851,8 @@ __global__ void __launch_bounds__(RM_THREADS)
                              double step_size, int n_steps, ModelArgs model, double fp_tol,
                              double fp_div, int fp_max, double rev_tol,
                              double* __restrict__ h_out, int32_t* __restrict__ status,
-                             int32_t* __restrict__ n_done, int32_t* __restrict__ fp_iters) {
+                             int32_t* __restrict__ n_done, int32_t* __restrict__ fp_iters,
+                             int n_mats) {
   extern __shared__ double smem[];
   Blk blk;
   blk.tid = threadIdx.x;
@@ -787,7 +861,7 @@ __global__ void __launch_bounds__(RM_THREADS)
   blk.warp = threadIdx.x >> 5;
   blk.nwarp = blockDim.x >> 5;
   RmWork w;
-  rm_carve(w, smem, dim, MetricT<Target>::N_MATS, blk);
+  rm_carve(w, smem, dim, n_mats, blk);
   const Target target(model, dim);
   MetricT<Target> metric(target, model);
   ImplicitLeapfrog<Target, MetricT<Target>> integ{blk, w, target, metric, fp_tol, fp_div, rev_tol, fp_max};
