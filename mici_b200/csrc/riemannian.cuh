@@ -262,6 +262,10 @@ __device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U
   if (scale == 0.0) return true;
   const double tol = 1e-15 * scale;
 
+  // thread grid for the update phases: tx indexes column pairs, ty strides over row pairs / rows
+  // (no integer divisions in the inner loops; the round's pair table is written once to w.top /
+  // w.bot by the parameter phase)
+  const int tx = k.tid & 31, ty = k.tid >> 5, ny = k.nthr >> 5;
   for (int sweep = 0; sweep < RM_MAX_SWEEPS; ++sweep) {
     double off = 0.0;
     for (int round = 0; round < np - 1; ++round) {
@@ -283,48 +287,48 @@ __device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U
         }
         w.rc[t] = c;
         w.rs[t] = s;
+        w.top[t] = p;
+        w.bot[t] = q;
       }
       __syncthreads();
       // --- A <- R^T A R on 2x2 blocks (pair a rows, pair b cols), U <- U R
-      for (int idx = k.tid; idx < m * m; idx += k.nthr) {
-        const int a = idx / m, b = idx - a * m;
-        int pa, qa, pb, qb;
-        rr_pair(np, round, a, pa, qa);
-        rr_pair(np, round, b, pb, qb);
-        const bool va = qa < n, vb = qb < n;  // pair contains the bye index?
-        const double ca = w.rc[a], sa = w.rs[a], cb = w.rc[b], sb = w.rs[b];
-        if (sa == 0.0 && sb == 0.0) continue;  // both rotations are the identity
-        if (va && vb) {
-          const double a00 = A[pa * ld + pb], a01 = A[pa * ld + qb];
-          const double a10 = A[qa * ld + pb], a11 = A[qa * ld + qb];
-          // rows: (r0, r1) = (ca*x0 - sa*x1, sa*x0 + ca*x1)
-          const double r00 = fma(ca, a00, -(sa * a10)), r01 = fma(ca, a01, -(sa * a11));
-          const double r10 = fma(sa, a00, ca * a10), r11 = fma(sa, a01, ca * a11);
-          // cols
-          A[pa * ld + pb] = fma(cb, r00, -(sb * r01));
-          A[pa * ld + qb] = fma(sb, r00, cb * r01);
-          A[qa * ld + pb] = fma(cb, r10, -(sb * r11));
-          A[qa * ld + qb] = fma(sb, r10, cb * r11);
-        } else if (va && !vb) {  // single column pb (< n), rotated rows only
-          const double a0 = A[pa * ld + pb], a1 = A[qa * ld + pb];
-          A[pa * ld + pb] = fma(ca, a0, -(sa * a1));
-          A[qa * ld + pb] = fma(sa, a0, ca * a1);
-        } else if (!va && vb) {  // single row pa (< n), rotated cols only
-          const double a0 = A[pa * ld + pb], a1 = A[pa * ld + qb];
-          A[pa * ld + pb] = fma(cb, a0, -(sb * a1));
-          A[pa * ld + qb] = fma(sb, a0, cb * a1);
+      for (int b = tx; b < m; b += 32) {
+        const int pb = w.top[b], qb = w.bot[b];
+        const double cb = w.rc[b], sb = w.rs[b];
+        const bool vb = qb < n;
+        for (int a = ty; a < m; a += ny) {
+          const double sa = w.rs[a];
+          if (sa == 0.0 && sb == 0.0) continue;  // both rotations are the identity
+          const int pa = w.top[a], qa = w.bot[a];
+          const double ca = w.rc[a];
+          const bool va = qa < n;
+          if (va && vb) {
+            const double a00 = A[pa * ld + pb], a01 = A[pa * ld + qb];
+            const double a10 = A[qa * ld + pb], a11 = A[qa * ld + qb];
+            // rows: (r0, r1) = (ca*x0 - sa*x1, sa*x0 + ca*x1)
+            const double r00 = fma(ca, a00, -(sa * a10)), r01 = fma(ca, a01, -(sa * a11));
+            const double r10 = fma(sa, a00, ca * a10), r11 = fma(sa, a01, ca * a11);
+            // cols
+            A[pa * ld + pb] = fma(cb, r00, -(sb * r01));
+            A[pa * ld + qb] = fma(sb, r00, cb * r01);
+            A[qa * ld + pb] = fma(cb, r10, -(sb * r11));
+            A[qa * ld + qb] = fma(sb, r10, cb * r11);
+          } else if (va && !vb) {  // single column pb (< n), rotated rows only
+            const double a0 = A[pa * ld + pb], a1 = A[qa * ld + pb];
+            A[pa * ld + pb] = fma(ca, a0, -(sa * a1));
+            A[qa * ld + pb] = fma(sa, a0, ca * a1);
+          } else if (!va && vb) {  // single row pa (< n), rotated cols only
+            const double a0 = A[pa * ld + pb], a1 = A[pa * ld + qb];
+            A[pa * ld + pb] = fma(cb, a0, -(sb * a1));
+            A[pa * ld + qb] = fma(sb, a0, cb * a1);
+          }
         }
-      }
-      for (int idx = k.tid; idx < n * m; idx += k.nthr) {
-        const int i = idx / m, b = idx - i * m;
-        int pb, qb;
-        rr_pair(np, round, b, pb, qb);
-        const double sb = w.rs[b];
-        if (qb < n && sb != 0.0) {
-          const double cb = w.rc[b];
-          const double u0 = U[i * ld + pb], u1 = U[i * ld + qb];
-          U[i * ld + pb] = fma(cb, u0, -(sb * u1));
-          U[i * ld + qb] = fma(sb, u0, cb * u1);
+        if (vb && sb != 0.0) {
+          for (int i = ty; i < n; i += ny) {
+            const double u0 = U[i * ld + pb], u1 = U[i * ld + qb];
+            U[i * ld + pb] = fma(cb, u0, -(sb * u1));
+            U[i * ld + qb] = fma(sb, u0, cb * u1);
+          }
         }
       }
       __syncthreads();
