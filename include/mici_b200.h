@@ -162,6 +162,21 @@ int mb200_hamiltonian_riemannian(const double* pos, const double* mom, int64_t n
                                  int32_t* status, void* workspace, int64_t workspace_bytes,
                                  void* stream);
 
+/*
+ * "Next" row N1: Metropolis accept / reject of a static-HMC transition for all chains.
+ * Replaces: MetropolisIntegrationTransition._sample_n_step, transitions.py:275-315 (the part
+ * after the trajectory): accept_prob = exp(min(0, h_init - h_prop)) (0 if NaN, 0 if the
+ * trajectory failed at its first step), accepted iff status == 0 and uniforms < accept_prob;
+ * pos/mom are overwritten with the proposal where accepted; dir is negated where rejected
+ * (:299, :314).  accept_prob / accept_stat / accepted may be NULL.
+ */
+int mb200_metropolis_select(double* pos, double* mom, const double* pos_prop,
+                            const double* mom_prop, const double* h_init, const double* h_prop,
+                            const int32_t* status, const int32_t* n_done, int32_t* dir,
+                            const double* uniforms, int64_t n_chains, int32_t dim,
+                            double* accept_prob, double* accept_stat, int32_t* accepted,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

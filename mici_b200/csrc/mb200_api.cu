@@ -18,6 +18,7 @@
 #ifndef MB200_NO_RIEMANNIAN
 #include "riemannian.cuh"
 #endif
+#include "transitions.cuh"
 
 namespace mb200 {
 
@@ -436,5 +437,24 @@ int mb200_hamiltonian_riemannian(const double* pos, const double* mom, int64_t n
                            status, nullptr, nullptr, (cudaStream_t)stream);
 }
 #endif
+
+int mb200_metropolis_select(double* pos, double* mom, const double* pos_prop,
+                            const double* mom_prop, const double* h_init, const double* h_prop,
+                            const int32_t* status, const int32_t* n_done, int32_t* dir,
+                            const double* uniforms, int64_t n_chains, int32_t dim,
+                            double* accept_prob, double* accept_stat, int32_t* accepted,
+                            void* stream) {
+  if (!pos || !mom || !pos_prop || !mom_prop || !h_init || !h_prop || !uniforms)
+    return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
+  if (n_chains < 0 || dim < 1) return fail(MB200_ERR_INVALID_ARG, "bad sizes");
+  if (n_chains == 0) return 0;
+  int64_t blocks = (n_chains * dim + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  metropolis_select_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      pos, mom, pos_prop, mom_prop, h_init, h_prop, status, n_done, dir, uniforms, n_chains, dim,
+      accept_prob, accept_stat, accepted);
+  return check_launch("metropolis_select_kernel");
+}
 
 }  // extern "C"

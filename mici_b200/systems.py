@@ -268,14 +268,31 @@ class EuclideanMetricSystem(TractableFlowSystem):
         state.pos = state.pos + _col(dt) * self.dh2_dmom(state)
 
     def sample_momentum(self, state, rng):
-        """``metric.sqrt @ N(0, I)`` (systems.py:365-366) with host ``numpy`` Generator draws
-        (so that a seeded reference run sees the same variates), product on the device."""
-        z = torch.as_tensor(rng.standard_normal(tuple(state.pos.shape)), device=state.pos.device)
+        """``metric.sqrt @ N(0, I)`` (systems.py:365-366).  The variates come from ``rng`` (a
+        NumPy generator, a sequence of per-chain NumPy generators, or a device
+        ``torch.Generator``: see ``mici_b200.transitions``); the product ``L z`` runs on the
+        device through ``mb200_euclidean_eval`` with the transposed factor in the metric slot."""
+        from .transitions import _normals  # noqa: PLC0415
+
+        pos = state.pos if state.pos.ndim == 2 else state.pos[None]
+        z = _normals(rng, tuple(pos.shape), pos.device).contiguous()
         m = self._metric
-        if m.kind == METRIC_IDENTITY:
-            return z
-        s = m.sqrt_device(z.device)
-        return z * s if m.kind == METRIC_DIAGONAL else z @ s.T
+        if m.kind != METRIC_IDENTITY:
+            n, dim = z.shape
+            out = torch.empty_like(z)
+            key = ("sqrt_t", str(z.device))
+            if key not in m._dev:
+                fac = m.sqrt if m.kind == METRIC_DIAGONAL else np.ascontiguousarray(m.sqrt.T)
+                m._dev[key] = torch.as_tensor(fac, device=z.device).contiguous()
+            model = self._model(z.device)
+            rc = _lib.load().mb200_euclidean_eval(
+                _lib.ptr(z), _lib.ptr(z), n, dim, m.kind, _lib.ptr(m._dev[key]),
+                ctypes.byref(model), None, None, _lib.ptr(out), None,
+                _lib.current_stream_ptr(z.device),
+            )
+            _lib.check(rc, "mb200_euclidean_eval")
+            z = out
+        return z if state.pos.ndim == 2 else z[0]
 
 
 def _col(dt):

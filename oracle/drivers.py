@@ -219,3 +219,59 @@ def reference_run(problem, n_steps, dirs=None, chains=None, **overrides):
         "h_init": h0,
         "call_counts": call_counts,
     }
+
+
+# ------------------------------------------------------------------ static HMC (row N1)
+
+
+def _sqrt_matvec(problem):
+    metric = mo.coerce_metric(problem.metric)
+    return metric.sqrt_matvec
+
+
+def oracle_hmc(problem, n_iter, n_step, seed, chains=None):
+    """``n_iter`` static-HMC iterations per chain through the oracle; per-chain generators
+    ``default_rng([seed, chain])``.  Euclidean systems only."""
+    step, h_fn, _ = oracle_step_fn(problem)
+    sl = slice(None) if chains is None else chains
+    q0, p0 = problem.pos[sl], problem.mom[sl]
+    n = q0.shape[0]
+    sqrt_mv = _sqrt_matvec(problem)
+    pos = np.empty((n_iter, n, q0.shape[1]))
+    stats = {k: np.empty((n_iter, n)) for k in ("n_step", "metrop_accept_prob", "accept_stat", "accepted")}
+    dirs = np.ones(n, dtype=np.int32)
+    for i in range(n):
+        rng = np.random.default_rng([seed, i])
+        q, p, d = q0[i].copy(), p0[i].copy(), 1
+        for it in range(n_iter):
+            q, p, d, st = mo.static_hmc_transition(q, p, d, rng, step, h_fn, sqrt_mv, n_step)
+            pos[it, i] = q
+            for k in stats:
+                stats[k][it, i] = st[k]
+        dirs[i] = d
+    return {"pos": pos, "dir": dirs, **stats}
+
+
+def reference_hmc(problem, n_iter, n_step, seed, chains=None):
+    """The same through the unmodified reference transitions (transitions.py:129-142, 256-352)."""
+    mici = import_reference()
+    system, integrator = build_reference(problem)
+    sl = slice(None) if chains is None else chains
+    q0, p0 = problem.pos[sl], problem.mom[sl]
+    n = q0.shape[0]
+    mom_tr = mici.transitions.IndependentMomentumTransition(system)
+    int_tr = mici.transitions.MetropolisStaticIntegrationTransition(system, integrator, n_step)
+    pos = np.empty((n_iter, n, q0.shape[1]))
+    stats = {k: np.empty((n_iter, n)) for k in ("n_step", "metrop_accept_prob", "accept_stat")}
+    dirs = np.ones(n, dtype=np.int32)
+    for i in range(n):
+        rng = np.random.default_rng([seed, i])
+        state = mici.states.ChainState(pos=q0[i].copy(), mom=p0[i].copy(), dir=1)
+        for it in range(n_iter):
+            state, _ = mom_tr.sample(state, rng)
+            state, st = int_tr.sample(state, rng)
+            pos[it, i] = state.pos
+            for k in stats:
+                stats[k][it, i] = st[k]
+        dirs[i] = state.dir
+    return {"pos": pos, "dir": dirs, **stats}

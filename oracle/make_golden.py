@@ -98,8 +98,34 @@ def solver_known_answers():
     np.savez(os.path.join(GOLDEN_DIR, "solver_known_answers.npz"), **out)
 
 
+HMC_CASES = {
+    # name -> (config, kwargs, n_iter, n_step, seed)
+    "hmc_c1_funnel_d16": ("C1", {"n_chains": 12, "dim": 16}, 6, 5, 11),
+    "hmc_c0_std_gaussian": ("C0", {"n_chains": 6, "dim": 10}, 8, 7, 12),
+}
+
+
+def hmc_cases():
+    """Static-HMC transitions (row N1) through the reference's own transition classes."""
+    for name, (cfg, kwargs, n_iter, n_step, seed) in HMC_CASES.items():
+        problem = pb.make_problem(cfg, **kwargs)
+        if cfg == "C1":
+            problem.step_size = 0.35
+        r = dr.reference_hmc(problem, n_iter, n_step, seed)
+        o = dr.oracle_hmc(problem, n_iter, n_step, seed)
+        np.testing.assert_allclose(o["pos"], r["pos"], rtol=1e-12, atol=1e-14, err_msg=name)
+        np.testing.assert_array_equal(o["dir"], r["dir"])
+        np.testing.assert_allclose(o["metrop_accept_prob"], r["metrop_accept_prob"], rtol=1e-10)
+        acc = float(o["accepted"].mean())
+        print(f"{name:32s} iters={n_iter} n_step={n_step} accept rate={acc:.2f}")
+        np.savez(os.path.join(GOLDEN_DIR, name + ".npz"), input_checksum=input_checksum(problem),
+                 step_size=np.array(problem.step_size), accepted=o["accepted"],
+                 **{k: r[k] for k in ("pos", "dir", "n_step", "metrop_accept_prob", "accept_stat")})
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    hmc_cases()
     for name, (cfg, kwargs, steps, ov) in CASES.items():
         generate_case(name, cfg, kwargs, steps, ov)
     for name, (cfg, kwargs, eps, steps, ov) in FAILURE_CASES.items():

@@ -587,3 +587,46 @@ def run_batch(step_fn, q, p, dirs, n_steps):
             n_done[i] += 1
         q[i], p[i] = qi, pi
     return q, p, status, n_done
+
+
+# --------------------------------------------------------------------------------------
+# "Next" row N1: static-HMC transition (momentum refresh + Metropolis accept)
+# --------------------------------------------------------------------------------------
+
+
+def static_hmc_transition(q, p, d, rng, step_fn, h_fn, sqrt_matvec, n_step):
+    """IndependentMomentumTransition.sample (transitions.py:136-142) followed by
+    MetropolisIntegrationTransition._sample_n_step (transitions.py:275-315) for one chain.
+    ``step_fn(q, p, dir) -> (q, p)`` raises OracleIntegratorError on failure.
+    Returns ``(q, p, dir, stats)``."""
+    p = sqrt_matvec(rng.standard_normal(q.shape))  # systems.py:365-366
+    h_init = h_fn(q, p)
+    qp, pp, dp = q, p, d
+    error = None
+    n_done = 0
+    try:
+        for _ in range(n_step):
+            qp, pp = step_fn(qp, pp, dp)
+            n_done += 1
+    except OracleIntegratorError as e:
+        error = e.status
+    else:
+        dp = -dp
+    if n_done > 0 or error is None:
+        h_diff = h_init - h_fn(qp, pp)
+        accept_prob = 0.0 if np.isnan(h_diff) else np.exp(min(0, h_diff))
+    else:
+        accept_prob = 0.0
+    stats = {
+        "n_step": n_done,
+        "metrop_accept_prob": accept_prob,
+        "accept_stat": accept_prob if error is None else 0.0,
+        "convergence_error": error == STATUS_CONVERGENCE,
+        "non_reversible_step": error == STATUS_NON_REVERSIBLE,
+    }
+    accepted = error is None and rng.uniform() < accept_prob
+    if accepted:
+        q, p, d = qp, pp, dp
+    d = -d
+    stats["accepted"] = bool(accepted)
+    return q, p, d, stats

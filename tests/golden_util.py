@@ -44,3 +44,14 @@ def assert_matches_golden(out, g, n_steps, rtol=RTOL, atol=ATOL, label=""):
         np.testing.assert_allclose(
             np.asarray(out["h"])[ok], g[f"h_{n_steps}"][ok], rtol=rtol, atol=1e-9, err_msg=f"{label} h"
         )
+
+
+def load_hmc_case(name):
+    from oracle.make_golden import HMC_CASES
+
+    cfg, kwargs, n_iter, n_step, seed = HMC_CASES[name]
+    problem = pb.make_problem(cfg, **kwargs)
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    problem.step_size = float(g["step_size"])
+    np.testing.assert_allclose(input_checksum(problem), g["input_checksum"], rtol=1e-13)
+    return problem, n_iter, n_step, seed, g

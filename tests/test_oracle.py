@@ -84,3 +84,17 @@ def test_oracle_matches_live_reference(name):
     np.testing.assert_array_equal(o["status"], r["status"])
     np.testing.assert_allclose(o["pos"], r["pos"], rtol=1e-13, atol=1e-15)
     np.testing.assert_allclose(o["mom"], r["mom"], rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("name", ["hmc_c1_funnel_d16", "hmc_c0_std_gaussian"])
+def test_oracle_hmc_transition_matches_reference_fixture(name):
+    """Row N1: momentum refresh + Metropolis transition (transitions.py:129-142, 256-352)."""
+    from golden_util import load_hmc_case
+
+    problem, n_iter, n_step, seed, g = load_hmc_case(name)
+    o = dr.oracle_hmc(problem, n_iter, n_step, seed)
+    np.testing.assert_allclose(o["pos"], g["pos"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_array_equal(o["dir"], g["dir"])
+    np.testing.assert_array_equal(o["n_step"], g["n_step"])
+    np.testing.assert_allclose(o["metrop_accept_prob"], g["metrop_accept_prob"], rtol=1e-11)
+    assert 0.0 < o["accepted"].mean() <= 1.0

@@ -244,3 +244,44 @@ def test_host_buffer_path_equals_device_path():
     torch.cuda.synchronize()
     assert torch.equal(pos, ref.pos.cpu()) and torch.equal(mom, ref.mom.cpu())
     assert torch.equal(status, ref.status.cpu())
+
+
+@pytest.mark.parametrize("name", ["hmc_c1_funnel_d16", "hmc_c0_std_gaussian"])
+def test_batched_hmc_transition_matches_reference_fixture(name):
+    """Row N1 on the device: whole static-HMC iterations (momentum refresh, fused trajectory,
+    energy, Metropolis select, direction flips) against the reference's own transition classes,
+    every chain consuming the variates of its own seeded NumPy stream."""
+    from golden_util import load_hmc_case
+    from mici_b200 import transitions
+
+    problem, n_iter, n_step, seed, g = load_hmc_case(name)
+    integ = engine.build_integrator(problem)
+    state = engine.build_state(problem, DEV)
+    rngs = [np.random.default_rng([seed, i]) for i in range(problem.n_chains)]
+    final, stats, trace = transitions.sample_hmc(integ.system, integ, state, rngs, n_iter, n_step,
+                                                 trace_pos=True)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(stats["accepted"].cpu().numpy(), g["accepted"].astype(bool))
+    np.testing.assert_allclose(trace.cpu().numpy(), g["pos"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_array_equal(final.dir.cpu().numpy(), g["dir"])
+    np.testing.assert_array_equal(stats["n_step"].cpu().numpy(), g["n_step"])
+    np.testing.assert_allclose(stats["metrop_accept_prob"].cpu().numpy(), g["metrop_accept_prob"],
+                               rtol=1e-8, atol=1e-12)
+
+
+def test_batched_hmc_full_size_c1_device_rng():
+    """8192 chains x D=128, variates generated on the device: acceptance statistics are sane
+    and every state stays finite."""
+    from mici_b200 import transitions
+
+    problem = problems.make_problem("C1")
+    integ = engine.build_integrator(problem)
+    state = engine.build_state(problem, DEV)
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(1234)
+    final, stats, _ = transitions.sample_hmc(integ.system, integ, state, gen, 4, 20)
+    torch.cuda.synchronize()
+    assert torch.isfinite(final.pos).all() and torch.isfinite(final.mom).all()
+    acc = stats["accept_stat"].mean().item()
+    assert 0.5 < acc <= 1.0
+    assert (stats["n_step"] == 20).all()
