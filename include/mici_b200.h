@@ -177,6 +177,17 @@ int mb200_metropolis_select(double* pos, double* mom, const double* pos_prop,
                             double* accept_prob, double* accept_stat, int32_t* accepted,
                             void* stream);
 
+/*
+ * Diagnostic: the fused direct fixed-point solver (K4; solve_fixed_point_direct,
+ * solvers.py:47-94) on the reference's own known-answer problems
+ * (reference tests/test_solvers.py:25-47): func_id 0 babylonian (y/x + x)/2, 1 ratio
+ * (x+y)/(x+1), 2 cosine, 3 doubling 2x, 4 quadratic 1 + x^2; x0, y, x_out are [n*dim].
+ */
+int mb200_selftest_fixed_point_direct(int32_t func_id, const double* x0, const double* y,
+                                      int64_t n, int32_t dim, double convergence_tol,
+                                      double divergence_tol, int32_t max_iters, double* x_out,
+                                      int32_t* iters_out, int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,10 @@ SIGNATURES = {
         + [_P, _P, _P, _P, _P, _I64, _P],
     ),
     "mb200_implicit_workspace_bytes": (_I64, [_I64, _I32, _MP]),
+    "mb200_selftest_fixed_point_direct": (
+        ctypes.c_int,
+        [_I32, _P, _P, _I64, _I32, _F64, _F64, _I32, _P, _P, _P, _P],
+    ),
     "mb200_metropolis_select": (
         ctypes.c_int,
         [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P],

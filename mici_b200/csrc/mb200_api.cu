@@ -457,4 +457,21 @@ int mb200_metropolis_select(double* pos, double* mom, const double* pos_prop,
   return check_launch("metropolis_select_kernel");
 }
 
+#ifndef MB200_NO_RIEMANNIAN
+int mb200_selftest_fixed_point_direct(int32_t func_id, const double* x0, const double* y,
+                                      int64_t n, int32_t dim, double convergence_tol,
+                                      double divergence_tol, int32_t max_iters, double* x_out,
+                                      int32_t* iters_out, int32_t* status, void* stream) {
+  if (!x0 || !y || !x_out || !iters_out || !status)
+    return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
+  if (n < 0 || dim < 1 || func_id < 0 || func_id > 4) return fail(MB200_ERR_INVALID_ARG, "bad arguments");
+  if (n == 0) return 0;
+  const size_t smem = (size_t)(2 * dim + 40) * sizeof(double);
+  int64_t blocks = n < 4096 ? n : 4096;
+  fixed_point_selftest_kernel<<<(unsigned)blocks, 64, smem, (cudaStream_t)stream>>>(
+      func_id, x0, y, n, dim, convergence_tol, divergence_tol, max_iters, x_out, iters_out, status);
+  return check_launch("fixed_point_selftest_kernel");
+}
+#endif
+
 }  // extern "C"

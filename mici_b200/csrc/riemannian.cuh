@@ -699,6 +699,82 @@ struct Rank1WoodburyMetric {
 };
 
 // ---------------------------------------------------------------------------------------------
+// K4: solve_fixed_point_direct (solvers.py:47-94) for one chain, block-cooperative.
+// `func(x_in, x_out)` returns 0 or a failure code (any failure inside the solver is a
+// ConvergenceError, :89-92).  The same iterate sequence and the same stopping rule as the
+// reference: x = func(x0); error = max|x - x0| (NaN-propagating); diverged if error > div_tol or
+// NaN; converged -- returning the NEW iterate -- if error < tol; else x0 = x.  Iterates alternate
+// between the buffers xa (holding x0 on entry) and xb; on success *result points at the solution.
+// ---------------------------------------------------------------------------------------------
+template <class F>
+__device__ inline int fixed_point_direct(const Blk& k, int dim, double* xa, double* xb, F func,
+                                         double tol, double div_tol, int max_iters,
+                                         double** result, int& iters) {
+  double* xin = xa;
+  double* xout = xb;
+  for (int i = 0; i < max_iters; ++i) {
+    if (func(xin, xout) != 0) return MB200_STATUS_CONVERGENCE;
+    double e = 0.0;
+    for (int j = k.tid; j < dim; j += k.nthr) e = nanmax(e, fabs(xout[j] - xin[j]));
+    const double err = block_nanmax(k, e);
+    ++iters;
+    if (err > div_tol || err != err) return MB200_STATUS_CONVERGENCE;
+    if (err < tol) {
+      *result = xout;
+      return 0;
+    }
+    double* tmp = xin;
+    xin = xout;
+    xout = tmp;
+  }
+  return MB200_STATUS_CONVERGENCE;
+}
+
+// Diagnostic kernel: K4 on the reference's own known-answer problems
+// (reference tests/test_solvers.py:25-47): 0 babylonian (y/x + x)/2, 1 ratio (x+y)/(x+1),
+// 2 cosine, 3 doubling 2x, 4 quadratic 1 + x^2.  One CTA per problem instance.
+__global__ void __launch_bounds__(64)
+    fixed_point_selftest_kernel(int func_id, const double* __restrict__ x0,
+                                const double* __restrict__ y, int64_t n, int dim, double tol,
+                                double div_tol, int max_iters, double* __restrict__ x_out,
+                                int32_t* __restrict__ iters_out, int32_t* __restrict__ status) {
+  extern __shared__ double smem[];
+  Blk k;
+  k.tid = threadIdx.x, k.nthr = blockDim.x, k.lane = threadIdx.x & 31;
+  k.warp = threadIdx.x >> 5, k.nwarp = blockDim.x >> 5;
+  double* xa = smem;
+  double* xb = smem + dim;
+  k.red = smem + 2 * dim;
+  for (int64_t ch = blockIdx.x; ch < n; ch += gridDim.x) {
+    __syncthreads();
+    for (int j = k.tid; j < dim; j += k.nthr) xa[j] = x0[ch * dim + j];
+    __syncthreads();
+    auto func = [&](const double* xin, double* xout) {
+      for (int j = k.tid; j < dim; j += k.nthr) {
+        const double x = xin[j], yy = y[ch * dim + j];
+        double r;
+        if (func_id == 0) r = (yy / x + x) / 2.0;
+        else if (func_id == 1) r = (x + yy) / (x + 1.0);
+        else if (func_id == 2) r = cos(x);
+        else if (func_id == 3) r = 2.0 * x;
+        else r = 1.0 + x * x;
+        xout[j] = r;
+      }
+      __syncthreads();
+      return 0;
+    };
+    double* sol = xa;
+    int iters = 0;
+    const int st = fixed_point_direct(k, dim, xa, xb, func, tol, div_tol, max_iters, &sol, iters);
+    for (int j = k.tid; j < dim; j += k.nthr) x_out[ch * dim + j] = sol[j];
+    if (k.tid == 0) {
+      iters_out[ch] = iters;
+      status[ch] = st;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K4 + K5: the integrator
 // ---------------------------------------------------------------------------------------------
 template <class Target, class Metric>
@@ -710,29 +786,10 @@ struct ImplicitLeapfrog {
   double fp_tol, fp_div, rev_tol;
   int fp_max;
 
-  // K4: solve_fixed_point_direct (solvers.py:47-94).  `func(x_in, x_out)` returns 0 or a failure
-  // code (any failure inside the solver is a ConvergenceError, :89-92).  Iterates alternate
-  // between w.x0 and w.x1; on success the solution is in *result.
+  // K4 on this chain's buffers (see fixed_point_direct below)
   template <class F>
   __device__ int fixed_point(F func, double** result, int& iters) {
-    double* xin = w.x0;
-    double* xout = w.x1;
-    for (int i = 0; i < fp_max; ++i) {
-      if (func(xin, xout) != 0) return MB200_STATUS_CONVERGENCE;
-      double e = 0.0;
-      for (int j = k.tid; j < w.dim; j += k.nthr) e = nanmax(e, fabs(xout[j] - xin[j]));
-      const double err = block_nanmax(k, e);
-      ++iters;
-      if (err > fp_div || err != err) return MB200_STATUS_CONVERGENCE;
-      if (err < fp_tol) {
-        *result = xout;
-        return 0;
-      }
-      double* tmp = xin;
-      xin = xout;
-      xout = tmp;
-    }
-    return MB200_STATUS_CONVERGENCE;
+    return fixed_point_direct(k, w.dim, w.x0, w.x1, func, fp_tol, fp_div, fp_max, result, iters);
   }
 
   // dh1_dpos = grad l + vjp(grad_log_abs_det) / 2   (systems.py:1381-1385); metric of q current

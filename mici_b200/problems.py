@@ -174,12 +174,53 @@ def c4_dense_riemannian(n_chains=8192, dim=512, seed=BASE_SEED + 4, coeff=0.1):
     )
 
 
+def sphere_constrained(n_chains=64, dim=10, seed=BASE_SEED + 5, metric_kind="dense"):
+    """Extra parity case for K6 beyond C3: unit sphere in R^dim, tilted Gaussian density,
+    optional diagonal / dense metric (exercises the general-dimension constrained path)."""
+    rng = np.random.default_rng(seed)
+    pos = rng.standard_normal((n_chains, dim))
+    pos /= np.linalg.norm(pos, axis=1, keepdims=True)
+    mom = rng.standard_normal((n_chains, dim))
+    if metric_kind == "dense":
+        metric = dense_spd_metric(rng, dim)
+    elif metric_kind == "diagonal":
+        metric = rng.uniform(0.5, 2.0, dim)
+    else:
+        metric = None
+    # project the momentum onto the cotangent space: p -= J^T (J M^-1 J^T)^-1 J M^-1 p, J = 2 q^T
+    if metric is None:
+        minv_j = pos
+        minv_p = mom
+    elif metric.ndim == 1:
+        minv_j = pos / metric
+        minv_p = mom / metric
+    else:
+        minv = np.linalg.inv(metric)
+        minv_j = pos @ minv
+        minv_p = mom @ minv
+    lam = (pos * minv_p).sum(-1) / (pos * minv_j).sum(-1)
+    mom = mom - lam[:, None] * pos
+    return Problem(
+        name="S1",
+        integrator="constrained_leapfrog",
+        system="constrained_euclidean",
+        target="sphere",
+        target_params={"dim": dim},
+        step_size=0.2,
+        pos=pos,
+        mom=mom,
+        metric=metric,
+        integrator_kwargs={"n_inner_step": 1},
+    )
+
+
 CONFIGS = {
     "C0": c0_std_gaussian,
     "C1": c1_funnel,
     "C2": c2_softabs_banana,
     "C3": c3_torus,
     "C4": c4_dense_riemannian,
+    "S1": sphere_constrained,
 }
 
 

@@ -35,6 +35,9 @@ CASES = {
     "c2_softabs_banana_d8": ("C2", {"n_chains": 32, "dim": 8}, (1, 5, 20), {}),
     "c3_torus": ("C3", {"n_chains": 64}, (1, 5, 20), {}),
     "c3_torus_inner3": ("C3", {"n_chains": 32}, (1, 5), {"n_inner_step": 3}),
+    "s1_sphere_dense_d10": ("S1", {"n_chains": 32, "dim": 10}, (1, 5, 20), {}),
+    "s1_sphere_diag_d70_inner2": ("S1", {"n_chains": 8, "dim": 70, "metric_kind": "diagonal"}, (1, 5), {"n_inner_step": 2}),
+    "s1_sphere_identity_d5": ("S1", {"n_chains": 16, "dim": 5, "metric_kind": "identity"}, (1, 20), {}),
     "c4_dense_riemannian_d64": ("C4", {"n_chains": 8, "dim": 64}, (1, 5), {}),
     "c4_dense_riemannian_d512": ("C4", {"n_chains": 2, "dim": 512}, (1,), {}),
 }
