@@ -64,3 +64,40 @@ def test_gather_at_write_out_gloo_world2(tmp_path, n_total):
     np.testing.assert_array_equal(g["mom"], prob.mom + 1.0)
     lo1, _ = parallel.shard_bounds(n_total, 1, world)
     assert (g["status"][:lo1] == 0).all() and (g["status"][lo1:] == 1).all()
+
+
+def _trace_worker(rank, world, port, n_total, n_iter, out_dir):
+    from mici_b200 import traces
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = parallel.shard_bounds(n_total, rank, world)
+    buf = traces.TraceBuffer(n_iter, hi - lo, (3,), device="cpu")
+    stat = traces.TraceBuffer(n_iter, hi - lo, (), device="cpu")
+    for it in range(n_iter):
+        chains = torch.arange(lo, hi, dtype=torch.float64)
+        buf.append(chains[:, None] * 100 + it + torch.arange(3, dtype=torch.float64)[None] / 10)
+        stat.append(chains + it / 100)
+    full = traces.gather_traces({"pos": buf.data, "accept_stat": stat.data}, n_total, dst=0)
+    if rank == 0:
+        traces.write_chain_traces(out_dir, "trace", full)
+    else:
+        assert full is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_trace_write_out_gloo_world2_reference_file_layout(tmp_path):
+    """Row N2: one gather at write-out, then one `{prefix}_{chain}_{key}.npy` per chain and key
+    (reference samplers.py:104-138), readable as a memmap."""
+    n_total, n_iter = 7, 5
+    mp.spawn(_trace_worker, args=(2, _free_port(), n_total, n_iter, str(tmp_path)), nprocs=2,
+             join=True)
+    for c in range(n_total):
+        pos = np.load(tmp_path / f"trace_{c}_pos.npy", mmap_mode="r")
+        acc = np.load(tmp_path / f"trace_{c}_accept_stat.npy", mmap_mode="r")
+        assert pos.shape == (n_iter, 3) and acc.shape == (n_iter,)
+        for it in range(n_iter):
+            np.testing.assert_allclose(pos[it], c * 100 + it + np.arange(3) / 10)
+            np.testing.assert_allclose(acc[it], c + it / 100)
