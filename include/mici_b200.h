@@ -188,6 +188,22 @@ int mb200_selftest_fixed_point_direct(int32_t func_id, const double* x0, const d
                                       double divergence_tol, int32_t max_iters, double* x_out,
                                       int32_t* iters_out, int32_t* status, void* stream);
 
+/*
+ * "Next" row N4: symmetric composition (splitting) integrators on a Euclidean-metric system --
+ * SymmetricCompositionIntegrator and the BCSS 2/3/4-stage schemes (integrators.py:176-378):
+ * each step applies n_flows (odd) alternating flows a, b, a, ..., a over coefficients[i] * dt,
+ * a = h1_flow (kick) if initial_h1_flow_step else h2_flow (drift).  `coefficients` is a HOST
+ * array of the full symmetric sequence (integrators.py:268-277).  Same other arguments and
+ * conventions as mb200_leapfrog_euclidean (which is the schedule {0.5, 1, 0.5}).
+ */
+int mb200_composition_euclidean(const double* pos_in, const double* mom_in, double* pos_out,
+                                double* mom_out, const int32_t* dir, int64_t n_chains,
+                                int32_t dim, double step_size, int32_t n_steps, int32_t n_flows,
+                                const double* coefficients, int32_t initial_h1_flow_step,
+                                int32_t metric_kind, const double* metric_inv,
+                                const mb200_model* model, double* h_out, int32_t* status,
+                                int32_t* n_done, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

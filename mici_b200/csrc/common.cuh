@@ -43,4 +43,14 @@ struct ModelArgs {
   const double* maux;
 };
 
+// Splitting schedule of a symmetric composition integrator (integrators.py:176-378): flow i is
+// h1_flow (momentum kick) or h2_flow (position drift) over coef[i] * dt.  Leapfrog is
+// {0.5 kick, 1 drift, 0.5 kick}.
+constexpr int MB200_MAX_FLOWS = 16;
+struct FlowSchedule {
+  int n;
+  unsigned drift_mask;  // bit i set: flow i is an h2_flow (drift), else an h1_flow (kick)
+  double coef[MB200_MAX_FLOWS];
+};
+
 }  // namespace mb200

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128)
     leapfrog_generic_kernel(const double* q_in, const double* p_in,
                             double* q_out, double* p_out,
                             const int32_t* __restrict__ dir, int64_t n_chains, int dim,
-                            double step_size, int n_steps, int metric_kind,
+                            double step_size, int n_steps, FlowSchedule sched, int metric_kind,
                             const double* __restrict__ minv,
                             ModelArgs model, double* __restrict__ h_out,
                             int32_t* __restrict__ status, int32_t* __restrict__ n_done) {
@@ -121,20 +121,28 @@ __global__ void __launch_bounds__(128)
       K::grad(target, dim, lane, q[c], g[c]);
     }
     for (int s = 0; s < n_steps; ++s) {
-      // h1_flow(dt/2): p -= (0.5*dt) * grad  -- product and subtraction rounded separately,
-      // exactly as NumPy evaluates `state.mom -= dt * self.dh1_dpos(state)` (systems.py:152)
+      for (int f = 0; f < sched.n; ++f) {
+        if ((sched.drift_mask >> f) & 1u) {
+          // h2_flow: q += (c*dt) * M^-1 p (systems.py:362-363); gradient re-evaluated at the new q
+          // (the reference's cache on `pos` is invalidated: states.py:248-258)
+          inv_metric_apply<KP, CPW>(metric_kind, minv, dim, lane, psm, p, v);
 #pragma unroll
-      for (int c = 0; c < CPW; ++c)
+          for (int c = 0; c < CPW; ++c) {
+            const double dtf = sched.coef[f] * dt[c];
 #pragma unroll
-        for (int e = 0; e < NV; ++e) p[c][e] = __dsub_rn(p[c][e], __dmul_rn(0.5 * dt[c], g[c][e]));
-      inv_metric_apply<KP, CPW>(metric_kind, minv, dim, lane, psm, p, v);
+            for (int e = 0; e < NV; ++e) q[c][e] = __dadd_rn(q[c][e], __dmul_rn(dtf, v[c][e]));
+            K::grad(target, dim, lane, q[c], g[c]);
+          }
+        } else {
+          // h1_flow: p -= (c*dt) * grad -- product and difference rounded separately, exactly
+          // as NumPy evaluates `state.mom -= dt * self.dh1_dpos(state)` (systems.py:152)
 #pragma unroll
-      for (int c = 0; c < CPW; ++c) {
+          for (int c = 0; c < CPW; ++c) {
+            const double dtf = sched.coef[f] * dt[c];
 #pragma unroll
-        for (int e = 0; e < NV; ++e) q[c][e] = __dadd_rn(q[c][e], __dmul_rn(dt[c], v[c][e]));
-        K::grad(target, dim, lane, q[c], g[c]);
-#pragma unroll
-        for (int e = 0; e < NV; ++e) p[c][e] = __dsub_rn(p[c][e], __dmul_rn(0.5 * dt[c], g[c][e]));
+            for (int e = 0; e < NV; ++e) p[c][e] = __dsub_rn(p[c][e], __dmul_rn(dtf, g[c][e]));
+          }
+        }
       }
     }
     if (h_out != nullptr) inv_metric_apply<KP, CPW>(metric_kind, minv, dim, lane, psm, p, v);

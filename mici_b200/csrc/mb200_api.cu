@@ -64,7 +64,7 @@ static int num_sms() {
 template <class Target, int KP, int CPW>
 static int launch_generic(const double* q_in, const double* p_in, double* q_out, double* p_out,
                           const int32_t* dir, int64_t n, int dim, double eps, int n_steps,
-                          int metric_kind, const double* minv, const ModelArgs& m, double* h_out,
+                          const FlowSchedule& sched, int metric_kind, const double* minv, const ModelArgs& m, double* h_out,
                           int32_t* status, int32_t* n_done, cudaStream_t st) {
   constexpr int WARPS = 4;
   auto kern = leapfrog_generic_kernel<Target, KP, CPW>;
@@ -80,20 +80,20 @@ static int launch_generic(const double* q_in, const double* p_in, double* q_out,
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(q_in, p_in, q_out, p_out, dir, n, dim, eps,
-                                                   n_steps, metric_kind, minv, m, h_out, status,
-                                                   n_done);
+                                                   n_steps, sched, metric_kind, minv, m, h_out,
+                                                   status, n_done);
   return check_launch("leapfrog_generic_kernel");
 }
 
 template <class Target>
 static int dispatch_generic_dim(const double* q_in, const double* p_in, double* q_out,
                                 double* p_out, const int32_t* dir, int64_t n, int dim, double eps,
-                                int n_steps, int metric_kind, const double* minv,
+                                int n_steps, const FlowSchedule& sched, int metric_kind, const double* minv,
                                 const ModelArgs& m, double* h_out, int32_t* status,
                                 int32_t* n_done, cudaStream_t st) {
 #define MB200_GEN(KP, CPW)                                                                    \
   return launch_generic<Target, KP, CPW>(q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, \
-                                         metric_kind, minv, m, h_out, status, n_done, st)
+                                         sched, metric_kind, minv, m, h_out, status, n_done, st)
   if (dim <= 64) MB200_GEN(1, 4);
   if (dim <= 128) MB200_GEN(2, 4);
   if (dim <= 256) MB200_GEN(4, 2);
@@ -103,11 +103,23 @@ static int dispatch_generic_dim(const double* q_in, const double* p_in, double* 
   return fail(MB200_ERR_UNSUPPORTED, "dim %d > 1024 not supported by the Euclidean leapfrog", dim);
 }
 
+static FlowSchedule leapfrog_schedule() {
+  FlowSchedule s;
+  memset(&s, 0, sizeof(s));
+  s.n = 3;
+  s.drift_mask = 0x2u;
+  s.coef[0] = 0.5, s.coef[1] = 1.0, s.coef[2] = 0.5;
+  return s;
+}
+
 static int leapfrog_euclidean_impl(const double* q_in, const double* p_in, double* q_out,
                                    double* p_out, const int32_t* dir, int64_t n, int dim,
                                    double eps, int n_steps, int metric_kind, const double* minv,
                                    const mb200_model* model, double* h_out, int32_t* status,
-                                   int32_t* n_done, cudaStream_t st, bool allow_dmma) {
+                                   int32_t* n_done, cudaStream_t st, bool allow_dmma,
+                                   const FlowSchedule* schedule = nullptr) {
+  const FlowSchedule sched = schedule ? *schedule : leapfrog_schedule();
+  if (schedule) allow_dmma = false;
   if (!q_in || !p_in || !q_out || !p_out || !model)
     return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
   if (n < 0 || dim < 1 || n_steps < 0) return fail(MB200_ERR_INVALID_ARG, "bad sizes");
@@ -131,9 +143,9 @@ static int leapfrog_euclidean_impl(const double* q_in, const double* p_in, doubl
     if (rc != MB200_ERR_UNSUPPORTED) return fail(rc, "leapfrog_dmma launch failed");
   }
 #endif
-#define MB200_ARGS                                                                            \
-  q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, metric_kind, minv, m, h_out, status, \
-      n_done, st
+#define MB200_ARGS                                                                         \
+  q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, sched, metric_kind, minv, m, h_out, \
+      status, n_done, st
   switch (m.target_id) {
     case MB200_TARGET_STD_GAUSSIAN:
       return dispatch_generic_dim<StdGaussianTarget>(MB200_ARGS);
@@ -473,5 +485,28 @@ int mb200_selftest_fixed_point_direct(int32_t func_id, const double* x0, const d
   return check_launch("fixed_point_selftest_kernel");
 }
 #endif
+
+int mb200_composition_euclidean(const double* pos_in, const double* mom_in, double* pos_out,
+                                double* mom_out, const int32_t* dir, int64_t n_chains,
+                                int32_t dim, double step_size, int32_t n_steps, int32_t n_flows,
+                                const double* coefficients, int32_t initial_h1_flow_step,
+                                int32_t metric_kind, const double* metric_inv,
+                                const mb200_model* model, double* h_out, int32_t* status,
+                                int32_t* n_done, void* stream) {
+  if (!coefficients || n_flows < 1 || n_flows > MB200_MAX_FLOWS || (n_flows & 1) == 0)
+    return fail(MB200_ERR_INVALID_ARG, "n_flows must be odd and in [1, %d]", MB200_MAX_FLOWS);
+  FlowSchedule s;
+  memset(&s, 0, sizeof(s));
+  s.n = n_flows;
+  for (int i = 0; i < n_flows; ++i) {
+    s.coef[i] = coefficients[i];
+    const bool is_a = (i & 1) == 0;  // flows alternate a, b, a, ... (integrators.py:279-281)
+    const bool drift = initial_h1_flow_step ? !is_a : is_a;
+    if (drift) s.drift_mask |= 1u << i;
+  }
+  return leapfrog_euclidean_impl(pos_in, mom_in, pos_out, mom_out, dir, n_chains, dim, step_size,
+                                 n_steps, metric_kind, metric_inv, model, h_out, status, n_done,
+                                 (cudaStream_t)stream, false, &s);
+}
 
 }  // extern "C"

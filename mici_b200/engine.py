@@ -30,6 +30,9 @@ def build_integrator(problem, system=None, **overrides):
         "leapfrog": integrators.LeapfrogIntegrator,
         "implicit_leapfrog": integrators.ImplicitLeapfrogIntegrator,
         "constrained_leapfrog": integrators.ConstrainedLeapfrogIntegrator,
+        "bcss2": integrators.BCSSTwoStageIntegrator,
+        "bcss3": integrators.BCSSThreeStageIntegrator,
+        "bcss4": integrators.BCSSFourStageIntegrator,
     }[problem.integrator]
     return cls(system, problem.step_size, **kw)
 

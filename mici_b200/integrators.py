@@ -210,6 +210,69 @@ class LeapfrogIntegrator(TractableFlowIntegrator):
         _lib.check(rc, "mb200_leapfrog_euclidean")
 
 
+class SymmetricCompositionIntegrator(TractableFlowIntegrator):
+    """Symmetric composition (splitting) integrator for ``EuclideanMetricSystem`` s
+    (integrators.py:176-289) -- "next" row N4.  Same constructor as the reference: the full
+    symmetric coefficient sequence is derived from ``free_coefficients`` exactly as in
+    integrators.py:268-277; flows alternate ``a, b, ..., a`` with ``a = h1_flow`` if
+    ``initial_h1_flow_step`` else ``h2_flow`` (:278-281)."""
+
+    def __init__(self, system, free_coefficients, *, step_size=None, initial_h1_flow_step=True):
+        super().__init__(system, step_size)
+        if not isinstance(system, EuclideanMetricSystem) or isinstance(
+            system, ConstrainedEuclideanMetricSystem
+        ):
+            raise TypeError("Composition integrators need an (unconstrained) EuclideanMetricSystem.")
+        self.initial_h1_flow_step = initial_h1_flow_step
+        n_free_coefficients = len(free_coefficients)
+        coefficients = list(free_coefficients)
+        coefficients.append(0.5 - sum(free_coefficients[(n_free_coefficients) % 2 :: 2]))
+        coefficients.append(1 - 2 * sum(free_coefficients[(n_free_coefficients + 1) % 2 :: 2]))
+        self.coefficients = coefficients + coefficients[-2::-1]
+
+    def _launch(self, pos, mom, pos_out, mom_out, dirs, n_steps, h, status, n_done):
+        n, dim = pos.shape
+        dev = pos.device
+        sysm = self.system
+        model = sysm._model(dev)
+        coefs = (ctypes.c_double * len(self.coefficients))(*self.coefficients)
+        rc = _lib.load().mb200_composition_euclidean(
+            _lib.ptr(pos), _lib.ptr(mom), _lib.ptr(pos_out), _lib.ptr(mom_out), _lib.ptr(dirs),
+            n, dim, float(self.step_size), n_steps, len(self.coefficients),
+            ctypes.cast(coefs, ctypes.c_void_p), 1 if self.initial_h1_flow_step else 0,
+            sysm.metric.kind, _lib.ptr(sysm.metric.inv_device(dev)), ctypes.byref(model),
+            _lib.ptr(h), _lib.ptr(status), _lib.ptr(n_done), _lib.current_stream_ptr(dev),
+        )
+        _lib.check(rc, "mb200_composition_euclidean")
+
+
+class BCSSTwoStageIntegrator(SymmetricCompositionIntegrator):
+    """Blanes-Casas-Sanz-Serna two-stage integrator (integrators.py:292-316)."""
+
+    def __init__(self, system, step_size=None):
+        a_0 = (3 - 3**0.5) / 6
+        super().__init__(system, (a_0,), step_size=step_size, initial_h1_flow_step=True)
+
+
+class BCSSThreeStageIntegrator(SymmetricCompositionIntegrator):
+    """Three-stage BCSS integrator (integrators.py:319-347)."""
+
+    def __init__(self, system, step_size=None):
+        a_0 = 0.11888010966548
+        b_1 = 0.29619504261126
+        super().__init__(system, (a_0, b_1), step_size=step_size, initial_h1_flow_step=True)
+
+
+class BCSSFourStageIntegrator(SymmetricCompositionIntegrator):
+    """Four-stage BCSS integrator (integrators.py:350-378)."""
+
+    def __init__(self, system, step_size=None):
+        a_0 = 0.071353913450279725904
+        b_1 = 0.191667800000000000000
+        a_1 = 0.268548791161230105820
+        super().__init__(system, (a_0, b_1, a_1), step_size=step_size, initial_h1_flow_step=True)
+
+
 class ImplicitLeapfrogIntegrator(Integrator):
     """Implicit generalised leapfrog for non-separable Hamiltonians (integrators.py:381-544),
     for ``RiemannianMetricSystem`` s.  Fixed-point solves and reversibility checks run inside

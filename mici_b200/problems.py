@@ -81,7 +81,8 @@ def c0_std_gaussian(n_chains=4, dim=10, seed=BASE_SEED + 0):
     )
 
 
-def c1_funnel(n_chains=8192, dim=128, seed=BASE_SEED + 1, metric_kind="dense"):
+def c1_funnel(n_chains=8192, dim=128, seed=BASE_SEED + 1, metric_kind="dense",
+              integrator="leapfrog"):
     rng = np.random.default_rng(seed)
     metric = dense_spd_metric(rng, dim)
     pos = 0.1 * rng.standard_normal((n_chains, dim))
@@ -96,7 +97,7 @@ def c1_funnel(n_chains=8192, dim=128, seed=BASE_SEED + 1, metric_kind="dense"):
         mom = z
     return Problem(
         name="C1",
-        integrator="leapfrog",
+        integrator=integrator,
         system="euclidean",
         target="neal_funnel",
         target_params={"dim": dim},

@@ -61,6 +61,14 @@ def oracle_step_fn(problem, counts=None, **overrides):
             return mo.leapfrog_steps(q, p, d * eps, 1, target, metric)
 
         return step, (lambda q, p: mo.euclidean_h(q, p, target, metric)), None
+    if problem.integrator in mo.BCSS_FREE_COEFFICIENTS:
+        metric = mo.coerce_metric(problem.metric)
+        coefs = mo.composition_coefficients(mo.BCSS_FREE_COEFFICIENTS[problem.integrator])
+
+        def step(q, p, d):
+            return mo.composition_steps(q, p, d * eps, 1, target, metric, coefs)
+
+        return step, (lambda q, p: mo.euclidean_h(q, p, target, metric)), None
     if problem.integrator == "implicit_leapfrog":
         kind = "softabs" if problem.system == "softabs_riemannian" else "dense"
         system = mo.RiemannianSystem(
@@ -171,6 +179,9 @@ def build_reference(problem, **overrides):
         "leapfrog": mici.integrators.LeapfrogIntegrator,
         "implicit_leapfrog": mici.integrators.ImplicitLeapfrogIntegrator,
         "constrained_leapfrog": mici.integrators.ConstrainedLeapfrogIntegrator,
+        "bcss2": mici.integrators.BCSSTwoStageIntegrator,
+        "bcss3": mici.integrators.BCSSThreeStageIntegrator,
+        "bcss4": mici.integrators.BCSSFourStageIntegrator,
     }[problem.integrator]
     return system, cls(system, problem.step_size, **ikw)
 

@@ -188,6 +188,42 @@ def leapfrog_steps(q, p, time_step, n_steps, target, metric):
     return q, p
 
 
+def composition_coefficients(free_coefficients):
+    """SymmetricCompositionIntegrator.__init__ (integrators.py:266-277)."""
+    n_free = len(free_coefficients)
+    coefficients = list(free_coefficients)
+    coefficients.append(0.5 - sum(free_coefficients[(n_free) % 2 :: 2]))
+    coefficients.append(1 - 2 * sum(free_coefficients[(n_free + 1) % 2 :: 2]))
+    return coefficients + coefficients[-2::-1]
+
+
+BCSS_FREE_COEFFICIENTS = {  # integrators.py:312-314, 337-345, 367-377
+    "bcss2": ((3 - 3**0.5) / 6,),
+    "bcss3": (0.11888010966548, 0.29619504261126),
+    "bcss4": (0.071353913450279725904, 0.191667800000000000000, 0.268548791161230105820),
+}
+
+
+def composition_steps(q, p, time_step, n_steps, target, metric, coefficients,
+                      initial_h1_flow_step=True):
+    """``n_steps`` of ``SymmetricCompositionIntegrator._step`` (integrators.py:283-289): flows
+    alternate a, b, ..., a; a = h1_flow if ``initial_h1_flow_step`` else h2_flow; the gradient is
+    re-evaluated whenever ``pos`` changed (cache on ``pos``)."""
+    q = np.array(q, dtype=np.float64)
+    p = np.array(p, dtype=np.float64)
+    metric = coerce_metric(metric)
+    grad = target.grad_neg_log_dens(q)
+    for _ in range(n_steps):
+        for i, c in enumerate(coefficients):
+            is_h1 = ((i % 2) == 0) == bool(initial_h1_flow_step)
+            if is_h1:
+                p -= (c * time_step) * grad
+            else:
+                q += (c * time_step) * metric.inv_matvec(p)
+                grad = target.grad_neg_log_dens(q)
+    return q, p
+
+
 # --------------------------------------------------------------------------------------
 # solve_fixed_point_direct
 # --------------------------------------------------------------------------------------
