@@ -54,7 +54,18 @@ __device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
 }
 
 constexpr int DMMA_TILES_PER_CTA = 7;
-constexpr int DMMA_GROUPS = 4;           // 4 warps each; tiles per group 2,2,2,1
+#ifndef MB200_DMMA_GROUPS
+#define MB200_DMMA_GROUPS 4
+#endif
+// groups of 4 warps; the 7 row tiles are dealt 2,2,2,1 (4 groups), 2,2,1,1,1 (5), 2,1,1,1,1,1 (6)
+// or 1 each (7): more groups = more warps per sub-partition to cover each other's serial
+// phases, at fewer registers per thread and less B-fragment reuse
+constexpr int DMMA_GROUPS = MB200_DMMA_GROUPS;
+__host__ __device__ constexpr int dmma_tile_start(int g) {
+  // first tile of group g: groups [0, 7 - G) own two tiles, the rest one
+  return g <= 7 - DMMA_GROUPS ? 2 * g : 2 * (7 - DMMA_GROUPS) + (g - (7 - DMMA_GROUPS));
+}
+__host__ __device__ constexpr int dmma_tile_count(int g) { return g < 7 - DMMA_GROUPS ? 2 : 1; }
 constexpr int DMMA_THREADS = 32 * 4 * DMMA_GROUPS;
 constexpr int DMMA_ROWS_PER_CTA = 8 * DMMA_TILES_PER_CTA;  // 56 chains
 constexpr int DMMA_MAX_RED = 4;
@@ -333,7 +344,7 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const int group = warp >> 2;  // tiles {0,1}, {2,3}, {4,5}, {6}
+  const int group = warp >> 2;  // 4 groups: tiles {0,1}, {2,3}, {4,5}, {6}
   // Column quarter owned by this warp.  warp & 3 is its SM sub-partition; rotating the quarters by
   // the group index puts each group's "coordinate 0" warp (which carries the target's per-chain
   // special work, e.g. exp(-v) of the funnel) on a different sub-partition -- otherwise one
@@ -391,9 +402,9 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
     const int64_t chain0 = blk * DMMA_ROWS_PER_CTA;
     const int64_t left = n_chains - chain0;
     const int tiles = (int)((left >= DMMA_ROWS_PER_CTA) ? DMMA_TILES_PER_CTA : (left + 7) / 8);
-    const int row0 = group * 16;
-    int mt = tiles - 2 * group;
-    mt = mt > 2 ? 2 : mt;
+    const int row0 = 8 * dmma_tile_start(group);
+    int mt = tiles - dmma_tile_start(group);
+    mt = mt > dmma_tile_count(group) ? dmma_tile_count(group) : mt;
 #define MB200_GROUP(MT)                                                                       \
   leapfrog_dmma_group<Target, DP, MT>(sm, target, q_in, p_in, q_out, p_out, dir, n_chains,    \
                                       dim, step_size, n_steps, h_out, status, n_done, chain0, \

@@ -120,6 +120,7 @@ static int leapfrog_euclidean_impl(const double* q_in, const double* p_in, doubl
                                    const FlowSchedule* schedule = nullptr) {
   const FlowSchedule sched = schedule ? *schedule : leapfrog_schedule();
   if (schedule) allow_dmma = false;
+  if (n == 0 && dim >= 1 && n_steps >= 0) return 0;  // empty batch: nothing to do
   if (!q_in || !p_in || !q_out || !p_out || !model)
     return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
   if (n < 0 || dim < 1 || n_steps < 0) return fail(MB200_ERR_INVALID_ARG, "bad sizes");
@@ -326,6 +327,7 @@ int mb200_leapfrog_euclidean_generic(const double* pos_in, const double* mom_in,
 int mb200_hamiltonian_euclidean(const double* pos, const double* mom, int64_t n_chains,
                                 int32_t dim, int32_t metric_kind, const double* metric_inv,
                                 const mb200_model* model, double* h_out, void* stream) {
+  if (n_chains == 0 && dim >= 1) return 0;
   if (!h_out) return fail(MB200_ERR_INVALID_ARG, "h_out is NULL");
   // zero leapfrog steps: loads the state, evaluates h, writes the (unchanged) state back in place
   return leapfrog_euclidean_impl(pos, mom, const_cast<double*>(pos), const_cast<double*>(mom),
@@ -337,6 +339,7 @@ int mb200_euclidean_eval(const double* pos, const double* mom, int64_t n_chains,
                          int32_t metric_kind, const double* metric_inv, const mb200_model* model,
                          double* nld_out, double* grad_out, double* vel_out, double* kin_out,
                          void* stream) {
+  if (n_chains == 0 && dim >= 1) return 0;
   if (!pos || !mom || !model) return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
   if (n_chains < 0 || dim < 1) return fail(MB200_ERR_INVALID_ARG, "bad sizes");
   if (metric_kind < 0 || metric_kind > 2) return fail(MB200_ERR_INVALID_ARG, "bad metric_kind");
@@ -366,6 +369,7 @@ int mb200_constrained_leapfrog_euclidean(
 #ifdef MB200_NO_CONSTRAINED
   return fail(MB200_ERR_UNSUPPORTED, "constrained leapfrog not compiled in");
 #else
+  if (n_chains == 0 && dim >= 1) return 0;
   if (!pos_in || !mom_in || !pos_out || !mom_out || !model)
     return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
   if (n_chains < 0 || dim < 1 || n_steps < 0 || n_inner_step < 1 || max_iters < 0)
@@ -409,6 +413,11 @@ int mb200_hamiltonian_riemannian(const double*, const double*, int64_t, int32_t,
                                  const mb200_model*, double*, int32_t*, void*, int64_t, void*) {
   return fail(MB200_ERR_UNSUPPORTED, "riemannian hamiltonian not compiled in");
 }
+int mb200_selftest_fixed_point_direct(int32_t, const double*, const double*, int64_t, int32_t,
+                                      double, double, int32_t, double*, int32_t*, int32_t*,
+                                      void*) {
+  return fail(MB200_ERR_UNSUPPORTED, "fixed-point self-test not compiled in");
+}
 #endif
 
 #ifndef MB200_NO_RIEMANNIAN
@@ -420,6 +429,7 @@ int mb200_implicit_leapfrog_riemannian(
     int32_t* n_done, int32_t* fp_iters, void* workspace, int64_t workspace_bytes, void* stream) {
   (void)workspace;
   (void)workspace_bytes;
+  if (n_chains == 0 && dim >= 1) return 0;
   if (!pos_in || !mom_in || !pos_out || !mom_out || !model)
     return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
   if (n_chains < 0 || dim < 1 || n_steps < 0 || fp_max_iters < 0)
@@ -440,6 +450,7 @@ int mb200_hamiltonian_riemannian(const double* pos, const double* mom, int64_t n
                                  void* stream) {
   (void)workspace;
   (void)workspace_bytes;
+  if (n_chains == 0 && dim >= 1) return 0;
   if (!pos || !mom || !model || !h_out) return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
   if (n_chains < 0 || dim < 1) return fail(MB200_ERR_INVALID_ARG, "bad sizes");
   if (n_chains == 0) return 0;
@@ -456,6 +467,7 @@ int mb200_metropolis_select(double* pos, double* mom, const double* pos_prop,
                             const double* uniforms, int64_t n_chains, int32_t dim,
                             double* accept_prob, double* accept_stat, int32_t* accepted,
                             void* stream) {
+  if (n_chains == 0 && dim >= 1) return 0;
   if (!pos || !mom || !pos_prop || !mom_prop || !h_init || !h_prop || !uniforms)
     return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
   if (n_chains < 0 || dim < 1) return fail(MB200_ERR_INVALID_ARG, "bad sizes");
