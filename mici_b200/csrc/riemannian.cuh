@@ -221,9 +221,18 @@ __device__ inline void rm_carve(RmWork& w, double* s, int dim, int n_mats, Blk& 
 // A [dim x dim, stride ld] is destroyed (its diagonal becomes lam); U receives the eigenvectors
 // as columns.  Returns false if not converged / non-finite (-> LinAlgError, matrices.py:437).
 // ---------------------------------------------------------------------------------------------
-// Round-robin (circle method) schedule: in round r of np-1, pair t couples
+// Round-robin (circle method) schedule over np "seats": in round r of np-1, pair t couples seats
 //   t == 0 : (np-1, r)          t > 0 : ((r+t) mod (np-1), (r-t) mod (np-1))
-// every unordered pair of the np players meets exactly once per sweep; no schedule arrays.
+// so every unordered pair meets exactly once per sweep; no schedule arrays.  Matrix indices are
+// dealt to the seats such that round 0 couples the adjacent indices (0,1), (2,3), ...: models
+// whose Hessian couples coordinates in consecutive pairs then finish all their rotations in the
+// first round and every other round is skipped by the look-ahead.
+__device__ __forceinline__ int rr_seat_index(int np, int seat) {
+  if (seat == np - 1) return 1;
+  if (seat == 0) return 0;
+  const int m = np >> 1;
+  return seat < m ? 2 * seat : 2 * (np - 1 - seat) + 1;
+}
 __device__ __forceinline__ void rr_pair(int np, int r, int t, int& p, int& q) {
   const int m1 = np - 1;
   int a, b;
@@ -236,6 +245,8 @@ __device__ __forceinline__ void rr_pair(int np, int r, int t, int& p, int& q) {
     b = r - t;
     if (b < 0) b += m1;
   }
+  a = rr_seat_index(np, a);
+  b = rr_seat_index(np, b);
   p = a < b ? a : b;
   q = a < b ? b : a;
 }
@@ -266,31 +277,60 @@ __device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U
   // (no integer divisions in the inner loops; the round's pair table is written once to w.top /
   // w.bot by the parameter phase)
   const int tx = k.tid & 31, ty = k.tid >> 5, ny = k.nthr >> 5;
+  // look-ahead votes: two banks of [nwarp] ints in the reduction scratch (k.red[16..32) is unused
+  // by block_sum / block_nanmax), alternated per pass so that no extra barrier protects them
+  int* flag_banks = reinterpret_cast<int*>(k.red + 16);
+  int pass = 0;
   for (int sweep = 0; sweep < RM_MAX_SWEEPS; ++sweep) {
     double off = 0.0;
-    for (int round = 0; round < np - 1; ++round) {
-      // --- rotation parameters for the m disjoint pairs of this round
-      for (int t = k.tid; t < m; t += k.nthr) {
-        int p, q;
-        rr_pair(np, round, t, p, q);
-        double c = 1.0, s = 0.0;
-        if (q < n) {
-          const double apq = A[p * ld + q];
-          off = fmax(off, fabs(apq));
-          if (fabs(apq) > 1e-300 && fabs(apq) > 1e-18 * scale) {
-            const double app = A[p * ld + p], aqq = A[q * ld + q];
-            const double tau = (aqq - app) / (2.0 * apq);
-            const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-            c = 1.0 / sqrt(1.0 + tt * tt);
-            s = tt * c;
+    for (int round = 0; round < np - 1;) {
+      // --- look-ahead: warp v examines round `round + v`.  Warp 0 also produces the rotation
+      // parameters of the current round.  Rounds in which no pair needs a rotation (every pair
+      // already decoupled: block-structured matrices, late sweeps) are skipped up to nwarp at a
+      // time with a single barrier; a matrix that needs every rotation pays the same two
+      // barriers per round as without the look-ahead.
+      const int rr = round + k.warp;
+      bool need = false;
+      double off_w = 0.0;
+      if (rr < np - 1) {
+        for (int t = k.lane; t < m; t += 32) {
+          int p, q;
+          rr_pair(np, rr, t, p, q);
+          double c = 1.0, s = 0.0;
+          if (q < n) {
+            const double apq = A[p * ld + q];
+            off_w = fmax(off_w, fabs(apq));
+            if (fabs(apq) > 1e-300 && fabs(apq) > 1e-18 * scale) {
+              need = true;
+              if (k.warp == 0) {
+                const double app = A[p * ld + p], aqq = A[q * ld + q];
+                const double tau = (aqq - app) / (2.0 * apq);
+                const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                c = 1.0 / sqrt(1.0 + tt * tt);
+                s = tt * c;
+              }
+            }
+          }
+          if (k.warp == 0) {
+            w.rc[t] = c;
+            w.rs[t] = s;
+            w.top[t] = p;
+            w.bot[t] = q;
           }
         }
-        w.rc[t] = c;
-        w.rs[t] = s;
-        w.top[t] = p;
-        w.bot[t] = q;
       }
+      int* flags = flag_banks + (pass & 1) * 16;
+      ++pass;
+      const bool warp_need = __any_sync(FULL_MASK, need);
+      if (k.lane == 0) flags[k.warp] = warp_need ? 1 : 0;
       __syncthreads();
+      int first = 0;
+      while (first < k.nwarp && flags[first] == 0) ++first;
+      if (k.warp <= first) off = fmax(off, off_w);  // rounds consumed now (skipped or rotated)
+      if (first > 0) {  // rounds round .. round+first-1 need no rotation
+        round += first;
+        continue;
+      }
       // --- A <- R^T A R on 2x2 blocks (pair a rows, pair b cols), U <- U R
       for (int b = tx; b < m; b += 32) {
         const int pb = w.top[b], qb = w.bot[b];
@@ -332,6 +372,7 @@ __device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U
         }
       }
       __syncthreads();
+      ++round;
     }
     const double offmax = block_nanmax(k, off);
     if (!(offmax == offmax)) return false;
@@ -362,6 +403,10 @@ __device__ inline void smem_matmul(const Blk& k, int n, int ld, const double* X,
         const int j = j0 + a;
         y[a] = (j < n) ? Y[kk * ld + j] : 0.0;
       }
+      // exact: skipping a product with an all-zero operand adds nothing (operands are finite)
+      if ((x[0] == 0.0 && x[1] == 0.0 && x[2] == 0.0 && x[3] == 0.0) ||
+          (y[0] == 0.0 && y[1] == 0.0 && y[2] == 0.0 && y[3] == 0.0))
+        continue;
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -437,10 +482,11 @@ struct SoftAbsMetric {
   const Target& t;
   double alpha;
   bool have_j;     // divided-difference matrix J built in w.M2 for the current metric?
+  bool j_finite;   // ... and all of its entries are finite
   bool have_prev;  // w.M1 holds the eigenvectors of the previous build (warm start available)
 
   __device__ SoftAbsMetric(const Target& tt, const ModelArgs& m)
-      : t(tt), alpha(m.mp[0]), have_j(false), have_prev(false) {}
+      : t(tt), alpha(m.mp[0]), have_j(false), j_finite(false), have_prev(false) {}
   // forget the previous eigenvectors (start of every integrator step: bounds the loss of
   // orthogonality from accumulating rotations over many warm-started solves)
   __device__ void reset() { have_prev = false; }
@@ -527,10 +573,14 @@ struct SoftAbsMetric {
                                     double* out) {
     const int n = w.dim, ld = w.ld;
     if (!have_j) {  // J depends on the metric only: build once per metric, reuse per iteration
+      bool bad = false;
       for (int idx = k.tid; idx < n * n; idx += k.nthr) {
         const int i = idx / n, j = idx - i * n;
-        w.M2[i * ld + j] = (i == j) ? w.gsa[i] : (w.sa[i] - w.sa[j]) / (w.lam[i] - w.lam[j]);
+        const double v = (i == j) ? w.gsa[i] : (w.sa[i] - w.sa[j]) / (w.lam[i] - w.lam[j]);
+        if (!isfinite(v)) bad = true;
+        w.M2[i * ld + j] = v;
       }
+      j_finite = !block_any(k, bad);  // (0 * inf must stay NaN: only skip zeros if J is finite)
       have_j = true;
     }
     for (int j = k.tid; j < n; j += k.nthr) {
@@ -548,7 +598,11 @@ struct SoftAbsMetric {
       for (int jn = 0; jn < Target::NEED; ++jn) acc[jn] = 0.0;
       for (int j = k.lane; j < n; j += 32) {
         double tj = 0.0;
-        for (int i = 0; i < n; ++i) tj = fma(w.M1[a * ld + i] * w.ev[i], w.M2[i * ld + j], tj);
+        for (int i = 0; i < n; ++i) {
+          const double ue = w.M1[a * ld + i] * w.ev[i];  // warp-uniform
+          if (ue == 0.0 && j_finite) continue;            // exact zero term (sparse eigenvectors)
+          tj = fma(ue, w.M2[i * ld + j], tj);
+        }
         tj *= w.ev[j];
 #pragma unroll
         for (int jn = 0; jn < Target::NEED; ++jn) {
