@@ -204,6 +204,16 @@ int mb200_composition_euclidean(const double* pos_in, const double* mom_in, doub
                                 const mb200_model* model, double* h_out, int32_t* status,
                                 int32_t* n_done, void* stream);
 
+/*
+ * Diagnostic: the per-chain symmetric eigensolver (K3, parallel cyclic Jacobi; replaces
+ * numpy.linalg.eigh at matrices.py:437, 1658) on arbitrary dense symmetric matrices
+ * [n_matrices x dim x dim].  eigvec holds the eigenvectors as columns (row-major), eigval is
+ * unsorted.  warm_from >= 0: each solve is warm-started from the eigenvectors of matrix
+ * `warm_from` (the V^T H V path used between successive fixed-point iterates); -1: cold.
+ */
+int mb200_selftest_eigh(const double* matrices, int64_t n_matrices, int32_t dim, int32_t warm_from,
+                        double* eigval, double* eigvec, int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

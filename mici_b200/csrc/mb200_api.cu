@@ -521,4 +521,29 @@ int mb200_composition_euclidean(const double* pos_in, const double* mom_in, doub
                                  (cudaStream_t)stream, false, &s);
 }
 
+#ifndef MB200_NO_RIEMANNIAN
+int mb200_selftest_eigh(const double* matrices, int64_t n_matrices, int32_t dim, int32_t warm_from,
+                        double* eigval, double* eigvec, int32_t* status, void* stream) {
+  if (!matrices || !eigval || !eigvec || !status)
+    return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
+  if (n_matrices < 0 || dim < 1 || warm_from >= n_matrices)
+    return fail(MB200_ERR_INVALID_ARG, "bad arguments");
+  if (n_matrices == 0) return 0;
+  const size_t smem = rm_smem_doubles(dim, 3) * sizeof(double);
+  if (smem > 227 * 1024) return fail(MB200_ERR_UNSUPPORTED, "dim %d too large for the self-test", dim);
+  cudaError_t e = cudaFuncSetAttribute(eigh_selftest_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(MB200_ERR_CUDA, "smem attr: %s", cudaGetErrorString(e));
+  int64_t blocks = n_matrices < 1024 ? n_matrices : 1024;
+  eigh_selftest_kernel<<<(unsigned)blocks, RM_THREADS, smem, (cudaStream_t)stream>>>(
+      matrices, n_matrices, dim, warm_from, eigval, eigvec, status);
+  return check_launch("eigh_selftest_kernel");
+}
+#else
+int mb200_selftest_eigh(const double*, int64_t, int32_t, int32_t, double*, double*, int32_t*,
+                        void*) {
+  return fail(MB200_ERR_UNSUPPORTED, "eigh self-test not compiled in");
+}
+#endif
+
 }  // extern "C"

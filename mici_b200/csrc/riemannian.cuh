@@ -421,6 +421,57 @@ __device__ inline void smem_matmul(const Blk& k, int n, int ld, const double* X,
   __syncthreads();
 }
 
+// Diagnostic kernel: K3 on arbitrary dense symmetric matrices (one CTA per matrix).  With
+// `warm_from` >= 0 the solve of matrix i is warm-started from the eigenvectors of matrix
+// `warm_from` (exercising the V^T H V path used between fixed-point iterates).
+__global__ void __launch_bounds__(RM_THREADS)
+    eigh_selftest_kernel(const double* __restrict__ mats, int64_t n_mats, int dim, int warm_from,
+                         double* __restrict__ eigval, double* __restrict__ eigvec,
+                         int32_t* __restrict__ status) {
+  extern __shared__ double smem[];
+  Blk blk;
+  blk.tid = threadIdx.x, blk.nthr = blockDim.x, blk.lane = threadIdx.x & 31;
+  blk.warp = threadIdx.x >> 5, blk.nwarp = blockDim.x >> 5;
+  RmWork w;
+  rm_carve(w, smem, dim, 3, blk);
+  const int ld = w.ld;
+  for (int64_t mi = blockIdx.x; mi < n_mats; mi += gridDim.x) {
+    __syncthreads();
+    bool ok = true;
+    bool warm = false;
+    if (warm_from >= 0) {
+      const double* src = mats + (size_t)warm_from * dim * dim;
+      for (int idx = blk.tid; idx < dim * dim; idx += blk.nthr)
+        w.M2[(idx / dim) * ld + idx % dim] = src[idx];
+      __syncthreads();
+      ok = jacobi_eigh(blk, w, w.M2, w.M1);
+      warm = ok;
+    }
+    const double* src = mats + (size_t)mi * dim * dim;
+    for (int idx = blk.tid; idx < dim * dim; idx += blk.nthr)
+      w.M2[(idx / dim) * ld + idx % dim] = src[idx];
+    __syncthreads();
+    if (warm) {
+      smem_matmul<false>(blk, dim, ld, w.M2, w.M1, w.M3);
+      smem_matmul<true>(blk, dim, ld, w.M1, w.M3, w.M2);
+      for (int idx = blk.tid; idx < dim * dim; idx += blk.nthr) {
+        const int i = idx / dim, j = idx - i * dim;
+        if (i < j) {
+          const double v = 0.5 * (w.M2[i * ld + j] + w.M2[j * ld + i]);
+          w.M2[i * ld + j] = v;
+          w.M2[j * ld + i] = v;
+        }
+      }
+      __syncthreads();
+    }
+    ok = jacobi_eigh(blk, w, w.M2, w.M1, warm);
+    for (int idx = blk.tid; idx < dim * dim; idx += blk.nthr)
+      eigvec[(size_t)mi * dim * dim + idx] = w.M1[(idx / dim) * ld + idx % dim];
+    for (int i = blk.tid; i < dim; i += blk.nthr) eigval[mi * dim + i] = w.M2[i * ld + i];
+    if (blk.tid == 0) status[mi] = ok ? 0 : MB200_STATUS_LINALG;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2: in-place lower Cholesky factor of the SPD matrix M [dim x dim, stride ld]
 // (numpy.linalg.cholesky, matrices.py:1165-1169).  Returns false on a non-positive / non-finite

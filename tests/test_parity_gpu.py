@@ -332,3 +332,39 @@ def test_fused_fixed_point_solver_divergence_and_max_iters(func_id):
     assert status[0] == 1  # ConvergenceError (reference test_solvers.py:83-93)
     _, _, status = _fixed_point_gpu(2, np.array([1.0]), np.array([0.0]), 1e-10, max_iters=1)
     assert status[0] == 1  # max_iters exceeded (reference test_solvers.py:96-107)
+
+
+# ---- K3 (Jacobi eigensolver) on dense symmetric matrices against numpy.linalg.eigh
+@pytest.mark.parametrize("dim", [1, 2, 3, 7, 16, 33, 64, 77])
+@pytest.mark.parametrize("warm", [False, True])
+def test_jacobi_eigensolver_dense_matrices(dim, warm):
+    from mici_b200 import _lib
+
+    rng = np.random.default_rng(100 + dim)
+    n = 6
+    base = rng.standard_normal((dim, dim))
+    mats = np.empty((n, dim, dim))
+    for i in range(n):
+        a = base + (0.05 if warm else 1.0) * rng.standard_normal((dim, dim))
+        mats[i] = 0.5 * (a + a.T)
+    if dim >= 7:
+        mats[1][np.abs(mats[1]) < 0.8] = 0.0  # sparse symmetric matrix (identity-rotation skips)
+        mats[1] = 0.5 * (mats[1] + mats[1].T)
+        mats[2] = np.diag(rng.standard_normal(dim))  # already diagonal
+    m = torch.as_tensor(mats, device=DEV).contiguous()
+    val = torch.empty((n, dim), dtype=torch.float64, device=DEV)
+    vec = torch.empty((n, dim, dim), dtype=torch.float64, device=DEV)
+    st = torch.empty(n, dtype=torch.int32, device=DEV)
+    rc = _lib.load().mb200_selftest_eigh(_lib.ptr(m), n, dim, 0 if warm else -1, _lib.ptr(val),
+                                         _lib.ptr(vec), _lib.ptr(st), _lib.current_stream_ptr(m.device))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert (st == 0).all()
+    val, vec = val.cpu().numpy(), vec.cpu().numpy()
+    for i in range(n):
+        ref = np.linalg.eigvalsh(mats[i])
+        scale = max(1.0, np.abs(ref).max())
+        np.testing.assert_allclose(np.sort(val[i]), ref, rtol=0, atol=5e-14 * scale)
+        u = vec[i]
+        np.testing.assert_allclose(u.T @ u, np.identity(dim), atol=1e-13)
+        np.testing.assert_allclose(u @ np.diag(val[i]) @ u.T, mats[i], atol=1e-13 * scale)
