@@ -38,6 +38,7 @@ from .systems import (
     RiemannianMetricSystem,
     _batched,
     _dir_tensor,
+    _like_input,
 )
 
 
@@ -77,8 +78,12 @@ class Integrator(ABC):
         h = torch.empty(n, dtype=torch.float64, device=dev) if return_h else None
         aux = self._launch(pos, mom, pos_out, mom_out, _dir_tensor(d, n, dev), int(n_steps), h,
                            status, n_done)
-        new = _new_state_like(state, pos_out[0] if single else pos_out,
-                              mom_out[0] if single else mom_out)
+        new = _new_state_like(state, _like_input(state.pos, pos_out[0] if single else pos_out),
+                              _like_input(state.pos, mom_out[0] if single else mom_out))
+        if not isinstance(new, ChainState):  # foreign (reference) state object: no extra slots
+            if single:
+                raise_for_status(int(status.item()), type(self).__name__ + ".step")
+            return new
         new.status = status
         new.n_done = n_done
         if return_h:

@@ -97,13 +97,27 @@ class _FixedMetric:
 
 
 def _batched(state):
-    """View of a state as ([n, D] pos, [n, D] mom, dir tensor-or-None, squeeze flag)."""
+    """View of a state as ([n, D] pos, [n, D] mom, dir tensor-or-None, squeeze flag).
+
+    NumPy arrays (the reference's own ``ChainState`` storage, states.py:160-305) are accepted
+    and moved to the current CUDA device; callers convert results back (``_like_input``)."""
     pos, mom = state.pos, state.mom
+    if isinstance(pos, np.ndarray):
+        pos = torch.as_tensor(np.ascontiguousarray(pos, dtype=np.float64), device="cuda")
+        mom = None if mom is None else torch.as_tensor(
+            np.ascontiguousarray(mom, dtype=np.float64), device="cuda")
     single = pos.ndim == 1
     if single:
         pos, mom = pos[None], (None if mom is None else mom[None])
     d = state.dir if "dir" in state else 1
     return pos, mom, d, single
+
+
+def _like_input(ref, value):
+    """Return ``value`` in the storage type of ``ref`` (NumPy in -> NumPy out)."""
+    if isinstance(ref, np.ndarray) and isinstance(value, torch.Tensor):
+        return value.cpu().numpy()
+    return value
 
 
 def _dir_tensor(d, n, device):
@@ -257,7 +271,7 @@ class EuclideanMetricSystem(TractableFlowSystem):
             _lib.current_stream_ptr(dev),
         )
         _lib.check(rc, "mb200_hamiltonian_euclidean")
-        return h[0] if single else h
+        return _like_input(state.pos, h[0] if single else h)
 
     def h1_flow(self, state, dt):
         """p -= dt * grad l(q) (systems.py:143-152); ``dt`` scalar or per-chain tensor."""
@@ -365,7 +379,7 @@ class RiemannianMetricSystem(System):
             _lib.ptr(h), _lib.ptr(status), _lib.ptr(ws), ws.numel(), _lib.current_stream_ptr(dev),
         )
         _lib.check(rc, "mb200_hamiltonian_riemannian")
-        return h[0] if single else h
+        return _like_input(state.pos, h[0] if single else h)
 
 
 class DenseRiemannianMetricSystem(RiemannianMetricSystem):

@@ -148,3 +148,35 @@ def test_non_finite_inputs_propagate_like_numpy():
     ok = np.isfinite(ref["pos"]).all(1)
     np.testing.assert_allclose(got[ok], ref["pos"][ok], rtol=RTOL, atol=ATOL)
     assert (out.status == 0).all()
+
+
+def test_numpy_chain_state_in_numpy_out():
+    """A state holding NumPy arrays (the reference's own ChainState storage) steps through the
+    same kernels and comes back as NumPy; a 1-D state raises the reference exceptions."""
+    problem = problems.make_problem("C1", n_chains=5, dim=24)
+    integ = engine.build_integrator(problem)
+    st = ChainState(pos=problem.pos[1].copy(), mom=problem.mom[1].copy(), dir=1)
+    new = integ.step(st)
+    assert isinstance(new.pos, np.ndarray) and new.pos.shape == (24,)
+    ref = dr.oracle_run(problem, 1)
+    np.testing.assert_allclose(new.pos, ref["pos"][1], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(new.mom, ref["mom"][1], rtol=RTOL, atol=ATOL)
+    np.testing.assert_array_equal(st.pos, problem.pos[1])  # argument untouched
+    h = integ.system.h(new)
+    np.testing.assert_allclose(h, ref["h"][1], rtol=RTOL)
+
+    class ForeignState:  # duck-typed stand-in for mici.states.ChainState
+        def __init__(self, pos, mom, dir):  # noqa: A002
+            self.pos, self.mom, self.dir = pos, mom, dir
+
+        def copy(self):
+            return ForeignState(self.pos.copy(), self.mom.copy(), self.dir)
+
+        def __contains__(self, name):
+            return name in ("pos", "mom", "dir")
+
+    fs = ForeignState(problem.pos[2].copy(), problem.mom[2].copy(), -1)
+    out = integ.step(fs)
+    assert isinstance(out, ForeignState) and out.dir == -1
+    ref2 = dr.oracle_run(problem, 1, dirs=-np.ones(5, dtype=np.int32))
+    np.testing.assert_allclose(out.pos, ref2["pos"][2], rtol=RTOL, atol=ATOL)
