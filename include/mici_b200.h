@@ -214,6 +214,21 @@ int mb200_composition_euclidean(const double* pos_in, const double* mom_in, doub
 int mb200_selftest_eigh(const double* matrices, int64_t n_matrices, int32_t dim, int32_t warm_from,
                         double* eigval, double* eigvec, int32_t* status, void* stream);
 
+/*
+ * "Next" row N4: n_steps implicit-midpoint steps on a Riemannian-metric system.
+ * Replaces: ImplicitMidpointIntegrator.step (integrators.py:547-681): a direct fixed-point solve
+ * in z = (q, p) for the forward half-step, an explicit Euler half-step, and a reversibility
+ * check by a second fixed-point solve.  fp_iters (optional, [n_chains*4]): iterations of the two
+ * solves of the last completed step in slots 0 and 1.  Other arguments as for
+ * mb200_implicit_leapfrog_riemannian.
+ */
+int mb200_implicit_midpoint_riemannian(
+    const double* pos_in, const double* mom_in, double* pos_out, double* mom_out,
+    const int32_t* dir, int64_t n_chains, int32_t dim, double step_size, int32_t n_steps,
+    const mb200_model* model, double fp_convergence_tol, double fp_divergence_tol,
+    int32_t fp_max_iters, double reverse_check_tol, double* h_out, int32_t* status,
+    int32_t* n_done, int32_t* fp_iters, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

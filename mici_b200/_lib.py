@@ -77,6 +77,11 @@ SIGNATURES = {
         [_P, _P, _P, _P, _P, _I64, _I32, _F64, _I32, _I32, _P, _I32, _I32, _P, _MP, _P, _P, _P, _P],
     ),
     "mb200_selftest_eigh": (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P, _P]),
+    "mb200_implicit_midpoint_riemannian": (
+        ctypes.c_int,
+        [_P, _P, _P, _P, _P, _I64, _I32, _F64, _I32, _MP, _F64, _F64, _I32, _F64]
+        + [_P, _P, _P, _P, _P],
+    ),
     "mb200_metropolis_select": (
         ctypes.c_int,
         [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P],

@@ -220,7 +220,7 @@ static int launch_implicit(const double* q_in, const double* p_in, double* q_out
                            const int32_t* dir, int64_t n, int dim, double eps, int n_steps,
                            const ModelArgs& m, double fp_tol, double fp_div, int fp_max,
                            double rev_tol, double* h_out, int32_t* status, int32_t* n_done,
-                           int32_t* fp_iters, cudaStream_t st) {
+                           int32_t* fp_iters, cudaStream_t st, int midpoint) {
   auto kern = implicit_leapfrog_kernel<Target, MetricT>;
   int n_mats = MetricT<Target>::N_MATS;
   // SoftAbs: a third matrix enables warm-started eigensolves; use it when two CTAs still fit
@@ -239,7 +239,8 @@ static int launch_implicit(const double* q_in, const double* p_in, double* q_out
   if (blocks > n) blocks = n;
   kern<<<(unsigned)blocks, RM_THREADS, smem, st>>>(q_in, p_in, q_out, p_out, dir, n, dim, eps,
                                                    n_steps, m, fp_tol, fp_div, fp_max, rev_tol,
-                                                   h_out, status, n_done, fp_iters, n_mats);
+                                                   h_out, status, n_done, fp_iters, n_mats,
+                                                   midpoint);
   return check_launch("implicit_leapfrog_kernel");
 }
 
@@ -247,10 +248,10 @@ static int implicit_dispatch(const double* q_in, const double* p_in, double* q_o
                              const int32_t* dir, int64_t n, int dim, double eps, int n_steps,
                              const ModelArgs& m, double fp_tol, double fp_div, int fp_max,
                              double rev_tol, double* h_out, int32_t* status, int32_t* n_done,
-                             int32_t* fp_iters, cudaStream_t st) {
+                             int32_t* fp_iters, cudaStream_t st, int midpoint = 0) {
 #define MB200_ARGS                                                                           \
   q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, m, fp_tol, fp_div, fp_max, rev_tol,   \
-      h_out, status, n_done, fp_iters, st
+      h_out, status, n_done, fp_iters, st, midpoint
   if (m.rmetric_id == MB200_RMETRIC_SOFTABS) {
     if (!(m.mp[0] > 0.0)) return fail(MB200_ERR_INVALID_ARG, "softabs_coeff must be positive");
     switch (m.target_id) {
@@ -543,6 +544,32 @@ int mb200_selftest_eigh(const double* matrices, int64_t n_matrices, int32_t dim,
 int mb200_selftest_eigh(const double*, int64_t, int32_t, int32_t, double*, double*, int32_t*,
                         void*) {
   return fail(MB200_ERR_UNSUPPORTED, "eigh self-test not compiled in");
+}
+#endif
+
+#ifndef MB200_NO_RIEMANNIAN
+int mb200_implicit_midpoint_riemannian(
+    const double* pos_in, const double* mom_in, double* pos_out, double* mom_out,
+    const int32_t* dir, int64_t n_chains, int32_t dim, double step_size, int32_t n_steps,
+    const mb200_model* model, double fp_convergence_tol, double fp_divergence_tol,
+    int32_t fp_max_iters, double reverse_check_tol, double* h_out, int32_t* status,
+    int32_t* n_done, int32_t* fp_iters, void* stream) {
+  if (n_chains == 0 && dim >= 1) return 0;
+  if (!pos_in || !mom_in || !pos_out || !mom_out || !model)
+    return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
+  if (n_chains < 0 || dim < 1 || n_steps < 0 || fp_max_iters < 0)
+    return fail(MB200_ERR_INVALID_ARG, "bad sizes");
+  return implicit_dispatch(pos_in, mom_in, pos_out, mom_out, dir, n_chains, dim, step_size,
+                           n_steps, to_args(model), fp_convergence_tol, fp_divergence_tol,
+                           fp_max_iters, reverse_check_tol, h_out, status, n_done, fp_iters,
+                           (cudaStream_t)stream, 1);
+}
+#else
+int mb200_implicit_midpoint_riemannian(const double*, const double*, double*, double*,
+                                       const int32_t*, int64_t, int32_t, double, int32_t,
+                                       const mb200_model*, double, double, int32_t, double,
+                                       double*, int32_t*, int32_t*, int32_t*, void*) {
+  return fail(MB200_ERR_UNSUPPORTED, "implicit midpoint not compiled in");
 }
 #endif
 

@@ -169,6 +169,7 @@ struct RmWork {
   int dim, ld;
   double *M1, *M2, *M3;  // [dim*ld] each (M2: SoftAbs; M3: SoftAbs warm start, when it fits)
   double *q, *p, *qs, *ps, *x0, *x1, *base, *v1, *v2, *v3, *lam, *sa, *gsa, *ev, *Vn;
+  double *z0, *z1, *zb, *zp;  // [2*dim] implicit midpoint: iterates, base, previous state (q, p)
   double *rc, *rs;  // rotation cos / sin [dim/2 + 1]
   int *top, *bot;   // round-robin index arrays [dim/2 + 1]
 };
@@ -181,6 +182,7 @@ __host__ __device__ inline size_t rm_smem_doubles(int dim, int n_mats) {
   size_t n = (size_t)dim * ld * n_mats;
   n += (size_t)15 * dpad;      // vectors (Vn counts double: NEED <= 2)
   n += (size_t)dpad;           // second half of Vn
+  n += (size_t)8 * dpad;       // z0, z1, zb, zp (2 * dpad each)
   n += 2 * (size_t)(dpad / 2 + 2);  // rc, rs
   n += (size_t)(dpad / 2 + 2);      // top, bot (ints, 2 per double)
   n += 40;                     // reduction scratch
@@ -205,6 +207,14 @@ __device__ inline void rm_carve(RmWork& w, double* s, int dim, int n_mats, Blk& 
     s += dpad;
   }
   w.Vn = s;
+  s += 2 * dpad;
+  w.z0 = s;
+  s += 2 * dpad;
+  w.z1 = s;
+  s += 2 * dpad;
+  w.zb = s;
+  s += 2 * dpad;
+  w.zp = s;
   s += 2 * dpad;
   w.rc = s;
   s += dpad / 2 + 2;
@@ -996,6 +1006,75 @@ struct ImplicitLeapfrog {
     return MB200_STATUS_OK;
   }
 
+  // ---- ImplicitMidpointIntegrator (integrators.py:547-681), "next" row N4 ----------------
+  // dh/dz at (q, p): vel = dh_dmom = M(q)^-1 p; force = dh_dpos = dh1_dpos + dh2_dpos
+  // (systems.py:198-207, 1381-1399).  Returns 0 or the metric-build failure.
+  __device__ int hamiltonian_gradient(const double* q, const double* p, double* vel,
+                                      double* force) {
+    if (m.build(k, w, q) != 0) return 1;
+    m.inv_matvec(k, w, p, vel);
+    t.grad(k, q, w.v1);
+    m.vjp_grad_log_abs_det(k, w, q, w.v2);
+    m.vjp_grad_quad_inv(k, w, q, p, w.v3);
+    for (int i = k.tid; i < w.dim; i += k.nthr)
+      force[i] = __dadd_rn(__dadd_rn(w.v1[i], __dmul_rn(0.5, w.v2[i])), __dmul_rn(0.5, w.v3[i]));
+    __syncthreads();
+    return 0;
+  }
+
+  // _step_a_fwd (:609-626): fixed point z = z0 + [dt dh_dmom(z); -dt dh_dpos(z)] in z = (q, p),
+  // starting from (and based at) the (q, p) held in w.zb.  Solution pointer in *sol.
+  __device__ int midpoint_fwd(double dt, double** sol, int& iters) {
+    const int n = w.dim;
+    for (int i = k.tid; i < 2 * n; i += k.nthr) w.z0[i] = w.zb[i];
+    __syncthreads();
+    auto func = [&](const double* zin, double* zout) {
+      if (hamiltonian_gradient(zin, zin + n, w.x0, w.x1) != 0) return 1;
+      for (int i = k.tid; i < n; i += k.nthr) {
+        zout[i] = __dadd_rn(w.zb[i], __dmul_rn(dt, w.x0[i]));
+        zout[n + i] = __dadd_rn(w.zb[n + i], __dmul_rn(-dt, w.x1[i]));
+      }
+      __syncthreads();
+      return 0;
+    };
+    return fixed_point_direct(k, 2 * n, w.z0, w.z1, func, fp_tol, fp_div, fp_max, sol, iters);
+  }
+
+  // one implicit-midpoint step (:679-681): _step_a_fwd(dt/2) then _step_a_adj(dt/2)
+  __device__ int midpoint_step(double dt_full, int* iters4) {
+    const int n = w.dim;
+    const double dt = dt_full / 2;
+    m.reset();
+    int it_fwd = 0, it_rev = 0;
+    double* sol;
+    for (int i = k.tid; i < n; i += k.nthr) w.zb[i] = w.q[i], w.zb[n + i] = w.p[i];
+    __syncthreads();
+    int st = midpoint_fwd(dt, &sol, it_fwd);
+    iters4[0] = it_fwd;
+    if (st != 0) return st;
+    for (int i = k.tid; i < n; i += k.nthr) w.q[i] = sol[i], w.p[i] = sol[n + i];
+    __syncthreads();
+    // _step_a_adj (:628-647): explicit Euler half-step from state_prev ...
+    if (hamiltonian_gradient(w.q, w.p, w.x0, w.x1) != 0) return MB200_STATUS_LINALG;
+    for (int i = k.tid; i < n; i += k.nthr) {
+      w.zp[i] = w.q[i], w.zp[n + i] = w.p[i];  // state_prev
+      w.q[i] = __dadd_rn(w.q[i], __dmul_rn(dt, w.x0[i]));
+      w.p[i] = __dsub_rn(w.p[i], __dmul_rn(dt, w.x1[i]));
+    }
+    __syncthreads();
+    // ... then the reversibility check: _step_a_fwd(state_back, -dt) must return to state_prev
+    for (int i = k.tid; i < n; i += k.nthr) w.zb[i] = w.q[i], w.zb[n + i] = w.p[i];
+    __syncthreads();
+    st = midpoint_fwd(-dt, &sol, it_rev);
+    iters4[1] = it_rev;
+    if (st != 0) return st;
+    double e = 0.0;
+    for (int i = k.tid; i < 2 * n; i += k.nthr) e = nanmax(e, fabs(sol[i] - w.zp[i]));
+    const double rev = block_nanmax(k, e);
+    if (rev > rev_tol) return MB200_STATUS_NON_REVERSIBLE;
+    return MB200_STATUS_OK;
+  }
+
   // h = l(q) + log|M|/2 + p.M^-1 p/2   (systems.py:1375-1390); NaN if the metric cannot be built
   __device__ double hamiltonian() {
     m.reset();
@@ -1018,7 +1097,7 @@ __global__ void __launch_bounds__(RM_THREADS)
                              double fp_div, int fp_max, double rev_tol,
                              double* __restrict__ h_out, int32_t* __restrict__ status,
                              int32_t* __restrict__ n_done, int32_t* __restrict__ fp_iters,
-                             int n_mats) {
+                             int n_mats, int midpoint) {
   extern __shared__ double smem[];
   Blk blk;
   blk.tid = threadIdx.x;
@@ -1046,7 +1125,7 @@ __global__ void __launch_bounds__(RM_THREADS)
       for (int i = blk.tid; i < dim; i += blk.nthr) w.qs[i] = w.q[i], w.ps[i] = w.p[i];
       __syncthreads();
       int it_step[4] = {0, 0, 0, 0};
-      st = integ.step(dt, it_step);
+      st = midpoint ? integ.midpoint_step(dt, it_step) : integ.step(dt, it_step);
       if (st == MB200_STATUS_OK) {
         ++done;
 #pragma unroll

@@ -30,6 +30,7 @@ def build_integrator(problem, system=None, **overrides):
         "leapfrog": integrators.LeapfrogIntegrator,
         "implicit_leapfrog": integrators.ImplicitLeapfrogIntegrator,
         "constrained_leapfrog": integrators.ConstrainedLeapfrogIntegrator,
+        "implicit_midpoint": integrators.ImplicitMidpointIntegrator,
         "bcss2": integrators.BCSSTwoStageIntegrator,
         "bcss3": integrators.BCSSThreeStageIntegrator,
         "bcss4": integrators.BCSSFourStageIntegrator,

@@ -318,6 +318,45 @@ class ImplicitLeapfrogIntegrator(Integrator):
         return iters
 
 
+class ImplicitMidpointIntegrator(Integrator):
+    """Implicit midpoint integrator for general Hamiltonians (integrators.py:547-681) --
+    "next" row N4 -- for ``RiemannianMetricSystem`` s: a fixed-point solve in ``(q, p)`` for the
+    forward half-step, an explicit Euler half-step and a reversibility check, all inside the
+    kernel.  Same constructor as the reference."""
+
+    def __init__(self, system, step_size=None, reverse_check_tol=2e-8,
+                 reverse_check_norm=maximum_norm, fixed_point_solver=solve_fixed_point_direct,
+                 fixed_point_solver_kwargs=None):
+        super().__init__(system, step_size)
+        if not isinstance(system, RiemannianMetricSystem):
+            raise TypeError("ImplicitMidpointIntegrator needs a RiemannianMetricSystem.")
+        if reverse_check_norm is not maximum_norm:
+            raise ValueError("Only `maximum_norm` is available for the reversibility check.")
+        if fixed_point_solver is not solve_fixed_point_direct:
+            raise ValueError("Only `solve_fixed_point_direct` is fused into the kernels.")
+        self.reverse_check_tol = reverse_check_tol
+        self.reverse_check_norm = reverse_check_norm
+        self.fixed_point_solver = fixed_point_solver
+        self.fixed_point_solver_kwargs = dict(fixed_point_solver_kwargs or {})
+
+    def _launch(self, pos, mom, pos_out, mom_out, dirs, n_steps, h, status, n_done):
+        n, dim = pos.shape
+        dev = pos.device
+        sysm = self.system
+        kw = self.fixed_point_solver.resolve_kwargs(self.fixed_point_solver_kwargs)
+        model = sysm._model(dev)
+        iters = torch.zeros((n, 4), dtype=torch.int32, device=dev)
+        rc = _lib.load().mb200_implicit_midpoint_riemannian(
+            _lib.ptr(pos), _lib.ptr(mom), _lib.ptr(pos_out), _lib.ptr(mom_out), _lib.ptr(dirs),
+            n, dim, float(self.step_size), n_steps, ctypes.byref(model),
+            float(kw["convergence_tol"]), float(kw["divergence_tol"]), int(kw["max_iters"]),
+            float(self.reverse_check_tol), _lib.ptr(h), _lib.ptr(status), _lib.ptr(n_done),
+            _lib.ptr(iters), _lib.current_stream_ptr(dev),
+        )
+        _lib.check(rc, "mb200_implicit_midpoint_riemannian")
+        return iters
+
+
 class ConstrainedLeapfrogIntegrator(TractableFlowIntegrator):
     """Leapfrog for constrained systems: RATTLE / geodesic integrator with Newton projection
     and reversibility check (integrators.py:684-984)."""

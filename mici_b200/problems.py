@@ -108,11 +108,11 @@ def c1_funnel(n_chains=8192, dim=128, seed=BASE_SEED + 1, metric_kind="dense",
     )
 
 
-def c2_softabs_banana(n_chains=2048, dim=64, seed=BASE_SEED + 2):
+def c2_softabs_banana(n_chains=2048, dim=64, seed=BASE_SEED + 2, integrator="implicit_leapfrog"):
     rng = np.random.default_rng(seed)
     return Problem(
         name="C2",
-        integrator="implicit_leapfrog",
+        integrator=integrator,
         system="softabs_riemannian",
         target="banana",
         target_params={"dim": dim, "b": 0.5},
@@ -154,7 +154,8 @@ def c3_torus(n_chains=4096, seed=BASE_SEED + 3, R=1.0, r=0.5, alpha=0.9):
     )
 
 
-def c4_dense_riemannian(n_chains=8192, dim=512, seed=BASE_SEED + 4, coeff=0.1):
+def c4_dense_riemannian(n_chains=8192, dim=512, seed=BASE_SEED + 4, coeff=0.1,
+                        integrator="implicit_leapfrog"):
     rng = np.random.default_rng(seed)
     g = rng.standard_normal((dim, dim))
     prec = np.identity(dim) + 0.1 * (g @ g.T) / dim
@@ -163,7 +164,7 @@ def c4_dense_riemannian(n_chains=8192, dim=512, seed=BASE_SEED + 4, coeff=0.1):
     mom = rng.standard_normal((n_chains, dim)) @ np.linalg.cholesky(base).T
     return Problem(
         name="C4",
-        integrator="implicit_leapfrog",
+        integrator=integrator,
         system="dense_riemannian",
         target="quadratic",
         target_params={"prec": prec},

@@ -69,7 +69,7 @@ def oracle_step_fn(problem, counts=None, **overrides):
             return mo.composition_steps(q, p, d * eps, 1, target, metric, coefs)
 
         return step, (lambda q, p: mo.euclidean_h(q, p, target, metric)), None
-    if problem.integrator == "implicit_leapfrog":
+    if problem.integrator in ("implicit_leapfrog", "implicit_midpoint"):
         kind = "softabs" if problem.system == "softabs_riemannian" else "dense"
         system = mo.RiemannianSystem(
             target,
@@ -80,7 +80,9 @@ def oracle_step_fn(problem, counts=None, **overrides):
 
         def step(q, p, d):
             c = {} if counts is None else counts
-            out = mo.implicit_leapfrog_step(q, p, d * eps, system, counts=c, **ikw)
+            fn = (mo.implicit_midpoint_step if problem.integrator == "implicit_midpoint"
+                  else mo.implicit_leapfrog_step)
+            out = fn(q, p, d * eps, system, counts=c, **ikw)
             if counts is not None:
                 counts.setdefault("all_fp_iters", []).append(list(c.get("fp_iters", [])))
             return out
@@ -179,6 +181,7 @@ def build_reference(problem, **overrides):
         "leapfrog": mici.integrators.LeapfrogIntegrator,
         "implicit_leapfrog": mici.integrators.ImplicitLeapfrogIntegrator,
         "constrained_leapfrog": mici.integrators.ConstrainedLeapfrogIntegrator,
+        "implicit_midpoint": mici.integrators.ImplicitMidpointIntegrator,
         "bcss2": mici.integrators.BCSSTwoStageIntegrator,
         "bcss3": mici.integrators.BCSSThreeStageIntegrator,
         "bcss4": mici.integrators.BCSSFourStageIntegrator,

@@ -38,6 +38,8 @@ CASES = {
     "n4_bcss2_funnel_d24": ("C1", {"n_chains": 12, "dim": 24, "integrator": "bcss2"}, (1, 5, 20), {}),
     "n4_bcss3_funnel_d40_diag": ("C1", {"n_chains": 8, "dim": 40, "metric_kind": "diagonal", "integrator": "bcss3"}, (1, 20), {}),
     "n4_bcss4_funnel_d130": ("C1", {"n_chains": 6, "dim": 130, "integrator": "bcss4"}, (1, 5), {}),
+    "n4_midpoint_softabs_d8": ("C2", {"n_chains": 16, "dim": 8, "integrator": "implicit_midpoint"}, (1, 5, 20), {}),
+    "n4_midpoint_dense_d32": ("C4", {"n_chains": 6, "dim": 32, "integrator": "implicit_midpoint"}, (1, 5), {}),
     "s1_sphere_dense_d10": ("S1", {"n_chains": 32, "dim": 10}, (1, 5, 20), {}),
     "s1_sphere_diag_d70_inner2": ("S1", {"n_chains": 8, "dim": 70, "metric_kind": "diagonal"}, (1, 5), {"n_inner_step": 2}),
     "s1_sphere_identity_d5": ("S1", {"n_chains": 16, "dim": 5, "metric_kind": "identity"}, (1, 20), {}),
@@ -49,6 +51,7 @@ CASES = {
 FAILURE_CASES = {
     "c2_softabs_banana_bigstep": ("C2", {"n_chains": 32, "dim": 8}, 0.6, (3,), {}),
     "c3_torus_bigstep": ("C3", {"n_chains": 64}, 0.4, (3,), {}),
+    "n4_midpoint_softabs_bigstep": ("C2", {"n_chains": 32, "dim": 8, "integrator": "implicit_midpoint"}, 0.9, (3,), {}),
 }
 
 

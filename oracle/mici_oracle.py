@@ -448,6 +448,53 @@ def implicit_leapfrog_step(
     return q, p
 
 
+def implicit_midpoint_step(q, p, time_step, system, reverse_check_tol=2e-8,
+                           fixed_point_solver_kwargs=None, counts=None):
+    """One ``ImplicitMidpointIntegrator.step`` (integrators.py:609-681) on a Riemannian system:
+    ``_step_a_fwd(dt/2)`` (fixed point in the concatenated (pos, mom)), then ``_step_a_adj(dt/2)``
+    (explicit Euler from the previous state + reversibility check)."""
+    kw = {} if fixed_point_solver_kwargs is None else fixed_point_solver_kwargs
+    q = np.array(q, dtype=np.float64)
+    p = np.array(p, dtype=np.float64)
+    its = []
+
+    def dh_dmom(q, p, m):
+        return system.dh2_dmom(q, p, m)
+
+    def dh_dpos(q, p, m):  # System.dh_dpos: dh1_dpos + dh2_dpos (systems.py:198-201)
+        return system.dh1_dpos(q, m) + system.dh2_dpos(q, p, m)
+
+    def step_a_fwd(q, p, dt):
+        z_init = np.concatenate([q, p])
+
+        def func(z):
+            zq, zp = np.split(z, 2)
+            m = system.metric(zq)
+            return z_init + np.concatenate([dt * dh_dmom(zq, zp, m), -dt * dh_dpos(zq, zp, m)])
+
+        z, n = solve_fixed_point_direct(func, z_init, **kw)
+        its.append(n)
+        return np.split(z, 2)
+
+    try:
+        dt = time_step / 2
+        q, p = step_a_fwd(q, p, dt)
+        m = system.metric(q)
+        q_prev, p_prev = q.copy(), p.copy()
+        q = q + dt * dh_dmom(q_prev, p_prev, m)
+        p = p - dt * dh_dpos(q_prev, p_prev, m)
+        q_back, p_back = step_a_fwd(q.copy(), p.copy(), -dt)
+        rev_diff = maximum_norm(np.concatenate([q_back - q_prev, p_back - p_prev]))
+        if rev_diff > reverse_check_tol:
+            raise OracleIntegratorError(STATUS_NON_REVERSIBLE, f"rev diff {rev_diff}")
+    except (ValueError, _LinAlgError) as e:
+        raise OracleIntegratorError(STATUS_LINALG, str(e)) from e
+    finally:
+        if counts is not None:
+            counts["fp_iters"] = its
+    return q, p
+
+
 # --------------------------------------------------------------------------------------
 # Constrained leapfrog (RATTLE / geodesic integrator) on a Euclidean-metric system
 # --------------------------------------------------------------------------------------
