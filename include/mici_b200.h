@@ -65,6 +65,10 @@ extern "C" {
 #define MB200_RMETRIC_SOFTABS 0 /* SoftAbs of target Hessian (matrices.py:1631-1685); params: softabs_coeff */
 #define MB200_RMETRIC_RANK1 1   /* dense M(q) = B + c q q^T;  aux: [B | B^-1] (2*dim*dim), params: c, log|B|, force_woodbury */
 
+/* fixed-point solvers fused into the implicit integrators (solvers.py:47-94, 97-154) */
+#define MB200_FP_SOLVER_DIRECT 0
+#define MB200_FP_SOLVER_STEFFENSEN 1
+
 #define MB200_MAX_PARAMS 8
 
 typedef struct mb200_model {
@@ -140,7 +144,8 @@ int mb200_constrained_leapfrog_euclidean(
  * n_steps implicit generalised-leapfrog steps on a Riemannian-metric system, fixed-point
  * solves by direct iteration.
  * Replaces: ImplicitLeapfrogIntegrator.step (integrators.py:482-544; NB every sub-map gets the
- *           full dir*step_size) + solve_fixed_point_direct (solvers.py:47-94) +
+ *           full dir*step_size) + solve_fixed_point_direct / _steffensen
+ *           (solvers.py:47-154, selected by fp_solver) +
  *           RiemannianMetricSystem derivatives (systems.py:1360-1402) +
  *           DensePositiveDefiniteMatrix / SoftAbsRegularizedPositiveDefiniteMatrix arithmetic
  *           (matrices.py:1161-1188, 1631-1685).
@@ -150,9 +155,10 @@ int mb200_constrained_leapfrog_euclidean(
 int mb200_implicit_leapfrog_riemannian(
     const double* pos_in, const double* mom_in, double* pos_out, double* mom_out,
     const int32_t* dir, int64_t n_chains, int32_t dim, double step_size, int32_t n_steps,
-    const mb200_model* model, double fp_convergence_tol, double fp_divergence_tol,
-    int32_t fp_max_iters, double reverse_check_tol, double* h_out, int32_t* status,
-    int32_t* n_done, int32_t* fp_iters, void* workspace, int64_t workspace_bytes, void* stream);
+    const mb200_model* model, int32_t fp_solver, double fp_convergence_tol,
+    double fp_divergence_tol, int32_t fp_max_iters, double reverse_check_tol, double* h_out,
+    int32_t* status, int32_t* n_done, int32_t* fp_iters, void* workspace, int64_t workspace_bytes,
+    void* stream);
 
 int64_t mb200_implicit_workspace_bytes(int64_t n_chains, int32_t dim, const mb200_model* model);
 
@@ -178,15 +184,16 @@ int mb200_metropolis_select(double* pos, double* mom, const double* pos_prop,
                             void* stream);
 
 /*
- * Diagnostic: the fused direct fixed-point solver (K4; solve_fixed_point_direct,
- * solvers.py:47-94) on the reference's own known-answer problems
+ * Diagnostic: the fused fixed-point solvers (K4; fp_solver = MB200_FP_SOLVER_*:
+ * solve_fixed_point_direct solvers.py:47-94, solve_fixed_point_steffensen :97-154) on the
+ * reference's own known-answer problems
  * (reference tests/test_solvers.py:25-47): func_id 0 babylonian (y/x + x)/2, 1 ratio
  * (x+y)/(x+1), 2 cosine, 3 doubling 2x, 4 quadratic 1 + x^2; x0, y, x_out are [n*dim].
  */
-int mb200_selftest_fixed_point_direct(int32_t func_id, const double* x0, const double* y,
-                                      int64_t n, int32_t dim, double convergence_tol,
-                                      double divergence_tol, int32_t max_iters, double* x_out,
-                                      int32_t* iters_out, int32_t* status, void* stream);
+int mb200_selftest_fixed_point(int32_t func_id, int32_t fp_solver, const double* x0,
+                               const double* y, int64_t n, int32_t dim, double convergence_tol,
+                               double divergence_tol, int32_t max_iters, double* x_out,
+                               int32_t* iters_out, int32_t* status, void* stream);
 
 /*
  * "Next" row N4: symmetric composition (splitting) integrators on a Euclidean-metric system --
@@ -225,9 +232,9 @@ int mb200_selftest_eigh(const double* matrices, int64_t n_matrices, int32_t dim,
 int mb200_implicit_midpoint_riemannian(
     const double* pos_in, const double* mom_in, double* pos_out, double* mom_out,
     const int32_t* dir, int64_t n_chains, int32_t dim, double step_size, int32_t n_steps,
-    const mb200_model* model, double fp_convergence_tol, double fp_divergence_tol,
-    int32_t fp_max_iters, double reverse_check_tol, double* h_out, int32_t* status,
-    int32_t* n_done, int32_t* fp_iters, void* stream);
+    const mb200_model* model, int32_t fp_solver, double fp_convergence_tol,
+    double fp_divergence_tol, int32_t fp_max_iters, double reverse_check_tol, double* h_out,
+    int32_t* status, int32_t* n_done, int32_t* fp_iters, void* stream);
 
 #ifdef __cplusplus
 }

@@ -64,13 +64,13 @@ SIGNATURES = {
     ),
     "mb200_implicit_leapfrog_riemannian": (
         ctypes.c_int,
-        [_P, _P, _P, _P, _P, _I64, _I32, _F64, _I32, _MP, _F64, _F64, _I32, _F64]
+        [_P, _P, _P, _P, _P, _I64, _I32, _F64, _I32, _MP, _I32, _F64, _F64, _I32, _F64]
         + [_P, _P, _P, _P, _P, _I64, _P],
     ),
     "mb200_implicit_workspace_bytes": (_I64, [_I64, _I32, _MP]),
-    "mb200_selftest_fixed_point_direct": (
+    "mb200_selftest_fixed_point": (
         ctypes.c_int,
-        [_I32, _P, _P, _I64, _I32, _F64, _F64, _I32, _P, _P, _P, _P],
+        [_I32, _I32, _P, _P, _I64, _I32, _F64, _F64, _I32, _P, _P, _P, _P],
     ),
     "mb200_composition_euclidean": (
         ctypes.c_int,
@@ -79,7 +79,7 @@ SIGNATURES = {
     "mb200_selftest_eigh": (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P, _P]),
     "mb200_implicit_midpoint_riemannian": (
         ctypes.c_int,
-        [_P, _P, _P, _P, _P, _I64, _I32, _F64, _I32, _MP, _F64, _F64, _I32, _F64]
+        [_P, _P, _P, _P, _P, _I64, _I32, _F64, _I32, _MP, _I32, _F64, _F64, _I32, _F64]
         + [_P, _P, _P, _P, _P],
     ),
     "mb200_metropolis_select": (

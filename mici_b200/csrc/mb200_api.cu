@@ -220,7 +220,7 @@ static int launch_implicit(const double* q_in, const double* p_in, double* q_out
                            const int32_t* dir, int64_t n, int dim, double eps, int n_steps,
                            const ModelArgs& m, double fp_tol, double fp_div, int fp_max,
                            double rev_tol, double* h_out, int32_t* status, int32_t* n_done,
-                           int32_t* fp_iters, cudaStream_t st, int midpoint) {
+                           int32_t* fp_iters, cudaStream_t st, int midpoint, int fp_solver) {
   auto kern = implicit_leapfrog_kernel<Target, MetricT>;
   int n_mats = MetricT<Target>::N_MATS;
   // SoftAbs: a third matrix enables warm-started eigensolves; use it when two CTAs still fit
@@ -240,7 +240,7 @@ static int launch_implicit(const double* q_in, const double* p_in, double* q_out
   kern<<<(unsigned)blocks, RM_THREADS, smem, st>>>(q_in, p_in, q_out, p_out, dir, n, dim, eps,
                                                    n_steps, m, fp_tol, fp_div, fp_max, rev_tol,
                                                    h_out, status, n_done, fp_iters, n_mats,
-                                                   midpoint);
+                                                   midpoint, fp_solver);
   return check_launch("implicit_leapfrog_kernel");
 }
 
@@ -248,10 +248,13 @@ static int implicit_dispatch(const double* q_in, const double* p_in, double* q_o
                              const int32_t* dir, int64_t n, int dim, double eps, int n_steps,
                              const ModelArgs& m, double fp_tol, double fp_div, int fp_max,
                              double rev_tol, double* h_out, int32_t* status, int32_t* n_done,
-                             int32_t* fp_iters, cudaStream_t st, int midpoint = 0) {
+                             int32_t* fp_iters, cudaStream_t st, int midpoint = 0,
+                             int fp_solver = 0) {
+  if (fp_solver != MB200_FP_SOLVER_DIRECT && fp_solver != MB200_FP_SOLVER_STEFFENSEN)
+    return fail(MB200_ERR_INVALID_ARG, "unknown fixed-point solver %d", fp_solver);
 #define MB200_ARGS                                                                           \
   q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, m, fp_tol, fp_div, fp_max, rev_tol,   \
-      h_out, status, n_done, fp_iters, st, midpoint
+      h_out, status, n_done, fp_iters, st, midpoint, fp_solver
   if (m.rmetric_id == MB200_RMETRIC_SOFTABS) {
     if (!(m.mp[0] > 0.0)) return fail(MB200_ERR_INVALID_ARG, "softabs_coeff must be positive");
     switch (m.target_id) {
@@ -404,7 +407,7 @@ int mb200_constrained_leapfrog_euclidean(
 #ifdef MB200_NO_RIEMANNIAN
 int mb200_implicit_leapfrog_riemannian(const double*, const double*, double*, double*,
                                        const int32_t*, int64_t, int32_t, double, int32_t,
-                                       const mb200_model*, double, double, int32_t, double,
+                                       const mb200_model*, int32_t, double, double, int32_t, double,
                                        double*, int32_t*, int32_t*, int32_t*, void*, int64_t,
                                        void*) {
   return fail(MB200_ERR_UNSUPPORTED, "implicit leapfrog not compiled in");
@@ -414,9 +417,8 @@ int mb200_hamiltonian_riemannian(const double*, const double*, int64_t, int32_t,
                                  const mb200_model*, double*, int32_t*, void*, int64_t, void*) {
   return fail(MB200_ERR_UNSUPPORTED, "riemannian hamiltonian not compiled in");
 }
-int mb200_selftest_fixed_point_direct(int32_t, const double*, const double*, int64_t, int32_t,
-                                      double, double, int32_t, double*, int32_t*, int32_t*,
-                                      void*) {
+int mb200_selftest_fixed_point(int32_t, int32_t, const double*, const double*, int64_t, int32_t,
+                               double, double, int32_t, double*, int32_t*, int32_t*, void*) {
   return fail(MB200_ERR_UNSUPPORTED, "fixed-point self-test not compiled in");
 }
 #endif
@@ -425,9 +427,10 @@ int mb200_selftest_fixed_point_direct(int32_t, const double*, const double*, int
 int mb200_implicit_leapfrog_riemannian(
     const double* pos_in, const double* mom_in, double* pos_out, double* mom_out,
     const int32_t* dir, int64_t n_chains, int32_t dim, double step_size, int32_t n_steps,
-    const mb200_model* model, double fp_convergence_tol, double fp_divergence_tol,
-    int32_t fp_max_iters, double reverse_check_tol, double* h_out, int32_t* status,
-    int32_t* n_done, int32_t* fp_iters, void* workspace, int64_t workspace_bytes, void* stream) {
+    const mb200_model* model, int32_t fp_solver, double fp_convergence_tol,
+    double fp_divergence_tol, int32_t fp_max_iters, double reverse_check_tol, double* h_out,
+    int32_t* status, int32_t* n_done, int32_t* fp_iters, void* workspace, int64_t workspace_bytes,
+    void* stream) {
   (void)workspace;
   (void)workspace_bytes;
   if (n_chains == 0 && dim >= 1) return 0;
@@ -439,7 +442,7 @@ int mb200_implicit_leapfrog_riemannian(
   return implicit_dispatch(pos_in, mom_in, pos_out, mom_out, dir, n_chains, dim, step_size,
                            n_steps, to_args(model), fp_convergence_tol, fp_divergence_tol,
                            fp_max_iters, reverse_check_tol, h_out, status, n_done, fp_iters,
-                           (cudaStream_t)stream);
+                           (cudaStream_t)stream, 0, fp_solver);
 }
 
 // every per-chain buffer of the implicit kernels lives in shared memory for the supported sizes
@@ -483,18 +486,19 @@ int mb200_metropolis_select(double* pos, double* mom, const double* pos_prop,
 }
 
 #ifndef MB200_NO_RIEMANNIAN
-int mb200_selftest_fixed_point_direct(int32_t func_id, const double* x0, const double* y,
-                                      int64_t n, int32_t dim, double convergence_tol,
+int mb200_selftest_fixed_point(int32_t func_id, int32_t fp_solver, const double* x0,
+                               const double* y, int64_t n, int32_t dim, double convergence_tol,
                                       double divergence_tol, int32_t max_iters, double* x_out,
                                       int32_t* iters_out, int32_t* status, void* stream) {
   if (!x0 || !y || !x_out || !iters_out || !status)
     return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
   if (n < 0 || dim < 1 || func_id < 0 || func_id > 4) return fail(MB200_ERR_INVALID_ARG, "bad arguments");
   if (n == 0) return 0;
-  const size_t smem = (size_t)(2 * dim + 40) * sizeof(double);
+  const size_t smem = (size_t)(3 * dim + 40) * sizeof(double);
   int64_t blocks = n < 4096 ? n : 4096;
   fixed_point_selftest_kernel<<<(unsigned)blocks, 64, smem, (cudaStream_t)stream>>>(
-      func_id, x0, y, n, dim, convergence_tol, divergence_tol, max_iters, x_out, iters_out, status);
+      func_id, fp_solver, x0, y, n, dim, convergence_tol, divergence_tol, max_iters, x_out, iters_out,
+      status);
   return check_launch("fixed_point_selftest_kernel");
 }
 #endif
@@ -551,9 +555,9 @@ int mb200_selftest_eigh(const double*, int64_t, int32_t, int32_t, double*, doubl
 int mb200_implicit_midpoint_riemannian(
     const double* pos_in, const double* mom_in, double* pos_out, double* mom_out,
     const int32_t* dir, int64_t n_chains, int32_t dim, double step_size, int32_t n_steps,
-    const mb200_model* model, double fp_convergence_tol, double fp_divergence_tol,
-    int32_t fp_max_iters, double reverse_check_tol, double* h_out, int32_t* status,
-    int32_t* n_done, int32_t* fp_iters, void* stream) {
+    const mb200_model* model, int32_t fp_solver, double fp_convergence_tol,
+    double fp_divergence_tol, int32_t fp_max_iters, double reverse_check_tol, double* h_out,
+    int32_t* status, int32_t* n_done, int32_t* fp_iters, void* stream) {
   if (n_chains == 0 && dim >= 1) return 0;
   if (!pos_in || !mom_in || !pos_out || !mom_out || !model)
     return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
@@ -562,12 +566,12 @@ int mb200_implicit_midpoint_riemannian(
   return implicit_dispatch(pos_in, mom_in, pos_out, mom_out, dir, n_chains, dim, step_size,
                            n_steps, to_args(model), fp_convergence_tol, fp_divergence_tol,
                            fp_max_iters, reverse_check_tol, h_out, status, n_done, fp_iters,
-                           (cudaStream_t)stream, 1);
+                           (cudaStream_t)stream, 1, fp_solver);
 }
 #else
 int mb200_implicit_midpoint_riemannian(const double*, const double*, double*, double*,
                                        const int32_t*, int64_t, int32_t, double, int32_t,
-                                       const mb200_model*, double, double, int32_t, double,
+                                       const mb200_model*, int32_t, double, double, int32_t, double,
                                        double*, int32_t*, int32_t*, int32_t*, void*) {
   return fail(MB200_ERR_UNSUPPORTED, "implicit midpoint not compiled in");
 }

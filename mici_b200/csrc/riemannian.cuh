@@ -168,8 +168,8 @@ struct StdGaussianRTarget {
 struct RmWork {
   int dim, ld;
   double *M1, *M2, *M3;  // [dim*ld] each (M2: SoftAbs; M3: SoftAbs warm start, when it fits)
-  double *q, *p, *qs, *ps, *x0, *x1, *base, *v1, *v2, *v3, *lam, *sa, *gsa, *ev, *Vn;
-  double *z0, *z1, *zb, *zp;  // [2*dim] implicit midpoint: iterates, base, previous state (q, p)
+  double *q, *p, *qs, *ps, *x0, *x1, *x2, *base, *v1, *v2, *v3, *lam, *sa, *gsa, *ev, *Vn;
+  double *z0, *z1, *z2, *zb, *zp;  // [2*dim] implicit midpoint: iterates, base, previous (q, p)
   double *rc, *rs;  // rotation cos / sin [dim/2 + 1]
   int *top, *bot;   // round-robin index arrays [dim/2 + 1]
 };
@@ -180,9 +180,9 @@ __host__ __device__ inline size_t rm_smem_doubles(int dim, int n_mats) {
   const int ld = dim + 1;
   const int dpad = (dim + 1) & ~1;
   size_t n = (size_t)dim * ld * n_mats;
-  n += (size_t)15 * dpad;      // vectors (Vn counts double: NEED <= 2)
+  n += (size_t)16 * dpad;      // vectors (Vn counts double: NEED <= 2)
   n += (size_t)dpad;           // second half of Vn
-  n += (size_t)8 * dpad;       // z0, z1, zb, zp (2 * dpad each)
+  n += (size_t)10 * dpad;      // z0, z1, z2, zb, zp (2 * dpad each)
   n += 2 * (size_t)(dpad / 2 + 2);  // rc, rs
   n += (size_t)(dpad / 2 + 2);      // top, bot (ints, 2 per double)
   n += 40;                     // reduction scratch
@@ -200,7 +200,7 @@ __device__ inline void rm_carve(RmWork& w, double* s, int dim, int n_mats, Blk& 
   if (n_mats >= 2) s += (size_t)dim * ld;
   w.M3 = n_mats >= 3 ? s : nullptr;
   if (n_mats >= 3) s += (size_t)dim * ld;
-  double** vecs[] = {&w.q, &w.p, &w.qs, &w.ps, &w.x0, &w.x1, &w.base, &w.v1,
+  double** vecs[] = {&w.q, &w.p, &w.qs, &w.ps, &w.x0, &w.x1, &w.x2, &w.base, &w.v1,
                      &w.v2, &w.v3, &w.lam, &w.sa, &w.gsa, &w.ev};
   for (auto v : vecs) {
     *v = s;
@@ -211,6 +211,8 @@ __device__ inline void rm_carve(RmWork& w, double* s, int dim, int n_mats, Blk& 
   w.z0 = s;
   s += 2 * dpad;
   w.z1 = s;
+  s += 2 * dpad;
+  w.z2 = s;
   s += 2 * dpad;
   w.zb = s;
   s += 2 * dpad;
@@ -845,11 +847,48 @@ __device__ inline int fixed_point_direct(const Blk& k, int dim, double* xa, doub
   return MB200_STATUS_CONVERGENCE;
 }
 
+// solve_fixed_point_steffensen (solvers.py:97-154): Aitken-extrapolated iteration, two function
+// evaluations per iteration: x1 = f(x0), x2 = f(x1), x = x0 - (x1 - x0)^2 / (x2 - 2 x1 + x0) with
+// exact-zero denominators replaced by machine epsilon (:130-133); same divergence / convergence
+// tests on |x - x0| as the direct solver.  Iterates live in xa (x0 on entry), xb, xc.
+template <class F>
+__device__ inline int fixed_point_steffensen(const Blk& k, int dim, double* xa, double* xb,
+                                             double* xc, F func, double tol, double div_tol,
+                                             int max_iters, double** result, int& iters) {
+  double* x0 = xa;
+  double* x1 = xb;
+  double* x2 = xc;
+  for (int i = 0; i < max_iters; ++i) {
+    if (func(x0, x1) != 0) return MB200_STATUS_CONVERGENCE;
+    if (func(x1, x2) != 0) return MB200_STATUS_CONVERGENCE;
+    double e = 0.0;
+    for (int j = k.tid; j < dim; j += k.nthr) {
+      double denom = __dadd_rn(__dsub_rn(x2[j], __dmul_rn(2.0, x1[j])), x0[j]);
+      if (fabs(denom) == 0.0) denom = DBL_EPSILON;
+      const double d1 = __dsub_rn(x1[j], x0[j]);
+      const double x = __dsub_rn(x0[j], __dmul_rn(d1, d1) / denom);
+      e = nanmax(e, fabs(x - x0[j]));
+      x2[j] = x;
+    }
+    const double err = block_nanmax(k, e);
+    ++iters;
+    if (err > div_tol || err != err) return MB200_STATUS_CONVERGENCE;
+    if (err < tol) {
+      *result = x2;
+      return 0;
+    }
+    double* tmp = x0;
+    x0 = x2;
+    x2 = tmp;
+  }
+  return MB200_STATUS_CONVERGENCE;
+}
+
 // Diagnostic kernel: K4 on the reference's own known-answer problems
 // (reference tests/test_solvers.py:25-47): 0 babylonian (y/x + x)/2, 1 ratio (x+y)/(x+1),
 // 2 cosine, 3 doubling 2x, 4 quadratic 1 + x^2.  One CTA per problem instance.
 __global__ void __launch_bounds__(64)
-    fixed_point_selftest_kernel(int func_id, const double* __restrict__ x0,
+    fixed_point_selftest_kernel(int func_id, int solver, const double* __restrict__ x0,
                                 const double* __restrict__ y, int64_t n, int dim, double tol,
                                 double div_tol, int max_iters, double* __restrict__ x_out,
                                 int32_t* __restrict__ iters_out, int32_t* __restrict__ status) {
@@ -859,7 +898,8 @@ __global__ void __launch_bounds__(64)
   k.warp = threadIdx.x >> 5, k.nwarp = blockDim.x >> 5;
   double* xa = smem;
   double* xb = smem + dim;
-  k.red = smem + 2 * dim;
+  double* xc = smem + 2 * dim;
+  k.red = smem + 3 * dim;
   for (int64_t ch = blockIdx.x; ch < n; ch += gridDim.x) {
     __syncthreads();
     for (int j = k.tid; j < dim; j += k.nthr) xa[j] = x0[ch * dim + j];
@@ -880,7 +920,10 @@ __global__ void __launch_bounds__(64)
     };
     double* sol = xa;
     int iters = 0;
-    const int st = fixed_point_direct(k, dim, xa, xb, func, tol, div_tol, max_iters, &sol, iters);
+    const int st = solver == 1 ? fixed_point_steffensen(k, dim, xa, xb, xc, func, tol, div_tol,
+                                                        max_iters, &sol, iters)
+                               : fixed_point_direct(k, dim, xa, xb, func, tol, div_tol, max_iters,
+                                                    &sol, iters);
     for (int j = k.tid; j < dim; j += k.nthr) x_out[ch * dim + j] = sol[j];
     if (k.tid == 0) {
       iters_out[ch] = iters;
@@ -900,10 +943,14 @@ struct ImplicitLeapfrog {
   Metric& m;
   double fp_tol, fp_div, rev_tol;
   int fp_max;
+  int fp_solver;  // MB200_FP_SOLVER_DIRECT / MB200_FP_SOLVER_STEFFENSEN
 
   // K4 on this chain's buffers (see fixed_point_direct below)
   template <class F>
   __device__ int fixed_point(F func, double** result, int& iters) {
+    if (fp_solver == MB200_FP_SOLVER_STEFFENSEN)
+      return fixed_point_steffensen(k, w.dim, w.x0, w.x1, w.x2, func, fp_tol, fp_div, fp_max,
+                                    result, iters);
     return fixed_point_direct(k, w.dim, w.x0, w.x1, func, fp_tol, fp_div, fp_max, result, iters);
   }
 
@@ -1037,6 +1084,9 @@ struct ImplicitLeapfrog {
       __syncthreads();
       return 0;
     };
+    if (fp_solver == MB200_FP_SOLVER_STEFFENSEN)
+      return fixed_point_steffensen(k, 2 * n, w.z0, w.z1, w.z2, func, fp_tol, fp_div, fp_max, sol,
+                                    iters);
     return fixed_point_direct(k, 2 * n, w.z0, w.z1, func, fp_tol, fp_div, fp_max, sol, iters);
   }
 
@@ -1097,7 +1147,7 @@ __global__ void __launch_bounds__(RM_THREADS)
                              double fp_div, int fp_max, double rev_tol,
                              double* __restrict__ h_out, int32_t* __restrict__ status,
                              int32_t* __restrict__ n_done, int32_t* __restrict__ fp_iters,
-                             int n_mats, int midpoint) {
+                             int n_mats, int midpoint, int fp_solver) {
   extern __shared__ double smem[];
   Blk blk;
   blk.tid = threadIdx.x;
@@ -1109,7 +1159,8 @@ __global__ void __launch_bounds__(RM_THREADS)
   rm_carve(w, smem, dim, n_mats, blk);
   const Target target(model, dim);
   MetricT<Target> metric(target, model);
-  ImplicitLeapfrog<Target, MetricT<Target>> integ{blk, w, target, metric, fp_tol, fp_div, rev_tol, fp_max};
+  ImplicitLeapfrog<Target, MetricT<Target>> integ{blk,    w,      target,  metric,
+                                                  fp_tol, fp_div, rev_tol, fp_max, fp_solver};
 
   for (int64_t ch = blockIdx.x; ch < n_chains; ch += gridDim.x) {
     __syncthreads();

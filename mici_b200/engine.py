@@ -26,6 +26,10 @@ def build_integrator(problem, system=None, **overrides):
     system = build_system(problem) if system is None else system
     kw = dict(problem.integrator_kwargs)
     kw.update(overrides)
+    if isinstance(kw.get("fixed_point_solver"), str):  # solver named by string in the fixtures
+        from . import solvers  # noqa: PLC0415
+
+        kw["fixed_point_solver"] = getattr(solvers, "solve_fixed_point_" + kw["fixed_point_solver"])
     cls = {
         "leapfrog": integrators.LeapfrogIntegrator,
         "implicit_leapfrog": integrators.ImplicitLeapfrogIntegrator,

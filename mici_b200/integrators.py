@@ -29,8 +29,11 @@ from .errors import AdaptationError, raise_for_status
 from .solvers import (
     maximum_norm,
     solve_fixed_point_direct,
+    solve_fixed_point_steffensen,
     solve_projection_onto_manifold_newton,
 )
+
+_FUSED_FIXED_POINT_SOLVERS = (solve_fixed_point_direct, solve_fixed_point_steffensen)
 from .states import ChainState
 from .systems import (
     ConstrainedEuclideanMetricSystem,
@@ -292,8 +295,9 @@ class ImplicitLeapfrogIntegrator(Integrator):
             raise TypeError("ImplicitLeapfrogIntegrator needs a RiemannianMetricSystem.")
         if reverse_check_norm is not maximum_norm:
             raise ValueError("Only `maximum_norm` is available for the reversibility check.")
-        if fixed_point_solver is not solve_fixed_point_direct:
-            raise ValueError("Only `solve_fixed_point_direct` is fused into the kernels.")
+        if fixed_point_solver not in _FUSED_FIXED_POINT_SOLVERS:
+            raise ValueError("Only `solve_fixed_point_direct` and `solve_fixed_point_steffensen` "
+                             "are fused into the kernels.")
         self.reverse_check_tol = reverse_check_tol
         self.reverse_check_norm = reverse_check_norm
         self.fixed_point_solver = fixed_point_solver
@@ -310,7 +314,8 @@ class ImplicitLeapfrogIntegrator(Integrator):
         rc = _lib.load().mb200_implicit_leapfrog_riemannian(
             _lib.ptr(pos), _lib.ptr(mom), _lib.ptr(pos_out), _lib.ptr(mom_out), _lib.ptr(dirs),
             n, dim, float(self.step_size), n_steps, ctypes.byref(model),
-            float(kw["convergence_tol"]), float(kw["divergence_tol"]), int(kw["max_iters"]),
+            self.fixed_point_solver.kind, float(kw["convergence_tol"]),
+            float(kw["divergence_tol"]), int(kw["max_iters"]),
             float(self.reverse_check_tol), _lib.ptr(h), _lib.ptr(status), _lib.ptr(n_done),
             _lib.ptr(iters), _lib.ptr(ws), ws.numel(), _lib.current_stream_ptr(dev),
         )
@@ -332,8 +337,9 @@ class ImplicitMidpointIntegrator(Integrator):
             raise TypeError("ImplicitMidpointIntegrator needs a RiemannianMetricSystem.")
         if reverse_check_norm is not maximum_norm:
             raise ValueError("Only `maximum_norm` is available for the reversibility check.")
-        if fixed_point_solver is not solve_fixed_point_direct:
-            raise ValueError("Only `solve_fixed_point_direct` is fused into the kernels.")
+        if fixed_point_solver not in _FUSED_FIXED_POINT_SOLVERS:
+            raise ValueError("Only `solve_fixed_point_direct` and `solve_fixed_point_steffensen` "
+                             "are fused into the kernels.")
         self.reverse_check_tol = reverse_check_tol
         self.reverse_check_norm = reverse_check_norm
         self.fixed_point_solver = fixed_point_solver
@@ -349,7 +355,8 @@ class ImplicitMidpointIntegrator(Integrator):
         rc = _lib.load().mb200_implicit_midpoint_riemannian(
             _lib.ptr(pos), _lib.ptr(mom), _lib.ptr(pos_out), _lib.ptr(mom_out), _lib.ptr(dirs),
             n, dim, float(self.step_size), n_steps, ctypes.byref(model),
-            float(kw["convergence_tol"]), float(kw["divergence_tol"]), int(kw["max_iters"]),
+            self.fixed_point_solver.kind, float(kw["convergence_tol"]),
+            float(kw["divergence_tol"]), int(kw["max_iters"]),
             float(self.reverse_check_tol), _lib.ptr(h), _lib.ptr(status), _lib.ptr(n_done),
             _lib.ptr(iters), _lib.current_stream_ptr(dev),
         )

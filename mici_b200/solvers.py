@@ -17,9 +17,10 @@ from .errors import Error
 class _DeviceSolver:
     """Marker object for a solver that is fused into the CUDA integrator kernels."""
 
-    def __init__(self, name, defaults):
+    def __init__(self, name, defaults, kind=0):
         self.__name__ = name
         self.defaults = dict(defaults)
+        self.kind = kind  # MB200_FP_SOLVER_* for fixed-point solvers
 
     def resolve_kwargs(self, kwargs):
         out = dict(self.defaults)
@@ -52,6 +53,13 @@ def maximum_norm(vct):
 solve_fixed_point_direct = _DeviceSolver(
     "solve_fixed_point_direct",
     {"convergence_tol": 1e-9, "divergence_tol": 1e10, "max_iters": 100},
+)
+
+#: solvers.py:97-154 defaults (Aitken / Steffensen acceleration, two evaluations per iteration)
+solve_fixed_point_steffensen = _DeviceSolver(
+    "solve_fixed_point_steffensen",
+    {"convergence_tol": 1e-9, "divergence_tol": 1e10, "max_iters": 100},
+    kind=1,
 )
 
 #: solvers.py:346-469 defaults

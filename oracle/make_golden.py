@@ -40,6 +40,8 @@ CASES = {
     "n4_bcss4_funnel_d130": ("C1", {"n_chains": 6, "dim": 130, "integrator": "bcss4"}, (1, 5), {}),
     "n4_midpoint_softabs_d8": ("C2", {"n_chains": 16, "dim": 8, "integrator": "implicit_midpoint"}, (1, 5, 20), {}),
     "n4_midpoint_dense_d32": ("C4", {"n_chains": 6, "dim": 32, "integrator": "implicit_midpoint"}, (1, 5), {}),
+    "n4_steffensen_softabs_d8": ("C2", {"n_chains": 16, "dim": 8}, (1, 5), {"fixed_point_solver": "steffensen"}),
+    "n4_steffensen_midpoint_dense_d16": ("C4", {"n_chains": 6, "dim": 16, "integrator": "implicit_midpoint"}, (1, 5), {"fixed_point_solver": "steffensen"}),
     "s1_sphere_dense_d10": ("S1", {"n_chains": 32, "dim": 10}, (1, 5, 20), {}),
     "s1_sphere_diag_d70_inner2": ("S1", {"n_chains": 8, "dim": 70, "metric_kind": "diagonal"}, (1, 5), {"n_inner_step": 2}),
     "s1_sphere_identity_d5": ("S1", {"n_chains": 16, "dim": 5, "metric_kind": "identity"}, (1, 20), {}),
@@ -104,6 +106,8 @@ def solver_known_answers():
     for k, (f, x0) in probs.items():
         for tol in (1e-6, 1e-8, 1e-10):
             out[f"{k}_{tol:g}"] = mici.solvers.solve_fixed_point_direct(f, x0, convergence_tol=tol)
+            out[f"steffensen_{k}_{tol:g}"] = mici.solvers.solve_fixed_point_steffensen(
+                f, x0, convergence_tol=tol)
     np.savez(os.path.join(GOLDEN_DIR, "solver_known_answers.npz"), **out)
 
 

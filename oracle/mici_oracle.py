@@ -246,6 +246,30 @@ def solve_fixed_point_direct(func, x0, convergence_tol=1e-9, divergence_tol=1e10
     raise OracleIntegratorError(STATUS_CONVERGENCE, f"did not converge, last error {error}")
 
 
+def solve_fixed_point_steffensen(func, x0, convergence_tol=1e-9, divergence_tol=1e10, max_iters=100):
+    """solvers.py:97-154 with ``norm=maximum_norm``.  Returns ``(x, n_iters)``."""
+    error = np.nan
+    try:
+        for i in range(max_iters):
+            x1 = func(x0)
+            x2 = func(x1)
+            denom = x2 - 2 * x1 + x0
+            denom[abs(denom) == 0.0] = np.finfo(x0.dtype).eps
+            x = x0 - (x1 - x0) ** 2 / denom
+            error = maximum_norm(x - x0)
+            if error > divergence_tol or np.isnan(error):
+                raise OracleIntegratorError(STATUS_CONVERGENCE, f"diverged at iteration {i}")
+            if error < convergence_tol:
+                return x, i + 1
+            x0 = x
+    except (ValueError, _LinAlgError) as e:
+        raise OracleIntegratorError(STATUS_CONVERGENCE, f"{type(e)} in fixed point solver") from e
+    raise OracleIntegratorError(STATUS_CONVERGENCE, f"did not converge, last error {error}")
+
+
+FIXED_POINT_SOLVERS = {"direct": solve_fixed_point_direct, "steffensen": solve_fixed_point_steffensen}
+
+
 # --------------------------------------------------------------------------------------
 # Riemannian metrics (position dependent)
 # --------------------------------------------------------------------------------------
@@ -385,6 +409,7 @@ def implicit_leapfrog_step(
     reverse_check_tol=2e-8,
     fixed_point_solver_kwargs=None,
     counts=None,
+    fixed_point_solver="direct",
 ):
     """One ``ImplicitLeapfrogIntegrator.step`` (integrators.py:482-544).
 
@@ -400,7 +425,7 @@ def implicit_leapfrog_step(
     its = []
 
     def solve(func, x0):
-        x, n = solve_fixed_point_direct(func, x0, **kw)
+        x, n = FIXED_POINT_SOLVERS[fixed_point_solver](func, x0, **kw)
         its.append(n)
         return x
 
@@ -449,7 +474,8 @@ def implicit_leapfrog_step(
 
 
 def implicit_midpoint_step(q, p, time_step, system, reverse_check_tol=2e-8,
-                           fixed_point_solver_kwargs=None, counts=None):
+                           fixed_point_solver_kwargs=None, counts=None,
+                           fixed_point_solver="direct"):
     """One ``ImplicitMidpointIntegrator.step`` (integrators.py:609-681) on a Riemannian system:
     ``_step_a_fwd(dt/2)`` (fixed point in the concatenated (pos, mom)), then ``_step_a_adj(dt/2)``
     (explicit Euler from the previous state + reversibility check)."""
@@ -472,7 +498,7 @@ def implicit_midpoint_step(q, p, time_step, system, reverse_check_tol=2e-8,
             m = system.metric(zq)
             return z_init + np.concatenate([dt * dh_dmom(zq, zp, m), -dt * dh_dpos(zq, zp, m)])
 
-        z, n = solve_fixed_point_direct(func, z_init, **kw)
+        z, n = FIXED_POINT_SOLVERS[fixed_point_solver](func, z_init, **kw)
         its.append(n)
         return np.split(z, 2)
 

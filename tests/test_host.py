@@ -122,6 +122,9 @@ def test_integrator_constructor_contracts():
         il.fixed_point_solver.resolve_kwargs({"bogus": 1})
     with pytest.raises(ValueError):
         integrators.ImplicitLeapfrogIntegrator(rm, 0.1, fixed_point_solver=lambda f, x: x)
+    st = integrators.ImplicitLeapfrogIntegrator(
+        rm, 0.1, fixed_point_solver=solvers.solve_fixed_point_steffensen)
+    assert st.fixed_point_solver.kind == 1
     cs = systems.DenseConstrainedEuclideanMetricSystem(targets.Torus())
     cl = integrators.ConstrainedLeapfrogIntegrator(cs, 0.1, n_inner_step=3)
     assert cl.n_inner_step == 3

@@ -54,6 +54,9 @@ def test_fixed_point_direct_known_answers(prob, tol):
     assert mo.maximum_norm(x - fixed_point) < tol
     g = np.load(os.path.join(GOLDEN_DIR, "solver_known_answers.npz"))
     np.testing.assert_array_equal(x, g[f"{prob}_{tol:g}"])  # same iterate sequence
+    xs, _ = mo.solve_fixed_point_steffensen(func, x0, convergence_tol=tol)
+    assert mo.maximum_norm(xs - fixed_point) < tol
+    np.testing.assert_array_equal(xs, g[f"steffensen_{prob}_{tol:g}"])
 
 
 @pytest.mark.parametrize("func", [lambda x: 2 * x, lambda x: 1 + x**2])

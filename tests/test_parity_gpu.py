@@ -288,7 +288,7 @@ def test_batched_hmc_full_size_c1_device_rng():
 
 
 # ---- K4 on the reference's own solver known answers (reference tests/test_solvers.py:25-80)
-def _fixed_point_gpu(func_id, x0, y, tol, max_iters=100, div_tol=1e10):
+def _fixed_point_gpu(func_id, x0, y, tol, max_iters=100, div_tol=1e10, solver=0):
     from mici_b200 import _lib
 
     x0 = torch.as_tensor(np.atleast_2d(x0), device=DEV).contiguous()
@@ -297,17 +297,18 @@ def _fixed_point_gpu(func_id, x0, y, tol, max_iters=100, div_tol=1e10):
     out = torch.empty_like(x0)
     iters = torch.empty(n, dtype=torch.int32, device=DEV)
     status = torch.empty(n, dtype=torch.int32, device=DEV)
-    rc = _lib.load().mb200_selftest_fixed_point_direct(
-        func_id, _lib.ptr(x0), _lib.ptr(y), n, dim, tol, div_tol, max_iters, _lib.ptr(out),
+    rc = _lib.load().mb200_selftest_fixed_point(
+        func_id, solver, _lib.ptr(x0), _lib.ptr(y), n, dim, tol, div_tol, max_iters, _lib.ptr(out),
         _lib.ptr(iters), _lib.ptr(status), _lib.current_stream_ptr(x0.device))
     assert rc == 0
     torch.cuda.synchronize()
     return out.cpu().numpy(), iters.cpu().numpy(), status.cpu().numpy()
 
 
+@pytest.mark.parametrize("solver", [0, 1])
 @pytest.mark.parametrize("prob,func_id", [("babylonian", 0), ("ratio", 1), ("cosine", 2)])
 @pytest.mark.parametrize("tol", [1e-6, 1e-8, 1e-10])
-def test_fused_fixed_point_solver_known_answers(prob, func_id, tol):
+def test_fused_fixed_point_solver_known_answers(prob, func_id, tol, solver):
     import os
 
     from oracle import mici_oracle as mo
@@ -316,13 +317,15 @@ def test_fused_fixed_point_solver_known_answers(prob, func_id, tol):
     y = np.array([3.0, 5.0, 7.0]) if func_id < 2 else np.array([0.0])
     x0 = np.ones_like(y)
     fixed_point = y**0.5 if func_id < 2 else np.array([0.7390851332151607])
-    x, iters, status = _fixed_point_gpu(func_id, x0, y, tol)
+    x, iters, status = _fixed_point_gpu(func_id, x0, y, tol, solver=solver)
     assert status[0] == 0
     assert np.abs(x[0] - fixed_point).max() < tol  # reference test_solvers.py:65-80
     g = np.load(os.path.join(GOLDEN_DIR, "solver_known_answers.npz"))
-    np.testing.assert_allclose(x[0], g[f"{prob}_{tol:g}"], rtol=1e-14)  # same iterate returned
+    key = ("steffensen_" if solver else "") + f"{prob}_{tol:g}"
+    np.testing.assert_allclose(x[0], g[key], rtol=1e-13)  # same iterate returned
     funcs = {0: lambda v: (y / v + v) / 2, 1: lambda v: (v + y) / (v + 1), 2: np.cos}
-    _, n_ref = mo.solve_fixed_point_direct(funcs[func_id], x0, convergence_tol=tol)
+    ref_solver = mo.solve_fixed_point_steffensen if solver else mo.solve_fixed_point_direct
+    _, n_ref = ref_solver(funcs[func_id], x0, convergence_tol=tol)
     assert iters[0] == n_ref  # same stopping iteration (H2)
 
 
