@@ -69,6 +69,11 @@ extern "C" {
 #define MB200_FP_SOLVER_DIRECT 0
 #define MB200_FP_SOLVER_STEFFENSEN 1
 
+/* projection solvers fused into the constrained integrator (solvers.py:346-469, 195-343, 472-614) */
+#define MB200_PROJ_SOLVER_NEWTON 0
+#define MB200_PROJ_SOLVER_QUASI_NEWTON 1
+#define MB200_PROJ_SOLVER_NEWTON_LINE_SEARCH 2
+
 #define MB200_MAX_PARAMS 8
 
 typedef struct mb200_model {
@@ -127,7 +132,8 @@ int mb200_euclidean_eval(const double* pos, const double* mom, int64_t n_chains,
 /*
  * n_steps constrained (RATTLE / geodesic) leapfrog steps with Newton projection.
  * Replaces: ConstrainedLeapfrogIntegrator.step (integrators.py:929-984) +
- *           solve_projection_onto_manifold_newton (solvers.py:346-469) +
+ *           solve_projection_onto_manifold_{newton, quasi_newton, newton_with_line_search}
+ *           (solvers.py:346-469, 195-343, 472-614; projection_solver = MB200_PROJ_SOLVER_*) +
  *           DenseConstrainedEuclideanMetricSystem methods (systems.py:786-873, 1006-1022),
  *           dens_wrt_hausdorff=True.
  * newton_iters (optional, [n_chains]): total Newton iterations used by the chain.
@@ -136,9 +142,9 @@ int mb200_constrained_leapfrog_euclidean(
     const double* pos_in, const double* mom_in, double* pos_out, double* mom_out,
     const int32_t* dir, int64_t n_chains, int32_t dim, double step_size, int32_t n_steps,
     int32_t n_inner_step, int32_t metric_kind, const double* metric_inv, const mb200_model* model,
-    double constraint_tol, double position_tol, double divergence_tol, int32_t max_iters,
-    double reverse_check_tol, double* h_out, int32_t* status, int32_t* n_done,
-    int32_t* newton_iters, void* stream);
+    int32_t projection_solver, double constraint_tol, double position_tol, double divergence_tol,
+    int32_t max_iters, int32_t max_line_search_iters, double reverse_check_tol, double* h_out,
+    int32_t* status, int32_t* n_done, int32_t* newton_iters, void* stream);
 
 /*
  * n_steps implicit generalised-leapfrog steps on a Riemannian-metric system, fixed-point

@@ -60,7 +60,7 @@ SIGNATURES = {
     "mb200_constrained_leapfrog_euclidean": (
         ctypes.c_int,
         [_P, _P, _P, _P, _P, _I64, _I32, _F64, _I32, _I32, _I32, _P, _MP]
-        + [_F64, _F64, _F64, _I32, _F64, _P, _P, _P, _P, _P],
+        + [_I32, _F64, _F64, _F64, _I32, _I32, _F64, _P, _P, _P, _P, _P],
     ),
     "mb200_implicit_leapfrog_riemannian": (
         ctypes.c_int,

@@ -252,6 +252,7 @@ struct ConstrainedOps {
   const double* minv;
   int dim, lane;
   double* psm;
+  int solver, max_ls;
 
   __device__ __forceinline__ void inv_metric_rows(const double (&a)[C][NV],
                                                   double (&out)[C][NV]) const {
@@ -302,7 +303,7 @@ struct ConstrainedOps {
 
   // h2_flow then Newton retraction onto the manifold (integrators.py:929-942,
   // solvers.py:346-469).  Returns false on ConvergenceError.
-  __device__ __forceinline__ bool retract(double (&q)[NV], double (&p)[NV],
+  __device__ __forceinline__ bool retract_newton(double (&q)[NV], double (&p)[NV],
                                           const double (&q_prev)[NV], double dt,
                                           double constraint_tol, double position_tol,
                                           double divergence_tol, int max_iters,
@@ -358,6 +359,158 @@ struct ConstrainedOps {
     }
     return false;
   }
+
+  // solve_projection_onto_manifold_quasi_newton (solvers.py:195-343): the residual Jacobian is
+  // frozen at the previous state, J_prev (|dt| M^-1) J_prev^T (an SPD Gram matrix whose explicit
+  // inverse is built once from its Cholesky factor, systems.py:1013-1016, matrices.py:1161-1188).
+  __device__ __forceinline__ bool retract_quasi_newton(double (&q)[NV], double (&p)[NV],
+                                                       const double (&q_prev)[NV], double dt,
+                                                       double constraint_tol, double position_tol,
+                                                       double divergence_tol, int max_iters,
+                                                       int& iters) const {
+    double v[NV];
+    inv_metric_vec(p, v);
+#pragma unroll
+    for (int e = 0; e < NV; ++e) q[e] = __dadd_rn(q[e], __dmul_rn(dt, v[e]));
+    double mu[NV];
+#pragma unroll
+    for (int e = 0; e < NV; ++e) mu[e] = 0.0;
+    double cp[C], Jp[C][NV], S[C][NV], G[C][C];
+    t.constr_jacob(lane, dim, q_prev, cp, Jp);
+    const double adt = fabs(dt);
+    inv_metric_rows(Jp, S);
+#pragma unroll
+    for (int a = 0; a < C; ++a)
+#pragma unroll
+      for (int e = 0; e < NV; ++e) S[a][e] = adt * S[a][e];
+#pragma unroll
+    for (int a = 0; a < C; ++a)
+#pragma unroll
+      for (int b = 0; b < C; ++b) G[a][b] = dot(Jp[a], S[b]);
+    for (int i = 0; i < max_iters; ++i) {
+      double c[C], J[C][NV], x[C];
+      t.constr_jacob(lane, dim, q, c, J);  // (only c is used: the Jacobian stays frozen)
+      double err = 0.0;
+#pragma unroll
+      for (int a = 0; a < C; ++a) err = nanmax(err, fabs(c[a]));
+      spd_inverse_apply<C>(G, c, x);
+      double dmu[NV], dpos[NV];
+#pragma unroll
+      for (int e = 0; e < NV; ++e) {
+        double s = 0.0, d = 0.0;
+#pragma unroll
+        for (int a = 0; a < C; ++a) s = fma(Jp[a][e], x[a], s), d = fma(S[a][e], x[a], d);
+        dmu[e] = s;
+        dpos[e] = d;
+      }
+      ++iters;
+      if (err > divergence_tol || err != err) return false;
+      if (err < constraint_tol && maxabs(dpos) < position_tol) {
+        const double sgn = (dt > 0.0) ? 1.0 : ((dt < 0.0) ? -1.0 : 0.0);
+#pragma unroll
+        for (int e = 0; e < NV; ++e) p[e] = __dsub_rn(p[e], sgn * mu[e]);
+        return true;
+      }
+#pragma unroll
+      for (int e = 0; e < NV; ++e) {
+        mu[e] = __dadd_rn(mu[e], dmu[e]);
+        q[e] = __dsub_rn(q[e], dpos[e]);
+      }
+    }
+    return false;
+  }
+
+  // solve_projection_onto_manifold_newton_with_line_search (solvers.py:472-614): full Newton
+  // direction, step halved (at most max_ls times) until |c| decreases.  The reference's order of
+  // tests is kept: divergence only from the second iteration (:574), convergence tested before
+  // the update with the previous iteration's step (:580-584), and after an unsuccessful line
+  // search the position stays at the last trial step while mu advances by the halved one
+  // (:597-604).
+  __device__ __forceinline__ bool retract_newton_line_search(
+      double (&q)[NV], double (&p)[NV], const double (&q_prev)[NV], double dt,
+      double constraint_tol, double position_tol, double divergence_tol, int max_iters,
+      int max_ls, int& iters) const {
+    double v[NV];
+    inv_metric_vec(p, v);
+#pragma unroll
+    for (int e = 0; e < NV; ++e) q[e] = __dadd_rn(q[e], __dmul_rn(dt, v[e]));
+    double mu[NV], dpos[NV];
+#pragma unroll
+    for (int e = 0; e < NV; ++e) mu[e] = 0.0, dpos[e] = 0.0;
+    double cp[C], Jp[C][NV], S[C][NV];
+    t.constr_jacob(lane, dim, q_prev, cp, Jp);
+    const double adt = fabs(dt);
+    inv_metric_rows(Jp, S);
+#pragma unroll
+    for (int a = 0; a < C; ++a)
+#pragma unroll
+      for (int e = 0; e < NV; ++e) S[a][e] = adt * S[a][e];
+    double step = 1.0;
+    for (int i = 0; i < max_iters; ++i) {
+      double c[C], J[C][NV], R[C][C], x[C];
+      t.constr_jacob(lane, dim, q, c, J);
+      double err = 0.0;
+#pragma unroll
+      for (int a = 0; a < C; ++a) err = nanmax(err, fabs(c[a]));
+      ++iters;
+      if (i > 0 && (err > divergence_tol || err != err)) return false;
+      double sd[NV];
+#pragma unroll
+      for (int e = 0; e < NV; ++e) sd[e] = step * dpos[e];
+      if (err < constraint_tol && (i == 0 || maxabs(sd) < position_tol)) {
+        const double sgn = (dt > 0.0) ? 1.0 : ((dt < 0.0) ? -1.0 : 0.0);
+#pragma unroll
+        for (int e = 0; e < NV; ++e) p[e] = __dsub_rn(p[e], sgn * mu[e]);
+        return true;
+      }
+#pragma unroll
+      for (int a = 0; a < C; ++a)
+#pragma unroll
+        for (int b = 0; b < C; ++b) R[a][b] = dot(J[a], S[b]);
+      lu_solve<C>(R, c, x);
+      double dmu[NV], qc[NV];
+#pragma unroll
+      for (int e = 0; e < NV; ++e) {
+        double s = 0.0, d = 0.0;
+#pragma unroll
+        for (int a = 0; a < C; ++a) s = fma(Jp[a][e], x[a], s), d = fma(S[a][e], x[a], d);
+        dmu[e] = s;
+        dpos[e] = -d;
+        qc[e] = q[e];
+      }
+      step = 1.0;
+      for (int l = 0; l < max_ls; ++l) {
+#pragma unroll
+        for (int e = 0; e < NV; ++e) q[e] = __dadd_rn(qc[e], __dmul_rn(step, dpos[e]));
+        double c2[C], J2[C][NV];
+        t.constr_jacob(lane, dim, q, c2, J2);
+        double e2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < C; ++a) e2 = nanmax(e2, fabs(c2[a]));
+        if (e2 < err) break;
+        step *= 0.5;
+      }
+#pragma unroll
+      for (int e = 0; e < NV; ++e) mu[e] = __dadd_rn(mu[e], __dmul_rn(step, dmu[e]));
+    }
+    return false;
+  }
+
+  // projection solver selected by the integrator (integrators.py:862; MB200_PROJ_SOLVER_*)
+  __device__ __forceinline__ bool retract(double (&q)[NV], double (&p)[NV],
+                                          const double (&q_prev)[NV], double dt,
+                                          double constraint_tol, double position_tol,
+                                          double divergence_tol, int max_iters,
+                                          int& iters) const {
+    if (solver == MB200_PROJ_SOLVER_QUASI_NEWTON)
+      return retract_quasi_newton(q, p, q_prev, dt, constraint_tol, position_tol, divergence_tol,
+                                  max_iters, iters);
+    if (solver == MB200_PROJ_SOLVER_NEWTON_LINE_SEARCH)
+      return retract_newton_line_search(q, p, q_prev, dt, constraint_tol, position_tol,
+                                        divergence_tol, max_iters, max_ls, iters);
+    return retract_newton(q, p, q_prev, dt, constraint_tol, position_tol, divergence_tol,
+                          max_iters, iters);
+  }
 };
 
 template <class Target, int KP>
@@ -369,7 +522,8 @@ __global__ void __launch_bounds__(128)
                                 double constraint_tol, double position_tol, double divergence_tol,
                                 int max_iters, double rev_tol, double* __restrict__ h_out,
                                 int32_t* __restrict__ status, int32_t* __restrict__ n_done,
-                                int32_t* __restrict__ newton_iters) {
+                                int32_t* __restrict__ newton_iters, int proj_solver,
+                                int max_line_search_iters) {
   constexpr int NV = 2 * KP;
   constexpr int C = Target::NC;
   constexpr int SM_PER_WARP = (C > 1 ? C : 1) * 64 * KP;
@@ -378,8 +532,10 @@ __global__ void __launch_bounds__(128)
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   const Target target(model, dim);
-  const ConstrainedOps<Target, KP> ops{target, metric_kind, minv, dim, lane,
-                                       smem + (size_t)warp * SM_PER_WARP};
+  const ConstrainedOps<Target, KP> ops{target,      metric_kind,
+                                       minv,        dim,
+                                       lane,        smem + (size_t)warp * SM_PER_WARP,
+                                       proj_solver, max_line_search_iters};
   const bool even = (dim & 1) == 0;
 
   for (int64_t ch = (int64_t)blockIdx.x * wpb + warp; ch < n_chains;

@@ -199,7 +199,8 @@ static int launch_constrained(const double* q_in, const double* p_in, double* q_
                               int n_steps, int n_inner, int metric_kind, const double* minv,
                               const ModelArgs& m, double ctol, double ptol, double dtol,
                               int max_iters, double rev_tol, double* h_out, int32_t* status,
-                              int32_t* n_done, int32_t* iters, cudaStream_t st) {
+                              int32_t* n_done, int32_t* iters, cudaStream_t st, int proj_solver,
+                              int max_ls) {
   constexpr int WARPS = 4;
   auto kern = constrained_leapfrog_kernel<Target, KP>;
   const size_t smem = (size_t)WARPS * (Target::NC > 1 ? Target::NC : 1) * 64 * KP * sizeof(double);
@@ -209,7 +210,7 @@ static int launch_constrained(const double* q_in, const double* p_in, double* q_
   kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(q_in, p_in, q_out, p_out, dir, n, dim, eps,
                                                    n_steps, n_inner, metric_kind, minv, m, ctol,
                                                    ptol, dtol, max_iters, rev_tol, h_out, status,
-                                                   n_done, iters);
+                                                   n_done, iters, proj_solver, max_ls);
   return check_launch("constrained_leapfrog_kernel");
 }
 #endif
@@ -367,17 +368,20 @@ int mb200_constrained_leapfrog_euclidean(
     const double* pos_in, const double* mom_in, double* pos_out, double* mom_out,
     const int32_t* dir, int64_t n_chains, int32_t dim, double step_size, int32_t n_steps,
     int32_t n_inner_step, int32_t metric_kind, const double* metric_inv, const mb200_model* model,
-    double constraint_tol, double position_tol, double divergence_tol, int32_t max_iters,
-    double reverse_check_tol, double* h_out, int32_t* status, int32_t* n_done,
-    int32_t* newton_iters, void* stream) {
+    int32_t projection_solver, double constraint_tol, double position_tol, double divergence_tol,
+    int32_t max_iters, int32_t max_line_search_iters, double reverse_check_tol, double* h_out,
+    int32_t* status, int32_t* n_done, int32_t* newton_iters, void* stream) {
 #ifdef MB200_NO_CONSTRAINED
   return fail(MB200_ERR_UNSUPPORTED, "constrained leapfrog not compiled in");
 #else
   if (n_chains == 0 && dim >= 1) return 0;
   if (!pos_in || !mom_in || !pos_out || !mom_out || !model)
     return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
-  if (n_chains < 0 || dim < 1 || n_steps < 0 || n_inner_step < 1 || max_iters < 0)
+  if (n_chains < 0 || dim < 1 || n_steps < 0 || n_inner_step < 1 || max_iters < 0 ||
+      max_line_search_iters < 0)
     return fail(MB200_ERR_INVALID_ARG, "bad sizes");
+  if (projection_solver < 0 || projection_solver > 2)
+    return fail(MB200_ERR_INVALID_ARG, "unknown projection solver %d", projection_solver);
   if (metric_kind < 0 || metric_kind > 2) return fail(MB200_ERR_INVALID_ARG, "bad metric_kind");
   if (metric_kind != MB200_METRIC_IDENTITY && !metric_inv)
     return fail(MB200_ERR_INVALID_ARG, "metric_inv is NULL");
@@ -387,7 +391,8 @@ int mb200_constrained_leapfrog_euclidean(
 #define MB200_ARGS                                                                              \
   pos_in, mom_in, pos_out, mom_out, dir, n_chains, dim, step_size, n_steps, n_inner_step,       \
       metric_kind, metric_inv, m, constraint_tol, position_tol, divergence_tol, max_iters,      \
-      reverse_check_tol, h_out, status, n_done, newton_iters, st
+      reverse_check_tol, h_out, status, n_done, newton_iters, st, projection_solver,            \
+      max_line_search_iters
   switch (m.target_id) {
     case MB200_TARGET_TORUS:
       if (dim != 3) return fail(MB200_ERR_INVALID_ARG, "torus target needs dim == 3");

@@ -30,6 +30,11 @@ def build_integrator(problem, system=None, **overrides):
         from . import solvers  # noqa: PLC0415
 
         kw["fixed_point_solver"] = getattr(solvers, "solve_fixed_point_" + kw["fixed_point_solver"])
+    if isinstance(kw.get("projection_solver"), str):
+        from . import solvers  # noqa: PLC0415
+
+        kw["projection_solver"] = getattr(
+            solvers, "solve_projection_onto_manifold_" + kw["projection_solver"])
     cls = {
         "leapfrog": integrators.LeapfrogIntegrator,
         "implicit_leapfrog": integrators.ImplicitLeapfrogIntegrator,

@@ -31,9 +31,16 @@ from .solvers import (
     solve_fixed_point_direct,
     solve_fixed_point_steffensen,
     solve_projection_onto_manifold_newton,
+    solve_projection_onto_manifold_newton_with_line_search,
+    solve_projection_onto_manifold_quasi_newton,
 )
 
 _FUSED_FIXED_POINT_SOLVERS = (solve_fixed_point_direct, solve_fixed_point_steffensen)
+_FUSED_PROJECTION_SOLVERS = (
+    solve_projection_onto_manifold_newton,
+    solve_projection_onto_manifold_quasi_newton,
+    solve_projection_onto_manifold_newton_with_line_search,
+)
 from .states import ChainState
 from .systems import (
     ConstrainedEuclideanMetricSystem,
@@ -377,8 +384,9 @@ class ConstrainedLeapfrogIntegrator(TractableFlowIntegrator):
             raise TypeError("ConstrainedLeapfrogIntegrator needs a constrained Euclidean system.")
         if reverse_check_norm is not maximum_norm:
             raise ValueError("Only `maximum_norm` is available for the reversibility check.")
-        if projection_solver is not solve_projection_onto_manifold_newton:
-            raise ValueError("Only `solve_projection_onto_manifold_newton` is fused into the kernels.")
+        if projection_solver not in _FUSED_PROJECTION_SOLVERS:
+            raise ValueError("Only the Newton, quasi-Newton and Newton-with-line-search projection "
+                             "solvers of `mici_b200.solvers` are fused into the kernels.")
         self.n_inner_step = n_inner_step
         self.reverse_check_tol = reverse_check_tol
         self.reverse_check_norm = reverse_check_norm
@@ -396,8 +404,10 @@ class ConstrainedLeapfrogIntegrator(TractableFlowIntegrator):
             _lib.ptr(pos), _lib.ptr(mom), _lib.ptr(pos_out), _lib.ptr(mom_out), _lib.ptr(dirs),
             n, dim, float(self.step_size), n_steps, int(self.n_inner_step), sysm.metric.kind,
             _lib.ptr(sysm.metric.inv_device(dev)), ctypes.byref(model),
-            float(kw["constraint_tol"]), float(kw["position_tol"]), float(kw["divergence_tol"]),
-            int(kw["max_iters"]), float(self.reverse_check_tol), _lib.ptr(h), _lib.ptr(status),
+            self.projection_solver.kind, float(kw["constraint_tol"]), float(kw["position_tol"]),
+            float(kw["divergence_tol"]), int(kw["max_iters"]),
+            int(kw.get("max_line_search_iters", 10)), float(self.reverse_check_tol), _lib.ptr(h),
+            _lib.ptr(status),
             _lib.ptr(n_done), _lib.ptr(iters), _lib.current_stream_ptr(dev),
         )
         _lib.check(rc, "mb200_constrained_leapfrog_euclidean")

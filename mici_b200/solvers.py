@@ -67,3 +67,18 @@ solve_projection_onto_manifold_newton = _DeviceSolver(
     "solve_projection_onto_manifold_newton",
     {"constraint_tol": 1e-9, "position_tol": 1e-8, "divergence_tol": 1e10, "max_iters": 50},
 )
+
+#: solvers.py:195-343 defaults (residual Jacobian frozen at the previous state)
+solve_projection_onto_manifold_quasi_newton = _DeviceSolver(
+    "solve_projection_onto_manifold_quasi_newton",
+    {"constraint_tol": 1e-9, "position_tol": 1e-8, "divergence_tol": 1e10, "max_iters": 50},
+    kind=1,
+)
+
+#: solvers.py:472-614 defaults (full Newton direction with step halving)
+solve_projection_onto_manifold_newton_with_line_search = _DeviceSolver(
+    "solve_projection_onto_manifold_newton_with_line_search",
+    {"constraint_tol": 1e-9, "position_tol": 1e-8, "divergence_tol": 1e10, "max_iters": 50,
+     "max_line_search_iters": 10},
+    kind=2,
+)

@@ -186,6 +186,9 @@ def build_reference(problem, **overrides):
         "bcss3": mici.integrators.BCSSThreeStageIntegrator,
         "bcss4": mici.integrators.BCSSFourStageIntegrator,
     }[problem.integrator]
+    if isinstance(ikw.get("projection_solver"), str):
+        ikw["projection_solver"] = getattr(
+            mici.solvers, "solve_projection_onto_manifold_" + ikw["projection_solver"])
     if isinstance(ikw.get("fixed_point_solver"), str):
         ikw["fixed_point_solver"] = getattr(mici.solvers, "solve_fixed_point_" + ikw["fixed_point_solver"])
     return system, cls(system, problem.step_size, **ikw)

@@ -42,6 +42,10 @@ CASES = {
     "n4_midpoint_dense_d32": ("C4", {"n_chains": 6, "dim": 32, "integrator": "implicit_midpoint"}, (1, 5), {}),
     "n4_steffensen_softabs_d8": ("C2", {"n_chains": 16, "dim": 8}, (1, 5), {"fixed_point_solver": "steffensen"}),
     "n4_steffensen_midpoint_dense_d16": ("C4", {"n_chains": 6, "dim": 16, "integrator": "implicit_midpoint"}, (1, 5), {"fixed_point_solver": "steffensen"}),
+    "n4_quasi_newton_torus": ("C3", {"n_chains": 32}, (1, 5, 20), {"projection_solver": "quasi_newton"}),
+    "n4_line_search_torus": ("C3", {"n_chains": 32}, (1, 5, 20), {"projection_solver": "newton_with_line_search"}),
+    "n4_quasi_newton_sphere_dense_d10": ("S1", {"n_chains": 16, "dim": 10}, (1, 5), {"projection_solver": "quasi_newton", "n_inner_step": 2}),
+    "n4_line_search_sphere_diag_d12": ("S1", {"n_chains": 16, "dim": 12, "metric_kind": "diagonal"}, (1, 5), {"projection_solver": "newton_with_line_search"}),
     "s1_sphere_dense_d10": ("S1", {"n_chains": 32, "dim": 10}, (1, 5, 20), {}),
     "s1_sphere_diag_d70_inner2": ("S1", {"n_chains": 8, "dim": 70, "metric_kind": "diagonal"}, (1, 5), {"n_inner_step": 2}),
     "s1_sphere_identity_d5": ("S1", {"n_chains": 16, "dim": 5, "metric_kind": "identity"}, (1, 20), {}),
@@ -53,6 +57,8 @@ CASES = {
 FAILURE_CASES = {
     "c2_softabs_banana_bigstep": ("C2", {"n_chains": 32, "dim": 8}, 0.6, (3,), {}),
     "c3_torus_bigstep": ("C3", {"n_chains": 64}, 0.4, (3,), {}),
+    "n4_quasi_newton_torus_bigstep": ("C3", {"n_chains": 64}, 0.4, (3,), {"projection_solver": "quasi_newton"}),
+    "n4_line_search_torus_bigstep": ("C3", {"n_chains": 64}, 0.45, (3,), {"projection_solver": "newton_with_line_search"}),
     "n4_midpoint_softabs_bigstep": ("C2", {"n_chains": 32, "dim": 8, "integrator": "implicit_midpoint"}, 0.9, (3,), {}),
 }
 

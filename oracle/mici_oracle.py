@@ -613,6 +613,92 @@ def solve_projection_onto_manifold_newton(
     raise OracleIntegratorError(STATUS_CONVERGENCE, f"Newton did not converge, |c|={error}")
 
 
+def solve_projection_onto_manifold_quasi_newton(
+    q, p, q_prev, time_step, system, constraint_tol=1e-9, position_tol=1e-8,
+    divergence_tol=1e10, max_iters=50, counts=None,
+):
+    """solvers.py:195-343 for a Euclidean metric: the Gram matrix J_prev (|dt| M^-1) J_prev^T is a
+    DensePositiveDefiniteMatrix whose explicit inverse is applied every iteration."""
+    q = q.copy()
+    p = p.copy()
+    mu = np.zeros_like(q)
+    jac_prev = system.jacob_constr(q_prev)
+    adt = abs(time_step)
+    error = np.nan
+    try:
+        gram = _chkfinite(jac_prev @ _scaled_inv_metric(system, adt, jac_prev.T))
+        inv_gram = dense_spd_inverse(gram)
+        for i in range(max_iters):
+            c = system.constr(q)
+            error = maximum_norm(c)
+            delta_mu = jac_prev.T @ (inv_gram @ c)
+            delta_pos = _scaled_inv_metric(system, adt, delta_mu)
+            if error > divergence_tol or np.isnan(error):
+                raise OracleIntegratorError(STATUS_CONVERGENCE, f"quasi-Newton diverged at {i}")
+            if error < constraint_tol and maximum_norm(delta_pos) < position_tol:
+                p -= np.sign(time_step) * mu
+                if counts is not None:
+                    counts.setdefault("newton_iters", []).append(i + 1)
+                return q, p
+            mu += delta_mu
+            q -= delta_pos
+    except (ValueError, _LinAlgError) as e:
+        raise OracleIntegratorError(STATUS_CONVERGENCE, f"{type(e)} in quasi-Newton solver") from e
+    raise OracleIntegratorError(STATUS_CONVERGENCE, f"quasi-Newton did not converge, |c|={error}")
+
+
+def solve_projection_onto_manifold_newton_with_line_search(
+    q, p, q_prev, time_step, system, constraint_tol=1e-9, position_tol=1e-8,
+    divergence_tol=1e10, max_iters=50, max_line_search_iters=10, counts=None,
+):
+    """solvers.py:472-614 for a Euclidean metric (order of tests and the line-search bookkeeping
+    exactly as in the reference)."""
+    q = q.copy()
+    p = p.copy()
+    mu = np.zeros_like(q)
+    jac_prev = system.jacob_constr(q_prev)
+    adt = abs(time_step)
+    delta_pos, step_size = None, None
+    error = np.nan
+    for i in range(max_iters):
+        try:
+            jac = system.jacob_constr(q)
+            c = system.constr(q)
+            error = maximum_norm(c)
+            if i > 0 and (error > divergence_tol or np.isnan(error)):
+                raise OracleIntegratorError(STATUS_CONVERGENCE, f"Newton diverged at {i}")
+            if error < constraint_tol and (
+                i == 0 or maximum_norm(step_size * delta_pos) < position_tol
+            ):
+                p -= np.sign(time_step) * mu
+                if counts is not None:
+                    counts.setdefault("newton_iters", []).append(i + 1)
+                return q, p
+            res_jac = _chkfinite(jac @ _scaled_inv_metric(system, adt, jac_prev.T))
+            lu_piv = sla.lu_factor(res_jac, check_finite=False)
+            delta_mu = jac_prev.T @ sla.lu_solve(lu_piv, c, 0, check_finite=False)
+            delta_pos = -_scaled_inv_metric(system, adt, delta_mu)
+            pos_curr = q.copy()
+            step_size = 1.0
+            for _ in range(max_line_search_iters):
+                q = pos_curr + step_size * delta_pos
+                new_error = maximum_norm(system.constr(q))
+                if new_error < error:
+                    break
+                step_size *= 0.5
+            mu += step_size * delta_mu
+        except (ValueError, _LinAlgError) as e:
+            raise OracleIntegratorError(STATUS_CONVERGENCE, f"{type(e)} in Newton solver") from e
+    raise OracleIntegratorError(STATUS_CONVERGENCE, f"Newton did not converge, |c|={error}")
+
+
+PROJECTION_SOLVERS = {
+    "newton": solve_projection_onto_manifold_newton,
+    "quasi_newton": solve_projection_onto_manifold_quasi_newton,
+    "newton_with_line_search": solve_projection_onto_manifold_newton_with_line_search,
+}
+
+
 def _scaled_inv_metric(system, scale, a):
     """``(scale * metric.inv) @ a`` with the reference's order of operations."""
     m = system.metric
@@ -633,6 +719,7 @@ def constrained_leapfrog_step(
     reverse_check_tol=2e-8,
     projection_solver_kwargs=None,
     counts=None,
+    projection_solver="newton",
 ):
     """One ``ConstrainedLeapfrogIntegrator.step`` (integrators.py:929-984)."""
     kw = {} if projection_solver_kwargs is None else projection_solver_kwargs
@@ -643,7 +730,7 @@ def constrained_leapfrog_step(
     def h2_flow_retraction(q, p, q_prev, dt):
         # :929-942 ; h2_flow systems.py:362-363
         q = q + dt * system.inv_metric_mat(p)
-        return solve_projection_onto_manifold_newton(q, p, q_prev, dt, system, counts=counts, **kw)
+        return PROJECTION_SOLVERS[projection_solver](q, p, q_prev, dt, system, counts=counts, **kw)
 
     try:
         # _step_a(dt/2) :947-949

@@ -31,9 +31,23 @@ def load_case(name):
     return problem, g["dirs"], overrides, g
 
 
-def assert_matches_golden(out, g, n_steps, rtol=RTOL, atol=ATOL, label=""):
-    """Compare a run's (pos, mom, status, n_done[, h]) with the reference fixture."""
-    np.testing.assert_array_equal(out["status"], g[f"status_{n_steps}"], err_msg=f"{label} status")
+def assert_matches_golden(out, g, n_steps, rtol=RTOL, atol=ATOL, label="", kind_flip_frac=0.0):
+    """Compare a run's (pos, mom, status, n_done[, h]) with the reference fixture.
+
+    ``kind_flip_frac`` (failure-path fixtures only): which chains fail, and at which step, must
+    match exactly, but for at most this fraction of the FAILED chains the failure kind
+    (ConvergenceError vs NonReversibleStepError) may differ.  When a diverging Newton / line-search
+    iteration is chaotic the kind is ill-conditioned: the reference itself flips between the two
+    under 1e-15 relative perturbations of the input (checked for chain 8 of
+    ``n4_line_search_torus_bigstep``: 10 / 30 split over 40 perturbed runs)."""
+    ref_status = g[f"status_{n_steps}"]
+    if kind_flip_frac > 0.0:
+        np.testing.assert_array_equal(out["status"] != 0, ref_status != 0, err_msg=f"{label} failed")
+        n_failed = max(int((ref_status != 0).sum()), 1)
+        n_flip = int((out["status"] != ref_status).sum())
+        assert n_flip <= kind_flip_frac * n_failed, (label, n_flip, n_failed)
+    else:
+        np.testing.assert_array_equal(out["status"], ref_status, err_msg=f"{label} status")
     np.testing.assert_array_equal(out["n_done"], g[f"n_done_{n_steps}"], err_msg=f"{label} n_done")
     for key in ("pos", "mom"):
         np.testing.assert_allclose(

@@ -43,7 +43,8 @@ def test_cuda_matches_reference_fixture(name):
         out["h"] = np.where(ok, out["h"], np.nan)
         gg = dict(g)
         gg[f"h_{n_steps}"] = np.where(ok, g[f"h_{n_steps}"], np.nan)
-        assert_matches_golden(out, gg, int(n_steps), label=f"{name}[{n_steps}]")
+        assert_matches_golden(out, gg, int(n_steps), label=f"{name}[{n_steps}]",
+                              kind_flip_frac=0.05 if name.endswith("bigstep") else 0.0)
 
 
 @pytest.mark.parametrize("cfg,kwargs", [
