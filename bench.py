@@ -31,6 +31,11 @@ N_CHAINS = 8192
 DIM = 128
 LEAPFROG_PER_LAUNCH = 50
 FP64_PEAK_TFLOPS = 37.1  # measured DMMA peak on this pool's B200 (profiles/r01_fp64_peak.txt)
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel at this
+# workload, from the `ncu --set full` capture summarised in
+# profiles/r01_c1_dmma_v3_ncu_summary.txt (16 970 496 B read, 0 B written: the outputs are still
+# in L2 when the kernel ends).  Algorithmic bytes per launch: 8192 x 4096 B = 33.5 MB.
+NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH = 16970496
 HBM_FALLBACK_GBS = 6650.0
 
 
@@ -319,7 +324,7 @@ def run_cuda(args, rank, local_rank, world):
             "peak": hbm_peak,
             "unit": "GB/s",
             "frac": achieved_gbs / hbm_peak,
-            "traffic": None,
+            "traffic": NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH if (n, dim) == (8192, 128) else None,
             "peak_source": peak_src,
             "kernel": "leapfrog_dmma_kernel<NealFunnelTarget,128>",
             "algorithmic_bytes_per_chain_step": b_alg,
