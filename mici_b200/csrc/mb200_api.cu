@@ -11,6 +11,9 @@
 #ifdef MB200_DMMA_V2  // experimental second-generation kernel (slower: profiles/r01_notes.md)
 #include "leapfrog_dmma2.cuh"
 #endif
+#ifdef MB200_DMMA_V3  // warp-specialised generation (drift warps / update warps)
+#include "leapfrog_dmma3.cuh"
+#endif
 #endif
 #ifndef MB200_NO_CONSTRAINED
 #include "constrained.cuh"
@@ -133,7 +136,10 @@ static int leapfrog_euclidean_impl(const double* q_in, const double* p_in, doubl
     return fail(MB200_ERR_INVALID_ARG, "banana target needs even dim");
 #ifndef MB200_NO_DMMA
   if (allow_dmma && metric_kind == MB200_METRIC_DENSE && n_steps > 0) {
-#ifdef MB200_DMMA_V2
+#if defined(MB200_DMMA_V3)
+    int rc = leapfrog_dmma3_dispatch(q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, minv, m,
+                                     h_out, status, n_done, st);
+#elif defined(MB200_DMMA_V2)
     int rc = leapfrog_dmma2_dispatch(q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, minv, m,
                                      h_out, status, n_done, st);
 #else
