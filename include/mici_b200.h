@@ -242,6 +242,70 @@ int mb200_implicit_midpoint_riemannian(
     double fp_divergence_tol, int32_t fp_max_iters, double reverse_check_tol, double* h_out,
     int32_t* status, int32_t* n_done, int32_t* fp_iters, void* stream);
 
+/*
+ * Momentum refresh for the non-Euclidean systems (row N1).
+ *  - mb200_project_onto_cotangent_space: p -= J^T (J M^-1 J^T)^-1 J M^-1 p for every chain
+ *    (ConstrainedEuclideanMetricSystem.project_onto_cotangent_space, systems.py:863-873; the
+ *    second half of ConstrainedTractableFlowSystem.sample_momentum, systems.py:613-616).
+ *  - mb200_sample_momentum_riemannian: mom = sqrt(M(q)) z (RiemannianMetricSystem.sample_momentum,
+ *    systems.py:1401-1402; sqrt = U sqrt(softabs) U^T for SoftAbs, the Cholesky factor for dense
+ *    metrics); `normals` are standard-normal variates [n*dim]; status 3 where M(q) cannot be built.
+ */
+int mb200_project_onto_cotangent_space(const double* pos, const double* mom_in, double* mom_out,
+                                       int64_t n_chains, int32_t dim, int32_t metric_kind,
+                                       const double* metric_inv, const mb200_model* model,
+                                       void* stream);
+int mb200_sample_momentum_riemannian(const double* pos, const double* normals, double* mom_out,
+                                     int64_t n_chains, int32_t dim, const mb200_model* model,
+                                     int32_t* status, void* stream);
+
+/*
+ * "Next" row N3 (and the random-length transition of N1): explicit leapfrog / symmetric
+ * composition with PER-CHAIN step sizes and, optionally, per-chain trajectory lengths.
+ *   step_sizes         [n_chains] device array -- during warm-up every chain carries its own
+ *                      dual-averaging step size (adapters.py:262-283, 373); the initial coarse
+ *                      search halves / doubles it chain by chain (adapters.py:285-343)
+ *   n_steps_per_chain  [n_chains] device array or NULL; chain c takes
+ *                      min(n_steps_per_chain[c], max_n_steps) steps
+ *                      (MetropolisRandomIntegrationTransition, transitions.py:355-412)
+ *   coefficients       HOST array of n_flows composition coefficients or NULL for the leapfrog
+ *                      schedule {0.5, 1, 0.5} (then n_flows / initial_h1_flow_step are ignored)
+ * n_done[c] receives the number of steps chain c took.  Other arguments as
+ * mb200_leapfrog_euclidean.  Runs on the general-dimension kernel (the tensor-core kernel
+ * folds one shared step size into the staged metric).
+ */
+int mb200_leapfrog_euclidean_per_chain(const double* pos_in, const double* mom_in, double* pos_out,
+                                       double* mom_out, const int32_t* dir, int64_t n_chains,
+                                       int32_t dim, const double* step_sizes,
+                                       const int32_t* n_steps_per_chain, int32_t max_n_steps,
+                                       int32_t n_flows, const double* coefficients,
+                                       int32_t initial_h1_flow_step, int32_t metric_kind,
+                                       const double* metric_inv, const mb200_model* model,
+                                       double* h_out, int32_t* status, int32_t* n_done,
+                                       void* stream);
+
+/*
+ * "Next" row N4: GaussianEuclideanMetricSystem (systems.py:369-474) -- the target density is
+ * given relative to the standard Gaussian measure, h1 = l(q), h2 = q.q/2 + p.M^-1 p/2 and
+ * h2_flow is the exact rotation of (q, p) in the eigenbasis of M (systems.py:464-474).  Leapfrog
+ * (coefficients NULL) or a symmetric composition over these flows; h_out includes q.q/2.
+ *   rotation  identity metric: NULL.  diagonal metric: the metric diagonal [dim] (device).
+ *             dense metric: for every drift flow of the schedule, in order, three symmetric
+ *             [dim x dim] device matrices  U cos(w t) U^T | U (sin(w t) w) U^T |
+ *             -U (sin(w t) / w) U^T  with (eigval, U) = eigh(M), w = eigval^-1/2,
+ *             t = coefficient * step_size (the sign of dir is applied by the kernel).
+ *   step_sizes  optional per-chain step sizes (identity / diagonal metric only), else NULL.
+ * n_steps = 0 with h_out evaluates the Hamiltonian only.
+ */
+int mb200_leapfrog_gaussian_euclidean(const double* pos_in, const double* mom_in, double* pos_out,
+                                      double* mom_out, const int32_t* dir, int64_t n_chains,
+                                      int32_t dim, double step_size, const double* step_sizes,
+                                      int32_t n_steps, int32_t n_flows, const double* coefficients,
+                                      int32_t initial_h1_flow_step, int32_t metric_kind,
+                                      const double* metric_inv, const double* rotation,
+                                      const mb200_model* model, double* h_out, int32_t* status,
+                                      int32_t* n_done, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

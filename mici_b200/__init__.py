@@ -7,17 +7,31 @@ per kernel launch.  Hand-written sm_100a CUDA behind a C ABI (``include/mici_b20
 There is no CPU fallback: without the built library every compute call raises.
 """
 
-from . import errors, integrators, problems, solvers, states, systems, targets
+from . import (
+    adapters,
+    errors,
+    integrators,
+    problems,
+    solvers,
+    stagers,
+    states,
+    systems,
+    targets,
+    transitions,
+)
 from .states import ChainState
 
 __all__ = [
     "ChainState",
+    "adapters",
     "errors",
     "integrators",
     "problems",
     "solvers",
+    "stagers",
     "states",
     "systems",
     "targets",
+    "transitions",
 ]
 __version__ = "0.1.0"

@@ -82,6 +82,17 @@ SIGNATURES = {
         [_P, _P, _P, _P, _P, _I64, _I32, _F64, _I32, _MP, _I32, _F64, _F64, _I32, _F64]
         + [_P, _P, _P, _P, _P],
     ),
+    "mb200_project_onto_cotangent_space": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _MP, _P]),
+    "mb200_sample_momentum_riemannian": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _MP, _P, _P]),
+    "mb200_leapfrog_euclidean_per_chain": (
+        ctypes.c_int,
+        [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _I32, _I32, _P, _I32, _I32, _P, _MP, _P, _P, _P, _P],
+    ),
+    "mb200_leapfrog_gaussian_euclidean": (
+        ctypes.c_int,
+        [_P, _P, _P, _P, _P, _I64, _I32, _F64, _P, _I32, _I32, _P, _I32, _I32, _P, _P, _MP, _P, _P,
+         _P, _P],
+    ),
     "mb200_metropolis_select": (
         ctypes.c_int,
         [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P],

@@ -51,6 +51,17 @@ struct FlowSchedule {
   int n;
   unsigned drift_mask;  // bit i set: flow i is an h2_flow (drift), else an h1_flow (kick)
   double coef[MB200_MAX_FLOWS];
+  // optional per-chain overrides (device arrays [n_chains]; NULL = the scalar arguments):
+  // step sizes (one adapter state per chain during warm-up, adapters.py:262-283, 373) and
+  // trajectory lengths (MetropolisRandomIntegrationTransition, transitions.py:355-412)
+  const double* step_sizes;
+  const int32_t* n_steps;
+  // GaussianEuclideanMetricSystem (systems.py:369-474): h2 = q.q/2 + p.M^-1 p/2 and the drift is
+  // the exact rotation of (q, p).  rot: metric diagonal [dim] (diagonal metric) or, for a dense
+  // metric, per drift flow the three symmetric matrices [U cos U^T | U (sin w) U^T |
+  // -U (sin / w) U^T] built on the host from eigh(M) for |dt| = coef * step_size.
+  int gaussian;
+  const double* rot;
 };
 
 }  // namespace mb200

@@ -636,4 +636,40 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// Projection of momenta onto the cotangent space of the constraint manifold for all chains:
+// ConstrainedTractableFlowSystem.sample_momentum (systems.py:613-616) draws from N(0, M) and
+// then applies project_onto_cotangent_space (systems.py:863-873); this is that second half.
+template <class Target, int KP>
+__global__ void __launch_bounds__(128)
+    constrained_project_kernel(const double* __restrict__ q_in, const double* p_in, double* p_out,
+                               int64_t n_chains, int dim, int metric_kind,
+                               const double* __restrict__ minv, ModelArgs model) {
+  constexpr int NV = 2 * KP;
+  constexpr int C = Target::NC;
+  constexpr int SM_PER_WARP = (C > 1 ? C : 1) * 64 * KP;
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const Target target(model, dim);
+  const ConstrainedOps<Target, KP> ops{target, metric_kind, minv, dim, lane,
+                                       smem + (size_t)warp * SM_PER_WARP, 0, 0};
+  for (int64_t ch = (int64_t)blockIdx.x * wpb + warp; ch < n_chains;
+       ch += (int64_t)gridDim.x * wpb) {
+    double q[NV], p[NV];
+#pragma unroll
+    for (int e = 0; e < NV; ++e) {
+      const int i = 2 * lane + 64 * (e >> 1) + (e & 1);
+      q[e] = (i < dim) ? q_in[(size_t)ch * dim + i] : 0.0;
+      p[e] = (i < dim) ? p_in[(size_t)ch * dim + i] : 0.0;
+    }
+    ops.project(p, q);
+#pragma unroll
+    for (int e = 0; e < NV; ++e) {
+      const int i = 2 * lane + 64 * (e >> 1) + (e & 1);
+      if (i < dim) p_out[(size_t)ch * dim + i] = p[e];
+    }
+  }
+}
+
 }  // namespace mb200

@@ -72,7 +72,7 @@ struct LeapfrogGeneric {
 
 };
 
-template <class Target, int KP, int CPW>
+template <class Target, int KP, int CPW, bool GAUSS = false>
 __global__ void __launch_bounds__(128)
     leapfrog_generic_kernel(const double* q_in, const double* p_in,
                             double* q_out, double* p_out,
@@ -96,11 +96,16 @@ __global__ void __launch_bounds__(128)
        grp += (int64_t)gridDim.x * warps_per_block) {
     double q[CPW][NV], p[CPW][NV], g[CPW][NV], v[CPW][NV];
     double dt[CPW];
+    int ns[CPW];
+    int ns_max = 0;
 #pragma unroll
     for (int c = 0; c < CPW; ++c) {
       const int64_t ch = grp * CPW + c;
       const bool live = ch < n_chains;
-      dt[c] = (live && dir != nullptr) ? (double)dir[ch] * step_size : step_size;
+      const double eps = (live && sched.step_sizes != nullptr) ? sched.step_sizes[ch] : step_size;
+      dt[c] = (live && dir != nullptr) ? (double)dir[ch] * eps : eps;
+      ns[c] = !live ? 0 : (sched.n_steps != nullptr ? min(sched.n_steps[ch], n_steps) : n_steps);
+      ns_max = max(ns_max, ns[c]);
 #pragma unroll
       for (int k = 0; k < KP; ++k) {
         const int i = 2 * lane + 64 * k;
@@ -120,14 +125,71 @@ __global__ void __launch_bounds__(128)
       }
       K::grad(target, dim, lane, q[c], g[c]);
     }
-    for (int s = 0; s < n_steps; ++s) {
+    for (int s = 0; s < ns_max; ++s) {
+      // chains whose own trajectory length is reached stop moving (updates predicated off)
       for (int f = 0; f < sched.n; ++f) {
-        if ((sched.drift_mask >> f) & 1u) {
+        if (GAUSS && ((sched.drift_mask >> f) & 1u)) {
+          // GaussianEuclideanMetricSystem.h2_flow (systems.py:464-474): exact flow of
+          // h2 = q.q/2 + p.M^-1 p/2 in the eigenbasis of M, w = 1/sqrt(eigval):
+          //   q' = U (cos(w dt) U^T q + (sin(w dt) w) U^T p)
+          //   p' = U (cos(w dt) U^T p - (sin(w dt) / w) U^T q)
+          if (metric_kind == MB200_METRIC_DENSE) {
+            int drift_idx = 0;
+            for (int ff = 0; ff < f; ++ff) drift_idx += (sched.drift_mask >> ff) & 1u;
+            const double* cqq = sched.rot + (size_t)drift_idx * 3 * dim * dim;
+            const double* cqp = cqq + (size_t)dim * dim;
+            const double* cpq = cqp + (size_t)dim * dim;
+            double w1[CPW][NV], w2[CPW][NV];
+            inv_metric_apply<KP, CPW>(metric_kind, cqq, dim, lane, psm, q, v);
+            inv_metric_apply<KP, CPW>(metric_kind, cqp, dim, lane, psm, p, w1);
+            inv_metric_apply<KP, CPW>(metric_kind, cpq, dim, lane, psm, q, w2);
+#pragma unroll
+            for (int c = 0; c < CPW; ++c) {
+              const double sgn = dt[c] < 0.0 ? -1.0 : 1.0;  // sin is odd in dt
+#pragma unroll
+              for (int e = 0; e < NV; ++e)
+                if (s < ns[c]) q[c][e] = __dadd_rn(v[c][e], __dmul_rn(sgn, w1[c][e]));
+            }
+            inv_metric_apply<KP, CPW>(metric_kind, cqq, dim, lane, psm, p, v);
+#pragma unroll
+            for (int c = 0; c < CPW; ++c) {
+              if (s >= ns[c]) continue;
+              const double sgn = dt[c] < 0.0 ? -1.0 : 1.0;
+#pragma unroll
+              for (int e = 0; e < NV; ++e) p[c][e] = __dadd_rn(v[c][e], __dmul_rn(sgn, w2[c][e]));
+              K::grad(target, dim, lane, q[c], g[c]);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < CPW; ++c) {
+              if (s >= ns[c]) continue;
+              const double dtf = sched.coef[f] * dt[c];
+#pragma unroll
+              for (int k = 0; k < KP; ++k) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const int i = 2 * lane + 64 * k + h;
+                  const int e = 2 * k + h;
+                  double om = 1.0;
+                  if (metric_kind == MB200_METRIC_DIAGONAL)
+                    om = (i < dim) ? 1.0 / sqrt(sched.rot[i]) : 1.0;
+                  double sn, cs;
+                  sincos(__dmul_rn(om, dtf), &sn, &cs);
+                  const double qe = q[c][e], pe = p[c][e];
+                  q[c][e] = __dadd_rn(__dmul_rn(cs, qe), __dmul_rn(__dmul_rn(sn, om), pe));
+                  p[c][e] = __dsub_rn(__dmul_rn(cs, pe), __dmul_rn(__ddiv_rn(sn, om), qe));
+                }
+              }
+              K::grad(target, dim, lane, q[c], g[c]);
+            }
+          }
+        } else if ((sched.drift_mask >> f) & 1u) {
           // h2_flow: q += (c*dt) * M^-1 p (systems.py:362-363); gradient re-evaluated at the new q
           // (the reference's cache on `pos` is invalidated: states.py:248-258)
           inv_metric_apply<KP, CPW>(metric_kind, minv, dim, lane, psm, p, v);
 #pragma unroll
           for (int c = 0; c < CPW; ++c) {
+            if (s >= ns[c]) continue;
             const double dtf = sched.coef[f] * dt[c];
 #pragma unroll
             for (int e = 0; e < NV; ++e) q[c][e] = __dadd_rn(q[c][e], __dmul_rn(dtf, v[c][e]));
@@ -138,6 +200,7 @@ __global__ void __launch_bounds__(128)
           // as NumPy evaluates `state.mom -= dt * self.dh1_dpos(state)` (systems.py:152)
 #pragma unroll
           for (int c = 0; c < CPW; ++c) {
+            if (s >= ns[c]) continue;
             const double dtf = sched.coef[f] * dt[c];
 #pragma unroll
             for (int e = 0; e < NV; ++e) p[c][e] = __dsub_rn(p[c][e], __dmul_rn(dtf, g[c][e]));
@@ -169,12 +232,18 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
         for (int e = 0; e < NV; ++e) kin = fma(p[c][e], v[c][e], kin);
         kin = warp_sum(kin);
-        const double l = K::neg_log_dens(target, dim, lane, q[c]);
+        double l = K::neg_log_dens(target, dim, lane, q[c]);
+        if (GAUSS) {  // h2 = q.q/2 + p.M^-1 p/2 (systems.py:450-453)
+          double qq = 0.0;
+#pragma unroll
+          for (int e = 0; e < NV; ++e) qq = fma(q[c][e], q[c][e], qq);
+          l += 0.5 * warp_sum(qq);
+        }
         if (lane == 0) h_out[ch] = l + 0.5 * kin;
       }
       if (lane == 0) {
         if (status != nullptr) status[ch] = MB200_STATUS_OK;
-        if (n_done != nullptr) n_done[ch] = n_steps;
+        if (n_done != nullptr) n_done[ch] = ns[c];
       }
     }
   }

@@ -64,13 +64,13 @@ static int num_sms() {
   return sms;
 }
 
-template <class Target, int KP, int CPW>
+template <class Target, int KP, int CPW, bool GAUSS = false>
 static int launch_generic(const double* q_in, const double* p_in, double* q_out, double* p_out,
                           const int32_t* dir, int64_t n, int dim, double eps, int n_steps,
                           const FlowSchedule& sched, int metric_kind, const double* minv, const ModelArgs& m, double* h_out,
                           int32_t* status, int32_t* n_done, cudaStream_t st) {
   constexpr int WARPS = 4;
-  auto kern = leapfrog_generic_kernel<Target, KP, CPW>;
+  auto kern = leapfrog_generic_kernel<Target, KP, CPW, GAUSS>;
   const size_t smem = (size_t)WARPS * CPW * 64 * KP * sizeof(double);
   if (smem > 48 * 1024) {
     cudaError_t e =
@@ -94,9 +94,14 @@ static int dispatch_generic_dim(const double* q_in, const double* p_in, double* 
                                 int n_steps, const FlowSchedule& sched, int metric_kind, const double* minv,
                                 const ModelArgs& m, double* h_out, int32_t* status,
                                 int32_t* n_done, cudaStream_t st) {
-#define MB200_GEN(KP, CPW)                                                                    \
-  return launch_generic<Target, KP, CPW>(q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, \
-                                         sched, metric_kind, minv, m, h_out, status, n_done, st)
+#define MB200_GEN(KP, CPW)                                                                      \
+  return sched.gaussian                                                                         \
+             ? launch_generic<Target, KP, CPW, true>(q_in, p_in, q_out, p_out, dir, n, dim, eps, \
+                                                     n_steps, sched, metric_kind, minv, m,      \
+                                                     h_out, status, n_done, st)                 \
+             : launch_generic<Target, KP, CPW, false>(q_in, p_in, q_out, p_out, dir, n, dim,    \
+                                                      eps, n_steps, sched, metric_kind, minv,   \
+                                                      m, h_out, status, n_done, st)
   if (dim <= 64) MB200_GEN(1, 4);
   if (dim <= 128) MB200_GEN(2, 4);
   if (dim <= 256) MB200_GEN(4, 2);
@@ -299,6 +304,39 @@ static int implicit_dispatch(const double* q_in, const double* p_in, double* q_o
   }
 #undef MB200_ARGS
   return fail(MB200_ERR_INVALID_ARG, "unknown rmetric_id %d", m.rmetric_id);
+}
+#endif
+
+#ifndef MB200_NO_CONSTRAINED
+template <class Target, int KP>
+static int launch_project(const double* q, const double* p_in, double* p_out, int64_t n, int dim,
+                          int metric_kind, const double* minv, const ModelArgs& m,
+                          cudaStream_t st) {
+  constexpr int WARPS = 4;
+  const size_t smem = (size_t)WARPS * (Target::NC > 1 ? Target::NC : 1) * 64 * KP * sizeof(double);
+  int64_t blocks = (n + WARPS - 1) / WARPS;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  constrained_project_kernel<Target, KP><<<(unsigned)blocks, WARPS * 32, smem, st>>>(
+      q, p_in, p_out, n, dim, metric_kind, minv, m);
+  return check_launch("constrained_project_kernel");
+}
+#endif
+
+#ifndef MB200_NO_RIEMANNIAN
+template <class Target, template <class> class MetricT>
+static int launch_sample_momentum(const double* q, const double* z, double* p_out, int64_t n,
+                                  int dim, const ModelArgs& m, int32_t* status, cudaStream_t st) {
+  auto kern = riemannian_sample_momentum_kernel<Target, MetricT>;
+  const int n_mats = MetricT<Target>::N_MATS;
+  const size_t smem = rm_smem_doubles(dim, n_mats) * sizeof(double);
+  if (smem > 227 * 1024) return fail(MB200_ERR_UNSUPPORTED, "dim %d too large", dim);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(MB200_ERR_CUDA, "smem attr: %s", cudaGetErrorString(e));
+  int64_t blocks = (int64_t)num_sms() * 2;
+  if (blocks > n) blocks = n;
+  kern<<<(unsigned)blocks, RM_THREADS, smem, st>>>(q, z, p_out, n, dim, m, status, n_mats);
+  return check_launch("riemannian_sample_momentum_kernel");
 }
 #endif
 
@@ -587,5 +625,132 @@ int mb200_implicit_midpoint_riemannian(const double*, const double*, double*, do
   return fail(MB200_ERR_UNSUPPORTED, "implicit midpoint not compiled in");
 }
 #endif
+
+int mb200_project_onto_cotangent_space(const double* pos, const double* mom_in, double* mom_out,
+                                       int64_t n_chains, int32_t dim, int32_t metric_kind,
+                                       const double* metric_inv, const mb200_model* model,
+                                       void* stream) {
+#ifdef MB200_NO_CONSTRAINED
+  return fail(MB200_ERR_UNSUPPORTED, "constrained systems not compiled in");
+#else
+  if (n_chains == 0 && dim >= 1) return 0;
+  if (!pos || !mom_in || !mom_out || !model) return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
+  if (n_chains < 0 || dim < 1) return fail(MB200_ERR_INVALID_ARG, "bad sizes");
+  if (metric_kind < 0 || metric_kind > 2) return fail(MB200_ERR_INVALID_ARG, "bad metric_kind");
+  if (metric_kind != MB200_METRIC_IDENTITY && !metric_inv)
+    return fail(MB200_ERR_INVALID_ARG, "metric_inv is NULL");
+  const ModelArgs m = to_args(model);
+  cudaStream_t st = (cudaStream_t)stream;
+#define MB200_ARGS pos, mom_in, mom_out, n_chains, dim, metric_kind, metric_inv, m, st
+  switch (m.target_id) {
+    case MB200_TARGET_TORUS:
+      if (dim != 3) return fail(MB200_ERR_INVALID_ARG, "torus target needs dim == 3");
+      return launch_project<TorusTarget, 1>(MB200_ARGS);
+    case MB200_TARGET_SPHERE:
+      if (dim <= 64) return launch_project<SphereTarget, 1>(MB200_ARGS);
+      if (dim <= 128) return launch_project<SphereTarget, 2>(MB200_ARGS);
+      if (dim <= 256) return launch_project<SphereTarget, 4>(MB200_ARGS);
+      return fail(MB200_ERR_UNSUPPORTED, "sphere target: dim %d > 256 not supported", dim);
+    default:
+      return fail(MB200_ERR_UNSUPPORTED, "target %d defines no constraint", m.target_id);
+  }
+#undef MB200_ARGS
+#endif
+}
+
+int mb200_sample_momentum_riemannian(const double* pos, const double* normals, double* mom_out,
+                                     int64_t n_chains, int32_t dim, const mb200_model* model,
+                                     int32_t* status, void* stream) {
+#ifdef MB200_NO_RIEMANNIAN
+  return fail(MB200_ERR_UNSUPPORTED, "riemannian systems not compiled in");
+#else
+  if (n_chains == 0 && dim >= 1) return 0;
+  if (!pos || !normals || !mom_out || !model) return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
+  if (n_chains < 0 || dim < 1) return fail(MB200_ERR_INVALID_ARG, "bad sizes");
+  const ModelArgs m = to_args(model);
+  cudaStream_t st = (cudaStream_t)stream;
+#define MB200_ARGS pos, normals, mom_out, n_chains, dim, m, status, st
+  if (m.rmetric_id == MB200_RMETRIC_SOFTABS) {
+    if (m.target_id == MB200_TARGET_BANANA) return launch_sample_momentum<BananaRTarget, SoftAbsMetric>(MB200_ARGS);
+    return fail(MB200_ERR_UNSUPPORTED, "target %d has no device Hessian", m.target_id);
+  }
+  if (m.rmetric_id == MB200_RMETRIC_RANK1) {
+    if (!m.maux) return fail(MB200_ERR_INVALID_ARG, "rank-1 metric needs its base matrix");
+    if (rm_smem_doubles(dim, 1) * sizeof(double) > 227 * 1024)
+      return fail(MB200_ERR_UNSUPPORTED,
+                  "dim %d: the Cholesky factor of M(q) does not fit in shared memory", dim);
+    switch (m.target_id) {
+      case MB200_TARGET_QUADRATIC: return launch_sample_momentum<QuadraticRTarget, Rank1DenseMetric>(MB200_ARGS);
+      case MB200_TARGET_STD_GAUSSIAN: return launch_sample_momentum<StdGaussianRTarget, Rank1DenseMetric>(MB200_ARGS);
+      case MB200_TARGET_BANANA: return launch_sample_momentum<BananaRTarget, Rank1DenseMetric>(MB200_ARGS);
+      default: return fail(MB200_ERR_UNSUPPORTED, "target %d not available", m.target_id);
+    }
+  }
+#undef MB200_ARGS
+  return fail(MB200_ERR_INVALID_ARG, "unknown rmetric_id %d", m.rmetric_id);
+#endif
+}
+
+int mb200_leapfrog_euclidean_per_chain(const double* pos_in, const double* mom_in, double* pos_out,
+                                       double* mom_out, const int32_t* dir, int64_t n_chains,
+                                       int32_t dim, const double* step_sizes,
+                                       const int32_t* n_steps_per_chain, int32_t max_n_steps,
+                                       int32_t n_flows, const double* coefficients,
+                                       int32_t initial_h1_flow_step, int32_t metric_kind,
+                                       const double* metric_inv, const mb200_model* model,
+                                       double* h_out, int32_t* status, int32_t* n_done,
+                                       void* stream) {
+  if (n_chains > 0 && !step_sizes) return fail(MB200_ERR_INVALID_ARG, "step_sizes is NULL");
+  FlowSchedule s = leapfrog_schedule();
+  if (coefficients != nullptr) {
+    if (n_flows < 1 || n_flows > MB200_MAX_FLOWS || (n_flows & 1) == 0)
+      return fail(MB200_ERR_INVALID_ARG, "n_flows must be odd and in [1, %d]", MB200_MAX_FLOWS);
+    memset(&s, 0, sizeof(s));
+    s.n = n_flows;
+    for (int i = 0; i < n_flows; ++i) {
+      s.coef[i] = coefficients[i];
+      const bool is_a = (i & 1) == 0;
+      if (initial_h1_flow_step ? !is_a : is_a) s.drift_mask |= 1u << i;
+    }
+  }
+  s.step_sizes = step_sizes;
+  s.n_steps = n_steps_per_chain;
+  return leapfrog_euclidean_impl(pos_in, mom_in, pos_out, mom_out, dir, n_chains, dim, 0.0,
+                                 max_n_steps, metric_kind, metric_inv, model, h_out, status,
+                                 n_done, (cudaStream_t)stream, false, &s);
+}
+
+int mb200_leapfrog_gaussian_euclidean(const double* pos_in, const double* mom_in, double* pos_out,
+                                      double* mom_out, const int32_t* dir, int64_t n_chains,
+                                      int32_t dim, double step_size, const double* step_sizes,
+                                      int32_t n_steps, int32_t n_flows, const double* coefficients,
+                                      int32_t initial_h1_flow_step, int32_t metric_kind,
+                                      const double* metric_inv, const double* rotation,
+                                      const mb200_model* model, double* h_out, int32_t* status,
+                                      int32_t* n_done, void* stream) {
+  FlowSchedule s = leapfrog_schedule();
+  if (coefficients != nullptr) {
+    if (n_flows < 1 || n_flows > MB200_MAX_FLOWS || (n_flows & 1) == 0)
+      return fail(MB200_ERR_INVALID_ARG, "n_flows must be odd and in [1, %d]", MB200_MAX_FLOWS);
+    memset(&s, 0, sizeof(s));
+    s.n = n_flows;
+    for (int i = 0; i < n_flows; ++i) {
+      s.coef[i] = coefficients[i];
+      const bool is_a = (i & 1) == 0;
+      if (initial_h1_flow_step ? !is_a : is_a) s.drift_mask |= 1u << i;
+    }
+  }
+  if (metric_kind != MB200_METRIC_IDENTITY && !rotation && n_chains > 0)
+    return fail(MB200_ERR_INVALID_ARG, "rotation is NULL");
+  if (metric_kind == MB200_METRIC_DENSE && step_sizes)
+    return fail(MB200_ERR_UNSUPPORTED,
+                "per-chain step sizes need per-chain rotation matrices for a dense metric");
+  s.gaussian = 1;
+  s.rot = rotation;
+  s.step_sizes = step_sizes;
+  return leapfrog_euclidean_impl(pos_in, mom_in, pos_out, mom_out, dir, n_chains, dim, step_size,
+                                 n_steps, metric_kind, metric_inv, model, h_out, status, n_done,
+                                 (cudaStream_t)stream, false, &s);
+}
 
 }  // extern "C"

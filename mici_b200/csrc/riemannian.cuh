@@ -615,6 +615,24 @@ struct SoftAbsMetric {
     }
     __syncthreads();
   }
+  // out = sqrt(M) v = U (sqrt(s) o (U^T v))   (EigendecomposedPositiveDefiniteMatrix.sqrt,
+  // matrices.py:1618-1628); out must not alias v
+  __device__ bool sqrt_matvec(const Blk& k, RmWork& w, const double* v, double* out) const {
+    const int n = w.dim, ld = w.ld;
+    for (int j = k.tid; j < n; j += k.nthr) {
+      double s = 0.0;
+      for (int i = 0; i < n; ++i) s = fma(w.M1[i * ld + j], v[i], s);
+      w.ev[j] = sqrt(w.sa[j]) * s;
+    }
+    __syncthreads();
+    for (int i = k.tid; i < n; i += k.nthr) {
+      double s = 0.0;
+      for (int j = 0; j < n; ++j) s = fma(w.M1[i * ld + j], w.ev[j], s);
+      out[i] = s;
+    }
+    __syncthreads();
+    return true;
+  }
   // out = vjp(grad_log_abs_det), grad_log_abs_det = U diag(gs/s) U^T   (:1673-1676)
   __device__ void vjp_grad_log_abs_det(const Blk& k, RmWork& w, const double* q, double* out) const {
     const int n = w.dim, ld = w.ld;
@@ -720,6 +738,16 @@ struct Rank1DenseMetric {
   __device__ void inv_matvec(const Blk& k, RmWork& w, const double* v, double* out) const {
     cholesky_solve(k, w.M1, w.dim, w.ld, v, out);
   }
+  // out = L v (sqrt of a DensePositiveDefiniteMatrix is its Cholesky factor, matrices.py:1212-1216)
+  __device__ bool sqrt_matvec(const Blk& k, RmWork& w, const double* v, double* out) const {
+    for (int i = k.tid; i < w.dim; i += k.nthr) {
+      double s = 0.0;
+      for (int j = 0; j <= i; ++j) s = fma(w.M1[i * w.ld + j], v[j], s);
+      out[i] = s;
+    }
+    __syncthreads();
+    return true;
+  }
   __device__ void vjp_grad_log_abs_det(const Blk& k, RmWork& w, const double* q, double* out) const {
     cholesky_solve(k, w.M1, w.dim, w.ld, q, w.ev);  // M^-1 q
     for (int i = k.tid; i < w.dim; i += k.nthr) out[i] = c * (w.ev[i] + w.ev[i]);
@@ -786,6 +814,8 @@ struct Rank1WoodburyMetric {
     return 0;
   }
   __device__ double log_abs_det(const Blk&, RmWork&) const { return logdet_b + log(denom); }
+  // the Cholesky factor of M(q) is not available in this form
+  __device__ bool sqrt_matvec(const Blk&, RmWork&, const double*, double*) const { return false; }
   __device__ void inv_matvec(const Blk& k, RmWork& w, const double* v, double* out) const {
     binv_matvec(k, w.dim, v, out);
     double s = 0.0;
@@ -1201,6 +1231,36 @@ __global__ void __launch_bounds__(RM_THREADS)
       if (fp_iters != nullptr)
         for (int j = 0; j < 4; ++j) fp_iters[ch * 4 + j] = it4[j];
     }
+  }
+}
+
+// mom = sqrt(M(q)) z for every chain: RiemannianMetricSystem.sample_momentum (systems.py:1401-1402).
+template <class Target, template <class> class MetricT>
+__global__ void __launch_bounds__(RM_THREADS)
+    riemannian_sample_momentum_kernel(const double* __restrict__ q_in, const double* __restrict__ z,
+                                      double* __restrict__ p_out, int64_t n_chains, int dim,
+                                      ModelArgs model, int32_t* __restrict__ status, int n_mats) {
+  extern __shared__ double smem[];
+  Blk blk;
+  blk.tid = threadIdx.x, blk.nthr = blockDim.x, blk.lane = threadIdx.x & 31;
+  blk.warp = threadIdx.x >> 5, blk.nwarp = blockDim.x >> 5;
+  RmWork w;
+  rm_carve(w, smem, dim, n_mats, blk);
+  const Target target(model, dim);
+  MetricT<Target> metric(target, model);
+  for (int64_t ch = blockIdx.x; ch < n_chains; ch += gridDim.x) {
+    __syncthreads();
+    for (int i = blk.tid; i < dim; i += blk.nthr) {
+      w.q[i] = q_in[(size_t)ch * dim + i];
+      w.v1[i] = z[(size_t)ch * dim + i];
+    }
+    __syncthreads();
+    metric.reset();
+    int st = metric.build(blk, w, w.q) != 0 ? MB200_STATUS_LINALG : MB200_STATUS_OK;
+    if (st == MB200_STATUS_OK && !metric.sqrt_matvec(blk, w, w.v1, w.v2)) st = MB200_STATUS_LINALG;
+    for (int i = blk.tid; i < dim; i += blk.nthr)
+      p_out[(size_t)ch * dim + i] = (st == MB200_STATUS_OK) ? w.v2[i] : nan("");
+    if (blk.tid == 0 && status != nullptr) status[ch] = st;
   }
 }
 

@@ -12,6 +12,8 @@ def build_system(problem):
     target = targets.make_target(problem.target, **problem.target_params)
     if problem.system == "euclidean":
         return systems.EuclideanMetricSystem(target, metric=problem.metric)
+    if problem.system == "gaussian_euclidean":
+        return systems.GaussianEuclideanMetricSystem(target, metric=problem.metric)
     if problem.system == "constrained_euclidean":
         return systems.DenseConstrainedEuclideanMetricSystem(target, target, metric=problem.metric)
     if problem.system == "softabs_riemannian":

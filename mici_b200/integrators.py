@@ -45,6 +45,7 @@ from .states import ChainState
 from .systems import (
     ConstrainedEuclideanMetricSystem,
     EuclideanMetricSystem,
+    GaussianEuclideanMetricSystem,
     RiemannianMetricSystem,
     _batched,
     _dir_tensor,
@@ -86,7 +87,9 @@ class Integrator(ABC):
         status = torch.empty(n, dtype=torch.int32, device=dev)
         n_done = torch.empty(n, dtype=torch.int32, device=dev)
         h = torch.empty(n, dtype=torch.float64, device=dev) if return_h else None
-        aux = self._launch(pos, mom, pos_out, mom_out, _dir_tensor(d, n, dev), int(n_steps), h,
+        if not isinstance(n_steps, torch.Tensor):
+            n_steps = int(n_steps)
+        aux = self._launch(pos, mom, pos_out, mom_out, _dir_tensor(d, n, dev), n_steps, h,
                            status, n_done)
         new = _new_state_like(state, _like_input(state.pos, pos_out[0] if single else pos_out),
                               _like_input(state.pos, mom_out[0] if single else mom_out))
@@ -199,6 +202,106 @@ class TractableFlowIntegrator(Integrator):
             raise ValueError(msg)
         super().__init__(system, step_size)
 
+    def _launch_per_chain(self, pos, mom, pos_out, mom_out, dirs, n_steps, h, status, n_done,
+                          coefficients=None, initial_h1_flow_step=True):
+        """Per-chain step sizes (``self.step_size`` a ``[n_chains]`` tensor: one dual-averaging
+        state per chain during warm-up, adapters.py:262-283, 373) and / or per-chain trajectory
+        lengths (``n_steps`` an integer tensor: transitions.py:355-412)."""
+        n, dim = pos.shape
+        dev = pos.device
+        sysm = self.system
+        model = sysm._model(dev)
+        eps = self.step_size
+        if isinstance(eps, torch.Tensor) and eps.ndim == 1:
+            if eps.shape[0] != n:
+                raise ValueError(f"per-chain step_size has {eps.shape[0]} entries for {n} chains")
+            eps = eps.to(device=dev, dtype=torch.float64).contiguous()
+        else:
+            eps = torch.full((n,), float(eps), dtype=torch.float64, device=dev)
+        if isinstance(n_steps, torch.Tensor):
+            if n_steps.shape != (n,):
+                raise ValueError("per-chain n_steps must have one entry per chain")
+            ns = n_steps.to(device=dev, dtype=torch.int32).contiguous()
+            max_n = int(ns.max().item()) if n > 0 else 0
+        else:
+            ns, max_n = None, int(n_steps)
+        if coefficients is None:
+            coefs, n_flows = None, 0
+        else:
+            coefs = ctypes.cast((ctypes.c_double * len(coefficients))(*coefficients),
+                                ctypes.c_void_p)
+            n_flows = len(coefficients)
+        rc = _lib.load().mb200_leapfrog_euclidean_per_chain(
+            _lib.ptr(pos), _lib.ptr(mom), _lib.ptr(pos_out), _lib.ptr(mom_out), _lib.ptr(dirs),
+            n, dim, _lib.ptr(eps), _lib.ptr(ns), max_n, n_flows, coefs,
+            1 if initial_h1_flow_step else 0, sysm.metric.kind,
+            _lib.ptr(sysm.metric.inv_device(dev)), ctypes.byref(model), _lib.ptr(h),
+            _lib.ptr(status), _lib.ptr(n_done), _lib.current_stream_ptr(dev),
+        )
+        _lib.check(rc, "mb200_leapfrog_euclidean_per_chain")
+
+
+def _launch_gaussian(system, step_size, pos, mom, pos_out, mom_out, dirs, n_steps, h, status,
+                     n_done, coefficients=None, initial_h1_flow_step=True):
+    """``mb200_leapfrog_gaussian_euclidean``: leapfrog / composition over the flows of a
+    ``GaussianEuclideanMetricSystem`` (systems.py:369-474)."""
+    n, dim = pos.shape
+    dev = pos.device
+    if isinstance(n_steps, torch.Tensor):
+        raise NotImplementedError("per-chain trajectory lengths: plain Euclidean systems only")
+    model = system._model(dev)
+    per_chain = isinstance(step_size, torch.Tensor) and step_size.ndim == 1
+    eps_t = step_size.to(device=dev, dtype=torch.float64).contiguous() if per_chain else None
+    eps = 0.0 if per_chain else float(step_size)
+    if coefficients is None:
+        coefs, n_flows, drift = None, 0, [1.0]
+    else:
+        coefs = ctypes.cast((ctypes.c_double * len(coefficients))(*coefficients), ctypes.c_void_p)
+        n_flows = len(coefficients)
+        first_drift = 1 if initial_h1_flow_step else 0
+        drift = list(coefficients[first_drift::2])
+    if per_chain and system.metric.kind == 2:
+        raise NotImplementedError("per-chain step sizes with a dense Gaussian-split metric")
+    rot = system.rotation_device(dev, eps, drift)
+    rc = _lib.load().mb200_leapfrog_gaussian_euclidean(
+        _lib.ptr(pos), _lib.ptr(mom), _lib.ptr(pos_out), _lib.ptr(mom_out), _lib.ptr(dirs), n,
+        dim, eps, _lib.ptr(eps_t), n_steps, n_flows, coefs, 1 if initial_h1_flow_step else 0,
+        system.metric.kind, _lib.ptr(system.metric.inv_device(dev)), _lib.ptr(rot),
+        ctypes.byref(model), _lib.ptr(h), _lib.ptr(status), _lib.ptr(n_done),
+        _lib.current_stream_ptr(dev),
+    )
+    _lib.check(rc, "mb200_leapfrog_gaussian_euclidean")
+
+
+def _gaussian_flow(system, state, dt):
+    """In-place ``h2_flow`` of a Gaussian-split system: a one-flow schedule {drift 1.0}."""
+    pos, mom, _, single = _batched(state)
+    pos, mom = pos.contiguous(), mom.contiguous()
+    n = pos.shape[0]
+    pos_out, mom_out = torch.empty_like(pos), torch.empty_like(mom)
+    if isinstance(dt, torch.Tensor) and dt.ndim == 1:
+        dirs = torch.where(dt < 0, -1, 1).to(torch.int32)
+        eps = dt.abs()
+    else:
+        dirs = None if float(dt) >= 0 else torch.full((n,), -1, dtype=torch.int32, device=pos.device)
+        eps = abs(float(dt))
+    _launch_gaussian(system, eps, pos, mom, pos_out, mom_out, dirs, 1, None, None, None,
+                     coefficients=[1.0], initial_h1_flow_step=False)
+    state.pos = _like_input(state.pos, pos_out[0] if single else pos_out)
+    state.mom = _like_input(state.mom, mom_out[0] if single else mom_out)
+
+
+def _reject_per_chain(integrator, n_steps):
+    if _is_per_chain(integrator.step_size, n_steps):
+        raise NotImplementedError(
+            f"{type(integrator).__name__}: per-chain step sizes / trajectory lengths are only "
+            "available for the explicit Euclidean integrators.")
+
+
+def _is_per_chain(step_size, n_steps):
+    return (isinstance(step_size, torch.Tensor) and step_size.ndim == 1) or isinstance(
+        n_steps, torch.Tensor)
+
 
 class LeapfrogIntegrator(TractableFlowIntegrator):
     """Explicit leapfrog Psi(t) = Phi_1(t/2) o Phi_2(t) o Phi_1(t/2) (integrators.py:134-173)
@@ -212,6 +315,12 @@ class LeapfrogIntegrator(TractableFlowIntegrator):
             raise TypeError("LeapfrogIntegrator needs an (unconstrained) EuclideanMetricSystem.")
 
     def _launch(self, pos, mom, pos_out, mom_out, dirs, n_steps, h, status, n_done):
+        if isinstance(self.system, GaussianEuclideanMetricSystem):
+            return _launch_gaussian(self.system, self.step_size, pos, mom, pos_out, mom_out, dirs,
+                                    n_steps, h, status, n_done)
+        if _is_per_chain(self.step_size, n_steps):
+            return self._launch_per_chain(pos, mom, pos_out, mom_out, dirs, n_steps, h, status,
+                                          n_done)
         n, dim = pos.shape
         dev = pos.device
         sysm = self.system
@@ -246,6 +355,13 @@ class SymmetricCompositionIntegrator(TractableFlowIntegrator):
         self.coefficients = coefficients + coefficients[-2::-1]
 
     def _launch(self, pos, mom, pos_out, mom_out, dirs, n_steps, h, status, n_done):
+        if isinstance(self.system, GaussianEuclideanMetricSystem):
+            return _launch_gaussian(self.system, self.step_size, pos, mom, pos_out, mom_out, dirs,
+                                    n_steps, h, status, n_done, self.coefficients,
+                                    self.initial_h1_flow_step)
+        if _is_per_chain(self.step_size, n_steps):
+            return self._launch_per_chain(pos, mom, pos_out, mom_out, dirs, n_steps, h, status,
+                                          n_done, self.coefficients, self.initial_h1_flow_step)
         n, dim = pos.shape
         dev = pos.device
         sysm = self.system
@@ -314,6 +430,7 @@ class ImplicitLeapfrogIntegrator(Integrator):
         n, dim = pos.shape
         dev = pos.device
         sysm = self.system
+        _reject_per_chain(self, n_steps)
         kw = self.fixed_point_solver.resolve_kwargs(self.fixed_point_solver_kwargs)
         model = sysm._model(dev)
         ws = sysm._workspace(n, dim, dev)
@@ -353,6 +470,7 @@ class ImplicitMidpointIntegrator(Integrator):
         self.fixed_point_solver_kwargs = dict(fixed_point_solver_kwargs or {})
 
     def _launch(self, pos, mom, pos_out, mom_out, dirs, n_steps, h, status, n_done):
+        _reject_per_chain(self, n_steps)
         n, dim = pos.shape
         dev = pos.device
         sysm = self.system
@@ -394,6 +512,7 @@ class ConstrainedLeapfrogIntegrator(TractableFlowIntegrator):
         self.projection_solver_kwargs = dict(projection_solver_kwargs or {})
 
     def _launch(self, pos, mom, pos_out, mom_out, dirs, n_steps, h, status, n_done):
+        _reject_per_chain(self, n_steps)
         n, dim = pos.shape
         dev = pos.device
         sysm = self.system

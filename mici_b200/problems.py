@@ -108,6 +108,37 @@ def c1_funnel(n_chains=8192, dim=128, seed=BASE_SEED + 1, metric_kind="dense",
     )
 
 
+def g1_gaussian_split(n_chains=256, dim=32, seed=BASE_SEED + 6, metric_kind="dense",
+                      integrator="leapfrog", target="banana"):
+    """Extra parity case for row N4: ``GaussianEuclideanMetricSystem`` (systems.py:369-474) --
+    the registered target is the density relative to the standard Gaussian measure, the
+    drift is the exact rotation in the eigenbasis of the metric."""
+    rng = np.random.default_rng(seed)
+    metric = dense_spd_metric(rng, dim)
+    pos = 0.7 * rng.standard_normal((n_chains, dim))
+    z = rng.standard_normal((n_chains, dim))
+    if metric_kind == "dense":
+        mom = z @ np.linalg.cholesky(metric).T
+    elif metric_kind == "diagonal":
+        metric = np.ascontiguousarray(metric.diagonal())
+        mom = z * np.sqrt(metric)
+    else:
+        metric = None
+        mom = z
+    params = {"dim": dim, "b": 0.5} if target == "banana" else {"dim": dim}
+    return Problem(
+        name="G1",
+        integrator=integrator,
+        system="gaussian_euclidean",
+        target=target,
+        target_params=params,
+        step_size=0.15,
+        pos=pos,
+        mom=mom,
+        metric=metric,
+    )
+
+
 def c2_softabs_banana(n_chains=2048, dim=64, seed=BASE_SEED + 2, integrator="implicit_leapfrog"):
     rng = np.random.default_rng(seed)
     return Problem(
@@ -223,6 +254,7 @@ CONFIGS = {
     "C3": c3_torus,
     "C4": c4_dense_riemannian,
     "S1": sphere_constrained,
+    "G1": g1_gaussian_split,
 }
 
 

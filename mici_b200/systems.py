@@ -69,6 +69,23 @@ class _FixedMetric:
                 raise ValueError(msg)
         self._dev = {}
 
+    @classmethod
+    def from_covariance(cls, covar):
+        """The metric ``DensePositiveDefiniteMatrix(covar).inv`` that the covariance adapter
+        assigns (adapters.py:642): with ``L = chol(covar)`` its array is the explicit inverse
+        ``L^-T L^-1`` and its factor ``L^-T`` (matrices.py:1183-1188, 1209-1216), so ``metric.inv``
+        multiplies by ``L L^T`` (matrices.py:1041-1046, 1060-1061) and ``metric.sqrt @ z`` solves
+        ``L^T x = z`` (matrices.py:897-903) -- held here as the explicit upper-triangular factor."""
+        covar = np.asarray(covar, dtype=np.float64)
+        chol, explicit_inv = _explicit_spd_inverse(covar)
+        self = cls.__new__(cls)
+        self.kind, self.array = METRIC_DENSE, explicit_inv
+        self.inv = chol @ chol.T
+        self.sqrt = sla.solve_triangular(chol.T, np.identity(covar.shape[0]), lower=False,
+                                         check_finite=False)
+        self._dev = {}
+        return self
+
     @property
     def shape(self):
         return (None, None) if self.array is None else (self.array.shape[0],) * 2
@@ -309,12 +326,77 @@ class EuclideanMetricSystem(TractableFlowSystem):
         return z if state.pos.ndim == 2 else z[0]
 
 
+class GaussianEuclideanMetricSystem(EuclideanMetricSystem):
+    """Euclidean system whose target density is given relative to the standard Gaussian measure
+    (systems.py:369-474) -- "next" row N4: ``h1 = l(q)``, ``h2 = q.q/2 + p.M^-1 p/2`` and
+    ``h2_flow`` is the exact rotation of ``(q, p)`` in the eigenbasis of ``M``.  The tractable-
+    flow integrators (leapfrog, symmetric compositions) drive it through
+    ``mb200_leapfrog_gaussian_euclidean``."""
+
+    def h2(self, state):
+        """``q.q/2 + p.M^-1 p/2`` (systems.py:450-453)."""
+        pos = torch.as_tensor(state.pos)
+        return super().h2(state) + _like_input(state.pos, 0.5 * (pos * pos).sum(-1))
+
+    def dh2_dpos(self, state):
+        """systems.py:460-462."""
+        return state.pos
+
+    def dh_dpos(self, state):
+        return self.dh1_dpos(state) + state.pos
+
+    def h(self, state):
+        return self.h1(state) + self.h2(state)
+
+    def _eig(self):
+        """``(eigval, eigvec)`` of the metric as the reference obtains them: ``numpy.linalg.eigh``
+        of the dense array (matrices.py:436-438); identity eigenvectors for identity / diagonal
+        metrics (matrices.py:519-528, 743-749)."""
+        m = self._metric
+        if "eig" not in m._dev:
+            m._dev["eig"] = np.linalg.eigh(m.array)
+        return m._dev["eig"]
+
+    def rotation_device(self, device, step_size, drift_coefficients):
+        """Device operand ``rotation`` of ``mb200_leapfrog_gaussian_euclidean``."""
+        m = self._metric
+        if m.kind == METRIC_IDENTITY:
+            return None
+        if m.kind == METRIC_DIAGONAL:
+            key = ("diag", str(device))
+            if key not in m._dev:
+                m._dev[key] = torch.as_tensor(np.ascontiguousarray(m.array), device=device)
+            return m._dev[key]
+        key = ("rot", str(device), float(step_size), tuple(float(c) for c in drift_coefficients))
+        if key not in m._dev:
+            eigval, u = self._eig()
+            omega = 1.0 / eigval**0.5
+            mats = []
+            for c in drift_coefficients:
+                t = float(c) * float(step_size)
+                sn, cs = np.sin(omega * t), np.cos(omega * t)
+                mats += [(u * cs) @ u.T, (u * (sn * omega)) @ u.T, -(u * (sn / omega)) @ u.T]
+            m._dev[key] = torch.as_tensor(np.ascontiguousarray(np.stack(mats)), device=device)
+        return m._dev[key]
+
+    def h2_flow(self, state, dt):
+        """Exact flow of ``h2`` over ``dt`` (systems.py:464-474), all chains in one launch."""
+        from .integrators import _gaussian_flow  # noqa: PLC0415
+
+        _gaussian_flow(self, state, dt)
+
+
 def _col(dt):
     return dt[..., None] if isinstance(dt, torch.Tensor) and dt.ndim >= 1 else dt
 
 
 class ConstrainedTractableFlowSystem(TractableFlowSystem):
     """systems.py:477-616."""
+
+    def sample_momentum(self, state, rng):
+        """Draw from N(0, M), then project onto the cotangent space (systems.py:613-616)."""
+        mom = super().sample_momentum(state, rng)
+        return self.project_onto_cotangent_space(mom, state)
 
 
 class ConstrainedEuclideanMetricSystem(ConstrainedTractableFlowSystem, EuclideanMetricSystem):
@@ -337,6 +419,31 @@ class ConstrainedEuclideanMetricSystem(ConstrainedTractableFlowSystem, Euclidean
         if not dens_wrt_hausdorff:
             raise NotImplementedError("Only `dens_wrt_hausdorff=True` is implemented.")
         self.dens_wrt_hausdorff = dens_wrt_hausdorff
+
+    def project_onto_cotangent_space(self, mom, state):
+        """``mom - J^T (J M^-1 J^T)^-1 J M^-1 mom`` at ``state.pos`` (systems.py:863-873) for all
+        chains in one launch (``mb200_project_onto_cotangent_space``)."""
+        pos = state.pos
+        single = pos.ndim == 1
+        ref = mom
+        pos_t = torch.as_tensor(pos)
+        if pos_t.device.type != "cuda":
+            pos_t = pos_t.to("cuda")
+        pos_t = (pos_t[None] if single else pos_t).contiguous()
+        mom_t = torch.as_tensor(mom).to(pos_t.device)
+        mom_t = (mom_t[None] if mom_t.ndim == 1 else mom_t).contiguous()
+        n, dim = pos_t.shape
+        dev = pos_t.device
+        out = torch.empty_like(mom_t)
+        m = self._metric
+        minv = None if m.kind == METRIC_IDENTITY else m.inv_device(dev)
+        model = self._model(dev)
+        rc = _lib.load().mb200_project_onto_cotangent_space(
+            _lib.ptr(pos_t), _lib.ptr(mom_t), _lib.ptr(out), n, dim, m.kind, _lib.ptr(minv),
+            ctypes.byref(model), _lib.current_stream_ptr(dev),
+        )
+        _lib.check(rc, "mb200_project_onto_cotangent_space")
+        return _like_input(ref, out[0] if single else out)
 
 
 class DenseConstrainedEuclideanMetricSystem(ConstrainedEuclideanMetricSystem):
@@ -380,6 +487,34 @@ class RiemannianMetricSystem(System):
         )
         _lib.check(rc, "mb200_hamiltonian_riemannian")
         return _like_input(state.pos, h[0] if single else h)
+
+    def sample_momentum(self, state, rng):
+        """``metric(state).sqrt @ N(0, I)`` (systems.py:1401-1402): the factor of M(q) is built
+        per chain on the device (``mb200_sample_momentum_riemannian``).  Chains whose metric
+        cannot be built raise ``LinAlgError`` as in the reference."""
+        from .errors import LinAlgError  # noqa: PLC0415
+        from .transitions import _normals  # noqa: PLC0415
+
+        pos = torch.as_tensor(state.pos)
+        single = pos.ndim == 1
+        if pos.device.type != "cuda":
+            pos = pos.to("cuda")
+        pos = (pos[None] if single else pos).contiguous()
+        n, dim = pos.shape
+        dev = pos.device
+        z = _normals(rng, (n, dim), dev).contiguous()
+        out = torch.empty_like(z)
+        status = torch.empty(n, dtype=torch.int32, device=dev)
+        model = self._model(dev)
+        rc = _lib.load().mb200_sample_momentum_riemannian(
+            _lib.ptr(pos), _lib.ptr(z), _lib.ptr(out), n, dim, ctypes.byref(model),
+            _lib.ptr(status), _lib.current_stream_ptr(dev),
+        )
+        _lib.check(rc, "mb200_sample_momentum_riemannian")
+        if bool((status != 0).any()):
+            bad = int((status != 0).sum())
+            raise LinAlgError(f"metric factorisation failed for {bad} of {n} chains")
+        return _like_input(state.pos, out[0] if single else out)
 
 
 class DenseRiemannianMetricSystem(RiemannianMetricSystem):

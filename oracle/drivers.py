@@ -54,6 +54,16 @@ def oracle_step_fn(problem, counts=None, **overrides):
     ikw = dict(problem.integrator_kwargs)
     ikw.update(overrides)
     eps = problem.step_size
+    if problem.system == "gaussian_euclidean":
+        metric = mo.coerce_metric(problem.metric)
+        coefs = (0.5, 1.0, 0.5)
+        if problem.integrator in mo.BCSS_FREE_COEFFICIENTS:
+            coefs = mo.composition_coefficients(mo.BCSS_FREE_COEFFICIENTS[problem.integrator])
+
+        def step(q, p, d):
+            return mo.gaussian_composition_steps(q, p, d * eps, 1, target, metric, coefs)
+
+        return step, (lambda q, p: mo.gaussian_euclidean_h(q, p, target, metric)), None
     if problem.integrator == "leapfrog":
         metric = mo.coerce_metric(problem.metric)
 
@@ -146,6 +156,12 @@ def build_reference(problem, **overrides):
     ikw.update(overrides)
     if problem.system == "euclidean":
         system = mici.systems.EuclideanMetricSystem(
+            neg_log_dens=target.neg_log_dens,
+            metric=problem.metric,
+            grad_neg_log_dens=target.grad_neg_log_dens,
+        )
+    elif problem.system == "gaussian_euclidean":
+        system = mici.systems.GaussianEuclideanMetricSystem(
             neg_log_dens=target.neg_log_dens,
             metric=problem.metric,
             grad_neg_log_dens=target.grad_neg_log_dens,
@@ -243,19 +259,22 @@ def reference_run(problem, n_steps, dirs=None, chains=None, **overrides):
 # ------------------------------------------------------------------ static HMC (row N1)
 
 
-def _sqrt_matvec(problem):
-    metric = mo.coerce_metric(problem.metric)
-    return metric.sqrt_matvec
+def _sample_momentum(problem, system):
+    if problem.system in ("euclidean", "gaussian_euclidean"):
+        return mo.euclidean_sample_momentum(mo.coerce_metric(problem.metric))
+    if problem.system == "constrained_euclidean":
+        return mo.constrained_sample_momentum(system)
+    return mo.riemannian_sample_momentum(system)
 
 
 def oracle_hmc(problem, n_iter, n_step, seed, chains=None):
     """``n_iter`` static-HMC iterations per chain through the oracle; per-chain generators
-    ``default_rng([seed, chain])``.  Euclidean systems only."""
-    step, h_fn, _ = oracle_step_fn(problem)
+    ``default_rng([seed, chain])``."""
+    step, h_fn, system = oracle_step_fn(problem)
     sl = slice(None) if chains is None else chains
     q0, p0 = problem.pos[sl], problem.mom[sl]
     n = q0.shape[0]
-    sqrt_mv = _sqrt_matvec(problem)
+    sample_mom = _sample_momentum(problem, system)
     pos = np.empty((n_iter, n, q0.shape[1]))
     stats = {k: np.empty((n_iter, n)) for k in ("n_step", "metrop_accept_prob", "accept_stat", "accepted")}
     dirs = np.ones(n, dtype=np.int32)
@@ -263,7 +282,7 @@ def oracle_hmc(problem, n_iter, n_step, seed, chains=None):
         rng = np.random.default_rng([seed, i])
         q, p, d = q0[i].copy(), p0[i].copy(), 1
         for it in range(n_iter):
-            q, p, d, st = mo.static_hmc_transition(q, p, d, rng, step, h_fn, sqrt_mv, n_step)
+            q, p, d, st = mo.static_hmc_transition(q, p, d, rng, step, h_fn, sample_mom, n_step)
             pos[it, i] = q
             for k in stats:
                 stats[k][it, i] = st[k]
@@ -279,7 +298,10 @@ def reference_hmc(problem, n_iter, n_step, seed, chains=None):
     q0, p0 = problem.pos[sl], problem.mom[sl]
     n = q0.shape[0]
     mom_tr = mici.transitions.IndependentMomentumTransition(system)
-    int_tr = mici.transitions.MetropolisStaticIntegrationTransition(system, integrator, n_step)
+    if isinstance(n_step, tuple):
+        int_tr = mici.transitions.MetropolisRandomIntegrationTransition(system, integrator, n_step)
+    else:
+        int_tr = mici.transitions.MetropolisStaticIntegrationTransition(system, integrator, n_step)
     pos = np.empty((n_iter, n, q0.shape[1]))
     stats = {k: np.empty((n_iter, n)) for k in ("n_step", "metrop_accept_prob", "accept_stat")}
     dirs = np.ones(n, dtype=np.int32)
@@ -294,3 +316,147 @@ def reference_hmc(problem, n_iter, n_step, seed, chains=None):
                 stats[k][it, i] = st[k]
         dirs[i] = state.dir
     return {"pos": pos, "dir": dirs, **stats}
+
+
+# ------------------------------------------------------- adaptive staged sampling (row N3)
+
+
+def _make_reference_adapters(mici, specs):
+    out = []
+    for name, kw in specs:
+        cls = {
+            "dual_averaging": mici.adapters.DualAveragingStepSizeAdapter,
+            "online_variance": mici.adapters.OnlineVarianceMetricAdapter,
+            "online_covariance": mici.adapters.OnlineCovarianceMetricAdapter,
+        }[name]
+        kw = dict(kw)
+        if "log_step_size_reducer" in kw:
+            kw["log_step_size_reducer"] = getattr(mici.adapters, kw["log_step_size_reducer"])
+        out.append(cls(**kw))
+    return out
+
+
+def reference_sample_chains(problem, n_warm_up_iter, n_main_iter, n_step, seed, adapter_specs,
+                            stager_kwargs=None):
+    """The reference's own ``StaticMetropolisHMC.sample_chains`` (samplers.py:1271-1432) with
+    adapters and stager, sequential chains, warm-up traced.  Per-chain generators are the
+    reference's (``default_rng(base.bit_generator.jumped(i))``, samplers.py:559-560)."""
+    mici = import_reference()
+    system, integrator = build_reference(problem)
+    rng = np.random.default_rng(seed)
+    sampler = mici.samplers.StaticMetropolisHMC(system, integrator, rng, n_step=n_step)
+    adapters = _make_reference_adapters(mici, adapter_specs)
+    stager = None
+    if stager_kwargs is not None:
+        stager = mici.stagers.WindowedWarmUpStager(**stager_kwargs)
+    init_states = [
+        mici.states.ChainState(pos=problem.pos[i].copy(), mom=problem.mom[i].copy(), dir=1)
+        for i in range(problem.n_chains)
+    ]
+    final_states, traces, stats = sampler.sample_chains(
+        n_warm_up_iter, n_main_iter, init_states, adapters=adapters, stager=stager,
+        trace_warm_up=True, n_worker=1, display_progress=False,
+    )
+    metric = system.metric
+    if isinstance(metric, mici.matrices.IdentityMatrix):
+        metric_arr = np.zeros(0)
+    elif isinstance(metric, mici.matrices.PositiveDiagonalMatrix):
+        metric_arr = np.asarray(metric.diagonal)
+    else:
+        metric_arr = np.asarray(metric.array)
+    return {
+        "pos": np.stack(traces["pos"], axis=1),  # [n_iter, n_chains, dim]
+        "accept_stat": np.stack(stats["accept_stat"], axis=1),
+        "n_step": np.stack(stats["n_step"], axis=1),
+        "final_pos": np.stack([s.pos for s in final_states]),
+        "final_mom": np.stack([s.mom for s in final_states]),
+        "final_dir": np.array([s.dir for s in final_states], dtype=np.int32),
+        "step_size": np.array(float(integrator.step_size)),
+        "metric": metric_arr,
+    }
+
+
+class _AdaptiveContext:
+    """What the adapters mutate: the integrator step size and the system metric."""
+
+    def __init__(self, problem):
+        self.target = build_target(problem)
+        self.metric = mo.coerce_metric(problem.metric)
+        self.step_size = problem.step_size
+        if problem.integrator != "leapfrog":
+            raise KeyError("adaptive oracle driver: leapfrog only")
+
+    def copy(self):
+        c = object.__new__(type(self))
+        c.__dict__.update(self.__dict__)
+        return c
+
+    def step_eps(self, q, p, d, eps):
+        return mo.leapfrog_steps(q, p, d * eps, 1, self.target, self.metric)
+
+    def step(self, q, p, d):
+        return self.step_eps(q, p, d, self.step_size)
+
+    def h(self, q, p):
+        return mo.euclidean_h(q, p, self.target, self.metric)
+
+
+def _make_oracle_adapters(specs):
+    cls = {"dual_averaging": mo.DualAveragingOracle, "online_variance": mo.OnlineVarianceOracle,
+           "online_covariance": mo.OnlineCovarianceOracle}
+    return [cls[name](**kw) for name, kw in specs]
+
+
+def oracle_sample_chains(problem, stages, n_step, seed, adapter_specs):
+    """Staged adaptive static HMC through the oracle.  ``stages``: list of ``(n_iter, which)``
+    with ``which`` one of ``"all"``, ``"fast"``, ``None`` (samplers.py:1075-1141 with the stage
+    list of stagers.py).  Chains run one after the other inside every stage, each from a copy of
+    the shared parameters, exactly like ``_sample_chains_sequential`` with per-chain deep-copied
+    transitions (samplers.py:1118-1129); the adapters are finalised over all chains at the end
+    of the stage (samplers.py:1131-1138)."""
+    ctx = _AdaptiveContext(problem)
+    adapters = _make_oracle_adapters(adapter_specs)
+    n = problem.n_chains
+    base = np.random.default_rng(seed)
+    rngs = [np.random.default_rng(base.bit_generator.jumped(i)) for i in range(n)]
+    q = [problem.pos[i].copy() for i in range(n)]
+    p = [problem.mom[i].copy() for i in range(n)]
+    d = [1] * n
+    pos, acc, nst, eps_trace = [], [], [], []
+    for n_iter, which in stages:
+        active = [] if which is None else [a for a in adapters if which == "all" or a.is_fast]
+        stage_pos = np.empty((n_iter, n, problem.dim))
+        stage_acc = np.empty((n_iter, n))
+        stage_nst = np.empty((n_iter, n))
+        stage_eps = np.empty((n_iter, n))
+        chain_states = []
+        for i in range(n):
+            c = ctx.copy()
+            states = [a.initialize(q[i], p[i], d[i], c) for a in active]
+            for it in range(n_iter):
+                stage_eps[it, i] = c.step_size
+                q[i], p[i], d[i], st = mo.static_hmc_transition(
+                    q[i], p[i], d[i], rngs[i], c.step, c.h,
+                    mo.euclidean_sample_momentum(c.metric), n_step)
+                for a, a_st in zip(active, states):
+                    a.update(a_st, q[i], st, c)
+                stage_pos[it, i] = q[i]
+                stage_acc[it, i] = st["accept_stat"]
+                stage_nst[it, i] = st["n_step"]
+            chain_states.append(states)
+        for k, a in enumerate(active):
+            if a.finalize([cs[k] for cs in chain_states], ctx):
+                for i in range(n):
+                    p[i] = mo.euclidean_sample_momentum(ctx.metric)(q[i], rngs[i])
+        pos.append(stage_pos), acc.append(stage_acc), nst.append(stage_nst)
+        eps_trace.append(stage_eps)
+    metric = ctx.metric
+    metric_arr = (metric.diagonal if metric.kind == "diagonal"
+                  else np.zeros(0) if metric.kind == "identity" else metric.array)
+    return {
+        "pos": np.concatenate(pos), "accept_stat": np.concatenate(acc),
+        "n_step": np.concatenate(nst), "step_size_trace": np.concatenate(eps_trace),
+        "final_pos": np.stack(q), "final_mom": np.stack(p),
+        "final_dir": np.array(d, dtype=np.int32), "step_size": np.array(float(ctx.step_size)),
+        "metric": metric_arr,
+    }

@@ -35,6 +35,11 @@ CASES = {
     "c2_softabs_banana_d8": ("C2", {"n_chains": 32, "dim": 8}, (1, 5, 20), {}),
     "c3_torus": ("C3", {"n_chains": 64}, (1, 5, 20), {}),
     "c3_torus_inner3": ("C3", {"n_chains": 32}, (1, 5), {"n_inner_step": 3}),
+    # GaussianEuclideanMetricSystem (exact h2 flow in the eigenbasis of the metric)
+    "n4_gaussian_split_dense_d32": ("G1", {"n_chains": 12}, (1, 5, 20), {}),
+    "n4_gaussian_split_diag_d40": ("G1", {"n_chains": 8, "dim": 40, "metric_kind": "diagonal"}, (1, 20), {}),
+    "n4_gaussian_split_identity_funnel_d9": ("G1", {"n_chains": 8, "dim": 9, "metric_kind": "identity", "target": "neal_funnel"}, (1, 20), {}),
+    "n4_gaussian_split_bcss3_dense_d70": ("G1", {"n_chains": 6, "dim": 70, "integrator": "bcss3"}, (1, 5), {}),
     "n4_bcss2_funnel_d24": ("C1", {"n_chains": 12, "dim": 24, "integrator": "bcss2"}, (1, 5, 20), {}),
     "n4_bcss3_funnel_d40_diag": ("C1", {"n_chains": 8, "dim": 40, "metric_kind": "diagonal", "integrator": "bcss3"}, (1, 20), {}),
     "n4_bcss4_funnel_d130": ("C1", {"n_chains": 6, "dim": 130, "integrator": "bcss4"}, (1, 5), {}),
@@ -121,6 +126,27 @@ HMC_CASES = {
     # name -> (config, kwargs, n_iter, n_step, seed)
     "hmc_c1_funnel_d16": ("C1", {"n_chains": 12, "dim": 16}, 6, 5, 11),
     "hmc_c0_std_gaussian": ("C0", {"n_chains": 6, "dim": 10}, 8, 7, 12),
+    # momentum refresh of the non-Euclidean systems (sqrt(M(q)) z; cotangent-space projection)
+    "hmc_c2_softabs_d8": ("C2", {"n_chains": 6, "dim": 8}, 4, 3, 13),
+    "hmc_c4_dense_d12": ("C4", {"n_chains": 6, "dim": 12}, 4, 3, 14),
+    "hmc_c3_torus": ("C3", {"n_chains": 10}, 6, 4, 15),
+    # per-chain random trajectory lengths (MetropolisRandomIntegrationTransition)
+    "hmc_c1_random_n_step": ("C1", {"n_chains": 10, "dim": 16}, 6, (2, 9), 17),
+    "hmc_g1_gaussian_split_d16": ("G1", {"n_chains": 8, "dim": 16}, 6, 4, 18),
+    "hmc_s1_sphere_d20_dense": ("S1", {"n_chains": 6, "dim": 20, "metric_kind": "dense"}, 5, 4, 16),
+}
+
+
+# step sizes chosen so that the fixtures contain rejections (and, for the implicit / constrained
+# integrators, a few failed trajectories)
+HMC_STEP_SIZES = {
+    "hmc_c1_funnel_d16": 0.35,
+    "hmc_c1_random_n_step": 0.35,
+    "hmc_g1_gaussian_split_d16": 0.5,
+    "hmc_c2_softabs_d8": 0.3,
+    "hmc_c4_dense_d12": 0.8,
+    "hmc_c3_torus": 0.25,
+    "hmc_s1_sphere_d20_dense": 0.2,
 }
 
 
@@ -128,8 +154,8 @@ def hmc_cases():
     """Static-HMC transitions (row N1) through the reference's own transition classes."""
     for name, (cfg, kwargs, n_iter, n_step, seed) in HMC_CASES.items():
         problem = pb.make_problem(cfg, **kwargs)
-        if cfg == "C1":
-            problem.step_size = 0.35
+        if name in HMC_STEP_SIZES:
+            problem.step_size = HMC_STEP_SIZES[name]
         r = dr.reference_hmc(problem, n_iter, n_step, seed)
         o = dr.oracle_hmc(problem, n_iter, n_step, seed)
         np.testing.assert_allclose(o["pos"], r["pos"], rtol=1e-12, atol=1e-14, err_msg=name)
@@ -142,9 +168,77 @@ def hmc_cases():
                  **{k: r[k] for k in ("pos", "dir", "n_step", "metrop_accept_prob", "accept_stat")})
 
 
+ADAPT_CASES = {
+    # name -> (config, kwargs, adapter specs, windowed-stager kwargs or None, n_warm_up, n_main,
+    #          n_step, seed): staged adaptive sampling (row N3) through the reference's own
+    # StaticMetropolisHMC.sample_chains with its adapters and stagers
+    "adapt_c1_dualavg_variance": (
+        "C1", {"n_chains": 6, "dim": 16}, [("dual_averaging", {}), ("online_variance", {})],
+        {"n_init_slow_window_iter": 5, "n_init_fast_stage_iter": 4, "n_final_fast_stage_iter": 3},
+        20, 5, 4, 21),
+    "adapt_c1_dualavg_covariance": (
+        "C1", {"n_chains": 5, "dim": 12},
+        [("dual_averaging", {"log_step_size_reducer": "geometric_mean_log_step_size_reducer"}),
+         ("online_covariance", {})],
+        {"n_init_slow_window_iter": 8, "n_init_fast_stage_iter": 5, "n_final_fast_stage_iter": 4},
+        40, 6, 5, 33),
+    "adapt_c0_dualavg_min": (
+        "C0", {"n_chains": 4, "dim": 10},
+        [("dual_averaging", {"adapt_stat_target": 0.65,
+                             "log_step_size_reducer": "min_log_step_size_reducer"})],
+        None, 15, 5, 6, 33),
+    "adapt_c0_variance_first": (
+        "C0", {"n_chains": 4, "dim": 10},
+        [("online_variance", {"reg_iter_offset": 3}), ("dual_averaging", {})], None, 30, 4, 3, 33),
+}
+STAGE_CODES = {None: 0, "fast": 1, "all": 2}
+
+
+def reference_stage_list(specs, stager_kwargs, n_warm_up_iter, n_main_iter):
+    """Stage list ``[(n_iter, None | "fast" | "all")]`` from the reference's own stagers
+    (default choice as in samplers.py:1075-1082)."""
+    mici = dr.import_reference()
+
+    class _Flag:
+        def __init__(self, fast):
+            self.is_fast = fast
+
+    flags = [_Flag(name == "dual_averaging") for name, _ in specs]
+    if stager_kwargs is not None:
+        stager = mici.stagers.WindowedWarmUpStager(**stager_kwargs)
+    elif all(f.is_fast for f in flags):
+        stager = mici.stagers.WarmUpStager()
+    else:
+        stager = mici.stagers.WindowedWarmUpStager()
+    stages = stager.stages(n_warm_up_iter, n_main_iter, {"k": flags}, None)
+    return [(v.n_iter, None if v.adapters is None else
+             ("all" if len(v.adapters["k"]) == len(flags) else "fast")) for v in stages.values()]
+
+
+def adapt_cases():
+    import warnings
+
+    for name, (cfg, kwargs, specs, sk, n_warm, n_main, n_step, seed) in ADAPT_CASES.items():
+        problem = pb.make_problem(cfg, **kwargs)
+        stages = reference_stage_list(specs, sk, n_warm, n_main)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")  # overflow in the coarse step-size search (eps = 1)
+            r = dr.reference_sample_chains(problem, n_warm, n_main, n_step, seed, specs, sk)
+            o = dr.oracle_sample_chains(problem, stages, n_step, seed, specs)
+        for k in r:
+            np.testing.assert_allclose(o[k], r[k], rtol=1e-12, atol=1e-14, err_msg=f"{name} {k}")
+        print(f"{name:32s} stages={stages} step_size={float(r['step_size']):.4f} "
+              f"accept={r['accept_stat'].mean():.2f}")
+        np.savez(os.path.join(GOLDEN_DIR, name + ".npz"), input_checksum=input_checksum(problem),
+                 stage_n_iter=np.array([s[0] for s in stages]),
+                 stage_which=np.array([STAGE_CODES[s[1]] for s in stages]),
+                 step_size_trace=o["step_size_trace"], **r)
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     hmc_cases()
+    adapt_cases()
     for name, (cfg, kwargs, steps, ov) in CASES.items():
         generate_case(name, cfg, kwargs, steps, ov)
     for name, (cfg, kwargs, eps, steps, ov) in FAILURE_CASES.items():

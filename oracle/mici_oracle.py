@@ -29,6 +29,8 @@ import this module.  Nothing under ``mici_b200/`` does.
 
 from __future__ import annotations
 
+import math
+
 import numpy as np
 import numpy.linalg as nla
 import scipy.linalg as sla
@@ -148,8 +150,8 @@ def coerce_metric(metric):
     """EuclideanMetricSystem.__init__ metric coercion (systems.py:332-346)."""
     if metric is None:
         return IdentityMetric()
-    if isinstance(metric, (IdentityMetric, DiagonalMetric, DenseMetric)):
-        return metric
+    if hasattr(metric, "inv_matvec") and hasattr(metric, "sqrt_matvec"):
+        return metric  # already a metric object ("else pass-through", systems.py:345-346)
     metric = np.asarray(metric)
     if metric.ndim == 1:
         return DiagonalMetric(metric)
@@ -166,6 +168,56 @@ def coerce_metric(metric):
 def euclidean_h(q, p, target, metric):
     """System.h = h1 + h2 (systems.py:187-196); h2 = 0.5 p . M^-1 p (:348-350)."""
     return target.neg_log_dens(q) + 0.5 * (p @ metric.inv_matvec(p))
+
+
+def metric_eig(metric):
+    """``(eigval, eigvec or None)`` as the reference's matrix classes expose them: ones / the
+    diagonal with identity eigenvectors (matrices.py:519-528, 743-749), ``numpy.linalg.eigh`` of
+    the array for a dense matrix (matrices.py:436-438)."""
+    if metric.kind == "identity":
+        return 1.0, None
+    if metric.kind == "diagonal":
+        return metric.diagonal, None
+    if not hasattr(metric, "_eig"):
+        metric._eig = nla.eigh(metric.array)
+    return metric._eig
+
+
+def gaussian_h2_flow(q, p, dt, metric):
+    """GaussianEuclideanMetricSystem.h2_flow (systems.py:464-474)."""
+    eigval, u = metric_eig(metric)
+    omega = 1.0 / eigval**0.5
+    sin_omega_dt, cos_omega_dt = np.sin(omega * dt), np.cos(omega * dt)
+    ut_q = q if u is None else u.T @ q
+    ut_p = p if u is None else u.T @ p
+    q_new = cos_omega_dt * ut_q + (sin_omega_dt * omega) * ut_p
+    p_new = cos_omega_dt * ut_p - (sin_omega_dt / omega) * ut_q
+    if u is not None:
+        q_new, p_new = u @ q_new, u @ p_new
+    return q_new, p_new
+
+
+def gaussian_euclidean_h(q, p, target, metric):
+    """h1 + h2 with h2 = q.q/2 + p.M^-1 p/2 (systems.py:450-453)."""
+    return target.neg_log_dens(q) + (0.5 * q @ q + 0.5 * p @ metric.inv_matvec(p))
+
+
+def gaussian_composition_steps(q, p, time_step, n_steps, target, metric, coefficients=(0.5, 1.0, 0.5),
+                               initial_h1_flow_step=True):
+    """Leapfrog (default coefficients; integrators.py:170-173) or a symmetric composition
+    (integrators.py:283-289) over the flows of a ``GaussianEuclideanMetricSystem``."""
+    q = np.array(q, dtype=np.float64)
+    p = np.array(p, dtype=np.float64)
+    metric = coerce_metric(metric)
+    grad = target.grad_neg_log_dens(q)
+    for _ in range(n_steps):
+        for i, c in enumerate(coefficients):
+            if ((i % 2) == 0) == bool(initial_h1_flow_step):
+                p -= (c * time_step) * grad
+            else:
+                q, p = gaussian_h2_flow(q, p, c * time_step, metric)
+                grad = target.grad_neg_log_dens(q)
+    return q, p
 
 
 def leapfrog_steps(q, p, time_step, n_steps, target, metric):
@@ -790,12 +842,32 @@ def run_batch(step_fn, q, p, dirs, n_steps):
 # --------------------------------------------------------------------------------------
 
 
-def static_hmc_transition(q, p, d, rng, step_fn, h_fn, sqrt_matvec, n_step):
+def euclidean_sample_momentum(metric):
+    """EuclideanMetricSystem.sample_momentum (systems.py:365-366)."""
+    return lambda q, rng: metric.sqrt_matvec(rng.standard_normal(q.shape))
+
+
+def constrained_sample_momentum(system):
+    """ConstrainedTractableFlowSystem.sample_momentum (systems.py:613-616)."""
+    return lambda q, rng: system.project_onto_cotangent_space(
+        system.metric.sqrt_matvec(rng.standard_normal(q.shape)), q)
+
+
+def riemannian_sample_momentum(system):
+    """RiemannianMetricSystem.sample_momentum (systems.py:1401-1402)."""
+    return lambda q, rng: system.metric(q).sqrt_matvec(rng.normal(size=q.shape))
+
+
+def static_hmc_transition(q, p, d, rng, step_fn, h_fn, sample_momentum, n_step):
     """IndependentMomentumTransition.sample (transitions.py:136-142) followed by
     MetropolisIntegrationTransition._sample_n_step (transitions.py:275-315) for one chain.
-    ``step_fn(q, p, dir) -> (q, p)`` raises OracleIntegratorError on failure.
+    ``step_fn(q, p, dir) -> (q, p)`` raises OracleIntegratorError on failure;
+    ``sample_momentum(q, rng)`` is one of the three constructors above.
     Returns ``(q, p, dir, stats)``."""
-    p = sqrt_matvec(rng.standard_normal(q.shape))  # systems.py:365-366
+    p = sample_momentum(q, rng)
+    if isinstance(n_step, tuple):
+        # MetropolisRandomIntegrationTransition.sample (transitions.py:396-402)
+        n_step = int(rng.integers(*n_step))
     h_init = h_fn(q, p)
     qp, pp, dp = q, p, d
     error = None
@@ -826,3 +898,168 @@ def static_hmc_transition(q, p, d, rng, step_fn, h_fn, sqrt_matvec, n_step):
     d = -d
     stats["accepted"] = bool(accepted)
     return q, p, d, stats
+
+
+# --------------------------------------------------------------------------------------
+# Adapters (row N3), one chain at a time, states as dicts -- adapters.py:126-648
+# --------------------------------------------------------------------------------------
+
+LOG_STEP_SIZE_REDUCERS = {
+    # adapters.py:126-159
+    "arithmetic_mean_log_step_size_reducer": lambda xs: sum(math.exp(x) for x in xs) / len(xs),
+    "geometric_mean_log_step_size_reducer": lambda xs: math.exp(sum(xs) / len(xs)),
+    "min_log_step_size_reducer": lambda xs: math.exp(min(xs)),
+}
+
+
+def find_init_step_size(q, p, d, step_eps_fn, h_fn, max_iters=100):
+    """DualAveragingStepSizeAdapter._find_and_set_init_step_size (adapters.py:285-352).
+    ``step_eps_fn(q, p, d, eps) -> (q, p)`` raises OracleIntegratorError on failure."""
+    h_init = h_fn(q, p)
+    if np.isnan(h_init):
+        raise RuntimeError("Hamiltonian evaluating to NaN at initial state.")
+    eps = 1
+    threshold = math.log(2)
+    too_big = False
+    for s in range(max_iters):
+        try:
+            qn, pn = step_eps_fn(q, p, d, eps)
+            delta_h = abs(h_init - h_fn(qn, pn))
+            if s == 0 or np.isnan(delta_h):
+                too_big = bool(np.isnan(delta_h) or delta_h > threshold)
+            if (too_big and delta_h <= threshold) or (not too_big and delta_h > threshold):
+                return eps
+            eps = eps / 2 if too_big else eps * 2
+        except OracleIntegratorError:
+            too_big = True
+            eps = eps / 2
+    raise RuntimeError("Could not find reasonable initial step size")
+
+
+class DualAveragingOracle:
+    """adapters.py:172-391."""
+
+    is_fast = True
+
+    def __init__(self, adapt_stat_target=0.8, log_step_size_reg_target=None,
+                 log_step_size_reg_coefficient=0.05, iter_decay_coeff=0.75, iter_offset=10,
+                 max_init_step_size_iters=100,
+                 log_step_size_reducer="arithmetic_mean_log_step_size_reducer"):
+        self.target = adapt_stat_target
+        self.reg_target = log_step_size_reg_target
+        self.reg_coefficient = log_step_size_reg_coefficient
+        self.decay = iter_decay_coeff
+        self.offset = iter_offset
+        self.max_init = max_init_step_size_iters
+        self.reducer = LOG_STEP_SIZE_REDUCERS[log_step_size_reducer]
+
+    def initialize(self, q, p, d, ctx):
+        eps = find_init_step_size(q, p, d, ctx.step_eps, ctx.h, self.max_init)
+        ctx.step_size = eps
+        reg = math.log(10 * eps) if self.reg_target is None else self.reg_target
+        return {"iter": 0, "smoothed_log_step_size": 0.0, "adapt_stat_error": 0.0,
+                "log_step_size_reg_target": reg}
+
+    def update(self, st, q, stats, ctx):  # adapters.py:354-373
+        st["iter"] += 1
+        w = 1 / (self.offset + st["iter"])
+        st["adapt_stat_error"] *= 1 - w
+        st["adapt_stat_error"] += w * (self.target - stats["accept_stat"])
+        sw = (1 / st["iter"]) ** self.decay
+        log_eps = st["log_step_size_reg_target"] - (
+            st["adapt_stat_error"] * st["iter"] ** 0.5 / self.reg_coefficient)
+        st["smoothed_log_step_size"] *= 1 - sw
+        st["smoothed_log_step_size"] += sw * log_eps
+        ctx.step_size = math.exp(log_eps)
+
+    def finalize(self, states, ctx):  # adapters.py:375-390
+        ctx.step_size = self.reducer([s["smoothed_log_step_size"] for s in states])
+        return False
+
+
+class OnlineVarianceOracle:
+    """adapters.py:394-518."""
+
+    is_fast = False
+
+    def __init__(self, reg_iter_offset=5, reg_scale=1e-3):
+        self.reg_iter_offset, self.reg_scale = reg_iter_offset, reg_scale
+
+    def initialize(self, q, p, d, ctx):
+        return {"iter": 0, "mean": np.zeros_like(q), "m2": np.zeros_like(q)}
+
+    def update(self, st, q, stats, ctx):  # Welford, adapters.py:446-458
+        st["iter"] += 1
+        diff = q - st["mean"]
+        st["mean"] += diff / st["iter"]
+        st["m2"] += diff * (q - st["mean"])
+
+    def _merge(self, states, outer):  # Chan et al. / Schubert-Gertz, adapters.py:487-505, 615-634
+        for i, st in enumerate(states):
+            if i == 0:
+                n_iter, mean_est, m2 = st["iter"], st["mean"].copy(), st["m2"].copy()
+            else:
+                n_prev = n_iter
+                n_iter += st["iter"]
+                mean_diff = mean_est - st["mean"]
+                mean_est *= n_prev
+                mean_est += st["iter"] * st["mean"]
+                mean_est /= n_iter
+                m2 += st["m2"]
+                m2 += (np.outer(mean_diff, mean_diff) if outer else mean_diff**2) * (
+                    st["iter"] * n_prev) / n_iter
+        return n_iter, m2
+
+    def finalize(self, states, ctx):  # adapters.py:471-516
+        n_iter, var_est = self._merge(states, outer=False)
+        if n_iter < 2:
+            raise RuntimeError("At least two chain samples required")
+        var_est /= n_iter - 1
+        if self.reg_iter_offset is not None and self.reg_iter_offset != 0:
+            var_est *= n_iter / (self.reg_iter_offset + n_iter)
+            var_est += self.reg_scale * (self.reg_iter_offset / (self.reg_iter_offset + n_iter))
+        ctx.metric = DiagonalMetric(1.0 / var_est)  # PositiveDiagonalMatrix(var_est).inv
+        return True  # momenta are resampled
+
+
+class OnlineCovarianceOracle(OnlineVarianceOracle):
+    """adapters.py:521-648."""
+
+    def initialize(self, q, p, d, ctx):
+        return {"iter": 0, "mean": np.zeros_like(q), "m2": np.zeros((q.shape[0],) * 2)}
+
+    def update(self, st, q, stats, ctx):  # adapters.py:576-590
+        st["iter"] += 1
+        diff = q - st["mean"]
+        st["mean"] += diff / st["iter"]
+        st["m2"] += diff[None, :] * (q - st["mean"])[:, None]
+
+    def finalize(self, states, ctx):  # adapters.py:603-648
+        n_iter, covar = self._merge(states, outer=True)
+        if n_iter < 2:
+            raise RuntimeError("At least two chain samples required")
+        covar /= n_iter - 1
+        covar *= n_iter / (self.reg_iter_offset + n_iter)
+        covar[np.diag_indices_from(covar)] += self.reg_scale * (
+            self.reg_iter_offset / (self.reg_iter_offset + n_iter))
+        ctx.metric = CovarianceFactoredMetric(covar)  # DensePositiveDefiniteMatrix(covar).inv
+        return True
+
+
+class CovarianceFactoredMetric:
+    """``DensePositiveDefiniteMatrix(covar).inv`` as a metric: array ``L^-T L^-1`` with factor
+    ``L^-T`` (matrices.py:1183-1188, 1209-1216); its own ``.inv`` multiplies by ``L L^T``
+    (matrices.py:1041-1046, 1060-1061) and ``sqrt @ z`` solves ``L^T x = z`` (:897-903)."""
+
+    kind = "dense"
+
+    def __init__(self, covar):
+        self.chol = dense_spd_factor(covar)
+        self.array = dense_spd_inverse(covar, self.chol)
+        self.inv_array = self.chol @ self.chol.T
+
+    def inv_matvec(self, v):
+        return self.inv_array @ v
+
+    def sqrt_matvec(self, v):
+        return sla.solve_triangular(self.chol.T, v, lower=False, check_finite=False)

@@ -69,3 +69,17 @@ def load_hmc_case(name):
     problem.step_size = float(g["step_size"])
     np.testing.assert_allclose(input_checksum(problem), g["input_checksum"], rtol=1e-13)
     return problem, n_iter, n_step, seed, g
+
+
+STAGE_NAMES = {0: None, 1: "fast", 2: "all"}
+
+
+def load_adapt_case(name):
+    from oracle.make_golden import ADAPT_CASES
+
+    cfg, kwargs, specs, stager_kwargs, n_warm, n_main, n_step, seed = ADAPT_CASES[name]
+    problem = pb.make_problem(cfg, **kwargs)
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    np.testing.assert_allclose(input_checksum(problem), g["input_checksum"], rtol=1e-13)
+    stages = [(int(n), STAGE_NAMES[int(w)]) for n, w in zip(g["stage_n_iter"], g["stage_which"])]
+    return problem, specs, stager_kwargs, n_warm, n_main, n_step, seed, stages, g

@@ -176,3 +176,82 @@ def test_compute_call_without_gpu_fails_loudly():
     state = engine.build_state(prob, "cpu")
     with pytest.raises(Exception):  # noqa: B017 - no CPU fallback exists
         integ.step(state)
+
+
+def test_stagers_match_reference_stage_lists():
+    """stagers.py:79-291: the stage schedule stored with the adaptation fixtures (generated by
+    the reference's stagers) and a sweep of closed-form properties."""
+    from golden_util import load_adapt_case
+    from mici_b200 import stagers
+    from oracle.make_golden import ADAPT_CASES
+
+    class Flag:
+        def __init__(self, fast):
+            self.is_fast = fast
+
+    for name in ADAPT_CASES:
+        _, specs, sk, n_warm, n_main, _, _, stages, _ = load_adapt_case(name)
+        flags = [Flag(n == "dual_averaging") for n, _ in specs]
+        if sk is not None:
+            stager = stagers.WindowedWarmUpStager(**sk)
+        elif all(f.is_fast for f in flags):
+            stager = stagers.WarmUpStager()
+        else:
+            stager = stagers.WindowedWarmUpStager()
+        mine = stager.stages(n_warm, n_main, flags)
+        got = [(st.n_iter, None if st.adapters is None else
+                ("all" if len(st.adapters) == len(flags) else "fast")) for st in mine.values()]
+        if all(f.is_fast for f in flags):  # a fast-only list is both "all" and "fast"
+            got = [(n, w if w is None else "all") for n, w in got]
+            stages = [(n, w if w is None else "all") for n, w in stages]
+        assert got == stages, name
+    for n_warm in (1, 9, 100, 150, 151, 1000, 2777):
+        n0, windows, n1 = stagers.WindowedWarmUpStager().slow_windows(n_warm)
+        assert n0 + sum(windows) + n1 == n_warm and all(w > 0 for w in windows)
+
+
+def test_adapter_reducers_and_moment_merge():
+    """adapters.py:126-159 reducers; the Chan / Schubert-Gertz merge against a direct estimate."""
+    import math
+
+    import torch
+
+    from mici_b200 import adapters
+
+    logs = [math.log(0.1), math.log(0.2), math.log(0.4)]
+    assert adapters.arithmetic_mean_log_step_size_reducer(logs) == pytest.approx(0.7 / 3, rel=1e-14)
+    assert adapters.geometric_mean_log_step_size_reducer(logs) == pytest.approx(0.2, rel=1e-14)
+    assert adapters.min_log_step_size_reducer(logs) == pytest.approx(0.1, rel=1e-14)
+    rng = np.random.default_rng(0)
+    x = torch.as_tensor(rng.standard_normal((3, 40, 5)))  # three "ranks" of 40 samples
+    parts = []
+    for r in range(3):
+        mean = x[r].mean(0)
+        parts.append((40, mean, (x[r] - mean).T @ (x[r] - mean)))
+    n, mean, m2 = adapters._merge_moments(parts, outer=True)
+    flat = x.reshape(-1, 5)
+    assert n == 120
+    np.testing.assert_allclose(mean.numpy(), flat.mean(0).numpy(), rtol=1e-13)
+    np.testing.assert_allclose((m2 / (n - 1)).numpy(), np.cov(flat.numpy().T), rtol=1e-12, atol=1e-14)
+    parts_v = [(c, m, torch.diagonal(s).clone()) for c, m, s in parts]
+    _, _, v2 = adapters._merge_moments(parts_v, outer=False)
+    np.testing.assert_allclose((v2 / (n - 1)).numpy(), flat.var(0, unbiased=True).numpy(), rtol=1e-12)
+
+
+def test_covariance_factored_metric_matches_reference_semantics():
+    """``DensePositiveDefiniteMatrix(covar).inv`` as assigned by the covariance adapter
+    (adapters.py:642): array = explicit inverse, inv = L L^T, sqrt = L^-T."""
+    import scipy.linalg as sla
+
+    from mici_b200.systems import _FixedMetric
+
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((7, 7))
+    covar = a @ a.T + 7 * np.eye(7)
+    m = _FixedMetric.from_covariance(covar)
+    chol = np.linalg.cholesky(covar)
+    np.testing.assert_allclose(m.inv, covar, rtol=1e-13)
+    np.testing.assert_allclose(m.array @ covar, np.eye(7), atol=1e-12)
+    z = rng.standard_normal(7)
+    np.testing.assert_allclose(m.sqrt @ z, sla.solve_triangular(chol.T, z, lower=False), rtol=1e-12)
+    np.testing.assert_allclose(m.sqrt @ m.sqrt.T, m.array, rtol=1e-11, atol=1e-14)

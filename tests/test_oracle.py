@@ -9,6 +9,10 @@ from oracle import mici_oracle as mo
 
 from golden_util import assert_matches_golden, case_names, load_case
 
+HMC_NAMES = ["hmc_c1_funnel_d16", "hmc_c0_std_gaussian", "hmc_c2_softabs_d8", "hmc_c4_dense_d12",
+             "hmc_c3_torus", "hmc_s1_sphere_d20_dense", "hmc_c1_random_n_step",
+             "hmc_g1_gaussian_split_d16"]
+
 
 @pytest.mark.parametrize("name", case_names() + case_names(failures=True))
 def test_oracle_matches_reference_fixture(name):
@@ -89,7 +93,7 @@ def test_oracle_matches_live_reference(name):
     np.testing.assert_allclose(o["mom"], r["mom"], rtol=1e-13, atol=1e-15)
 
 
-@pytest.mark.parametrize("name", ["hmc_c1_funnel_d16", "hmc_c0_std_gaussian"])
+@pytest.mark.parametrize("name", HMC_NAMES)
 def test_oracle_hmc_transition_matches_reference_fixture(name):
     """Row N1: momentum refresh + Metropolis transition (transitions.py:129-142, 256-352)."""
     from golden_util import load_hmc_case
@@ -101,3 +105,24 @@ def test_oracle_hmc_transition_matches_reference_fixture(name):
     np.testing.assert_array_equal(o["n_step"], g["n_step"])
     np.testing.assert_allclose(o["metrop_accept_prob"], g["metrop_accept_prob"], rtol=1e-11)
     assert 0.0 < o["accepted"].mean() <= 1.0
+
+
+ADAPT_NAMES = ["adapt_c1_dualavg_variance", "adapt_c1_dualavg_covariance", "adapt_c0_dualavg_min",
+               "adapt_c0_variance_first"]
+
+
+@pytest.mark.parametrize("name", ADAPT_NAMES)
+def test_oracle_adaptive_sampling_matches_reference_fixture(name):
+    """Row N3: dual averaging / online variance / online covariance adapters and the windowed
+    stager, against the reference's own ``sample_chains`` (adapters.py, stagers.py)."""
+    import warnings
+
+    from golden_util import load_adapt_case
+
+    problem, specs, _, _, _, n_step, seed, stages, g = load_adapt_case(name)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o = dr.oracle_sample_chains(problem, stages, n_step, seed, specs)
+    for k in ("pos", "accept_stat", "n_step", "final_pos", "final_mom", "step_size", "metric"):
+        np.testing.assert_allclose(o[k], g[k], rtol=1e-12, atol=1e-14, err_msg=k)
+    np.testing.assert_array_equal(o["final_dir"], g["final_dir"])

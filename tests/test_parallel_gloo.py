@@ -101,3 +101,93 @@ def test_trace_write_out_gloo_world2_reference_file_layout(tmp_path):
         for it in range(n_iter):
             np.testing.assert_allclose(pos[it], c * 100 + it + np.arange(3) / 10)
             np.testing.assert_allclose(acc[it], c + it / 100)
+
+
+class _FakeSystem:
+    """Stand-in for the device system: records the assigned metric (the kernels need a GPU)."""
+
+    metric = None
+
+    def sample_momentum(self, state, rngs):
+        return torch.zeros_like(state.pos)
+
+
+class _FakeTransition:
+    def __init__(self):
+        self.system = _FakeSystem()
+        self.integrator = type("I", (), {"step_size": None})()
+
+
+def _adapt_worker(rank, world, port, n_total, n_iter, out_path):
+    from mici_b200 import adapters
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = parallel.shard_bounds(n_total, rank, world)
+    draws = np.random.default_rng(5).standard_normal((n_iter, n_total, 6)) * np.arange(1, 7)
+    accept = np.random.default_rng(6).uniform(0.3, 1.0, (n_iter, n_total))
+    state = ChainState(pos=torch.as_tensor(draws[0, lo:hi]), mom=torch.zeros(hi - lo, 6), dir=1)
+    var_ad, cov_ad = adapters.OnlineVarianceMetricAdapter(), adapters.OnlineCovarianceMetricAdapter()
+    da = adapters.DualAveragingStepSizeAdapter(
+        log_step_size_reducer=adapters.geometric_mean_log_step_size_reducer)
+    tr_v, tr_c, tr_d = _FakeTransition(), _FakeTransition(), _FakeTransition()
+    st_v, st_c = var_ad.initialize(state, tr_v), cov_ad.initialize(state, tr_c)
+    st_d = {"iter": 0, "smoothed_log_step_size": torch.zeros(hi - lo, dtype=torch.float64),
+            "adapt_stat_error": torch.zeros(hi - lo, dtype=torch.float64),
+            "log_step_size_reg_target": torch.full((hi - lo,), np.log(10 * 0.25),
+                                                   dtype=torch.float64)}
+    for it in range(n_iter):
+        state.pos = torch.as_tensor(draws[it, lo:hi])
+        stats = {"accept_stat": torch.as_tensor(accept[it, lo:hi])}
+        var_ad.update(st_v, state, stats, tr_v)
+        cov_ad.update(st_c, state, stats, tr_c)
+        da.update(st_d, state, stats, tr_d)
+    var_ad.finalize(st_v, state, tr_v, None)
+    cov_ad.finalize(st_c, state, tr_c, None)
+    da.finalize(st_d, state, tr_d, None)
+    np.savez(out_path.format(rank=rank), diag=tr_v.system.metric, dense=tr_c.system.metric.array,
+             dense_inv=tr_c.system.metric.inv, step_size=tr_d.integrator.step_size)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_adapter_finalize_merges_all_ranks_gloo_world2(tmp_path):
+    """Row N3 across ranks: every rank adapts on its own chains; ``finalize`` merges the
+    per-rank moments / log step sizes with one all_gather and every rank ends with the same
+    parameters -- equal to the oracle's chain-by-chain merge (adapters.py:375-390, 471-516,
+    603-648) over ALL chains."""
+    from oracle import mici_oracle as mo
+
+    world, n_total, n_iter = 2, 9, 12
+    out = str(tmp_path / "adapt_{rank}.npz")
+    mp.spawn(_adapt_worker, args=(world, _free_port(), n_total, n_iter, out), nprocs=world,
+             join=True)
+    g0, g1 = np.load(out.format(rank=0)), np.load(out.format(rank=1))
+    for k in g0.files:
+        np.testing.assert_array_equal(g0[k], g1[k])
+    draws = np.random.default_rng(5).standard_normal((n_iter, n_total, 6)) * np.arange(1, 7)
+    accept = np.random.default_rng(6).uniform(0.3, 1.0, (n_iter, n_total))
+
+    class Ctx:
+        metric, step_size = None, None
+
+    ov, oc = mo.OnlineVarianceOracle(), mo.OnlineCovarianceOracle()
+    od = mo.DualAveragingOracle(log_step_size_reducer="geometric_mean_log_step_size_reducer")
+    sv, sc, sd = [], [], []
+    for c in range(n_total):
+        a, b = ov.initialize(draws[0, c], None, 1, None), oc.initialize(draws[0, c], None, 1, None)
+        d = {"iter": 0, "smoothed_log_step_size": 0.0, "adapt_stat_error": 0.0,
+             "log_step_size_reg_target": np.log(10 * 0.25)}
+        ctx = Ctx()
+        for it in range(n_iter):
+            ov.update(a, draws[it, c], None, None)
+            oc.update(b, draws[it, c], None, None)
+            od.update(d, draws[it, c], {"accept_stat": accept[it, c]}, ctx)
+        sv.append(a), sc.append(b), sd.append(d)
+    cv, cc, cd = Ctx(), Ctx(), Ctx()
+    ov.finalize(sv, cv), oc.finalize(sc, cc), od.finalize(sd, cd)
+    np.testing.assert_allclose(g0["diag"], cv.metric.diagonal, rtol=1e-12)
+    np.testing.assert_allclose(g0["dense"], cc.metric.array, rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(g0["dense_inv"], cc.metric.inv_array, rtol=1e-11, atol=1e-14)
+    assert float(g0["step_size"]) == pytest.approx(cd.step_size, rel=1e-13)

@@ -14,6 +14,10 @@ from golden_util import ATOL, RTOL, assert_matches_golden, case_names, load_case
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
+HMC_NAMES = ["hmc_c1_funnel_d16", "hmc_c0_std_gaussian", "hmc_c2_softabs_d8", "hmc_c4_dense_d12",
+             "hmc_c3_torus", "hmc_s1_sphere_d20_dense", "hmc_c1_random_n_step",
+             "hmc_g1_gaussian_split_d16"]
+
 
 def run_cuda(problem, n_steps, dirs=None, overrides=None, chains=None, return_h=True):
     integ = engine.build_integrator(problem, **(overrides or {}))
@@ -247,7 +251,7 @@ def test_host_buffer_path_equals_device_path():
     assert torch.equal(status, ref.status.cpu())
 
 
-@pytest.mark.parametrize("name", ["hmc_c1_funnel_d16", "hmc_c0_std_gaussian"])
+@pytest.mark.parametrize("name", HMC_NAMES)
 def test_batched_hmc_transition_matches_reference_fixture(name):
     """Row N1 on the device: whole static-HMC iterations (momentum refresh, fused trajectory,
     energy, Metropolis select, direction flips) against the reference's own transition classes,
@@ -259,8 +263,12 @@ def test_batched_hmc_transition_matches_reference_fixture(name):
     integ = engine.build_integrator(problem)
     state = engine.build_state(problem, DEV)
     rngs = [np.random.default_rng([seed, i]) for i in range(problem.n_chains)]
-    final, stats, trace = transitions.sample_hmc(integ.system, integ, state, rngs, n_iter, n_step,
-                                                 trace_pos=True)
+    if isinstance(n_step, tuple):
+        final, stats, trace = transitions.sample_chains(integ.system, integ, state, rngs, 0, n_iter,
+                                                        n_step_range=n_step)
+    else:
+        final, stats, trace = transitions.sample_hmc(integ.system, integ, state, rngs, n_iter,
+                                                     n_step, trace_pos=True)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(stats["accepted"].cpu().numpy(), g["accepted"].astype(bool))
     np.testing.assert_allclose(trace.cpu().numpy(), g["pos"], rtol=1e-9, atol=1e-11)
@@ -372,3 +380,200 @@ def test_jacobi_eigensolver_dense_matrices(dim, warm):
         u = vec[i]
         np.testing.assert_allclose(u.T @ u, np.identity(dim), atol=1e-13)
         np.testing.assert_allclose(u @ np.diag(val[i]) @ u.T, mats[i], atol=1e-13 * scale)
+
+
+@pytest.mark.parametrize("cfg,kwargs", [
+    ("C3", {"n_chains": 64}),
+    ("S1", {"n_chains": 48, "dim": 40, "metric_kind": "dense"}),
+    ("S1", {"n_chains": 48, "dim": 150, "metric_kind": "diagonal"}),
+])
+def test_project_onto_cotangent_space_matches_oracle(cfg, kwargs):
+    """systems.py:863-873 for all chains in one launch."""
+    from oracle import mici_oracle as mo
+
+    problem = problems.make_problem(cfg, **kwargs)
+    system = engine.build_system(problem)
+    rng = np.random.default_rng(3)
+    mom = rng.standard_normal(problem.pos.shape)
+    state = engine.build_state(problem, DEV)
+    got = system.project_onto_cotangent_space(torch.as_tensor(mom, device=DEV), state).cpu().numpy()
+    osys = mo.ConstrainedSystem(dr.build_target(problem), problem.metric)
+    want = np.stack([osys.project_onto_cotangent_space(mom[i], problem.pos[i])
+                     for i in range(problem.n_chains)])
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
+    # the projected momentum is in the cotangent space: J M^-1 p = 0
+    for i in range(0, problem.n_chains, 7):
+        jac = osys.jacob_constr(problem.pos[i])
+        resid = jac @ osys.inv_metric_mat(got[i][:, None])
+        assert np.abs(resid).max() < 1e-12 * max(1.0, np.abs(mom[i]).max() * np.abs(jac).max())
+
+
+@pytest.mark.parametrize("cfg,kwargs", [
+    ("C2", {"n_chains": 40, "dim": 16}),
+    ("C2", {"n_chains": 10, "dim": 64}),
+    ("C4", {"n_chains": 40, "dim": 24}),
+    ("C4", {"n_chains": 6, "dim": 128}),
+])
+def test_riemannian_sample_momentum_matches_oracle(cfg, kwargs):
+    """sqrt(M(q)) z (systems.py:1401-1402): U sqrt(softabs) U^T z for SoftAbs, L z for dense."""
+    problem = problems.make_problem(cfg, **kwargs)
+    system = engine.build_system(problem)
+    state = engine.build_state(problem, DEV)
+    _, _, osys = dr.oracle_step_fn(problem)
+    rngs = [np.random.default_rng([5, i]) for i in range(problem.n_chains)]
+    got = system.sample_momentum(state, rngs).cpu().numpy()
+    want = np.stack([osys.metric(problem.pos[i]).sqrt_matvec(
+        np.random.default_rng([5, i]).normal(size=problem.dim)) for i in range(problem.n_chains)])
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-11)
+
+
+def test_riemannian_sample_momentum_unavailable_in_low_rank_form():
+    problem = problems.make_problem("C4", n_chains=4, dim=512)
+    system = engine.build_system(problem)
+    state = engine.build_state(problem, DEV)
+    with pytest.raises(RuntimeError, match="does not fit"):
+        system.sample_momentum(state, np.random.default_rng(0))
+
+
+ADAPT_NAMES = ["adapt_c1_dualavg_variance", "adapt_c1_dualavg_covariance", "adapt_c0_dualavg_min",
+               "adapt_c0_variance_first"]
+
+
+def _build_adapters(specs):
+    from mici_b200 import adapters
+
+    cls = {"dual_averaging": adapters.DualAveragingStepSizeAdapter,
+           "online_variance": adapters.OnlineVarianceMetricAdapter,
+           "online_covariance": adapters.OnlineCovarianceMetricAdapter}
+    out = []
+    for name, kw in specs:
+        kw = dict(kw)
+        if "log_step_size_reducer" in kw:
+            kw["log_step_size_reducer"] = getattr(adapters, kw["log_step_size_reducer"])
+        out.append(cls[name](**kw))
+    return out
+
+
+@pytest.mark.parametrize("name", ADAPT_NAMES)
+def test_batched_adaptive_sampling_matches_reference_fixture(name):
+    """Row N3 on the device: staged warm-up (windowed stager, per-chain dual-averaging step sizes
+    through ``mb200_leapfrog_euclidean_per_chain``, online variance / covariance metric
+    adaptation, momentum resampling) + main stage, against the reference's own
+    ``StaticMetropolisHMC.sample_chains`` -- every chain consuming its own NumPy stream.
+    Chains run 25-46 transitions with adapted step sizes, so rounding differences of the
+    device arithmetic are amplified along the way: positions are compared at rtol 1e-7."""
+    from golden_util import load_adapt_case
+    from mici_b200 import stagers, transitions
+
+    problem, specs, sk, n_warm, n_main, n_step, seed, _, g = load_adapt_case(name)
+    integ = engine.build_integrator(problem)
+    state = engine.build_state(problem, DEV)
+    base = np.random.default_rng(seed)
+    rngs = [np.random.default_rng(base.bit_generator.jumped(i)) for i in range(problem.n_chains)]
+    stager = None if sk is None else stagers.WindowedWarmUpStager(**sk)
+    final, stats, trace = transitions.sample_chains(
+        integ.system, integ, state, rngs, n_warm, n_main, n_step=n_step,
+        adapters=_build_adapters(specs), stager=stager, trace_warm_up=True)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(stats["n_step"].cpu().numpy(), g["n_step"])
+    np.testing.assert_allclose(stats["step_size"].cpu().numpy(), g["step_size_trace"], rtol=1e-8)
+    np.testing.assert_allclose(stats["accept_stat"].cpu().numpy(), g["accept_stat"],
+                               rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(trace.cpu().numpy(), g["pos"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_array_equal(final.dir.cpu().numpy(), g["final_dir"])
+    np.testing.assert_allclose(final.mom.cpu().numpy(), g["final_mom"], rtol=1e-7, atol=1e-9)
+    assert isinstance(integ.step_size, float)
+    assert integ.step_size == pytest.approx(float(g["step_size"]), rel=1e-9)
+    m = integ.system.metric
+    if g["metric"].size:
+        np.testing.assert_allclose(m.array, g["metric"], rtol=1e-8, atol=1e-12)
+
+
+def test_per_chain_step_sizes_and_lengths_match_individual_launches():
+    """``mb200_leapfrog_euclidean_per_chain``: chain c with step size eps_c and n_c steps equals
+    chain c of a plain launch with the scalar (eps_c, n_c) -- bit for bit on the same kernel."""
+    problem = problems.make_problem("C1", n_chains=37, dim=48)
+    integ = engine.build_integrator(problem)
+    state = engine.build_state(problem, DEV)
+    rng = np.random.default_rng(9)
+    eps = rng.uniform(0.005, 0.05, problem.n_chains)
+    ns = rng.integers(0, 7, problem.n_chains).astype(np.int32)
+    dirs = torch.as_tensor(rng.choice([-1, 1], problem.n_chains).astype(np.int32), device=DEV)
+    state.dir = dirs
+    integ.step_size = torch.as_tensor(eps, device=DEV)
+    got = integ.step_n(state, torch.as_tensor(ns, device=DEV), return_h=True)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(got.n_done.cpu().numpy(), ns)
+    from oracle import mici_oracle as mo
+
+    target, metric = dr.build_target(problem), mo.coerce_metric(problem.metric)
+    for c in range(problem.n_chains):
+        q, p = mo.leapfrog_steps(problem.pos[c], problem.mom[c], float(dirs[c]) * eps[c],
+                                 int(ns[c]), target, metric)
+        np.testing.assert_allclose(got.pos[c].cpu().numpy(), q, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(got.mom[c].cpu().numpy(), p, rtol=RTOL, atol=ATOL)
+        assert float(got.h[c]) == pytest.approx(mo.euclidean_h(q, p, target, metric), rel=1e-10)
+    # composition integrators take the same per-chain arguments
+    problem2 = problems.make_problem("C1", n_chains=9, dim=20, integrator="bcss3")
+    integ2 = engine.build_integrator(problem2)
+    st2 = engine.build_state(problem2, DEV)
+    eps2 = np.linspace(0.01, 0.05, 9)
+    integ2.step_size = torch.as_tensor(eps2, device=DEV)
+    got2 = integ2.step_n(st2, 3)
+    for c in (0, 4, 8):
+        integ2.step_size = float(eps2[c])
+        ref = integ2.step_n(engine.build_state(problem2, DEV, chains=slice(c, c + 1)), 3)
+        assert torch.equal(got2.pos[c], ref.pos[0]) and torch.equal(got2.mom[c], ref.mom[0])
+
+
+def test_initial_step_size_search_matches_oracle():
+    """DualAveragingStepSizeAdapter._find_and_set_init_step_size (adapters.py:285-352), all
+    chains at once with per-chain halving / doubling."""
+    import warnings
+
+    from mici_b200 import adapters, transitions
+    from oracle import mici_oracle as mo
+
+    problem = problems.make_problem("C1", n_chains=64, dim=24)
+    integ = engine.build_integrator(problem)
+    state = engine.build_state(problem, DEV)
+    tr = transitions.MetropolisStaticIntegrationTransition(integ.system, integ, 1)
+    got = adapters.DualAveragingStepSizeAdapter()._find_and_set_init_step_size(
+        state, integ.system, integ).cpu().numpy()
+    target, metric = dr.build_target(problem), mo.coerce_metric(problem.metric)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = np.array([
+            mo.find_init_step_size(
+                problem.pos[c], problem.mom[c], 1,
+                lambda q, p, d, e: mo.leapfrog_steps(q, p, d * e, 1, target, metric),
+                lambda q, p: mo.euclidean_h(q, p, target, metric))
+            for c in range(problem.n_chains)])
+    np.testing.assert_array_equal(got, want)
+    assert tr.integrator.step_size is integ.step_size and len(set(got.tolist())) > 1
+
+
+@pytest.mark.parametrize("metric_kind,dim", [("identity", 9), ("diagonal", 40), ("dense", 33)])
+def test_gaussian_split_h2_flow_and_energy_match_oracle(metric_kind, dim):
+    """GaussianEuclideanMetricSystem.h2_flow / h2 / h (systems.py:450-474) on their own."""
+    from oracle import mici_oracle as mo
+
+    problem = problems.make_problem("G1", n_chains=24, dim=dim if dim % 2 == 0 else dim + 1,
+                                    metric_kind=metric_kind)
+    system = engine.build_system(problem)
+    metric = mo.coerce_metric(problem.metric)
+    target = dr.build_target(problem)
+    for dt in (0.3, -0.7):
+        state = engine.build_state(problem, DEV)
+        system.h2_flow(state, dt)
+        for c in range(0, problem.n_chains, 5):
+            q, p = mo.gaussian_h2_flow(problem.pos[c], problem.mom[c], dt, metric)
+            np.testing.assert_allclose(state.pos[c].cpu().numpy(), q, rtol=RTOL, atol=ATOL)
+            np.testing.assert_allclose(state.mom[c].cpu().numpy(), p, rtol=RTOL, atol=ATOL)
+    state = engine.build_state(problem, DEV)
+    h = system.h(state).cpu().numpy()
+    h2 = system.h2(state).cpu().numpy()
+    for c in range(0, problem.n_chains, 5):
+        want = mo.gaussian_euclidean_h(problem.pos[c], problem.mom[c], target, metric)
+        assert h[c] == pytest.approx(want, rel=1e-11)
+        assert h2[c] == pytest.approx(want - target.neg_log_dens(problem.pos[c]), rel=1e-10)
