@@ -306,6 +306,30 @@ int mb200_leapfrog_gaussian_euclidean(const double* pos_in, const double* mom_in
                                       const mb200_model* model, double* h_out, int32_t* status,
                                       int32_t* n_done, void* stream);
 
+/*
+ * Per-chain step sizes / trajectory lengths for the constrained and the implicit integrators
+ * (row N3: adapters drive one step size per chain during warm-up, adapters.py:262-283, 373; the
+ * coarse initial search relies on per-chain failures, adapters.py:338-340).  Arguments as the
+ * scalar entry points with `step_size` replaced by the device array `step_sizes[n_chains]` and
+ * `n_steps` by `max_n_steps` plus the optional device array `n_steps_per_chain[n_chains]`
+ * (NULL: every chain takes max_n_steps).  `midpoint` != 0 selects ImplicitMidpointIntegrator.
+ */
+int mb200_constrained_leapfrog_euclidean_per_chain(
+    const double* pos_in, const double* mom_in, double* pos_out, double* mom_out,
+    const int32_t* dir, int64_t n_chains, int32_t dim, const double* step_sizes,
+    const int32_t* n_steps_per_chain, int32_t max_n_steps, int32_t n_inner_step,
+    int32_t metric_kind, const double* metric_inv, const mb200_model* model,
+    int32_t projection_solver, double constraint_tol, double position_tol, double divergence_tol,
+    int32_t max_iters, int32_t max_line_search_iters, double reverse_check_tol, double* h_out,
+    int32_t* status, int32_t* n_done, int32_t* newton_iters, void* stream);
+int mb200_implicit_riemannian_per_chain(
+    const double* pos_in, const double* mom_in, double* pos_out, double* mom_out,
+    const int32_t* dir, int64_t n_chains, int32_t dim, const double* step_sizes,
+    const int32_t* n_steps_per_chain, int32_t max_n_steps, int32_t midpoint,
+    const mb200_model* model, int32_t fp_solver, double fp_convergence_tol,
+    double fp_divergence_tol, int32_t fp_max_iters, double reverse_check_tol, double* h_out,
+    int32_t* status, int32_t* n_done, int32_t* fp_iters, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

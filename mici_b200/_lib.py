@@ -93,6 +93,16 @@ SIGNATURES = {
         [_P, _P, _P, _P, _P, _I64, _I32, _F64, _P, _I32, _I32, _P, _I32, _I32, _P, _P, _MP, _P, _P,
          _P, _P],
     ),
+    "mb200_constrained_leapfrog_euclidean_per_chain": (
+        ctypes.c_int,
+        [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _I32, _I32, _I32, _P, _MP, _I32, _F64, _F64, _F64,
+         _I32, _I32, _F64, _P, _P, _P, _P, _P],
+    ),
+    "mb200_implicit_riemannian_per_chain": (
+        ctypes.c_int,
+        [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _I32, _I32, _MP, _I32, _F64, _F64, _I32, _F64, _P,
+         _P, _P, _P, _P],
+    ),
     "mb200_metropolis_select": (
         ctypes.c_int,
         [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P],

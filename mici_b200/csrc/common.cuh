@@ -41,6 +41,10 @@ struct ModelArgs {
   int rmetric_id;
   double mp[MB200_MAX_PARAMS];
   const double* maux;
+  // optional per-chain overrides of the scalar step_size / n_steps arguments of the implicit and
+  // constrained kernels (device arrays [n_chains] or NULL), set by the *_per_chain entry points
+  const double* step_sizes;
+  const int32_t* n_steps_pc;
 };
 
 // Splitting schedule of a symmetric composition integrator (integrators.py:176-378): flow i is

@@ -541,7 +541,9 @@ __global__ void __launch_bounds__(128)
   for (int64_t ch = (int64_t)blockIdx.x * wpb + warp; ch < n_chains;
        ch += (int64_t)gridDim.x * wpb) {
     double q[NV], p[NV], g[NV];
-    const double dt = (dir != nullptr) ? (double)dir[ch] * step_size : step_size;
+    const double eps = model.step_sizes != nullptr ? model.step_sizes[ch] : step_size;
+    const double dt = (dir != nullptr) ? (double)dir[ch] * eps : eps;
+    const int ns = model.n_steps_pc != nullptr ? min(model.n_steps_pc[ch], n_steps) : n_steps;
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
       const int i = 2 * lane + 64 * k;
@@ -562,7 +564,7 @@ __global__ void __launch_bounds__(128)
     target.grad(lane, dim, q, g);
     int st = MB200_STATUS_OK, done = 0, iters = 0;
     const double dt_inner = dt / n_inner;
-    for (int s = 0; s < n_steps && st == MB200_STATUS_OK; ++s) {
+    for (int s = 0; s < ns && st == MB200_STATUS_OK; ++s) {
       double qs[NV], ps[NV];
 #pragma unroll
       for (int e = 0; e < NV; ++e) qs[e] = q[e], ps[e] = p[e];

@@ -41,9 +41,20 @@ static int check_launch(const char* what) {
   return 0;
 }
 
+// Per-chain overrides travel from the *_per_chain entry points to the kernels through the calling
+// thread only (thread-local, scoped): the plain entry points stay re-entrant and unchanged.
+static thread_local const double* tl_step_sizes = nullptr;
+static thread_local const int32_t* tl_n_steps = nullptr;
+struct PerChainScope {
+  PerChainScope(const double* eps, const int32_t* ns) { tl_step_sizes = eps, tl_n_steps = ns; }
+  ~PerChainScope() { tl_step_sizes = nullptr, tl_n_steps = nullptr; }
+};
+
 static ModelArgs to_args(const mb200_model* m) {
   ModelArgs a;
   memset(&a, 0, sizeof(a));
+  a.step_sizes = tl_step_sizes;
+  a.n_steps_pc = tl_n_steps;
   a.target_id = m->target_id;
   for (int i = 0; i < MB200_MAX_PARAMS; ++i) a.tp[i] = m->target_params[i];
   a.taux = m->target_aux;
@@ -751,6 +762,44 @@ int mb200_leapfrog_gaussian_euclidean(const double* pos_in, const double* mom_in
   return leapfrog_euclidean_impl(pos_in, mom_in, pos_out, mom_out, dir, n_chains, dim, step_size,
                                  n_steps, metric_kind, metric_inv, model, h_out, status, n_done,
                                  (cudaStream_t)stream, false, &s);
+}
+
+int mb200_constrained_leapfrog_euclidean_per_chain(
+    const double* pos_in, const double* mom_in, double* pos_out, double* mom_out,
+    const int32_t* dir, int64_t n_chains, int32_t dim, const double* step_sizes,
+    const int32_t* n_steps_per_chain, int32_t max_n_steps, int32_t n_inner_step,
+    int32_t metric_kind, const double* metric_inv, const mb200_model* model,
+    int32_t projection_solver, double constraint_tol, double position_tol, double divergence_tol,
+    int32_t max_iters, int32_t max_line_search_iters, double reverse_check_tol, double* h_out,
+    int32_t* status, int32_t* n_done, int32_t* newton_iters, void* stream) {
+  if (n_chains > 0 && !step_sizes) return fail(MB200_ERR_INVALID_ARG, "step_sizes is NULL");
+  PerChainScope scope(step_sizes, n_steps_per_chain);
+  return mb200_constrained_leapfrog_euclidean(
+      pos_in, mom_in, pos_out, mom_out, dir, n_chains, dim, 0.0, max_n_steps, n_inner_step,
+      metric_kind, metric_inv, model, projection_solver, constraint_tol, position_tol,
+      divergence_tol, max_iters, max_line_search_iters, reverse_check_tol, h_out, status, n_done,
+      newton_iters, stream);
+}
+
+int mb200_implicit_riemannian_per_chain(
+    const double* pos_in, const double* mom_in, double* pos_out, double* mom_out,
+    const int32_t* dir, int64_t n_chains, int32_t dim, const double* step_sizes,
+    const int32_t* n_steps_per_chain, int32_t max_n_steps, int32_t midpoint,
+    const mb200_model* model, int32_t fp_solver, double fp_convergence_tol,
+    double fp_divergence_tol, int32_t fp_max_iters, double reverse_check_tol, double* h_out,
+    int32_t* status, int32_t* n_done, int32_t* fp_iters, void* stream) {
+  if (n_chains > 0 && !step_sizes) return fail(MB200_ERR_INVALID_ARG, "step_sizes is NULL");
+  PerChainScope scope(step_sizes, n_steps_per_chain);
+  if (midpoint)
+    return mb200_implicit_midpoint_riemannian(pos_in, mom_in, pos_out, mom_out, dir, n_chains, dim,
+                                              0.0, max_n_steps, model, fp_solver,
+                                              fp_convergence_tol, fp_divergence_tol, fp_max_iters,
+                                              reverse_check_tol, h_out, status, n_done, fp_iters,
+                                              stream);
+  return mb200_implicit_leapfrog_riemannian(pos_in, mom_in, pos_out, mom_out, dir, n_chains, dim,
+                                            0.0, max_n_steps, model, fp_solver, fp_convergence_tol,
+                                            fp_divergence_tol, fp_max_iters, reverse_check_tol,
+                                            h_out, status, n_done, fp_iters, nullptr, 0, stream);
 }
 
 }  // extern "C"

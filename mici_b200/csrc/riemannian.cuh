@@ -1199,10 +1199,12 @@ __global__ void __launch_bounds__(RM_THREADS)
       w.p[i] = p_in[(size_t)ch * dim + i];
     }
     __syncthreads();
-    const double dt = (dir != nullptr) ? (double)dir[ch] * step_size : step_size;
+    const double eps = model.step_sizes != nullptr ? model.step_sizes[ch] : step_size;
+    const double dt = (dir != nullptr) ? (double)dir[ch] * eps : eps;
+    const int ns = model.n_steps_pc != nullptr ? min(model.n_steps_pc[ch], n_steps) : n_steps;
     int st = MB200_STATUS_OK, done = 0;
     int it4[4] = {0, 0, 0, 0};
-    for (int s = 0; s < n_steps && st == MB200_STATUS_OK; ++s) {
+    for (int s = 0; s < ns && st == MB200_STATUS_OK; ++s) {
       for (int i = blk.tid; i < dim; i += blk.nthr) w.qs[i] = w.q[i], w.ps[i] = w.p[i];
       __syncthreads();
       int it_step[4] = {0, 0, 0, 0};

@@ -291,11 +291,37 @@ def _gaussian_flow(system, state, dt):
     state.mom = _like_input(state.mom, mom_out[0] if single else mom_out)
 
 
-def _reject_per_chain(integrator, n_steps):
-    if _is_per_chain(integrator.step_size, n_steps):
-        raise NotImplementedError(
-            f"{type(integrator).__name__}: per-chain step sizes / trajectory lengths are only "
-            "available for the explicit Euclidean integrators.")
+def _per_chain_args(step_size, n_steps, n, dev):
+    """``(step_sizes tensor, n_steps tensor or None, max_n_steps)`` for the *_per_chain entries."""
+    if isinstance(step_size, torch.Tensor) and step_size.ndim == 1:
+        if step_size.shape[0] != n:
+            raise ValueError(f"per-chain step_size has {step_size.shape[0]} entries for {n} chains")
+        eps = step_size.to(device=dev, dtype=torch.float64).contiguous()
+    else:
+        eps = torch.full((n,), float(step_size), dtype=torch.float64, device=dev)
+    if isinstance(n_steps, torch.Tensor):
+        if n_steps.shape != (n,):
+            raise ValueError("per-chain n_steps must have one entry per chain")
+        ns = n_steps.to(device=dev, dtype=torch.int32).contiguous()
+        return eps, ns, (int(ns.max().item()) if n > 0 else 0)
+    return eps, None, int(n_steps)
+
+
+def _launch_implicit_per_chain(integrator, midpoint, kw, model, pos, mom, pos_out, mom_out, dirs,
+                               n_steps, h, status, n_done, iters):
+    n, dim = pos.shape
+    dev = pos.device
+    eps, ns, max_n = _per_chain_args(integrator.step_size, n_steps, n, dev)
+    rc = _lib.load().mb200_implicit_riemannian_per_chain(
+        _lib.ptr(pos), _lib.ptr(mom), _lib.ptr(pos_out), _lib.ptr(mom_out), _lib.ptr(dirs), n, dim,
+        _lib.ptr(eps), _lib.ptr(ns), max_n, midpoint, ctypes.byref(model),
+        integrator.fixed_point_solver.kind, float(kw["convergence_tol"]),
+        float(kw["divergence_tol"]), int(kw["max_iters"]), float(integrator.reverse_check_tol),
+        _lib.ptr(h), _lib.ptr(status), _lib.ptr(n_done), _lib.ptr(iters),
+        _lib.current_stream_ptr(dev),
+    )
+    _lib.check(rc, "mb200_implicit_riemannian_per_chain")
+    return iters
 
 
 def _is_per_chain(step_size, n_steps):
@@ -430,11 +456,13 @@ class ImplicitLeapfrogIntegrator(Integrator):
         n, dim = pos.shape
         dev = pos.device
         sysm = self.system
-        _reject_per_chain(self, n_steps)
         kw = self.fixed_point_solver.resolve_kwargs(self.fixed_point_solver_kwargs)
         model = sysm._model(dev)
-        ws = sysm._workspace(n, dim, dev)
         iters = torch.zeros((n, 4), dtype=torch.int32, device=dev)
+        if _is_per_chain(self.step_size, n_steps):
+            return _launch_implicit_per_chain(self, 0, kw, model, pos, mom, pos_out, mom_out, dirs,
+                                              n_steps, h, status, n_done, iters)
+        ws = sysm._workspace(n, dim, dev)
         rc = _lib.load().mb200_implicit_leapfrog_riemannian(
             _lib.ptr(pos), _lib.ptr(mom), _lib.ptr(pos_out), _lib.ptr(mom_out), _lib.ptr(dirs),
             n, dim, float(self.step_size), n_steps, ctypes.byref(model),
@@ -470,13 +498,15 @@ class ImplicitMidpointIntegrator(Integrator):
         self.fixed_point_solver_kwargs = dict(fixed_point_solver_kwargs or {})
 
     def _launch(self, pos, mom, pos_out, mom_out, dirs, n_steps, h, status, n_done):
-        _reject_per_chain(self, n_steps)
         n, dim = pos.shape
         dev = pos.device
         sysm = self.system
         kw = self.fixed_point_solver.resolve_kwargs(self.fixed_point_solver_kwargs)
         model = sysm._model(dev)
         iters = torch.zeros((n, 4), dtype=torch.int32, device=dev)
+        if _is_per_chain(self.step_size, n_steps):
+            return _launch_implicit_per_chain(self, 1, kw, model, pos, mom, pos_out, mom_out, dirs,
+                                              n_steps, h, status, n_done, iters)
         rc = _lib.load().mb200_implicit_midpoint_riemannian(
             _lib.ptr(pos), _lib.ptr(mom), _lib.ptr(pos_out), _lib.ptr(mom_out), _lib.ptr(dirs),
             n, dim, float(self.step_size), n_steps, ctypes.byref(model),
@@ -512,13 +542,26 @@ class ConstrainedLeapfrogIntegrator(TractableFlowIntegrator):
         self.projection_solver_kwargs = dict(projection_solver_kwargs or {})
 
     def _launch(self, pos, mom, pos_out, mom_out, dirs, n_steps, h, status, n_done):
-        _reject_per_chain(self, n_steps)
         n, dim = pos.shape
         dev = pos.device
         sysm = self.system
         kw = self.projection_solver.resolve_kwargs(self.projection_solver_kwargs)
         model = sysm._model(dev)
         iters = torch.zeros(n, dtype=torch.int32, device=dev)
+        if _is_per_chain(self.step_size, n_steps):
+            eps, ns, max_n = _per_chain_args(self.step_size, n_steps, n, dev)
+            rc = _lib.load().mb200_constrained_leapfrog_euclidean_per_chain(
+                _lib.ptr(pos), _lib.ptr(mom), _lib.ptr(pos_out), _lib.ptr(mom_out),
+                _lib.ptr(dirs), n, dim, _lib.ptr(eps), _lib.ptr(ns), max_n,
+                int(self.n_inner_step), sysm.metric.kind, _lib.ptr(sysm.metric.inv_device(dev)),
+                ctypes.byref(model), self.projection_solver.kind, float(kw["constraint_tol"]),
+                float(kw["position_tol"]), float(kw["divergence_tol"]), int(kw["max_iters"]),
+                int(kw.get("max_line_search_iters", 10)), float(self.reverse_check_tol),
+                _lib.ptr(h), _lib.ptr(status), _lib.ptr(n_done), _lib.ptr(iters),
+                _lib.current_stream_ptr(dev),
+            )
+            _lib.check(rc, "mb200_constrained_leapfrog_euclidean_per_chain")
+            return iters
         rc = _lib.load().mb200_constrained_leapfrog_euclidean(
             _lib.ptr(pos), _lib.ptr(mom), _lib.ptr(pos_out), _lib.ptr(mom_out), _lib.ptr(dirs),
             n, dim, float(self.step_size), n_steps, int(self.n_inner_step), sysm.metric.kind,

@@ -315,7 +315,8 @@ class EuclideanMetricSystem(TractableFlowSystem):
             if key not in m._dev:
                 fac = m.sqrt if m.kind == METRIC_DIAGONAL else np.ascontiguousarray(m.sqrt.T)
                 m._dev[key] = torch.as_tensor(fac, device=z.device).contiguous()
-            model = self._model(z.device)
+            model = _lib.Model()  # the product L z does not involve the target
+            model.target_id = 0
             rc = _lib.load().mb200_euclidean_eval(
                 _lib.ptr(z), _lib.ptr(z), n, dim, m.kind, _lib.ptr(m._dev[key]),
                 ctypes.byref(model), None, None, _lib.ptr(out), None,
@@ -419,6 +420,25 @@ class ConstrainedEuclideanMetricSystem(ConstrainedTractableFlowSystem, Euclidean
         if not dens_wrt_hausdorff:
             raise NotImplementedError("Only `dens_wrt_hausdorff=True` is implemented.")
         self.dens_wrt_hausdorff = dens_wrt_hausdorff
+
+    def h(self, state):
+        """``l(q) + p.M^-1 p/2`` (``dens_wrt_hausdorff=True``: systems.py:842-851, 187-196),
+        evaluated by a zero-step launch of the constrained kernel."""
+        pos, mom, _, single = _batched(state)
+        n, dim = pos.shape
+        dev = pos.device
+        pos, mom = pos.contiguous(), mom.contiguous()
+        h = torch.empty(n, dtype=torch.float64, device=dev)
+        scratch_q, scratch_p = torch.empty_like(pos), torch.empty_like(mom)
+        m = self._metric
+        model = self._model(dev)
+        rc = _lib.load().mb200_constrained_leapfrog_euclidean(
+            _lib.ptr(pos), _lib.ptr(mom), _lib.ptr(scratch_q), _lib.ptr(scratch_p), None, n, dim,
+            0.0, 0, 1, m.kind, _lib.ptr(m.inv_device(dev)), ctypes.byref(model), 0, 1e-9, 1e-8,
+            1e10, 50, 10, 2e-8, _lib.ptr(h), None, None, None, _lib.current_stream_ptr(dev),
+        )
+        _lib.check(rc, "mb200_constrained_leapfrog_euclidean")
+        return _like_input(state.pos, h[0] if single else h)
 
     def project_onto_cotangent_space(self, mom, state):
         """``mom - J^T (J M^-1 J^T)^-1 J M^-1 mom`` at ``state.pos`` (systems.py:863-873) for all

@@ -357,8 +357,8 @@ def reference_sample_chains(problem, n_warm_up_iter, n_main_iter, n_step, seed, 
         n_warm_up_iter, n_main_iter, init_states, adapters=adapters, stager=stager,
         trace_warm_up=True, n_worker=1, display_progress=False,
     )
-    metric = system.metric
-    if isinstance(metric, mici.matrices.IdentityMatrix):
+    metric = getattr(system, "metric", None)
+    if problem.system != "euclidean" or isinstance(metric, mici.matrices.IdentityMatrix):
         metric_arr = np.zeros(0)
     elif isinstance(metric, mici.matrices.PositiveDiagonalMatrix):
         metric_arr = np.asarray(metric.diagonal)
@@ -377,14 +377,20 @@ def reference_sample_chains(problem, n_warm_up_iter, n_main_iter, n_step, seed, 
 
 
 class _AdaptiveContext:
-    """What the adapters mutate: the integrator step size and the system metric."""
+    """What the adapters mutate: the integrator step size and (Euclidean systems) the metric."""
 
     def __init__(self, problem):
-        self.target = build_target(problem)
-        self.metric = mo.coerce_metric(problem.metric)
+        import copy
+
+        self.problem = copy.copy(problem)
         self.step_size = problem.step_size
-        if problem.integrator != "leapfrog":
-            raise KeyError("adaptive oracle driver: leapfrog only")
+        self.euclidean = problem.system == "euclidean" and problem.integrator == "leapfrog"
+        if self.euclidean:
+            self.target = build_target(problem)
+            self.metric = mo.coerce_metric(problem.metric)
+        else:
+            _, self._h, self._system = oracle_step_fn(problem)
+            self.metric = None
 
     def copy(self):
         c = object.__new__(type(self))
@@ -392,13 +398,26 @@ class _AdaptiveContext:
         return c
 
     def step_eps(self, q, p, d, eps):
-        return mo.leapfrog_steps(q, p, d * eps, 1, self.target, self.metric)
+        if self.euclidean:
+            return mo.leapfrog_steps(q, p, d * eps, 1, self.target, self.metric)
+        import copy
+
+        prob = copy.copy(self.problem)
+        prob.step_size = eps
+        return oracle_step_fn(prob)[0](q, p, d)
 
     def step(self, q, p, d):
         return self.step_eps(q, p, d, self.step_size)
 
     def h(self, q, p):
-        return mo.euclidean_h(q, p, self.target, self.metric)
+        if self.euclidean:
+            return mo.euclidean_h(q, p, self.target, self.metric)
+        return self._h(q, p)
+
+    def sample_momentum(self):
+        if self.euclidean:
+            return mo.euclidean_sample_momentum(self.metric)
+        return _sample_momentum(self.problem, self._system)
 
 
 def _make_oracle_adapters(specs):
@@ -436,8 +455,7 @@ def oracle_sample_chains(problem, stages, n_step, seed, adapter_specs):
             for it in range(n_iter):
                 stage_eps[it, i] = c.step_size
                 q[i], p[i], d[i], st = mo.static_hmc_transition(
-                    q[i], p[i], d[i], rngs[i], c.step, c.h,
-                    mo.euclidean_sample_momentum(c.metric), n_step)
+                    q[i], p[i], d[i], rngs[i], c.step, c.h, c.sample_momentum(), n_step)
                 for a, a_st in zip(active, states):
                     a.update(a_st, q[i], st, c)
                 stage_pos[it, i] = q[i]
@@ -447,12 +465,12 @@ def oracle_sample_chains(problem, stages, n_step, seed, adapter_specs):
         for k, a in enumerate(active):
             if a.finalize([cs[k] for cs in chain_states], ctx):
                 for i in range(n):
-                    p[i] = mo.euclidean_sample_momentum(ctx.metric)(q[i], rngs[i])
+                    p[i] = ctx.sample_momentum()(q[i], rngs[i])
         pos.append(stage_pos), acc.append(stage_acc), nst.append(stage_nst)
         eps_trace.append(stage_eps)
     metric = ctx.metric
-    metric_arr = (metric.diagonal if metric.kind == "diagonal"
-                  else np.zeros(0) if metric.kind == "identity" else metric.array)
+    metric_arr = (np.zeros(0) if metric is None or metric.kind == "identity"
+                  else metric.diagonal if metric.kind == "diagonal" else metric.array)
     return {
         "pos": np.concatenate(pos), "accept_stat": np.concatenate(acc),
         "n_step": np.concatenate(nst), "step_size_trace": np.concatenate(eps_trace),

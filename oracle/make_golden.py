@@ -187,6 +187,12 @@ ADAPT_CASES = {
         [("dual_averaging", {"adapt_stat_target": 0.65,
                              "log_step_size_reducer": "min_log_step_size_reducer"})],
         None, 15, 5, 6, 33),
+    # step-size adaptation of the constrained and the implicit integrators (per-chain step sizes
+    # in the device kernels; failed steps drive the coarse initial search)
+    "adapt_c3_torus_dualavg": (
+        "C3", {"n_chains": 6}, [("dual_averaging", {})], None, 15, 5, 4, 41),
+    "adapt_c2_softabs_d6_dualavg": (
+        "C2", {"n_chains": 4, "dim": 6}, [("dual_averaging", {})], None, 10, 3, 3, 42),
     "adapt_c0_variance_first": (
         "C0", {"n_chains": 4, "dim": 10},
         [("online_variance", {"reg_iter_offset": 3}), ("dual_averaging", {})], None, 30, 4, 3, 33),

@@ -108,7 +108,7 @@ def test_oracle_hmc_transition_matches_reference_fixture(name):
 
 
 ADAPT_NAMES = ["adapt_c1_dualavg_variance", "adapt_c1_dualavg_covariance", "adapt_c0_dualavg_min",
-               "adapt_c0_variance_first"]
+               "adapt_c0_variance_first", "adapt_c3_torus_dualavg", "adapt_c2_softabs_d6_dualavg"]
 
 
 @pytest.mark.parametrize("name", ADAPT_NAMES)
