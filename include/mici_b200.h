@@ -330,6 +330,41 @@ int mb200_implicit_riemannian_per_chain(
     double fp_divergence_tol, int32_t fp_max_iters, double reverse_check_tol, double* h_out,
     int32_t* status, int32_t* n_done, int32_t* fp_iters, void* stream);
 
+/*
+ * "Next" row N4: dynamic-length HMC transitions (NUTS) on a Euclidean-metric system with the
+ * explicit leapfrog integrator, one whole transition per chain per call --
+ * DynamicIntegrationTransition.sample / _build_tree (transitions.py:610-770) with
+ * MultinomialDynamicIntegrationTransition (:773-809; slice_variant = 0) or
+ * SliceDynamicIntegrationTransition (:812-858; slice_variant = 1) weights and the
+ * riemannian_ (euclidean_criterion = 0, the reference's default) or euclidean_no_u_turn_criterion
+ * (:405-470).  Every chain builds its own tree (one warp per chain).
+ *   uniforms   [n_chains x n_uniforms] device array of U[0,1) variates; chain c consumes
+ *              uniforms[c][0 .. n_uniforms_used[c]) in the order the reference calls
+ *              rng.uniform().  2 max_tree_depth + 2^max_tree_depth variates always suffice;
+ *              a chain that runs out reports status 1.
+ *   workspace  >= mb200_nuts_workspace_bytes(n_chains, dim, max_tree_depth) bytes (device)
+ *   outputs    pos_out / mom_out the returned state; h_out its Hamiltonian; n_step,
+ *              av_metrop_accept_prob, reject_prob, tree_depth, diverging as the reference's
+ *              transition statistics (transitions.py:713-769); dir_out the `dir` attribute of
+ *              the returned state object (the direction its leaf was integrated in; for the
+ *              initial state the direction of the last doubling started from it,
+ *              transitions.py:731) -- the next stage's step-size search reads it
+ *              (adapters.py:321).  Any of these may be NULL.
+ * step_sizes: optional per-chain step sizes (device, [n_chains]) replacing step_size.
+ */
+int64_t mb200_nuts_workspace_bytes(int64_t n_chains, int32_t dim, int32_t max_tree_depth);
+int mb200_nuts_euclidean(const double* pos_in, const double* mom_in, double* pos_out,
+                         double* mom_out, int64_t n_chains, int32_t dim, double step_size,
+                         const double* step_sizes, int32_t metric_kind, const double* metric_inv,
+                         const mb200_model* model, int32_t slice_variant,
+                         int32_t euclidean_criterion, int32_t extra_subtree_checks,
+                         int32_t max_tree_depth, double max_delta_h, const double* uniforms,
+                         int32_t n_uniforms, void* workspace, int64_t workspace_bytes,
+                         double* h_out, int32_t* n_step, double* av_metrop_accept_prob,
+                         double* reject_prob, int32_t* tree_depth, int32_t* diverging,
+                         int32_t* n_uniforms_used, int32_t* dir_out, int32_t* status,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

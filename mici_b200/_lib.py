@@ -103,6 +103,12 @@ SIGNATURES = {
         [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _I32, _I32, _MP, _I32, _F64, _F64, _I32, _F64, _P,
          _P, _P, _P, _P],
     ),
+    "mb200_nuts_workspace_bytes": (ctypes.c_int64, [_I64, _I32, _I32]),
+    "mb200_nuts_euclidean": (
+        ctypes.c_int,
+        [_P, _P, _P, _P, _I64, _I32, _F64, _P, _I32, _P, _MP, _I32, _I32, _I32, _I32, _F64, _P,
+         _I32, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    ),
     "mb200_metropolis_select": (
         ctypes.c_int,
         [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P],

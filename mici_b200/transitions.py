@@ -164,6 +164,153 @@ class MetropolisRandomIntegrationTransition(MetropolisIntegrationTransition):
         return self._sample_n_step(state, n_step, rng)
 
 
+def euclidean_no_u_turn_criterion(system, state_1, state_2, _sum_mom):
+    """transitions.py:405-436: terminate when either terminal velocity points against
+    ``state_2.pos - state_1.pos``.  Passed to the dynamic transitions to select the fused test."""
+    diff = state_2.pos - state_1.pos
+    return ((system.dh_dmom(state_1) * diff).sum(-1) < 0) | (
+        (system.dh_dmom(state_2) * diff).sum(-1) < 0)
+
+
+def riemannian_no_u_turn_criterion(system, state_1, state_2, sum_mom):
+    """transitions.py:439-470: the same test against the sum of the trajectory's momenta."""
+    return ((system.dh_dmom(state_1) * sum_mom).sum(-1) < 0) | (
+        (system.dh_dmom(state_2) * sum_mom).sum(-1) < 0)
+
+
+class DynamicIntegrationTransition:
+    """Dynamic-length integration transition (NUTS) for all chains in ONE launch
+    (transitions.py:487-770): every chain builds its own binary trajectory tree inside
+    ``mb200_nuts_euclidean`` (one warp per chain).  Same constructor as the reference; use the
+    ``Multinomial...`` / ``Slice...`` subclasses.  Available for ``LeapfrogIntegrator`` on an
+    ``EuclideanMetricSystem`` (shared or per-chain step size).
+
+    Random numbers: the kernel consumes, per chain, exactly the uniform variates the reference
+    draws from that chain's generator, in the same order.  With a sequence of per-chain NumPy
+    generators each stream is left advanced by exactly the number its chain used."""
+
+    state_variables = frozenset({"pos", "mom", "dir"})
+    _slice = None
+
+    def __init__(self, system, integrator, *, max_tree_depth=10, max_delta_h=1000.0,
+                 termination_criterion=riemannian_no_u_turn_criterion,
+                 do_extra_subtree_checks=True):
+        from .integrators import LeapfrogIntegrator  # noqa: PLC0415
+        from .systems import (  # noqa: PLC0415
+            ConstrainedEuclideanMetricSystem,
+            EuclideanMetricSystem,
+            GaussianEuclideanMetricSystem,
+        )
+
+        if self._slice is None:
+            raise TypeError("Use MultinomialDynamicIntegrationTransition or "
+                            "SliceDynamicIntegrationTransition.")
+        if max_tree_depth <= 0:
+            raise ValueError("max_tree_depth must be non-negative.")
+        if termination_criterion not in (euclidean_no_u_turn_criterion,
+                                         riemannian_no_u_turn_criterion):
+            raise ValueError("Only the two no-U-turn criteria of this module are fused.")
+        if type(integrator) is not LeapfrogIntegrator or not isinstance(
+                system, EuclideanMetricSystem) or isinstance(
+                system, (ConstrainedEuclideanMetricSystem, GaussianEuclideanMetricSystem)):
+            raise NotImplementedError(
+                "Dynamic transitions are fused for LeapfrogIntegrator on EuclideanMetricSystem.")
+        self.system = system
+        self.integrator = integrator
+        self.max_tree_depth = int(max_tree_depth)
+        self.max_delta_h = float(max_delta_h)
+        self.termination_criterion = termination_criterion
+        self.do_extra_subtree_checks = bool(do_extra_subtree_checks)
+
+    @property
+    def n_uniforms(self):
+        """Upper bound on the ``rng.uniform()`` calls of one transition of one chain."""
+        return 2 * self.max_tree_depth + 2**self.max_tree_depth + (1 if self._slice else 0)
+
+    def sample(self, state, rng):
+        from .errors import AdaptationError  # noqa: PLC0415
+
+        if self.integrator.step_size is None:
+            raise AdaptationError("Integrator `step_size` is `None`.")
+        pos, mom = state.pos.contiguous(), state.mom.contiguous()
+        n, dim = pos.shape
+        dev = pos.device
+        n_uni = self.n_uniforms
+        saved = None
+        if isinstance(rng, torch.Generator):
+            uni = torch.rand((n, n_uni), dtype=torch.float64, device=dev, generator=rng)
+        elif isinstance(rng, Sequence):
+            saved = [g.bit_generator.state for g in rng]
+            uni = torch.as_tensor(np.stack([g.uniform(size=n_uni) for g in rng]), device=dev)
+        else:
+            uni = torch.as_tensor(rng.uniform(size=(n, n_uni)), device=dev)
+        lib = _lib.load()
+        nbytes = int(lib.mb200_nuts_workspace_bytes(n, dim, self.max_tree_depth))
+        if nbytes < 0:
+            raise ValueError("unsupported dim / max_tree_depth for the fused dynamic transition")
+        ws = self.system._dev.get(("nuts_ws", str(dev)))
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
+            self.system._dev[("nuts_ws", str(dev))] = ws
+        eps = self.integrator.step_size
+        per_chain = isinstance(eps, torch.Tensor) and eps.ndim == 1
+        eps_t = eps.to(device=dev, dtype=torch.float64).contiguous() if per_chain else None
+        pos_out, mom_out = torch.empty_like(pos), torch.empty_like(mom)
+        f64 = {"dtype": torch.float64, "device": dev}
+        i32 = {"dtype": torch.int32, "device": dev}
+        h, av, rej = torch.empty(n, **f64), torch.empty(n, **f64), torch.empty(n, **f64)
+        n_step, depth, div = torch.empty(n, **i32), torch.empty(n, **i32), torch.empty(n, **i32)
+        used, status, dir_out = torch.empty(n, **i32), torch.empty(n, **i32), torch.empty(n, **i32)
+        m = self.system.metric
+        model = self.system._model(dev)
+        rc = lib.mb200_nuts_euclidean(
+            _lib.ptr(pos), _lib.ptr(mom), _lib.ptr(pos_out), _lib.ptr(mom_out), n, dim,
+            0.0 if per_chain else float(eps), _lib.ptr(eps_t), m.kind,
+            _lib.ptr(m.inv_device(dev)), ctypes.byref(model), 1 if self._slice else 0,
+            1 if self.termination_criterion is euclidean_no_u_turn_criterion else 0,
+            1 if self.do_extra_subtree_checks else 0, self.max_tree_depth, self.max_delta_h,
+            _lib.ptr(uni), n_uni, _lib.ptr(ws), ws.numel(), _lib.ptr(h), _lib.ptr(n_step),
+            _lib.ptr(av), _lib.ptr(rej), _lib.ptr(depth), _lib.ptr(div), _lib.ptr(used),
+            _lib.ptr(dir_out), _lib.ptr(status), _lib.current_stream_ptr(dev),
+        )
+        _lib.check(rc, "mb200_nuts_euclidean")
+        if saved is not None:
+            # leave every chain's generator advanced by exactly what its chain consumed
+            for g, st, k in zip(rng, saved, used.cpu().tolist()):
+                g.bit_generator.state = st
+                if k:
+                    g.uniform(size=k)
+        if bool((status != 0).any()):
+            raise RuntimeError("dynamic transition ran out of uniform variates")
+        diverging = div.bool()
+        new = ChainState(pos=pos_out, mom=mom_out, dir=dir_out)
+        new.h = h
+        stats = {
+            "n_step": n_step.to(torch.int64),
+            "accept_stat": torch.where(diverging, torch.zeros_like(av), av),
+            "av_metrop_accept_prob": av,
+            "reject_prob": rej,
+            "tree_depth": depth.to(torch.int64),
+            "diverging": diverging,
+            "convergence_error": torch.zeros(n, dtype=torch.bool, device=dev),
+            "non_reversible_step": torch.zeros(n, dtype=torch.bool, device=dev),
+            "step_size": _step_size_stat(eps, n, dev),
+        }
+        return new, stats
+
+
+class MultinomialDynamicIntegrationTransition(DynamicIntegrationTransition):
+    """Progressive multinomial sampling of the next state (transitions.py:773-809)."""
+
+    _slice = False
+
+
+class SliceDynamicIntegrationTransition(DynamicIntegrationTransition):
+    """Progressive slice sampling, NUTS as in Hoffman & Gelman (transitions.py:812-858)."""
+
+    _slice = True
+
+
 def _run_stage(mom_tr, int_tr, state, rng, n_iter, adapters, record, all_stats, trace, group):
     """One sampling stage for every chain: the loop body of ``_sample_chain`` (samplers.py:459-513)
     then ``_finalize_adapters`` (samplers.py:1131-1138)."""
@@ -202,22 +349,25 @@ def sample_hmc(system, integrator, state, rng, n_iter, n_step, trace_pos=False, 
 
 
 def sample_chains(system, integrator, state, rng, n_warm_up_iter, n_main_iter, *, n_step=None,
-                  n_step_range=None, adapters=None, stager=None, trace_warm_up=False,
-                  trace_pos=True, group=None):
+                  n_step_range=None, integration_transition=None, adapters=None, stager=None,
+                  trace_warm_up=False, trace_pos=True, group=None):
     """Staged sampling of all chains: ``HamiltonianMonteCarlo.sample_chains``
     (samplers.py:875-1141) for the static (``n_step``) or random (``n_step_range``) Metropolis
-    HMC transitions, with the stage schedule of ``mici_b200.stagers`` (default: one warm-up stage
+    HMC transitions or a given ``integration_transition`` (e.g. a dynamic one), with the stage schedule of ``mici_b200.stagers`` (default: one warm-up stage
     if all adapters are fast, else windowed: samplers.py:1075-1082).  Adapter states are
     re-initialised at the start of every stage and finalised at its end (across all chains and,
     with a process group, across all ranks).  Returns ``(final_state, stats, traces)`` over the
     recorded stages (the main stage; also the warm-up if ``trace_warm_up``)."""
     from .stagers import WarmUpStager, WindowedWarmUpStager  # noqa: PLC0415
 
-    if (n_step is None) == (n_step_range is None):
-        raise ValueError("Give exactly one of `n_step` and `n_step_range`.")
+    if (n_step is not None) + (n_step_range is not None) + (integration_transition is not None) != 1:
+        raise ValueError(
+            "Give exactly one of `n_step`, `n_step_range` and `integration_transition`.")
     adapters = list(adapters or [])
     mom_tr = IndependentMomentumTransition(system)
-    if n_step is not None:
+    if integration_transition is not None:
+        int_tr = integration_transition
+    elif n_step is not None:
         int_tr = MetropolisStaticIntegrationTransition(system, integrator, n_step)
     else:
         int_tr = MetropolisRandomIntegrationTransition(system, integrator, n_step_range)

@@ -337,14 +337,26 @@ def _make_reference_adapters(mici, specs):
 
 
 def reference_sample_chains(problem, n_warm_up_iter, n_main_iter, n_step, seed, adapter_specs,
-                            stager_kwargs=None):
+                            stager_kwargs=None, dynamic=None):
     """The reference's own ``StaticMetropolisHMC.sample_chains`` (samplers.py:1271-1432) with
     adapters and stager, sequential chains, warm-up traced.  Per-chain generators are the
     reference's (``default_rng(base.bit_generator.jumped(i))``, samplers.py:559-560)."""
     mici = import_reference()
     system, integrator = build_reference(problem)
     rng = np.random.default_rng(seed)
-    sampler = mici.samplers.StaticMetropolisHMC(system, integrator, rng, n_step=n_step)
+    if dynamic is None:
+        sampler = mici.samplers.StaticMetropolisHMC(system, integrator, rng, n_step=n_step)
+    else:  # samplers.py:1588-1690; `dynamic`: keyword arguments of the dynamic transition
+        kw = dict(dynamic)
+        variant = kw.pop("variant", "multinomial")
+        # the sampler classes and the transition classes have different defaults
+        # (samplers.py:1606-1609, 1714-1717 vs transitions.py:494-497): always pass both
+        kw["termination_criterion"] = getattr(
+            mici.transitions, kw.pop("criterion", "riemannian") + "_no_u_turn_criterion")
+        kw["do_extra_subtree_checks"] = kw.pop("extra_checks", True)
+        cls = (mici.samplers.DynamicMultinomialHMC if variant == "multinomial"
+               else mici.samplers.DynamicSliceHMC)
+        sampler = cls(system, integrator, rng, **kw)
     adapters = _make_reference_adapters(mici, adapter_specs)
     stager = None
     if stager_kwargs is not None:
@@ -368,6 +380,8 @@ def reference_sample_chains(problem, n_warm_up_iter, n_main_iter, n_step, seed, 
         "pos": np.stack(traces["pos"], axis=1),  # [n_iter, n_chains, dim]
         "accept_stat": np.stack(stats["accept_stat"], axis=1),
         "n_step": np.stack(stats["n_step"], axis=1),
+        **({} if dynamic is None else {"tree_depth": np.stack(stats["tree_depth"], axis=1),
+                                      "diverging": np.stack(stats["diverging"], axis=1)}),
         "final_pos": np.stack([s.pos for s in final_states]),
         "final_mom": np.stack([s.mom for s in final_states]),
         "final_dir": np.array([s.dir for s in final_states], dtype=np.int32),
@@ -414,6 +428,11 @@ class _AdaptiveContext:
             return mo.euclidean_h(q, p, self.target, self.metric)
         return self._h(q, p)
 
+    def velocity(self, q, p):
+        if self.euclidean:
+            return self.metric.inv_matvec(p)
+        return _velocity_fn(self.problem, self._system)(q, p)
+
     def sample_momentum(self):
         if self.euclidean:
             return mo.euclidean_sample_momentum(self.metric)
@@ -426,7 +445,7 @@ def _make_oracle_adapters(specs):
     return [cls[name](**kw) for name, kw in specs]
 
 
-def oracle_sample_chains(problem, stages, n_step, seed, adapter_specs):
+def oracle_sample_chains(problem, stages, n_step, seed, adapter_specs, dynamic=None):
     """Staged adaptive static HMC through the oracle.  ``stages``: list of ``(n_iter, which)``
     with ``which`` one of ``"all"``, ``"fast"``, ``None`` (samplers.py:1075-1141 with the stage
     list of stagers.py).  Chains run one after the other inside every stage, each from a copy of
@@ -441,21 +460,30 @@ def oracle_sample_chains(problem, stages, n_step, seed, adapter_specs):
     q = [problem.pos[i].copy() for i in range(n)]
     p = [problem.mom[i].copy() for i in range(n)]
     d = [1] * n
-    pos, acc, nst, eps_trace = [], [], [], []
+    pos, acc, nst, eps_trace, depths, divs = [], [], [], [], [], []
     for n_iter, which in stages:
         active = [] if which is None else [a for a in adapters if which == "all" or a.is_fast]
         stage_pos = np.empty((n_iter, n, problem.dim))
         stage_acc = np.empty((n_iter, n))
         stage_nst = np.empty((n_iter, n))
         stage_eps = np.empty((n_iter, n))
+        stage_depth = np.empty((n_iter, n))
+        stage_div = np.empty((n_iter, n))
         chain_states = []
         for i in range(n):
             c = ctx.copy()
             states = [a.initialize(q[i], p[i], d[i], c) for a in active]
             for it in range(n_iter):
                 stage_eps[it, i] = c.step_size
-                q[i], p[i], d[i], st = mo.static_hmc_transition(
-                    q[i], p[i], d[i], rngs[i], c.step, c.h, c.sample_momentum(), n_step)
+                if dynamic is None:
+                    q[i], p[i], d[i], st = mo.static_hmc_transition(
+                        q[i], p[i], d[i], rngs[i], c.step, c.h, c.sample_momentum(), n_step)
+                else:
+                    p[i] = c.sample_momentum()(q[i], rngs[i])
+                    q[i], p[i], st = mo.nuts_transition(
+                        q[i], p[i], rngs[i].uniform, c.step, c.h, c.velocity, **dynamic)
+                    d[i] = st["dir"]
+                    stage_depth[it, i], stage_div[it, i] = st["tree_depth"], st["diverging"]
                 for a, a_st in zip(active, states):
                     a.update(a_st, q[i], st, c)
                 stage_pos[it, i] = q[i]
@@ -467,14 +495,93 @@ def oracle_sample_chains(problem, stages, n_step, seed, adapter_specs):
                 for i in range(n):
                     p[i] = ctx.sample_momentum()(q[i], rngs[i])
         pos.append(stage_pos), acc.append(stage_acc), nst.append(stage_nst)
-        eps_trace.append(stage_eps)
+        eps_trace.append(stage_eps), depths.append(stage_depth), divs.append(stage_div)
     metric = ctx.metric
     metric_arr = (np.zeros(0) if metric is None or metric.kind == "identity"
                   else metric.diagonal if metric.kind == "diagonal" else metric.array)
     return {
         "pos": np.concatenate(pos), "accept_stat": np.concatenate(acc),
         "n_step": np.concatenate(nst), "step_size_trace": np.concatenate(eps_trace),
+        **({} if dynamic is None else {"tree_depth": np.concatenate(depths),
+                                      "diverging": np.concatenate(divs)}),
         "final_pos": np.stack(q), "final_mom": np.stack(p),
         "final_dir": np.array(d, dtype=np.int32), "step_size": np.array(float(ctx.step_size)),
         "metric": metric_arr,
     }
+
+
+# ------------------------------------------------------------- dynamic HMC / NUTS (row N4)
+
+
+def _velocity_fn(problem, system):
+    """``system.dh_dmom`` for the oracle systems."""
+    if problem.system in ("euclidean", "gaussian_euclidean"):
+        metric = mo.coerce_metric(problem.metric)
+        return lambda q, p: metric.inv_matvec(p)
+    if problem.system == "constrained_euclidean":
+        return lambda q, p: system.inv_metric_mat(p)
+    return lambda q, p: system.dh2_dmom(q, p)
+
+
+NUTS_STATS = ("n_step", "av_metrop_accept_prob", "accept_stat", "reject_prob", "tree_depth",
+              "diverging")
+
+
+def oracle_nuts(problem, n_iter, seed, variant="multinomial", criterion="riemannian",
+                max_tree_depth=10, max_delta_h=1000.0, extra_checks=True, chains=None):
+    """``n_iter`` iterations of momentum refresh + dynamic integration transition per chain
+    through the oracle (``mo.nuts_transition``); generators ``default_rng([seed, chain])``."""
+    step, h_fn, system = oracle_step_fn(problem)
+    vel = _velocity_fn(problem, system)
+    sample_mom = _sample_momentum(problem, system)
+    sl = slice(None) if chains is None else chains
+    q0 = problem.pos[sl]
+    n = q0.shape[0]
+    pos = np.empty((n_iter, n, q0.shape[1]))
+    dirs = np.empty((n_iter, n))
+    stats = {k: np.empty((n_iter, n)) for k in NUTS_STATS}
+    for i in range(n):
+        rng = np.random.default_rng([seed, i])
+        q = q0[i].copy()
+        for it in range(n_iter):
+            p = sample_mom(q, rng)
+            q, p, st = mo.nuts_transition(
+                q, p, rng.uniform, step, h_fn, vel, max_tree_depth=max_tree_depth,
+                max_delta_h=max_delta_h, criterion=criterion, extra_checks=extra_checks,
+                variant=variant)
+            pos[it, i] = q
+            dirs[it, i] = st["dir"]
+            for k in NUTS_STATS:
+                stats[k][it, i] = st[k]
+    return {"pos": pos, "dir": dirs, **stats}
+
+
+def reference_nuts(problem, n_iter, seed, variant="multinomial", criterion="riemannian",
+                   max_tree_depth=10, max_delta_h=1000.0, extra_checks=True, chains=None):
+    """The same through the reference's own transition classes (transitions.py:487-858)."""
+    mici = import_reference()
+    system, integrator = build_reference(problem)
+    cls = (mici.transitions.MultinomialDynamicIntegrationTransition if variant == "multinomial"
+           else mici.transitions.SliceDynamicIntegrationTransition)
+    crit = (mici.transitions.riemannian_no_u_turn_criterion if criterion == "riemannian"
+            else mici.transitions.euclidean_no_u_turn_criterion)
+    int_tr = cls(system, integrator, max_tree_depth=max_tree_depth, max_delta_h=max_delta_h,
+                 termination_criterion=crit, do_extra_subtree_checks=extra_checks)
+    mom_tr = mici.transitions.IndependentMomentumTransition(system)
+    sl = slice(None) if chains is None else chains
+    q0, p0 = problem.pos[sl], problem.mom[sl]
+    n = q0.shape[0]
+    pos = np.empty((n_iter, n, q0.shape[1]))
+    dirs = np.empty((n_iter, n))
+    stats = {k: np.empty((n_iter, n)) for k in NUTS_STATS}
+    for i in range(n):
+        rng = np.random.default_rng([seed, i])
+        state = mici.states.ChainState(pos=q0[i].copy(), mom=p0[i].copy(), dir=1)
+        for it in range(n_iter):
+            state, _ = mom_tr.sample(state, rng)
+            state, st = int_tr.sample(state, rng)
+            pos[it, i] = state.pos
+            dirs[it, i] = state.dir
+            for k in NUTS_STATS:
+                stats[k][it, i] = st[k]
+    return {"pos": pos, "dir": dirs, **stats}

@@ -168,6 +168,39 @@ def hmc_cases():
                  **{k: r[k] for k in ("pos", "dir", "n_step", "metrop_accept_prob", "accept_stat")})
 
 
+NUTS_CASES = {
+    # name -> (config, kwargs, step_size, n_iter, seed, options): dynamic integration transitions
+    # (row N4) through the reference's own transition classes (transitions.py:487-858)
+    "nuts_c1_multinomial_d10": ("C1", {"n_chains": 8, "dim": 10}, 0.2, 6, 77, {}),
+    "nuts_c1_slice_euclidean_d16": ("C1", {"n_chains": 8, "dim": 16}, 0.15, 5, 78,
+                                    {"variant": "slice", "criterion": "euclidean"}),
+    "nuts_c0_depth4_no_extra_checks": ("C0", {"n_chains": 6, "dim": 10}, 0.3, 6, 79,
+                                       {"max_tree_depth": 4, "extra_checks": False}),
+    "nuts_c1_diag_divergent": ("C1", {"n_chains": 8, "dim": 8, "metric_kind": "diagonal"}, 0.9, 6,
+                               80, {"max_delta_h": 5.0}),
+    "nuts_c1_identity_d70": ("C1", {"n_chains": 4, "dim": 70, "metric_kind": "identity"}, 0.05, 3,
+                             81, {"max_tree_depth": 6}),
+}
+
+
+def nuts_cases():
+    import warnings
+
+    for name, (cfg, kwargs, eps, n_iter, seed, opts) in NUTS_CASES.items():
+        problem = pb.make_problem(cfg, **kwargs)
+        problem.step_size = eps
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            r = dr.reference_nuts(problem, n_iter, seed, **opts)
+            o = dr.oracle_nuts(problem, n_iter, seed, **opts)
+        for k in r:
+            np.testing.assert_allclose(o[k], r[k], rtol=1e-12, atol=1e-14, err_msg=f"{name} {k}")
+        print(f"{name:34s} mean n_step={r['n_step'].mean():5.1f} depths={np.unique(r['tree_depth'])}"
+              f" diverging={int(r['diverging'].sum())}")
+        np.savez(os.path.join(GOLDEN_DIR, name + ".npz"), input_checksum=input_checksum(problem),
+                 step_size=np.array(eps), **r)
+
+
 ADAPT_CASES = {
     # name -> (config, kwargs, adapter specs, windowed-stager kwargs or None, n_warm_up, n_main,
     #          n_step, seed): staged adaptive sampling (row N3) through the reference's own
@@ -196,6 +229,16 @@ ADAPT_CASES = {
     "adapt_c0_variance_first": (
         "C0", {"n_chains": 4, "dim": 10},
         [("online_variance", {"reg_iter_offset": 3}), ("dual_averaging", {})], None, 30, 4, 3, 33),
+    # the reference's default sampler: DynamicMultinomialHMC with dual averaging (n_step = the
+    # keyword arguments of the dynamic transition)
+    "adapt_nuts_c0_dualavg": (
+        "C0", {"n_chains": 4, "dim": 10}, [("dual_averaging", {})], None, 12, 4,
+        {"max_tree_depth": 5}, 51),
+    "adapt_nuts_c1_dualavg_variance": (
+        "C1", {"n_chains": 4, "dim": 8, "metric_kind": "diagonal"},
+        [("dual_averaging", {}), ("online_variance", {})],
+        {"n_init_slow_window_iter": 6, "n_init_fast_stage_iter": 4, "n_final_fast_stage_iter": 3},
+        16, 3, {"max_tree_depth": 6, "variant": "slice", "criterion": "euclidean"}, 52),
 }
 STAGE_CODES = {None: 0, "fast": 1, "all": 2}
 
@@ -229,8 +272,10 @@ def adapt_cases():
         stages = reference_stage_list(specs, sk, n_warm, n_main)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")  # overflow in the coarse step-size search (eps = 1)
-            r = dr.reference_sample_chains(problem, n_warm, n_main, n_step, seed, specs, sk)
-            o = dr.oracle_sample_chains(problem, stages, n_step, seed, specs)
+            dyn = n_step if isinstance(n_step, dict) else None
+            r = dr.reference_sample_chains(problem, n_warm, n_main, n_step, seed, specs, sk,
+                                           dynamic=dyn)
+            o = dr.oracle_sample_chains(problem, stages, n_step, seed, specs, dynamic=dyn)
         for k in r:
             np.testing.assert_allclose(o[k], r[k], rtol=1e-12, atol=1e-14, err_msg=f"{name} {k}")
         print(f"{name:32s} stages={stages} step_size={float(r['step_size']):.4f} "
@@ -244,6 +289,7 @@ def adapt_cases():
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     hmc_cases()
+    nuts_cases()
     adapt_cases()
     for name, (cfg, kwargs, steps, ov) in CASES.items():
         generate_case(name, cfg, kwargs, steps, ov)

@@ -1063,3 +1063,147 @@ class CovarianceFactoredMetric:
 
     def sqrt_matvec(self, v):
         return sla.solve_triangular(self.chol.T, v, lower=False, check_finite=False)
+
+
+# --------------------------------------------------------------------------------------
+# Dynamic (NUTS) integration transitions -- transitions.py:415-860, restated ITERATIVELY
+# (the recursion of `_build_tree` unrolled into a binary-counter stack: after leaf number k of a
+# doubling, one merge per trailing zero bit of k) so that the device kernel can follow it line by
+# line.  Random numbers are consumed in the reference's order: [slice: one at the start,]
+# per doubling one for the direction, one per completed internal node in post-order, one for
+# the progressive acceptance.
+# --------------------------------------------------------------------------------------
+
+
+def _log1p_exp(val):  # utils.py:50-54
+    return val + math.log1p(math.exp(-val)) if val > 0.0 else math.log1p(math.exp(val))
+
+
+def _log_sum_exp(a, b):  # utils.py:65-71
+    if a == -math.inf and b == -math.inf:
+        return -math.inf
+    return a + _log1p_exp(b - a) if a > b else b + _log1p_exp(a - b)
+
+
+def _exp(x):  # LogRepFloat.val (utils.py:110-115)
+    try:
+        return math.exp(x)
+    except OverflowError:
+        return math.inf
+
+
+def _no_u_turn(kind, vel_fn, q1, p1, q2, p2, sum_mom):
+    """euclidean_no_u_turn_criterion / riemannian_no_u_turn_criterion (transitions.py:405-470)."""
+    w = (q2 - q1) if kind == "euclidean" else sum_mom
+    return bool(np.sum(vel_fn(q1, p1) * w) < 0 or np.sum(vel_fn(q2, p2) * w) < 0)
+
+
+def nuts_transition(q, p, uniform, step_fn, h_fn, vel_fn, max_tree_depth=10, max_delta_h=1000.0,
+                    criterion="riemannian", extra_checks=True, variant="multinomial"):
+    """DynamicIntegrationTransition.sample (transitions.py:712-770) with
+    MultinomialDynamicIntegrationTransition (:773-809) or SliceDynamicIntegrationTransition
+    (:812-858) weights.  ``uniform()`` returns the chain's next ``rng.uniform()``;
+    ``step_fn(q, p, dir)`` raises OracleIntegratorError; ``vel_fn(q, p)`` is ``system.dh_dmom``.
+    Returns ``(q, p, stats)``."""
+    multinomial = variant == "multinomial"
+    h_init = h_fn(q, p)
+    log_u = None if multinomial else math.log(uniform()) - h_init  # :832-839
+
+    def leaf_weight(h):  # _weight_function
+        return -h if multinomial else int(log_u <= -h)
+
+    def add_w(a, b):
+        return _log_sum_exp(a, b) if multinomial else a + b
+
+    def ratio(num, den):  # _weight_ratio, as the probability the comparison `u < .` sees
+        if multinomial:
+            return min(_exp(num - den), 1)  # NaN (both -inf) compares False, like LogRepFloat
+        return min(num / den, 1) if den > 0 else min(num, 1)
+
+    def turn(t, neg_sub, pos_sub):  # _termination_criterion (:528-556)
+        if _no_u_turn(criterion, vel_fn, t["nq"], t["np"], t["pq"], t["pp"], t["sum"]):
+            return True
+        if t["depth"] > 1 and extra_checks:
+            return _no_u_turn(criterion, vel_fn, neg_sub["nq"], neg_sub["np"], pos_sub["nq"],
+                              pos_sub["np"], neg_sub["sum"] + pos_sub["np"]) or _no_u_turn(
+                criterion, vel_fn, neg_sub["pq"], neg_sub["pp"], pos_sub["pq"], pos_sub["pp"],
+                pos_sub["sum"] + neg_sub["pp"])
+        return False
+
+    def merge(neg_sub, pos_sub):  # _merge_subtrees (:571-581)
+        return {"nq": neg_sub["nq"], "np": neg_sub["np"], "pq": pos_sub["pq"], "pp": pos_sub["pp"],
+                "sum": neg_sub["sum"] + pos_sub["sum"], "w": add_w(neg_sub["w"], pos_sub["w"]),
+                "depth": neg_sub["depth"] + 1}
+
+    stats = {"n_step": 0, "reject_prob": 1.0, "diverging": False, "convergence_error": False,
+             "non_reversible_step": False}
+    sum_accept = 0.0
+    tree = {"nq": q, "np": p, "pq": q, "pp": p, "sum": np.asarray(p), "w": leaf_weight(h_init),
+            "depth": 0}
+    next_q, next_p = q, p
+    # `dir` of the returned state object.  Leaf states carry the direction they were integrated
+    # in; the INITIAL state object is both edges of the tree at first and has its `dir` overwritten
+    # (`state.dir = direction`, :731) by every doubling that starts from it.  The value is read
+    # again by the step-size initialisation of the next adaptive stage (adapters.py:321).
+    next_is_init, init_dir, next_dir = True, None, None
+    edge_is_init = {1: True, -1: True}
+    depth = 0
+    for depth in range(max_tree_depth):
+        direction = 2 * (uniform() < 0.5) - 1  # :729
+        if edge_is_init[direction]:
+            init_dir = direction
+        cq, cp = (tree["pq"], tree["pp"]) if direction == 1 else (tree["nq"], tree["np"])
+        # ---- _build_tree(depth, ...) unrolled (:610-710)
+        stack, terminate, cur = {}, False, None
+        for k in range(1, 2**depth + 1):
+            try:
+                cq, cp = step_fn(cq, cp, direction)
+                h = h_fn(cq, cp)
+                h = math.inf if np.isnan(h) else h
+                cur = {"nq": cq, "np": cp, "pq": cq, "pp": cp, "sum": np.asarray(cp),
+                       "w": leaf_weight(h), "depth": 0, "prop": (cq, cp)}
+                h_diff = h_init - h
+                sum_accept += 0.0 if np.isnan(h_diff) else math.exp(min(0, h_diff))
+                stats["n_step"] += 1
+                if (h - h_init if multinomial else h + log_u) > max_delta_h:  # _check_divergence
+                    stats["diverging"] = True
+                    terminate = True
+            except OracleIntegratorError as e:
+                stats["convergence_error"] |= e.status == STATUS_CONVERGENCE
+                stats["non_reversible_step"] |= e.status == STATUS_NON_REVERSIBLE
+                terminate = True
+            if terminate:
+                break
+            level, kk = 0, k
+            while kk % 2 == 0:  # one merge per trailing zero bit of the leaf count
+                inner, outer = stack.pop(level), cur
+                neg_sub, pos_sub = (inner, outer) if direction == 1 else (outer, inner)
+                cur = merge(neg_sub, pos_sub)
+                accept_outer = ratio(outer["w"], cur["w"])
+                cur["prop"] = outer["prop"] if uniform() < accept_outer else inner["prop"]
+                if turn(cur, neg_sub, pos_sub):
+                    terminate = True
+                    break
+                level, kk = level + 1, kk // 2
+            if terminate:
+                break
+            stack[level] = cur
+        if terminate:
+            break
+        new = cur
+        accept_prob = ratio(new["w"], tree["w"])  # :742
+        if uniform() < accept_prob:
+            next_q, next_p = new["prop"]
+            next_is_init, next_dir = False, direction
+        stats["reject_prob"] *= 1.0 - accept_prob
+        edge_is_init[direction] = False
+        neg_sub, pos_sub = (tree, new) if direction == 1 else (new, tree)
+        tree = merge(neg_sub, pos_sub)
+        if turn(tree, neg_sub, pos_sub):
+            break
+    stats["av_metrop_accept_prob"] = sum_accept / stats["n_step"] if stats["n_step"] > 0 else 0.0
+    failed = stats["diverging"] or stats["convergence_error"] or stats["non_reversible_step"]
+    stats["accept_stat"] = 0.0 if failed else stats["av_metrop_accept_prob"]
+    stats["tree_depth"] = depth
+    stats["dir"] = init_dir if next_is_init else next_dir
+    return next_q, next_p, stats

@@ -83,3 +83,14 @@ def load_adapt_case(name):
     np.testing.assert_allclose(input_checksum(problem), g["input_checksum"], rtol=1e-13)
     stages = [(int(n), STAGE_NAMES[int(w)]) for n, w in zip(g["stage_n_iter"], g["stage_which"])]
     return problem, specs, stager_kwargs, n_warm, n_main, n_step, seed, stages, g
+
+
+def load_nuts_case(name):
+    from oracle.make_golden import NUTS_CASES
+
+    cfg, kwargs, eps, n_iter, seed, opts = NUTS_CASES[name]
+    problem = pb.make_problem(cfg, **kwargs)
+    problem.step_size = eps
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    np.testing.assert_allclose(input_checksum(problem), g["input_checksum"], rtol=1e-13)
+    return problem, n_iter, seed, opts, g

@@ -108,7 +108,10 @@ def test_oracle_hmc_transition_matches_reference_fixture(name):
 
 
 ADAPT_NAMES = ["adapt_c1_dualavg_variance", "adapt_c1_dualavg_covariance", "adapt_c0_dualavg_min",
-               "adapt_c0_variance_first", "adapt_c3_torus_dualavg", "adapt_c2_softabs_d6_dualavg"]
+               "adapt_c0_variance_first", "adapt_c3_torus_dualavg", "adapt_c2_softabs_d6_dualavg",
+               "adapt_nuts_c0_dualavg", "adapt_nuts_c1_dualavg_variance"]
+NUTS_NAMES = ["nuts_c1_multinomial_d10", "nuts_c1_slice_euclidean_d16",
+              "nuts_c0_depth4_no_extra_checks", "nuts_c1_diag_divergent", "nuts_c1_identity_d70"]
 
 
 @pytest.mark.parametrize("name", ADAPT_NAMES)
@@ -122,7 +125,28 @@ def test_oracle_adaptive_sampling_matches_reference_fixture(name):
     problem, specs, _, _, _, n_step, seed, stages, g = load_adapt_case(name)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        o = dr.oracle_sample_chains(problem, stages, n_step, seed, specs)
+        o = dr.oracle_sample_chains(problem, stages, n_step, seed, specs,
+                                    dynamic=n_step if isinstance(n_step, dict) else None)
     for k in ("pos", "accept_stat", "n_step", "final_pos", "final_mom", "step_size", "metric"):
         np.testing.assert_allclose(o[k], g[k], rtol=1e-12, atol=1e-14, err_msg=k)
     np.testing.assert_array_equal(o["final_dir"], g["final_dir"])
+
+
+@pytest.mark.parametrize("name", NUTS_NAMES)
+def test_oracle_dynamic_transition_matches_reference_fixture(name):
+    """Row N4: the iterative restatement of ``DynamicIntegrationTransition`` (multinomial and
+    slice variants, both no-U-turn criteria, divergences) against the reference's recursion
+    (transitions.py:487-858) -- positions, statistics and the returned ``dir``."""
+    import warnings
+
+    from golden_util import load_nuts_case
+
+    problem, n_iter, seed, opts, g = load_nuts_case(name)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o = dr.oracle_nuts(problem, n_iter, seed, **opts)
+    np.testing.assert_allclose(o["pos"], g["pos"], rtol=1e-12, atol=1e-14)
+    for k in ("n_step", "tree_depth", "diverging", "dir"):
+        np.testing.assert_array_equal(o[k], g[k], err_msg=k)
+    for k in ("av_metrop_accept_prob", "accept_stat", "reject_prob"):
+        np.testing.assert_allclose(o[k], g[k], rtol=1e-12, atol=1e-15, err_msg=k)
