@@ -365,6 +365,26 @@ int mb200_nuts_euclidean(const double* pos_in, const double* mom_in, double* pos
                          int32_t* n_uniforms_used, int32_t* dir_out, int32_t* status,
                          void* stream);
 
+/*
+ * Host-buffer form of mb200_leapfrog_euclidean -- the call a NumPy-state caller makes
+ * (the reference's ChainState arrays live in host memory: states.py:160-305).  pos / mom / dir /
+ * status are HOST pointers (page-locked memory makes the copies asynchronous); metric_inv stays a
+ * device pointer.  The batch is cut into n_chunks row blocks aligned to the CTA granularity of
+ * the kernel; block k is copied in, stepped and copied out on streams[k % n_streams], so that the
+ * host->device copy of later blocks and the device->host copy of earlier blocks overlap the
+ * kernels (chains are independent: chunking changes no result).  `scratch` is a device buffer of
+ * at least mb200_host_scratch_bytes(n_chains, dim) bytes owned by the caller and must not be
+ * shared by concurrent calls.  synchronize != 0: wait for all streams before returning.
+ */
+int64_t mb200_host_scratch_bytes(int64_t n_chains, int32_t dim);
+int mb200_leapfrog_euclidean_host(const double* pos_in, const double* mom_in, double* pos_out,
+                                  double* mom_out, const int32_t* dir, int64_t n_chains,
+                                  int32_t dim, double step_size, int32_t n_steps,
+                                  int32_t metric_kind, const double* metric_inv,
+                                  const mb200_model* model, int32_t* status, int32_t n_chunks,
+                                  void* const* streams, int32_t n_streams, void* scratch,
+                                  int64_t scratch_bytes, int32_t synchronize);
+
 #ifdef __cplusplus
 }
 #endif

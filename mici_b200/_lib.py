@@ -109,6 +109,12 @@ SIGNATURES = {
         [_P, _P, _P, _P, _I64, _I32, _F64, _P, _I32, _P, _MP, _I32, _I32, _I32, _I32, _F64, _P,
          _I32, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     ),
+    "mb200_host_scratch_bytes": (ctypes.c_int64, [_I64, _I32]),
+    "mb200_leapfrog_euclidean_host": (
+        ctypes.c_int,
+        [_P, _P, _P, _P, _P, _I64, _I32, _F64, _I32, _I32, _P, _MP, _P, _I32, _P, _I32, _P, _I64,
+         _I32],
+    ),
     "mb200_metropolis_select": (
         ctypes.c_int,
         [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P],

@@ -359,13 +359,28 @@ static int launch_nuts(const double* q_in, const double* p_in, double* q_out, do
                        int32_t* n_step, double* av_accept, double* reject_prob, int32_t* depth,
                        int32_t* diverging, int32_t* n_used, int32_t* dir_out, int32_t* status,
                        cudaStream_t st) {
-  constexpr int WARPS = 4;
-  const size_t smem = (size_t)WARPS * 64 * KP * sizeof(double);
-  int64_t blocks = (n + WARPS - 1) / WARPS;
-  const int64_t cap = (int64_t)num_sms() * 16;
+  auto kern = nuts_euclidean_kernel<Target, KP>;
+  NutsArgs args = a;
+  // dense metric that fits in shared memory next to the staging rows: the warps of a CTA share it
+  // (12 warps when the register file allows: KP <= 2 uses < 150 registers per thread)
+  const size_t metric_bytes = (size_t)dim * dim * sizeof(double);
+  const int staged_warps = KP <= 2 ? 12 : 8;
+  args.stage_metric = metric_kind == MB200_METRIC_DENSE &&
+                      metric_bytes + staged_warps * 64 * KP * sizeof(double) <= 200 * 1024;
+  const int warps = args.stage_metric ? staged_warps : 4;
+  const size_t smem = (size_t)warps * 64 * KP * sizeof(double) + (args.stage_metric ? metric_bytes : 0);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(MB200_ERR_CUDA, "smem attr: %s", cudaGetErrorString(e));
+  }
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t blocks = (n + warps - 1) / warps;
+  const int64_t cap = (int64_t)num_sms() * per_sm;
   if (blocks > cap) blocks = cap;
-  nuts_euclidean_kernel<Target, KP><<<(unsigned)blocks, WARPS * 32, smem, st>>>(
-      q_in, p_in, q_out, p_out, n, dim, eps, metric_kind, minv, m, a, ws, h_out, n_step,
+  kern<<<(unsigned)blocks, warps * 32, smem, st>>>(
+      q_in, p_in, q_out, p_out, n, dim, eps, metric_kind, minv, m, args, ws, h_out, n_step,
       av_accept, reject_prob, depth, diverging, n_used, dir_out, status);
   return check_launch("nuts_euclidean_kernel");
 }
@@ -886,6 +901,7 @@ int mb200_nuts_euclidean(const double* pos_in, const double* mom_in, double* pos
   a.uniforms = uniforms;
   a.n_uniforms = n_uniforms;
   a.step_sizes = step_sizes;
+  a.stage_metric = 0;
   cudaStream_t st = (cudaStream_t)stream;
 #define MB200_ARGS                                                                             \
   pos_in, mom_in, pos_out, mom_out, n_chains, dim, step_size, metric_kind, metric_inv, m, a,   \
@@ -900,6 +916,68 @@ int mb200_nuts_euclidean(const double* pos_in, const double* mom_in, double* pos
                   m.target_id);
   }
 #undef MB200_ARGS
+}
+
+int64_t mb200_host_scratch_bytes(int64_t n_chains, int32_t dim) {
+  if (n_chains < 0 || dim < 1) return -1;
+  return n_chains * ((int64_t)4 * dim * (int64_t)sizeof(double) + 2 * (int64_t)sizeof(int32_t));
+}
+
+int mb200_leapfrog_euclidean_host(const double* pos_in, const double* mom_in, double* pos_out,
+                                  double* mom_out, const int32_t* dir, int64_t n_chains,
+                                  int32_t dim, double step_size, int32_t n_steps,
+                                  int32_t metric_kind, const double* metric_inv,
+                                  const mb200_model* model, int32_t* status, int32_t n_chunks,
+                                  void* const* streams, int32_t n_streams, void* scratch,
+                                  int64_t scratch_bytes, int32_t synchronize) {
+  if (n_chains == 0 && dim >= 1) return 0;
+  if (!pos_in || !mom_in || !pos_out || !mom_out || !model || !streams || !scratch)
+    return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
+  if (n_chains < 0 || dim < 1 || n_steps < 0 || n_chunks < 1 || n_streams < 1)
+    return fail(MB200_ERR_INVALID_ARG, "bad sizes");
+  if (scratch_bytes < mb200_host_scratch_bytes(n_chains, dim))
+    return fail(MB200_ERR_INVALID_ARG, "scratch too small");
+  const size_t nd = (size_t)n_chains * dim;
+  double* d_qi = (double*)scratch;
+  double* d_pi = d_qi + nd;
+  double* d_qo = d_pi + nd;
+  double* d_po = d_qo + nd;
+  int32_t* d_status = (int32_t*)(d_po + nd);
+  int32_t* d_dir = d_status + n_chains;
+  // chunk boundaries on the granularity of a CTA of the kernel that will run (56 chains for the
+  // tensor-core kernel, 16 for the general one), so that the chunks together launch no more CTAs
+  // than one launch over all chains would
+  const int64_t align = (metric_kind == MB200_METRIC_DENSE && dim <= 128) ? 56 : 16;
+  int64_t per = (n_chains + n_chunks - 1) / n_chunks;
+  per = (per + align - 1) / align * align;
+  int c = 0;
+  for (int64_t lo = 0; lo < n_chains; lo += per, ++c) {
+    const int64_t len = (lo + per <= n_chains) ? per : n_chains - lo;
+    cudaStream_t st = (cudaStream_t)streams[c % n_streams];
+    const size_t off = (size_t)lo * dim, bytes = (size_t)len * dim * sizeof(double);
+    cudaMemcpyAsync(d_qi + off, pos_in + off, bytes, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_pi + off, mom_in + off, bytes, cudaMemcpyHostToDevice, st);
+    if (dir) cudaMemcpyAsync(d_dir + lo, dir + lo, len * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+    const int rc = mb200_leapfrog_euclidean(d_qi + off, d_pi + off, d_qo + off, d_po + off,
+                                            dir ? d_dir + lo : nullptr, len, dim, step_size,
+                                            n_steps, metric_kind, metric_inv, model, nullptr,
+                                            d_status + lo, nullptr, st);
+    if (rc != 0) return rc;
+    cudaMemcpyAsync(pos_out + off, d_qo + off, bytes, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(mom_out + off, d_po + off, bytes, cudaMemcpyDeviceToHost, st);
+    if (status)
+      cudaMemcpyAsync(status + lo, d_status + lo, len * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MB200_ERR_CUDA, "host path: %s", cudaGetErrorString(e));
+  if (synchronize) {
+    const int used = c < n_streams ? c : n_streams;
+    for (int i = 0; i < used; ++i) {
+      e = cudaStreamSynchronize((cudaStream_t)streams[i]);
+      if (e != cudaSuccess) return fail(MB200_ERR_CUDA, "host path: %s", cudaGetErrorString(e));
+    }
+  }
+  return 0;
 }
 
 }  // extern "C"

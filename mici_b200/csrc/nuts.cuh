@@ -47,6 +47,7 @@ struct NutsArgs {
   const double* uniforms;
   int n_uniforms;
   const double* step_sizes;
+  int stage_metric;  // 1: copy the dense M^-1 into shared memory once per CTA
 };
 
 template <class Target, int KP>
@@ -147,11 +148,11 @@ __device__ __forceinline__ double nuts_ratio(bool slice, double num, double den)
 }
 
 template <class Target, int KP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(KP <= 2 ? 384 : 256)
     nuts_euclidean_kernel(const double* __restrict__ q_in, const double* __restrict__ p_in,
                           double* __restrict__ q_out, double* __restrict__ p_out, int64_t n_chains,
                           int dim, double step_size, int metric_kind,
-                          const double* __restrict__ minv, ModelArgs model, NutsArgs a,
+                          const double* minv, ModelArgs model, NutsArgs a,
                           double* __restrict__ workspace, double* __restrict__ h_out,
                           int32_t* __restrict__ n_step_out, double* __restrict__ av_accept_out,
                           double* __restrict__ reject_prob_out, int32_t* __restrict__ depth_out,
@@ -166,6 +167,14 @@ __global__ void __launch_bounds__(128)
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   double* psm = smem + (size_t)warp * DP;
+  if (a.stage_metric) {
+    // every chain multiplies by the same dense M^-1 twice per leapfrog step: keep it in shared
+    // memory for the life of the CTA instead of streaming it from L2 per chain
+    double* s_minv = smem + (size_t)wpb * DP;
+    for (int i = threadIdx.x; i < dim * dim; i += blockDim.x) s_minv[i] = minv[i];
+    __syncthreads();
+    minv = s_minv;
+  }
   const Target target(model, dim);
   const bool slice = a.slice != 0, euclid = a.euclidean_criterion != 0, extra = a.extra_checks != 0;
   const size_t ws_stride = (size_t)(7 + 2 + NUTS_REC * (1 + a.max_depth)) * DP;
@@ -252,13 +261,15 @@ __global__ void __launch_bounds__(128)
         if (h != h) h = INFINITY;  // transitions.py:626
         w_cur = leaf_weight(h);
         h_cur = h;
-        __syncwarp();
-        N::st(cur + NQ * DP, lane, q[0]), N::st(cur + PQ * DP, lane, q[0]);
-        N::st(cur + RQ * DP, lane, q[0]);
-        N::st(cur + NP * DP, lane, p[0]), N::st(cur + PP * DP, lane, p[0]);
-        N::st(cur + RP * DP, lane, p[0]), N::st(cur + SUMP * DP, lane, p[0]);
-        N::st(cur + NVEL * DP, lane, v[0]), N::st(cur + PVEL * DP, lane, v[0]);
-        __syncwarp();
+        // an odd-numbered leaf that is not the whole subtree is parked on level 0 untouched:
+        // write it there directly instead of into `cur`
+        const bool parked_leaf = (k & 1) && k < n_leaves;
+        double* leaf = parked_leaf ? levels : cur;
+        N::st(leaf + NQ * DP, lane, q[0]), N::st(leaf + PQ * DP, lane, q[0]);
+        N::st(leaf + RQ * DP, lane, q[0]);
+        N::st(leaf + NP * DP, lane, p[0]), N::st(leaf + PP * DP, lane, p[0]);
+        N::st(leaf + RP * DP, lane, p[0]), N::st(leaf + SUMP * DP, lane, p[0]);
+        N::st(leaf + NVEL * DP, lane, v[0]), N::st(leaf + PVEL * DP, lane, v[0]);
         const double h_diff = h_init - h;
         sum_accept += (h_diff != h_diff) ? 0.0 : exp(fmin(0.0, h_diff));
         ++n_step;
@@ -266,6 +277,10 @@ __global__ void __launch_bounds__(128)
           diverging = true;
           terminate = true;
           break;
+        }
+        if (parked_leaf) {
+          lw[0] = w_cur, lh[0] = h_cur;
+          continue;
         }
         int level = 0;
         for (int kk = k; (kk & 1) == 0; kk >>= 1, ++level) {

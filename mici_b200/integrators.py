@@ -125,6 +125,9 @@ class Integrator(ABC):
         out_mom = torch.empty_like(mom) if out_mom is None else out_mom
         out_status = torch.empty(n, dtype=torch.int32) if out_status is None else out_status
         n_chunks = max(1, min(int(n_chunks), n))
+        if self._host_fast_path(pos, mom, dir, out_pos, out_mom, out_status, n_steps, dev,
+                                n_chunks):
+            return out_pos, out_mom, out_status
         streams = _host_streams(dev, n_chunks)
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(dev))
@@ -146,6 +149,12 @@ class Integrator(ABC):
         for st in streams:
             st.synchronize()
         return out_pos, out_mom, out_status
+
+    def _host_fast_path(self, pos, mom, dir, out_pos, out_mom, out_status, n_steps, dev,  # noqa: A002
+                        n_chunks):
+        """Chunked host-buffer launch inside the library (``mb200_leapfrog_euclidean_host``) when
+        the integrator has one; returns False to fall back to the Python chunk loop."""
+        return False
 
     def _step(self, state, time_step):
         """In-place single step with an explicit signed time step (integrators.py:82-89)."""
@@ -339,6 +348,50 @@ class LeapfrogIntegrator(TractableFlowIntegrator):
             system, ConstrainedEuclideanMetricSystem
         ):
             raise TypeError("LeapfrogIntegrator needs an (unconstrained) EuclideanMetricSystem.")
+
+    def _host_fast_path(self, pos, mom, dir, out_pos, out_mom, out_status, n_steps, dev,  # noqa: A002
+                        n_chunks):
+        tensors = (pos, mom, out_pos, out_mom)
+        if (isinstance(self.system, GaussianEuclideanMetricSystem)
+                or _is_per_chain(self.step_size, n_steps) or self.step_size is None
+                or any(t.device.type != "cpu" or t.dtype != torch.float64 or not t.is_contiguous()
+                       for t in tensors)
+                or out_status.dtype != torch.int32 or not out_status.is_contiguous()):
+            return False
+        n, dim = pos.shape
+        dir_t = None
+        if isinstance(dir, torch.Tensor):
+            if dir.device.type != "cpu":
+                return False
+            dir_t = dir.to(torch.int32).contiguous()
+        elif int(dir) != 1:
+            dir_t = torch.full((n,), int(dir), dtype=torch.int32)
+        lib = _lib.load()
+        sysm = self.system
+        need = int(lib.mb200_host_scratch_bytes(n, dim))
+        key = ("host_scratch", str(dev))
+        scratch = sysm._dev.get(key)
+        if scratch is None or scratch.numel() < need:
+            scratch = torch.empty(max(need, 8), dtype=torch.uint8, device=dev)
+            sysm._dev[key] = scratch
+        n_streams = min(n_chunks, 8)
+        streams = _host_streams(dev, n_streams)
+        handles = (ctypes.c_void_p * n_streams)(*[s.cuda_stream for s in streams])
+        model = sysm._model(dev)
+        with torch.cuda.device(dev):
+            torch.cuda.current_stream(dev).synchronize()  # inputs / scratch of earlier work
+            rc = lib.mb200_leapfrog_euclidean_host(
+                ctypes.c_void_p(pos.data_ptr()), ctypes.c_void_p(mom.data_ptr()),
+                ctypes.c_void_p(out_pos.data_ptr()), ctypes.c_void_p(out_mom.data_ptr()),
+                None if dir_t is None else ctypes.c_void_p(dir_t.data_ptr()), n, dim,
+                float(self.step_size), int(n_steps), sysm.metric.kind,
+                _lib.ptr(sysm.metric.inv_device(dev)), ctypes.byref(model),
+                ctypes.c_void_p(out_status.data_ptr()), n_chunks,
+                ctypes.cast(handles, ctypes.c_void_p), n_streams, _lib.ptr(scratch),
+                scratch.numel(), 1,
+            )
+        _lib.check(rc, "mb200_leapfrog_euclidean_host")
+        return True
 
     def _launch(self, pos, mom, pos_out, mom_out, dirs, n_steps, h, status, n_done):
         if isinstance(self.system, GaussianEuclideanMetricSystem):
