@@ -362,9 +362,9 @@ static int launch_nuts(const double* q_in, const double* p_in, double* q_out, do
   auto kern = nuts_euclidean_kernel<Target, KP>;
   NutsArgs args = a;
   // dense metric that fits in shared memory next to the staging rows: the warps of a CTA share it
-  // (12 warps when the register file allows: KP <= 2 uses < 150 registers per thread)
+  // (12 warps for 64 < dim <= 128, where one CTA per SM fits; 8 otherwise -- measured)
   const size_t metric_bytes = (size_t)dim * dim * sizeof(double);
-  const int staged_warps = KP <= 2 ? 12 : 8;
+  const int staged_warps = KP == 2 ? 12 : 8;
   args.stage_metric = metric_kind == MB200_METRIC_DENSE &&
                       metric_bytes + staged_warps * 64 * KP * sizeof(double) <= 200 * 1024;
   const int warps = args.stage_metric ? staged_warps : 4;

@@ -148,7 +148,7 @@ __device__ __forceinline__ double nuts_ratio(bool slice, double num, double den)
 }
 
 template <class Target, int KP>
-__global__ void __launch_bounds__(KP <= 2 ? 384 : 256)
+__global__ void __launch_bounds__(KP == 2 ? 384 : 256)
     nuts_euclidean_kernel(const double* __restrict__ q_in, const double* __restrict__ p_in,
                           double* __restrict__ q_out, double* __restrict__ p_out, int64_t n_chains,
                           int dim, double step_size, int metric_kind,
