@@ -53,8 +53,9 @@ class Adapter(ABC):
 
 
 def _all_ranks(tensor, group=None):
-    """List of ``tensor`` from every rank (just ``[tensor]`` without a process group)."""
-    if not (dist.is_available() and dist.is_initialized()):
+    """List of ``tensor`` from every rank (just ``[tensor]`` without a process group, or with
+    ``group=False``: adapt on this rank's chains only)."""
+    if group is False or not (dist.is_available() and dist.is_initialized()):
         return [tensor]
     world = dist.get_world_size(group)
     if world == 1:
@@ -214,7 +215,8 @@ def _merge_moments(parts, outer):
 
 def _gather_moments(count, mean, m2, group):
     """Per-rank ``(count, mean, m2)`` -> merged over ranks (one all_gather)."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    if (group is False or not (dist.is_available() and dist.is_initialized())
+            or dist.get_world_size(group) == 1):
         return count, mean, m2
     flat = torch.cat([torch.tensor([float(count)], dtype=torch.float64, device=mean.device),
                       mean.reshape(-1), m2.reshape(-1)])[None]
