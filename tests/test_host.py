@@ -255,3 +255,42 @@ def test_covariance_factored_metric_matches_reference_semantics():
     z = rng.standard_normal(7)
     np.testing.assert_allclose(m.sqrt @ z, sla.solve_triangular(chol.T, z, lower=False), rtol=1e-12)
     np.testing.assert_allclose(m.sqrt @ m.sqrt.T, m.array, rtol=1e-11, atol=1e-14)
+
+
+@pytest.mark.parametrize("args", [(), (125, 50, 25, 3)])
+@pytest.mark.parametrize("n_warm_up_iter", [5, 10, 100, 107, 500, 1003])
+def test_windowed_stager_iteration_budget(args, n_warm_up_iter):
+    """Mirror of the reference's ``StagerTests.test_stages`` (reference tests/test_stagers.py:8-25)."""
+    from mici_b200 import stagers
+
+    class Flag:
+        def __init__(self, fast):
+            self.is_fast = fast
+
+    stages = stagers.WindowedWarmUpStager(*args).stages(n_warm_up_iter, 1, [Flag(True), Flag(False)])
+    assert all(isinstance(k, str) and isinstance(v, stagers.ChainStage) for k, v in stages.items())
+    assert all(v.n_iter >= 0 for v in stages.values())
+    assert sum(v.n_iter for v in stages.values()) == n_warm_up_iter + 1
+    stages = stagers.WarmUpStager().stages(1, 1, [Flag(True)])
+    assert sum(v.n_iter for v in stages.values()) == 2
+
+
+def test_transition_constructors_validate_like_reference():
+    """transitions.py:338-341, 388-392, 507-509 and the fused-only restrictions."""
+    from mici_b200 import integrators, systems, targets, transitions
+
+    system = systems.EuclideanMetricSystem(targets.StdGaussian(4))
+    integ = integrators.LeapfrogIntegrator(system, 0.1)
+    with pytest.raises(ValueError):
+        transitions.MetropolisStaticIntegrationTransition(system, integ, 0)
+    with pytest.raises(ValueError):
+        transitions.MetropolisRandomIntegrationTransition(system, integ, (3, 3))
+    with pytest.raises(ValueError):
+        transitions.MultinomialDynamicIntegrationTransition(system, integ, max_tree_depth=0)
+    with pytest.raises(TypeError):
+        transitions.DynamicIntegrationTransition(system, integ)
+    with pytest.raises(NotImplementedError):
+        transitions.SliceDynamicIntegrationTransition(
+            system, integrators.BCSSTwoStageIntegrator(system, 0.1))
+    tr = transitions.SliceDynamicIntegrationTransition(system, integ, max_tree_depth=5)
+    assert tr.n_uniforms == 2 * 5 + 2**5 + 1

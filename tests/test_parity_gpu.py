@@ -729,3 +729,91 @@ def test_dynamic_transition_full_size_device_rng():
     assert int(stats["n_step"].min()) >= 1 and int(stats["tree_depth"].max()) <= 5
     assert 0.3 < float(stats["accept_stat"].mean()) <= 1.0
     assert not bool(stats["diverging"].any())
+
+
+def _nuts_setup(cfg, kwargs, seed=3046987125):
+    from mici_b200 import transitions
+
+    problem = problems.make_problem(cfg, **kwargs)
+    integ = engine.build_integrator(problem)
+    state = engine.build_state(problem, DEV)
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(seed % (2**31))
+    tr = transitions.MultinomialDynamicIntegrationTransition(integ.system, integ)
+    return problem, integ, state, gen, tr, transitions.IndependentMomentumTransition(integ.system)
+
+
+def test_dual_averaging_controls_accept_statistic():
+    """Mirror of the reference's ``DualAveragingStepSizeAdapterTests.test_adaptation``
+    (reference tests/test_adapters.py:102-128): 500 adaptive dynamic transitions on a standard
+    Gaussian, then 500 with the finalised step size -- here for 32 chains at once, each with its
+    own step size while adapting."""
+    from mici_b200 import adapters
+
+    problem, integ, state, gen, tr, mom_tr = _nuts_setup("C0", {"n_chains": 32, "dim": 10})
+    integ.step_size = None
+    adapter = adapters.DualAveragingStepSizeAdapter()
+    a_state = adapter.initialize(state, tr)
+    assert integ.step_size.shape == (32,)
+    for _ in range(500):
+        state, _ = mom_tr.sample(state, gen)
+        state, stats = tr.sample(state, gen)
+        adapter.update(a_state, state, stats, tr)
+    adapter.finalize(a_state, state, tr, gen)
+    err = a_state["adapt_stat_error"].abs().cpu().numpy()
+    assert err.mean() < 0.02 and err.max() < 0.1
+    assert isinstance(integ.step_size, float) and 0.1 < integ.step_size < 3.0
+    total = 0.0
+    for _ in range(500):
+        state, _ = mom_tr.sample(state, gen)
+        state, stats = tr.sample(state, gen)
+        total += float(stats["accept_stat"].mean())
+    assert abs(adapter.adapt_stat_target - total / 500) < 0.05
+
+
+@pytest.mark.parametrize("kind", ["variance", "covariance"])
+def test_metric_adapters_match_direct_estimates(kind):
+    """Mirror of the reference's ``TestOnlineVarianceMetricAdapter`` /
+    ``TestOnlineCovarianceMetricAdapter`` (reference tests/test_adapters.py:212-300): Welford
+    states after 10 dynamic transitions and the finalised metric against NumPy estimates from
+    the recorded samples -- pooled over all chains, which is what the chain-by-chain merge of the
+    reference (adapters.py:487-505, 615-634) computes."""
+    from mici_b200 import adapters
+
+    problem, integ, state, gen, tr, mom_tr = _nuts_setup(
+        "C1", {"n_chains": 24, "dim": 10, "metric_kind": "identity"})
+    integ.step_size = 0.2
+    adapter = (adapters.OnlineVarianceMetricAdapter() if kind == "variance"
+               else adapters.OnlineCovarianceMetricAdapter())
+    a_state = adapter.initialize(state, tr)
+    samples = []
+    for _ in range(10):
+        state, _ = mom_tr.sample(state, gen)
+        state, stats = tr.sample(state, gen)
+        samples.append(state.pos.cpu().numpy().copy())
+        adapter.update(a_state, state, stats, tr)
+    samples = np.stack(samples)  # [10, n_chains, dim]
+    assert a_state["iter"] == 10
+    np.testing.assert_allclose(a_state["mean"].cpu().numpy(), samples.mean(0), rtol=1e-10, atol=1e-13)
+    centred = samples - samples.mean(0)
+    if kind == "variance":
+        np.testing.assert_allclose(a_state["sum_diff_sq"].cpu().numpy(), (centred**2).sum(0),
+                                   rtol=1e-9, atol=1e-12)
+    else:
+        np.testing.assert_allclose(a_state["sum_diff_outer"].cpu().numpy(),
+                                   np.einsum("tcj,tck->jk", centred, centred), rtol=1e-9, atol=1e-11)
+    adapter.finalize(a_state, state, tr, gen)
+    flat = samples.reshape(-1, problem.dim)
+    n = flat.shape[0]
+    weight = n / (adapter.reg_iter_offset + n)
+    metric = integ.system.metric
+    if kind == "variance":
+        reg = weight * flat.var(axis=0, ddof=1) + (1 - weight) * adapter.reg_scale
+        assert metric.kind == 1
+        np.testing.assert_allclose(metric.array, 1 / reg, rtol=1e-9)
+    else:
+        reg = weight * np.cov(flat, rowvar=False, ddof=1) + (
+            1 - weight) * adapter.reg_scale * np.identity(problem.dim)
+        assert metric.kind == 2
+        np.testing.assert_allclose(metric.inv, reg, rtol=1e-8, atol=1e-12)
+    assert bool(torch.isfinite(state.mom).all())  # momenta resampled under the new metric
