@@ -12,6 +12,7 @@ from . import (
     errors,
     integrators,
     problems,
+    samplers,
     solvers,
     stagers,
     states,
@@ -27,6 +28,7 @@ __all__ = [
     "errors",
     "integrators",
     "problems",
+    "samplers",
     "solvers",
     "stagers",
     "states",

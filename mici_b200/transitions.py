@@ -311,7 +311,8 @@ class SliceDynamicIntegrationTransition(DynamicIntegrationTransition):
     _slice = True
 
 
-def _run_stage(mom_tr, int_tr, state, rng, n_iter, adapters, record, all_stats, trace, group):
+def _run_stage(mom_tr, int_tr, state, rng, n_iter, adapters, record, all_stats, trace, group,
+               h_trace=None):
     """One sampling stage for every chain: the loop body of ``_sample_chain`` (samplers.py:459-513)
     then ``_finalize_adapters`` (samplers.py:1131-1138)."""
     adapters = adapters or []
@@ -326,6 +327,10 @@ def _run_stage(mom_tr, int_tr, state, rng, n_iter, adapters, record, all_stats, 
                 all_stats.setdefault(k, []).append(v)
             if trace is not None:
                 trace.append(state.pos.clone())
+                if h_trace is not None:
+                    # the reference's default trace function (samplers.py:1263-1269)
+                    h_trace.append(state.h.clone() if "h" in state._aux and state.h is not None
+                                   else int_tr.system.h(state))
     for a, a_state in zip(adapters, adapt_states):
         a.finalize(a_state, state, int_tr, rng, group=group)
     return state, adapt_states
@@ -350,14 +355,16 @@ def sample_hmc(system, integrator, state, rng, n_iter, n_step, trace_pos=False, 
 
 def sample_chains(system, integrator, state, rng, n_warm_up_iter, n_main_iter, *, n_step=None,
                   n_step_range=None, integration_transition=None, adapters=None, stager=None,
-                  trace_warm_up=False, trace_pos=True, group=None):
+                  trace_warm_up=False, trace_pos=True, trace_h=False, group=None):
     """Staged sampling of all chains: ``HamiltonianMonteCarlo.sample_chains``
     (samplers.py:875-1141) for the static (``n_step``) or random (``n_step_range``) Metropolis
     HMC transitions or a given ``integration_transition`` (e.g. a dynamic one), with the stage schedule of ``mici_b200.stagers`` (default: one warm-up stage
     if all adapters are fast, else windowed: samplers.py:1075-1082).  Adapter states are
     re-initialised at the start of every stage and finalised at its end (across all chains and,
     with a process group, across all ranks).  Returns ``(final_state, stats, traces)`` over the
-    recorded stages (the main stage; also the warm-up if ``trace_warm_up``)."""
+    recorded stages (the main stage; also the warm-up if ``trace_warm_up``); ``traces`` is the
+    position tensor ``[n_iter, n_chains, dim]``, or with ``trace_h`` a dictionary
+    ``{"pos", "hamiltonian"}`` like the reference's default trace function."""
     from .stagers import WarmUpStager, WindowedWarmUpStager  # noqa: PLC0415
 
     if (n_step is not None) + (n_step_range is not None) + (integration_transition is not None) != 1:
@@ -374,10 +381,14 @@ def sample_chains(system, integrator, state, rng, n_warm_up_iter, n_main_iter, *
     if stager is None:
         stager = WarmUpStager() if all(a.is_fast for a in adapters) else WindowedWarmUpStager()
     all_stats, trace = {}, ([] if trace_pos else None)
+    h_trace = [] if (trace_pos and trace_h) else None
     for stage in stager.stages(n_warm_up_iter, n_main_iter, adapters,
                                trace_warm_up=trace_warm_up).values():
         state, _ = _run_stage(mom_tr, int_tr, state, rng, stage.n_iter, stage.adapters,
                               stage.record_stats, all_stats, trace if stage.trace else None,
-                              group)
+                              group, h_trace if stage.trace else None)
     stats = {k: torch.stack(v) for k, v in all_stats.items()}
+    if h_trace is not None:  # dictionary of traces keyed like the reference's default trace
+        return state, stats, ({"pos": torch.stack(trace), "hamiltonian": torch.stack(h_trace)}
+                              if trace else None)
     return state, stats, (torch.stack(trace) if trace_pos and trace else None)

@@ -294,3 +294,31 @@ def test_transition_constructors_validate_like_reference():
             system, integrators.BCSSTwoStageIntegrator(system, 0.1))
     tr = transitions.SliceDynamicIntegrationTransition(system, integ, max_tree_depth=5)
     assert tr.n_uniforms == 2 * 5 + 2**5 + 1
+
+
+def test_sampler_front_ends_mirror_reference_signatures_and_defaults():
+    """samplers.py:1458-1465, 1527-1534, 1600-1611, 1708-1719: constructor signatures and the
+    (different) defaults of the two dynamic samplers; per-chain generators as samplers.py:559-560."""
+    import numpy as np
+
+    from mici_b200 import integrators, samplers, systems, targets, transitions
+
+    system = systems.EuclideanMetricSystem(targets.StdGaussian(4))
+    integ = integrators.LeapfrogIntegrator(system, 0.1)
+    rng = np.random.default_rng(1)
+    s1 = samplers.StaticMetropolisHMC(system, integ, rng, 7)
+    assert s1.n_step == 7 and s1.system is system and s1.rng is rng
+    assert list(s1.transitions) == ["momentum_transition", "integration_transition"]
+    s2 = samplers.RandomMetropolisHMC(system, integ, rng, (2, 9))
+    assert s2.n_step_range == (2, 9)
+    m = samplers.DynamicMultinomialHMC(system, integ, rng).transitions["integration_transition"]
+    sl = samplers.DynamicSliceHMC(system, integ, rng).transitions["integration_transition"]
+    assert m.termination_criterion is transitions.riemannian_no_u_turn_criterion
+    assert m.do_extra_subtree_checks and m.max_tree_depth == 10 and m.max_delta_h == 1000
+    assert sl.termination_criterion is transitions.euclidean_no_u_turn_criterion
+    assert not sl.do_extra_subtree_checks
+    gens = samplers._per_chain_rngs(rng, 3)
+    want = [np.random.default_rng(rng.bit_generator.jumped(i)).uniform() for i in range(3)]
+    assert [g.uniform() for g in gens] == want
+    with pytest.raises(TypeError):
+        s1.sample_chains(1, 1, np.zeros((2, 4)), not_an_argument=1)

@@ -482,15 +482,29 @@ def test_batched_adaptive_sampling_matches_reference_fixture(name):
     integ = engine.build_integrator(problem)
     state = engine.build_state(problem, DEV)
     base = np.random.default_rng(seed)
-    rngs = [np.random.default_rng(base.bit_generator.jumped(i)) for i in range(problem.n_chains)]
     stager = None if sk is None else stagers.WindowedWarmUpStager(**sk)
+    # through the sampler front ends (reference call signature); the per-chain generators are
+    # derived from the sampler's generator exactly as the reference derives them
+    from mici_b200 import samplers
+
     if isinstance(n_step, dict):
-        how = {"integration_transition": _dynamic_transition(integ, n_step)}
+        opts = dict(n_step)
+        cls = (samplers.DynamicSliceHMC if opts.pop("variant", "multinomial") == "slice"
+               else samplers.DynamicMultinomialHMC)
+        crit = getattr(transitions, opts.pop("criterion", "riemannian") + "_no_u_turn_criterion")
+        sampler = cls(integ.system, integ, base, termination_criterion=crit,
+                      do_extra_subtree_checks=opts.pop("extra_checks", True), **opts)
     else:
-        how = {"n_step": n_step}
-    final, stats, trace = transitions.sample_chains(
-        integ.system, integ, state, rngs, n_warm, n_main, adapters=_build_adapters(specs),
-        stager=stager, trace_warm_up=True, **how)
+        sampler = samplers.StaticMetropolisHMC(integ.system, integ, base, n_step)
+    out = sampler.sample_chains(n_warm, n_main, state, adapters=_build_adapters(specs),
+                                stager=stager, trace_warm_up=True, n_worker=1,
+                                display_progress=False)
+    final = out.final_states
+    trace = out.traces["pos"].transpose(0, 1)
+    stats = {k: v.transpose(0, 1) for k, v in out.statistics.items()}
+    h_last = out.traces["hamiltonian"][:, -1]
+    np.testing.assert_allclose(h_last.cpu().numpy(), integ.system.h(final).cpu().numpy(),
+                               rtol=1e-12)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(stats["n_step"].cpu().numpy(), g["n_step"])
     np.testing.assert_array_equal(final.dir.cpu().numpy(), g["final_dir"])
