@@ -66,9 +66,6 @@ class HamiltonianMonteCarlo:
     (samplers.py:1144-1432)."""
 
     def __init__(self, system, rng, integration_transition, momentum_transition=None):
-        if momentum_transition is not None and not isinstance(
-                momentum_transition, IndependentMomentumTransition):
-            raise NotImplementedError("Only IndependentMomentumTransition is batched.")
         self._system = system
         self._rng = rng
         self.transitions = {
@@ -126,7 +123,9 @@ class HamiltonianMonteCarlo:
         int_tr = self.transitions["integration_transition"]
         final, stats, trace = sample_chains(
             self._system, int_tr.integrator, state, _per_chain_rngs(self._rng, n), n_warm_up_iter,
-            n_main_iter, integration_transition=int_tr, adapters=adapters, stager=stager,
+            n_main_iter, integration_transition=int_tr,
+            momentum_transition=self.transitions["momentum_transition"], adapters=adapters,
+            stager=stager,
             trace_warm_up=trace_warm_up, trace_pos=True, trace_h=True, group=group)
         traces = {}
         if trace is not None:

@@ -76,6 +76,29 @@ def _integers(rng, lo, hi, n, device):
     return torch.as_tensor(k, device=device)
 
 
+class CorrelatedMomentumTransition:
+    """Partial momentum refresh ``mom <- sqrt(1 - c^2) mom + c * sample`` for every chain
+    (transitions.py:145-198)."""
+
+    state_variables = frozenset({"mom"})
+    statistic_types = None
+
+    def __init__(self, system, mom_resample_coeff=1.0):
+        if not (mom_resample_coeff >= 0 and mom_resample_coeff <= 1):
+            raise ValueError("mom_resample_coeff should have a value in the interval [0, 1].")
+        self.system = system
+        self.mom_resample_coeff = mom_resample_coeff
+
+    def sample(self, state, rng):
+        if state.mom is None or self.mom_resample_coeff == 1:
+            state.mom = self.system.sample_momentum(state, rng)
+        elif self.mom_resample_coeff != 0:
+            mom_ind = self.system.sample_momentum(state, rng)
+            state.mom = state.mom * (1.0 - self.mom_resample_coeff**2) ** 0.5 + (
+                self.mom_resample_coeff * mom_ind)
+        return state, None
+
+
 class MetropolisIntegrationTransition:
     """Trajectory + Metropolis accept step for all chains (transitions.py:235-315).  ``sample``
     returns ``(state, stats)`` where ``stats`` holds per-chain tensors with the reference's
@@ -354,8 +377,9 @@ def sample_hmc(system, integrator, state, rng, n_iter, n_step, trace_pos=False, 
 
 
 def sample_chains(system, integrator, state, rng, n_warm_up_iter, n_main_iter, *, n_step=None,
-                  n_step_range=None, integration_transition=None, adapters=None, stager=None,
-                  trace_warm_up=False, trace_pos=True, trace_h=False, group=None):
+                  n_step_range=None, integration_transition=None, momentum_transition=None,
+                  adapters=None, stager=None, trace_warm_up=False, trace_pos=True, trace_h=False,
+                  group=None):
     """Staged sampling of all chains: ``HamiltonianMonteCarlo.sample_chains``
     (samplers.py:875-1141) for the static (``n_step``) or random (``n_step_range``) Metropolis
     HMC transitions or a given ``integration_transition`` (e.g. a dynamic one), with the stage schedule of ``mici_b200.stagers`` (default: one warm-up stage
@@ -371,7 +395,8 @@ def sample_chains(system, integrator, state, rng, n_warm_up_iter, n_main_iter, *
         raise ValueError(
             "Give exactly one of `n_step`, `n_step_range` and `integration_transition`.")
     adapters = list(adapters or [])
-    mom_tr = IndependentMomentumTransition(system)
+    mom_tr = (IndependentMomentumTransition(system) if momentum_transition is None
+              else momentum_transition)
     if integration_transition is not None:
         int_tr = integration_transition
     elif n_step is not None:

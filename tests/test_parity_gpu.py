@@ -831,3 +831,24 @@ def test_metric_adapters_match_direct_estimates(kind):
         assert metric.kind == 2
         np.testing.assert_allclose(metric.inv, reg, rtol=1e-8, atol=1e-12)
     assert bool(torch.isfinite(state.mom).all())  # momenta resampled under the new metric
+
+
+def test_correlated_momentum_transition():
+    """transitions.py:145-198: partial refresh with the variates of each chain's own stream."""
+    from mici_b200 import transitions
+    from oracle import mici_oracle as mo
+
+    problem = problems.make_problem("C1", n_chains=6, dim=8)
+    system = engine.build_system(problem)
+    state = engine.build_state(problem, DEV)
+    rngs = [np.random.default_rng([3, i]) for i in range(problem.n_chains)]
+    coeff = 0.4
+    new, stats = transitions.CorrelatedMomentumTransition(system, coeff).sample(state, rngs)
+    assert stats is None
+    metric = mo.coerce_metric(problem.metric)
+    for i in range(problem.n_chains):
+        ind = metric.sqrt_matvec(np.random.default_rng([3, i]).standard_normal(problem.dim))
+        want = problem.mom[i] * (1.0 - coeff**2) ** 0.5 + coeff * ind
+        np.testing.assert_allclose(new.mom[i].cpu().numpy(), want, rtol=1e-12, atol=1e-14)
+    with pytest.raises(ValueError):
+        transitions.CorrelatedMomentumTransition(system, 1.5)
