@@ -180,7 +180,13 @@ NUTS_CASES = {
                                80, {"max_delta_h": 5.0}),
     "nuts_c1_identity_d70": ("C1", {"n_chains": 4, "dim": 70, "metric_kind": "identity"}, 0.05, 3,
                              81, {"max_tree_depth": 6}),
+    # constrained and implicit integrators inside dynamic transitions: pins the oracle for the
+    # systems the fused kernel does not cover yet (failed steps terminate the tree)
+    "nuts_c3_torus_constrained": ("C3", {"n_chains": 6}, 0.2, 5, 82, {"max_tree_depth": 5}),
+    "nuts_c2_softabs_d4_implicit": ("C2", {"n_chains": 3, "dim": 4}, 0.2, 4, 83,
+                                    {"max_tree_depth": 3}),
 }
+NUTS_DEVICE_CASES = [k for k in NUTS_CASES if not k.startswith(("nuts_c3", "nuts_c2"))]
 
 
 def nuts_cases():

@@ -294,6 +294,16 @@ def test_transition_constructors_validate_like_reference():
             system, integrators.BCSSTwoStageIntegrator(system, 0.1))
     tr = transitions.SliceDynamicIntegrationTransition(system, integ, max_tree_depth=5)
     assert tr.n_uniforms == 2 * 5 + 2**5 + 1
+    # systems the fused tree builder does not cover fail loudly at construction
+    torus = targets.make_target("torus")
+    csys = systems.DenseConstrainedEuclideanMetricSystem(torus, torus)
+    with pytest.raises(NotImplementedError):
+        transitions.MultinomialDynamicIntegrationTransition(
+            csys, integrators.ConstrainedLeapfrogIntegrator(csys, 0.1))
+    gsys = systems.GaussianEuclideanMetricSystem(targets.StdGaussian(4))
+    with pytest.raises(NotImplementedError):
+        transitions.MultinomialDynamicIntegrationTransition(
+            gsys, integrators.LeapfrogIntegrator(gsys, 0.1))
 
 
 def test_sampler_front_ends_mirror_reference_signatures_and_defaults():

@@ -111,7 +111,8 @@ ADAPT_NAMES = ["adapt_c1_dualavg_variance", "adapt_c1_dualavg_covariance", "adap
                "adapt_c0_variance_first", "adapt_c3_torus_dualavg", "adapt_c2_softabs_d6_dualavg",
                "adapt_nuts_c0_dualavg", "adapt_nuts_c1_dualavg_variance"]
 NUTS_NAMES = ["nuts_c1_multinomial_d10", "nuts_c1_slice_euclidean_d16",
-              "nuts_c0_depth4_no_extra_checks", "nuts_c1_diag_divergent", "nuts_c1_identity_d70"]
+              "nuts_c0_depth4_no_extra_checks", "nuts_c1_diag_divergent", "nuts_c1_identity_d70",
+              "nuts_c3_torus_constrained", "nuts_c2_softabs_d4_implicit"]
 
 
 @pytest.mark.parametrize("name", ADAPT_NAMES)
