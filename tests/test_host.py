@@ -332,3 +332,116 @@ def test_sampler_front_ends_mirror_reference_signatures_and_defaults():
     assert [g.uniform() for g in gens] == want
     with pytest.raises(TypeError):
         s1.sample_chains(1, 1, np.zeros((2, 4)), not_an_argument=1)
+
+
+class _OracleBackedIntegrator:
+    """CPU stand-in for a device integrator: steps every chain through the oracle (NumPy) and
+    reports status / Hamiltonian like ``Integrator.step_n`` -- lets the batched host logic of the
+    adapters be checked on a machine without a GPU."""
+
+    def __init__(self, problem):
+        from oracle import drivers as dr
+
+        self.ctx = dr._AdaptiveContext(problem)
+        self.step_size = None
+
+    def step_n(self, state, n_steps, *, return_h=False):
+        import torch
+
+        from mici_b200.states import ChainState
+        from oracle import mici_oracle as mo
+
+        assert n_steps == 1 and return_h
+        q, p = state.pos.numpy(), state.mom.numpy()
+        eps = self.step_size.numpy()
+        n = q.shape[0]
+        out_q, out_p = q.copy(), p.copy()
+        status, h = np.zeros(n, dtype=np.int32), np.full(n, np.nan)
+        for c in range(n):
+            try:
+                out_q[c], out_p[c] = self.ctx.step_eps(q[c], p[c], 1, float(eps[c]))
+                h[c] = self.ctx.h(out_q[c], out_p[c])
+            except mo.OracleIntegratorError as e:
+                status[c] = e.status
+        new = ChainState(pos=torch.as_tensor(out_q), mom=torch.as_tensor(out_p), dir=1)
+        new.status, new.h = torch.as_tensor(status), torch.as_tensor(h)
+        return new
+
+
+class _OracleBackedSystem:
+    def __init__(self, integrator):
+        self.ctx = integrator.ctx
+
+    def h(self, state):
+        import torch
+
+        q, p = state.pos.numpy(), state.mom.numpy()
+        return torch.as_tensor(np.array([self.ctx.h(q[c], p[c]) for c in range(q.shape[0])]))
+
+
+@pytest.mark.parametrize("cfg,kwargs", [("C1", {"n_chains": 24, "dim": 12}), ("C3", {"n_chains": 24}),
+                                        ("C0", {"n_chains": 6, "dim": 10})])
+def test_batched_initial_step_size_search_matches_oracle_on_cpu(cfg, kwargs):
+    """adapters.py:285-352 as batched tensor logic (per-chain halving / doubling, NaN energies
+    at step size 1 for the funnel, failed constrained steps for the torus) against the per-chain
+    oracle search -- with an oracle-backed integrator, so the comparison is exact."""
+    import warnings
+
+    import torch
+
+    from mici_b200 import adapters, problems
+    from mici_b200.states import ChainState
+    from oracle import mici_oracle as mo
+
+    problem = problems.make_problem(cfg, **kwargs)
+    integ = _OracleBackedIntegrator(problem)
+    system = _OracleBackedSystem(integ)
+    state = ChainState(pos=torch.as_tensor(problem.pos), mom=torch.as_tensor(problem.mom), dir=1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = adapters.DualAveragingStepSizeAdapter()._find_and_set_init_step_size(
+            state, system, integ).numpy()
+        want = np.array([mo.find_init_step_size(problem.pos[c], problem.mom[c], 1,
+                                                integ.ctx.step_eps, integ.ctx.h)
+                         for c in range(problem.n_chains)])
+    np.testing.assert_array_equal(got, want)
+    assert integ.step_size is not None and torch.equal(integ.step_size, torch.as_tensor(got))
+    if cfg != "C0":
+        assert len(set(got.tolist())) > 1  # chains really end on different step sizes
+
+
+def test_dual_averaging_update_matches_oracle_on_cpu():
+    """adapters.py:354-373 for a batch against the scalar restatement, 40 updates."""
+    import torch
+
+    from mici_b200 import adapters
+    from oracle import mici_oracle as mo
+
+    n = 7
+    rng = np.random.default_rng(4)
+    accept = rng.uniform(0.0, 1.0, (40, n))
+    eps0 = 2.0 ** rng.integers(-6, 1, n)
+    ad = adapters.DualAveragingStepSizeAdapter(adapt_stat_target=0.7)
+    st = {"iter": 0, "smoothed_log_step_size": torch.zeros(n, dtype=torch.float64),
+          "adapt_stat_error": torch.zeros(n, dtype=torch.float64),
+          "log_step_size_reg_target": torch.log(10 * torch.as_tensor(eps0))}
+    tr = type("T", (), {"integrator": type("I", (), {"step_size": None})()})()
+    od = mo.DualAveragingOracle(adapt_stat_target=0.7)
+
+    class Ctx:
+        step_size = None
+
+    ost = [{"iter": 0, "smoothed_log_step_size": 0.0, "adapt_stat_error": 0.0,
+            "log_step_size_reg_target": float(np.log(10 * eps0[c]))} for c in range(n)]
+    ctxs = [Ctx() for _ in range(n)]
+    for it in range(40):
+        ad.update(st, None, {"accept_stat": torch.as_tensor(accept[it])}, tr)
+        for c in range(n):
+            od.update(ost[c], None, {"accept_stat": accept[it, c]}, ctxs[c])
+        np.testing.assert_allclose(tr.integrator.step_size.numpy(),
+                                   [ctxs[c].step_size for c in range(n)], rtol=1e-13)
+    np.testing.assert_allclose(st["smoothed_log_step_size"].numpy(),
+                               [o["smoothed_log_step_size"] for o in ost], rtol=1e-13, atol=1e-15)
+    ad.finalize(st, None, tr, None)
+    od.finalize(ost, ctxs[0])
+    assert tr.integrator.step_size == pytest.approx(ctxs[0].step_size, rel=1e-13)
