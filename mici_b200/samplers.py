@@ -49,6 +49,23 @@ class HMCSampleChainsOutputs(NamedTuple):
     statistics: dict
 
 
+def write_chain_data(memmap_path, traces, statistics, first_chain_index=0):
+    """Write traces / statistics ``[chain, iteration, ...]`` as the per-chain ``.npy`` files the
+    reference creates when memory-mapping chain data: ``trace_{i}_{key}.npy`` and
+    ``stats_{i}_integration_transition_{key}.npy`` (samplers.py:104-113, 247-254, 278-289), so
+    that tooling written against those files keeps working.  ``first_chain_index``: global index
+    of this rank's first chain when chains are sharded over ranks."""
+    from .traces import write_chain_traces  # noqa: PLC0415
+
+    n = next(iter(traces.values())).shape[0] if traces else next(iter(statistics.values())).shape[0]
+    indices = range(first_chain_index, first_chain_index + n)
+    paths = write_chain_traces(memmap_path, "trace", traces, indices) if traces else {}
+    stat_paths = write_chain_traces(
+        memmap_path, "stats", {f"integration_transition_{k}": v for k, v in statistics.items()},
+        indices)
+    return paths, stat_paths
+
+
 def _per_chain_rngs(rng, n_chain):
     """samplers.py:546-565."""
     if isinstance(rng, torch.Generator):
@@ -105,13 +122,14 @@ class HamiltonianMonteCarlo:
         return state
 
     def sample_chains(self, n_warm_up_iter, n_main_iter, init_states, *, adapters="default",
-                      stager=None, trace_warm_up=False, trace_funcs=None, device="cuda",
-                      group=None, **ignored):
+                      stager=None, trace_warm_up=False, trace_funcs=None, memmap_path=None,
+                      first_chain_index=0, device="cuda", group=None, **ignored):
         """samplers.py:1271-1432.  ``adapters`` defaults to one ``DualAveragingStepSizeAdapter``
-        (samplers.py:1405-1406); pass ``None`` or ``[]`` for none."""
+        (samplers.py:1405-1406); pass ``None`` or ``[]`` for none.  With ``memmap_path`` the
+        traces and statistics are also written as the reference's per-chain ``.npy`` files."""
         unknown = set(ignored) - {"n_worker", "n_process", "use_thread_pool", "display_progress",
                                   "progress_bar_class", "max_threads_per_worker", "force_memmap",
-                                  "memmap_path", "monitor_stats"}
+                                  "monitor_stats"}
         if unknown:
             raise TypeError(f"unexpected keyword arguments {sorted(unknown)}")
         if trace_funcs is not None:
@@ -132,6 +150,8 @@ class HamiltonianMonteCarlo:
             traces["pos"] = trace["pos"].transpose(0, 1)
             traces["hamiltonian"] = trace["hamiltonian"].transpose(0, 1)
         statistics = {k: v.transpose(0, 1) for k, v in stats.items()}
+        if memmap_path is not None:
+            write_chain_data(memmap_path, traces, statistics, first_chain_index)
         return HMCSampleChainsOutputs(final, traces, statistics)
 
 
@@ -218,6 +238,7 @@ class DynamicSliceHMC(_DynamicHMC):
 
 
 __all__ = [
+    "write_chain_data",
     "DynamicMultinomialHMC",
     "DynamicSliceHMC",
     "HMCSampleChainsOutputs",

@@ -445,3 +445,26 @@ def test_dual_averaging_update_matches_oracle_on_cpu():
     ad.finalize(st, None, tr, None)
     od.finalize(ost, ctxs[0])
     assert tr.integrator.step_size == pytest.approx(ctxs[0].step_size, rel=1e-13)
+
+
+def test_sampler_chain_data_files_use_reference_names(tmp_path):
+    """samplers.py:104-113, 247-254, 278-289: per-chain memmap file names and contents."""
+    import torch
+
+    from mici_b200 import samplers
+
+    traces = {"pos": torch.arange(2 * 5 * 3, dtype=torch.float64).reshape(2, 5, 3),
+              "hamiltonian": torch.arange(10, dtype=torch.float64).reshape(2, 5)}
+    stats = {"accept_stat": torch.rand(2, 5, dtype=torch.float64),
+             "n_step": torch.arange(10).reshape(2, 5)}
+    samplers.write_chain_data(tmp_path, traces, stats, first_chain_index=4)
+    names = sorted(p.name for p in tmp_path.iterdir())
+    assert names == sorted([
+        "trace_4_pos.npy", "trace_5_pos.npy", "trace_4_hamiltonian.npy", "trace_5_hamiltonian.npy",
+        "stats_4_integration_transition_accept_stat.npy",
+        "stats_5_integration_transition_accept_stat.npy",
+        "stats_4_integration_transition_n_step.npy", "stats_5_integration_transition_n_step.npy"])
+    got = np.load(tmp_path / "trace_5_pos.npy", mmap_mode="r")
+    np.testing.assert_array_equal(got, traces["pos"][1].numpy())
+    got = np.load(tmp_path / "stats_4_integration_transition_n_step.npy")
+    np.testing.assert_array_equal(got, stats["n_step"][0].numpy())
