@@ -1,9 +1,14 @@
-"""Batched Markov transitions around the integrators -- "next" row N1 of SURVEY.md 8(f).
+"""Batched Markov transitions around the integrators -- "next" rows N1 / N4 of SURVEY.md 8(f).
 
-Mirrors, for all chains at once, the two reference transitions that make up static HMC:
+Mirrors, for all chains at once, the reference's transitions:
 
-* ``IndependentMomentumTransition``           transitions.py:129-142
-* ``MetropolisStaticIntegrationTransition``   transitions.py:256-352
+* ``IndependentMomentumTransition``             transitions.py:129-142
+* ``CorrelatedMomentumTransition``              transitions.py:145-198
+* ``MetropolisStaticIntegrationTransition``     transitions.py:256-352
+* ``MetropolisRandomIntegrationTransition``     transitions.py:355-402 (per-chain trajectory lengths)
+* ``MultinomialDynamicIntegrationTransition``   transitions.py:487-809 (fused NUTS kernel)
+* ``SliceDynamicIntegrationTransition``         transitions.py:812-858
+* ``sample_hmc`` / ``sample_chains``            samplers.py:459-513, 1075-1141 (staged sampling)
 
 so that a whole HMC iteration (momentum refresh, ``n_step`` fused integrator steps, energy,
 accept / reject, direction flips) stays on the GPU: two kernel launches for the trajectory
