@@ -83,4 +83,68 @@ __device__ __forceinline__ void inv_metric_apply(int METRIC, const double* __res
     }
   }
 
+// Round-2 candidate (NOT enabled by default, not yet validated on hardware; build with
+// -DMB200_NUTS_LDS_MATVEC): v = A p for ONE chain per warp with the dense symmetric A staged in
+// shared memory -- ld.shared.v2 row reads, four rows per trip with four independent accumulator
+// sets (the profile of the plain loop shows one row load + 4 FMAs per trip with the loop / bounds
+// logic around them and generic-address loads: profiles/r01_nuts_c1_ncu_lines.txt).  Requires
+// even `dim`.  Summation order differs from inv_metric_apply (four partial sums).
+template <int KP>
+__device__ __forceinline__ void inv_metric_apply_staged(const double* s_minv, int dim, int lane,
+                                                        double* psm, const double (&p)[1][2 * KP],
+                                                        double (&v)[1][2 * KP]) {
+  constexpr int NV = 2 * KP;
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    const int i = 2 * lane + 64 * k;
+    psm[i] = p[0][2 * k];
+    psm[i + 1] = p[0][2 * k + 1];
+  }
+  __syncwarp();
+  const unsigned base = (unsigned)__cvta_generic_to_shared(s_minv);
+  const unsigned pbase = (unsigned)__cvta_generic_to_shared(psm);
+  double acc[4][NV];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int e = 0; e < NV; ++e) acc[r][e] = 0.0;
+  const int dim4 = dim & ~3;
+  for (int j = 0; j < dim4; j += 4) {
+    double a[4][NV], pj[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(pj[r]) : "r"(pbase + (unsigned)(j + r) * 8u));
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        const int i = 2 * lane + 64 * k;
+        if (i < dim) {
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+                       : "=d"(a[r][2 * k]), "=d"(a[r][2 * k + 1])
+                       : "r"(base + (unsigned)((j + r) * dim + i) * 8u));
+        } else {
+          a[r][2 * k] = 0.0, a[r][2 * k + 1] = 0.0;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int e = 0; e < NV; ++e) acc[r][e] = fma(a[r][e], pj[r], acc[r][e]);
+  }
+  for (int j = dim4; j < dim; ++j) {
+    const double pj = psm[j];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int i = 2 * lane + 64 * k;
+      if (i < dim) {
+        acc[0][2 * k] = fma(s_minv[(size_t)j * dim + i], pj, acc[0][2 * k]);
+        acc[0][2 * k + 1] = fma(s_minv[(size_t)j * dim + i + 1], pj, acc[0][2 * k + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < NV; ++e) v[0][e] = (acc[0][e] + acc[1][e]) + (acc[2][e] + acc[3][e]);
+}
+
 }  // namespace mb200

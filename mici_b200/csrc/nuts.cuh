@@ -175,6 +175,16 @@ __global__ void __launch_bounds__(KP == 2 ? 384 : 256)
     __syncthreads();
     minv = s_minv;
   }
+#ifdef MB200_NUTS_LDS_MATVEC
+  const bool fast_mv = a.stage_metric && (dim & 1) == 0;
+#define MB200_NUTS_MATVEC(P, V)                                               \
+  do {                                                                        \
+    if (fast_mv) inv_metric_apply_staged<KP>(minv, dim, lane, psm, P, V);     \
+    else inv_metric_apply<KP, 1>(metric_kind, minv, dim, lane, psm, P, V);    \
+  } while (0)
+#else
+#define MB200_NUTS_MATVEC(P, V) inv_metric_apply<KP, 1>(metric_kind, minv, dim, lane, psm, P, V)
+#endif
   const Target target(model, dim);
   const bool slice = a.slice != 0, euclid = a.euclidean_criterion != 0, extra = a.extra_checks != 0;
   const size_t ws_stride = (size_t)(7 + 2 + NUTS_REC * (1 + a.max_depth)) * DP;
@@ -211,7 +221,7 @@ __global__ void __launch_bounds__(KP == 2 ? 384 : 256)
       kin = warp_sum(kin);
       return K::neg_log_dens(target, dim, lane, q[0]) + 0.5 * kin;
     };
-    inv_metric_apply<KP, 1>(metric_kind, minv, dim, lane, psm, p, v);
+    MB200_NUTS_MATVEC(p, v);
     const double h_init = energy();
     const double log_u = slice ? log(uniform()) - h_init : 0.0;  // transitions.py:832-839
     auto leaf_weight = [&](double h) -> double {
@@ -250,13 +260,13 @@ __global__ void __launch_bounds__(KP == 2 ? 384 : 256)
         // LeapfrogIntegrator._step (integrators.py:170-173), two separately rounded half kicks
 #pragma unroll
         for (int e = 0; e < NV; ++e) p[0][e] = __dsub_rn(p[0][e], __dmul_rn(0.5 * dt, g[e]));
-        inv_metric_apply<KP, 1>(metric_kind, minv, dim, lane, psm, p, v);
+        MB200_NUTS_MATVEC(p, v);
 #pragma unroll
         for (int e = 0; e < NV; ++e) q[0][e] = __dadd_rn(q[0][e], __dmul_rn(dt, v[0][e]));
         K::grad(target, dim, lane, q[0], g);
 #pragma unroll
         for (int e = 0; e < NV; ++e) p[0][e] = __dsub_rn(p[0][e], __dmul_rn(0.5 * dt, g[e]));
-        inv_metric_apply<KP, 1>(metric_kind, minv, dim, lane, psm, p, v);
+        MB200_NUTS_MATVEC(p, v);
         double h = energy();
         if (h != h) h = INFINITY;  // transitions.py:626
         w_cur = leaf_weight(h);
@@ -392,5 +402,7 @@ __global__ void __launch_bounds__(KP == 2 ? 384 : 256)
     }
   }
 }
+
+#undef MB200_NUTS_MATVEC
 
 }  // namespace mb200
