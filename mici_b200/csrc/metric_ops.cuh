@@ -83,8 +83,8 @@ __device__ __forceinline__ void inv_metric_apply(int METRIC, const double* __res
     }
   }
 
-// Round-2 candidate (NOT enabled by default, not yet validated on hardware; build with
-// -DMB200_NUTS_LDS_MATVEC): v = A p for ONE chain per warp with the dense symmetric A staged in
+// Experiment (NOT enabled by default; build with -DMB200_NUTS_LDS_MATVEC; parity-correct but
+// measured SLOWER than the plain loop in round 1: 47 vs 64 M steps/s, profiles/r01_notes.md): v = A p for ONE chain per warp with the dense symmetric A staged in
 // shared memory -- ld.shared.v2 row reads, four rows per trip with four independent accumulator
 // sets (the profile of the plain loop shows one row load + 4 FMAs per trip with the loop / bounds
 // logic around them and generic-address loads: profiles/r01_nuts_c1_ncu_lines.txt).  Requires
