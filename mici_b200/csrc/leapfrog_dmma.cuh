@@ -30,6 +30,8 @@
 //     update phase the other three keep the sub-partition's DMMA pipe fed (one warp alone
 //     reaches 80 % of the pipe, two 96 %: profiles/r01_notes.md).
 #pragma once
+#include <type_traits>
+
 #include "targets.cuh"
 
 namespace mb200 {
@@ -46,12 +48,17 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 __device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
-#if defined(MB200_EXP) && MB200_EXP == 4  // experiment: no group barriers (racy, results invalid)
-  __syncwarp();
-#else
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-#endif
 }
+
+// Profiling hook (profiles/tools/k1_bench.cu defines it to record clock64 per warp and phase);
+// expands to nothing in the library build.
+#ifndef MB200_K1_TRACE
+#define MB200_K1_TRACE(phase)
+#endif
+#ifndef MB200_K1_MARK
+#define MB200_K1_MARK(id)
+#endif
 
 constexpr int DMMA_TILES_PER_CTA = 7;
 #ifndef MB200_DMMA_GROUPS
@@ -68,14 +75,20 @@ __host__ __device__ constexpr int dmma_tile_start(int g) {
 __host__ __device__ constexpr int dmma_tile_count(int g) { return g < 7 - DMMA_GROUPS ? 2 : 1; }
 constexpr int DMMA_THREADS = 32 * 4 * DMMA_GROUPS;
 constexpr int DMMA_ROWS_PER_CTA = 8 * DMMA_TILES_PER_CTA;  // 56 chains
-constexpr int DMMA_MAX_RED = 4;
 
 template <int DP>
 struct DmmaSmem {
-  static constexpr int LDA = DP + 4;  // row stride (doubles): rows shift by 32 B mod 128 B
+  // row stride (doubles): rows shift by 64 B mod 128 B, so the 128-bit fragment loads of a
+  // quarter-warp (2 rows x 4 lanes x 16 B) touch every bank once
+  static constexpr int LDA = DP + 8;
   double A[DP * LDA];
   double P[DMMA_ROWS_PER_CTA * LDA];
-  double part[4][DMMA_MAX_RED][DMMA_ROWS_PER_CTA];  // [warp-in-group][reduction][row]
+  // per-chain exchange between the four warps that share a row: partial sums of the target's
+  // reduction ([row][column quarter], one 32-byte line per row) and the scalar evaluated by the
+  // owner of coordinate 0; `ex` is reused for the energy partials after the last step
+  double psum[DMMA_ROWS_PER_CTA][4];
+  double rscal[DMMA_ROWS_PER_CTA];
+  double ex[2][DMMA_ROWS_PER_CTA][4];
   unsigned long long mbar;
 };
 
@@ -87,36 +100,46 @@ struct DmmaSmem {
 //   drift: q += s . (eps * A)                == q + (dir*eps) * (A p)
 // so the per-chain direction only appears in the load and the store, sm.A holds eps*A (scaled
 // once after the TMA lands), and the drift is a DMMA whose accumulator operand IS q: positions
-// never leave the accumulator registers and the only fp64-ALU work per coordinate and step is
-// one FMA for the target's reduction and one per half-kick.  (Every fp64-ALU instruction costs
-// DMMA issue slots on the shared pipe -- measured ~8 cycles each, profiles/r01_notes.md.)
+// never leave the accumulator registers.
+//
+// Scheduling facts this is written around (profiles/r02_notes.md, fp64_arb / fp64_mix / k1_trace):
+// a warp whose next instruction is a scalar FP64 operation makes NO progress while two or more
+// other warps of its SM sub-partition stream DMMAs, so the per-step update phase of every group
+// ends up running after the drifts of the whole sub-partition (the groups lock-step) and the
+// step time is  drift (DMMA-pipe bound) + update phase (issue / latency bound).  The update phase
+// is therefore kept as short as possible: no bounds logic (phantom coordinates are zero and stay
+// zero under every registry target's kick), one FMA chain for the reduction, the per-chain scalar
+// (funnel: exp(-v)) published by its owner instead of being summed, own momenta pre-loaded
+// before the group barrier, two barriers per step.
 template <class Target, int DP, int MT>
 __device__ __forceinline__ void leapfrog_dmma_group(
     DmmaSmem<DP>& sm, const Target& target, const double* q_in, const double* p_in,
     double* q_out, double* p_out, const int32_t* __restrict__ dir, int64_t n_chains, int dim,
     double step_size, int n_steps, double* __restrict__ h_out, int32_t* __restrict__ status,
-    int32_t* __restrict__ n_done, int64_t chain0, int row0, int w, int lane, int bar_id) {
+    int32_t* __restrict__ n_done, int64_t chain0, int row0, int w, int lane, int bar_id, int cta_threads) {
   constexpr int LDA = DmmaSmem<DP>::LDA;
   constexpr int NT = DP / 32;  // 8-column tiles per warp
   constexpr int KS = DP / 4;   // k steps
-  constexpr int NRED = Target::NRED;
-  static_assert(NRED + 2 <= DMMA_MAX_RED, "too many reductions");
   const int r = lane >> 2, c = lane & 3;
   const int col0 = w * (DP / 4);  // first column of this warp's slice
   const double mh = -0.5 * step_size;
+  // the lane that holds coordinate 0 of its rows (in q[mt][0][0])
+  const bool owner = (w == 0) && (c == 0);
 
   // registers: positions of the slice in C-fragment layout (row 8mt + r, columns
   // col0 + 8nt + 2c + {0,1}); signed momenta live in sm.P with the same ownership
   double q[MT][NT][2], sgn[MT];
   bool live[MT];
   double2* pslot[MT];  // &sm.P[row][col0 + 2c]; + 4*nt double2 per column tile
+  int row[MT];
 
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
-    const int64_t ch = chain0 + row0 + 8 * mt + r;
+    row[mt] = row0 + 8 * mt + r;
+    const int64_t ch = chain0 + row[mt];
     live[mt] = ch < n_chains;
     sgn[mt] = (live[mt] && dir != nullptr && dir[ch] < 0) ? -1.0 : 1.0;
-    pslot[mt] = reinterpret_cast<double2*>(&sm.P[(row0 + 8 * mt + r) * LDA + col0 + 2 * c]);
+    pslot[mt] = reinterpret_cast<double2*>(&sm.P[row[mt] * LDA + col0 + 2 * c]);
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       const int i = col0 + 8 * nt + 2 * c;
@@ -130,138 +153,139 @@ __device__ __forceinline__ void leapfrog_dmma_group(
     }
   }
 
-  double red[MT][NRED + 1];
+  int s = -1;  // current step (read by the profiling hook only)
 
-  // per-chain sum reductions of the target over the full row: partial over this warp's slice,
-  // exchanged through shared memory.  The barrier also orders "all A-fragment reads of sm.P
-  // done" before the in-place momentum update that follows.
-  auto reduce_rows = [&]() {
-    if (NRED > 0) {
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        // independent per-tile terms, then a pairwise tree: keeps the dependent fp64 chain short
-        // (every dependent op queues behind other warps' DMMAs on the shared pipe)
-        double term[NT][NRED + 1];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-#pragma unroll
-          for (int k = 0; k < NRED; ++k) term[nt][k] = 0.0;
-          target.accumulate(col0 + 8 * nt + 2 * c, q[mt][nt][0], q[mt][nt][1], term[nt]);
-        }
-#pragma unroll
-        for (int k = 0; k < NRED; ++k) {
-          if (NT == 4) red[mt][k] = (term[0][k] + term[1][k]) + (term[2 % NT][k] + term[3 % NT][k]);
-          else if (NT == 3) red[mt][k] = (term[0][k] + term[1][k]) + term[2 % NT][k];
-          else if (NT == 2) red[mt][k] = term[0][k] + term[1 % NT][k];
-          else red[mt][k] = term[0][k];
-        }
-#pragma unroll
-        for (int k = 0; k < NRED; ++k) {
-          double v = red[mt][k];
-          v += __shfl_xor_sync(FULL_MASK, v, 1);
-          v += __shfl_xor_sync(FULL_MASK, v, 2);
-          if (c == 0) sm.part[w][k][row0 + 8 * mt + r] = v;
-        }
-      }
-    }
-    named_barrier_sync(bar_id, 128);
-    if (NRED > 0) {
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-        for (int k = 0; k < NRED; ++k) {
-          const int row = row0 + 8 * mt + r;
-          red[mt][k] = ((sm.part[0][k][row] + sm.part[1][k][row]) + sm.part[2][k][row]) +
-                       sm.part[3][k][row];
-        }
-    }
-  };
-
-  // s -= (eps/2) * grad l(q), `kicks` times (1 or 2: the two half-steps either side of a step
-  // boundary stay two separately rounded updates, systems.py:152), one FMA per coordinate and
-  // kick; then make the new momenta visible to the group.
-  auto kick_and_publish = [&](int kicks) {
+  // ---- update phase, part 1 (before the group barrier): this warp's share of the per-chain
+  // reduction and, on the owner lanes, the per-chain scalar
+  auto publish_partials = [&]() {
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      const double ks = target.kick_scalar(red[mt], mh);
+      if (Target::TILE_SUM) {
+        // sum of squares over the slice: two FMA chains per row
+        double t0 = q[mt][0][0] * q[mt][0][0];
+        if (Target::COORD0) t0 = owner ? 0.0 : t0;
+        t0 = fma(q[mt][0][1], q[mt][0][1], t0);
+        double t1 = 0.0;
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const int i = col0 + 8 * nt + 2 * c;
-        double2 pv = pslot[mt][4 * nt];
-        if (i < dim) {
-          if (kicks >= 1) target.kick_pair(i, q[mt][nt][0], q[mt][nt][1], red[mt], mh, ks, pv.x, pv.y);
-          if (kicks >= 2) target.kick_pair(i, q[mt][nt][0], q[mt][nt][1], red[mt], mh, ks, pv.x, pv.y);
+        for (int nt = 1; nt < NT; ++nt) {
+          double& t = (nt & 1) ? t1 : t0;
+          t = fma(q[mt][nt][0], q[mt][nt][0], t);
+          t = fma(q[mt][nt][1], q[mt][nt][1], t);
         }
-        pslot[mt][4 * nt] = pv;
+        double v = t0 + t1;
+        v += __shfl_xor_sync(FULL_MASK, v, 1);
+        v += __shfl_xor_sync(FULL_MASK, v, 2);
+        if (c == 0) sm.psum[row[mt]][w] = v;
       }
+      if (Target::ROW_SCALAR && owner) sm.rscal[row[mt]] = target.row_scalar(q[mt][0][0]);
     }
-    named_barrier_sync(bar_id, 128);
   };
 
-  // acc += S * (eps A) on the tensor pipe (acc = q for the drift, acc = 0 for the energy)
-  auto drift = [&](double (&acc)[MT][NT][2]) {
-    const double* a_base = &sm.P[(row0 + r) * LDA + c];
-    const double* b_base = &sm.A[(col0 + r) * LDA + c];
-#pragma unroll 8
-    for (int j = 0; j < KS; ++j) {
-      double a[MT], b[NT];
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) a[mt] = a_base[mt * 8 * LDA + 4 * j];
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) b[nt] = b_base[nt * 8 * LDA + 4 * j];
+  // ---- update phase, part 2: s -= (eps/2) * grad l(q), KICKS times (1 or 2: the two half-steps
+  // either side of a step boundary stay two separately rounded updates, systems.py:152), one FMA
+  // per coordinate and kick; then make the new momenta visible to the group.  The first barrier
+  // also orders "all A-fragment reads of sm.P done" before the in-place update.
+  auto kick_and_publish = [&](auto kicks_tag) {
+    constexpr int KICKS = decltype(kicks_tag)::value;
+    double2 pv[MT][NT];
+    if (KICKS > 0) {
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        for (int nt = 0; nt < NT; ++nt) pv[mt][nt] = pslot[mt][4 * nt];  // own slots: no hazard
+    }
+    MB200_K1_TRACE(2);
+    named_barrier_sync(bar_id, 128);
+    MB200_K1_TRACE(3);
+    if (KICKS == 0) return;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const double rs = Target::ROW_SCALAR ? sm.rscal[row[mt]] : 1.0;
+      const double coef = target.kick_coef(mh, rs);
+      double c00 = coef, a00 = q[mt][0][0];
+      if (Target::COORD0 && w == 0) {  // warp-uniform; only the owner lanes differ
+        const double4 ps = *reinterpret_cast<const double4*>(&sm.psum[row[mt]][0]);
+        const double g0 = target.grad0(q[mt][0][0], ((ps.x + ps.y) + ps.z) + ps.w, rs);
+        c00 = owner ? mh : coef;
+        a00 = owner ? g0 : a00;
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        double2 v = pv[mt][nt];
+        if (Target::LINEAR) {
+#pragma unroll
+          for (int k = 0; k < KICKS; ++k) {
+            v.x = (nt == 0) ? fma(c00, a00, v.x) : fma(coef, q[mt][nt][0], v.x);
+            v.y = fma(coef, q[mt][nt][1], v.y);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < KICKS; ++k)
+            target.kick_pair_nl(mh, q[mt][nt][0], q[mt][nt][1], v.x, v.y);
+        }
+        pslot[mt][4 * nt] = v;
+      }
+    }
+    MB200_K1_TRACE(4);
+#if defined(K1_LOCKSTEP)
+    named_barrier_sync(8, cta_threads);
+#else
+    named_barrier_sync(bar_id, 128);
+#endif
+    MB200_K1_TRACE(5);
+  };
+  using K0 = std::integral_constant<int, 0>;
+  using K1 = std::integral_constant<int, 1>;
+  using K2 = std::integral_constant<int, 2>;
+
+  // acc += S * (eps A) on the tensor pipe (acc = q for the drift, acc = 0 for the energy).
+  // Fragments are fetched with 128-bit loads: lane c of a row holds k = 8J + 2c and 8J + 2c + 1,
+  // the two DMMAs of a k-pair contract {8J, 8J+2, 8J+4, 8J+6} and {8J+1, ..., 8J+7} (the pairing of
+  // lanes with k is free as long as the A and B fragments agree).
+  auto drift = [&](double (&acc)[MT][NT][2]) {
+    const double2* a_base = reinterpret_cast<const double2*>(&sm.P[(row0 + r) * LDA + 2 * c]);
+    const double2* b_base = reinterpret_cast<const double2*>(&sm.A[(col0 + r) * LDA + 2 * c]);
+#pragma unroll 4
+    for (int j = 0; j < KS / 2; ++j) {
+      double2 a[MT], b[NT];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) a[mt] = a_base[mt * 4 * LDA + 4 * j];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) b[nt] = b_base[nt * 4 * LDA + 4 * j];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt].x, b[nt].x);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, b[nt].y);
     }
   };
 
-  reduce_rows();
-  kick_and_publish(n_steps > 0 ? 1 : 0);
-#ifndef MB200_EXP
-#define MB200_EXP 0
-#endif
-  for (int s = 0; s < n_steps; ++s) {
+  MB200_K1_MARK(4);
+  publish_partials();
+  if (n_steps > 0) kick_and_publish(K1{});
+  else kick_and_publish(K0{});
+  MB200_K1_MARK(5);
+  for (s = 0; s < n_steps - 1; ++s) {
+    MB200_K1_TRACE(0);
     drift(q);  // h2_flow (systems.py:363): q += dir*eps * (A p)
-#if MB200_EXP == 2 || MB200_EXP == 5 || MB200_EXP == 6  // experiment: drift only (results invalid)
-    continue;
-#endif
-    reduce_rows();
-#if MB200_EXP == 3  // experiment: one barrier per step (results invalid)
-    continue;
-#endif
-    // closes step s and (cached gradient) opens step s+1
-    kick_and_publish(s + 1 < n_steps ? 2 : 1);
+    MB200_K1_TRACE(1);
+    publish_partials();
+    kick_and_publish(K2{});  // closes step s and (cached gradient) opens step s+1
+  }
+  if (n_steps > 0) {
+    drift(q);
+    publish_partials();
+    kick_and_publish(K1{});
   }
 
-#if MB200_EXP == 8  // experiment 8: re-run the loop with per-phase cycle counters (CTA 0 only)
-  if (h_out != nullptr && blockIdx.x == 0) {
-    long long t_drift = 0, t_red = 0, t_kick = 0;
-    for (int s = 0; s < n_steps; ++s) {
-      const long long t0 = clock64();
-      drift(q);
-      const long long t1 = clock64();
-      reduce_rows();
-      const long long t2 = clock64();
-      kick_and_publish(2);
-      const long long t3 = clock64();
-      t_drift += t1 - t0, t_red += t2 - t1, t_kick += t3 - t2;
-    }
-    if (lane == 0) {
-      const int wid = (bar_id - 1) * 4 + w;
-      double* dbg = h_out + 4096;  // debug area in the h buffer (read by profiles/tools/phase_c1.py)
-      dbg[wid * 4 + 0] = (double)t_drift / n_steps;
-      dbg[wid * 4 + 1] = (double)t_red / n_steps;
-      dbg[wid * 4 + 2] = (double)t_kick / n_steps;
-      dbg[wid * 4 + 3] = (double)MT;
-    }
-    return;
-  }
-#endif
+  MB200_K1_MARK(6);
   // ---- store (p = dir * s)
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
-    const int64_t ch = chain0 + row0 + 8 * mt + r;
+    const int64_t ch = chain0 + row[mt];
     if (!live[mt]) continue;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
@@ -280,16 +304,24 @@ __device__ __forceinline__ void leapfrog_dmma_group(
     }
   }
 
+  MB200_K1_MARK(7);
   // ---- Hamiltonian of the final state: l(q) + p . (A p) / 2   (systems.py:187-196, 348-350)
+  // sm.psum / sm.rscal hold the reduction of the final positions (last update phase)
   if (h_out != nullptr) {
     double l[MT], kin[MT], u[MT][NT][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
+      double red[2] = {0.0, 1.0};
+      if (Target::TILE_SUM) {
+        const double4 ps = *reinterpret_cast<const double4*>(&sm.psum[row[mt]][0]);
+        red[0] = ((ps.x + ps.y) + ps.z) + ps.w;
+      }
+      if (Target::ROW_SCALAR) red[1] = sm.rscal[row[mt]];
       l[mt] = 0.0;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int i = col0 + 8 * nt + 2 * c;
-        if (i < dim) l[mt] += target.nld_pair(i, q[mt][nt][0], q[mt][nt][1], red[mt]);
+        if (i < dim) l[mt] += target.nld_pair(i, q[mt][nt][0], q[mt][nt][1], red);
         u[mt][nt][0] = 0.0, u[mt][nt][1] = 0.0;
       }
     }
@@ -307,25 +339,21 @@ __device__ __forceinline__ void leapfrog_dmma_group(
       kin[mt] += __shfl_xor_sync(FULL_MASK, kin[mt], 2);
       l[mt] += __shfl_xor_sync(FULL_MASK, l[mt], 1);
       l[mt] += __shfl_xor_sync(FULL_MASK, l[mt], 2);
-    }
-    named_barrier_sync(bar_id, 128);  // every warp has consumed the gradient partials
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
       if (c == 0) {
-        sm.part[w][0][row0 + 8 * mt + r] = kin[mt];
-        sm.part[w][1][row0 + 8 * mt + r] = l[mt];
+        sm.ex[0][row[mt]][w] = kin[mt];
+        sm.ex[1][row[mt]][w] = l[mt];
       }
+    }
     named_barrier_sync(bar_id, 128);
     if (w == 0 && c == 0) {
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         if (!live[mt]) continue;
-        const int row = row0 + 8 * mt + r;
-        const double ks = ((sm.part[0][0][row] + sm.part[1][0][row]) + sm.part[2][0][row]) +
-                          sm.part[3][0][row];
-        const double ls = ((sm.part[0][1][row] + sm.part[1][1][row]) + sm.part[2][1][row]) +
-                          sm.part[3][1][row];
-        h_out[chain0 + row] = ls + 0.5 * (ks / step_size);
+        const double4 k4 = *reinterpret_cast<const double4*>(&sm.ex[0][row[mt]][0]);
+        const double4 l4 = *reinterpret_cast<const double4*>(&sm.ex[1][row[mt]][0]);
+        const double ks = ((k4.x + k4.y) + k4.z) + k4.w;
+        const double ls = ((l4.x + l4.y) + l4.z) + l4.w;
+        h_out[chain0 + row[mt]] = ls + 0.5 * (ks / step_size);
       }
     }
   }
@@ -351,21 +379,17 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   // sub-partition is systematically slower and the other three idle at the group barriers.
   const int w = ((warp & 3) + group) & 3;
   const Target target(model, dim);
+  MB200_K1_MARK(0);
 
-  // ---- stage A = M^-1 into shared memory: one TMA bulk copy per row, one mbarrier
+  // ---- stage A = M^-1 into shared memory: one TMA bulk copy per row, one mbarrier.  Issued
+  // first; everything below until the wait overlaps the copies.
   const uint32_t mbar = smem_u32(&sm.mbar);
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  // zero the padding (rows >= dim, columns >= dim) -- disjoint from the TMA destinations
-  for (int idx = tid; idx < DP * LDA; idx += blockDim.x) {
-    const int row = idx / LDA, col = idx - row * LDA;
-    if (row >= dim || col >= dim) sm.A[idx] = 0.0;
-  }
-  for (int idx = tid; idx < DMMA_ROWS_PER_CTA * LDA; idx += blockDim.x) sm.P[idx] = 0.0;
-  __syncthreads();
-  if (warp == 0) {  // the 32 lanes of warp 0 issue the row copies (one TMA bulk copy per row)
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
     const uint32_t row_bytes = (uint32_t)dim * 8u;
     if (lane == 0)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar),
@@ -373,7 +397,7 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
                    : "memory");
     __syncwarp();
 #pragma unroll 1
-    for (int row = lane; row < dim; row += 32) {
+    for (int row = lane; row < dim; row += 32) {  // the 32 lanes issue the row copies
       const unsigned long long src =
           reinterpret_cast<unsigned long long>(minv) + (unsigned long long)row * row_bytes;
       asm volatile(
@@ -383,6 +407,28 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
           : "memory");
     }
   }
+  // pull this CTA's first block of state rows towards L2 while A is in flight
+  {
+    const int64_t chain0 = (int64_t)blockIdx.x * DMMA_ROWS_PER_CTA;
+    const int64_t left = n_chains - chain0;
+    const int64_t rows = left < DMMA_ROWS_PER_CTA ? left : DMMA_ROWS_PER_CTA;
+    const int64_t lines = (rows * dim * 8 + 127) / 128;
+    for (int64_t i = tid; i < 2 * lines; i += blockDim.x) {
+      const double* base = (i < lines ? q_in : p_in) + (size_t)chain0 * dim;
+      const char* ptr = reinterpret_cast<const char*>(base) + (i < lines ? i : i - lines) * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+    }
+  }
+  // zero the part of the padding that the fragment loads read (rows / columns in [dim, DP)) --
+  // disjoint from the TMA destinations; sm.P needs none (every slot that is read is written by
+  // the state load, phantom coordinates as zeros)
+  if (dim < DP) {
+    for (int idx = tid; idx < DP * DP; idx += blockDim.x) {
+      const int row = idx / DP, col = idx - row * DP;
+      if (row >= dim || col >= dim) sm.A[row * LDA + col] = 0.0;
+    }
+  }
+  MB200_K1_MARK(1);
   // wait for the bytes to land (phase 0), then scale the staged metric: sm.A = eps * A
   {
     uint32_t done = 0;
@@ -395,26 +441,33 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
           : "memory");
     }
   }
-  for (int idx = tid; idx < DP * LDA; idx += blockDim.x) sm.A[idx] = step_size * sm.A[idx];
+  MB200_K1_MARK(2);
+  __syncthreads();  // the zero-fill above is complete as well
+#pragma unroll 4
+  for (int idx = tid; idx < DP * (DP / 2); idx += blockDim.x) {
+    const int row = idx / (DP / 2), c2 = idx - row * (DP / 2);
+    double2* ptr = reinterpret_cast<double2*>(&sm.A[row * LDA]) + c2;
+    double2 v = *ptr;
+    v.x *= step_size, v.y *= step_size;
+    *ptr = v;
+  }
   __syncthreads();
+  MB200_K1_MARK(3);
 
   for (int64_t blk = blockIdx.x; blk * DMMA_ROWS_PER_CTA < n_chains; blk += gridDim.x) {
     const int64_t chain0 = blk * DMMA_ROWS_PER_CTA;
     const int64_t left = n_chains - chain0;
     const int tiles = (int)((left >= DMMA_ROWS_PER_CTA) ? DMMA_TILES_PER_CTA : (left + 7) / 8);
     const int row0 = 8 * dmma_tile_start(group);
+    int active_groups = 0;
+    for (int g = 0; g < DMMA_GROUPS; ++g) active_groups += tiles > dmma_tile_start(g);
+    const int cta_threads = 128 * active_groups;
     int mt = tiles - dmma_tile_start(group);
     mt = mt > dmma_tile_count(group) ? dmma_tile_count(group) : mt;
 #define MB200_GROUP(MT)                                                                       \
   leapfrog_dmma_group<Target, DP, MT>(sm, target, q_in, p_in, q_out, p_out, dir, n_chains,    \
                                       dim, step_size, n_steps, h_out, status, n_done, chain0, \
-                                      row0, w, lane, 1 + group)
-#if defined(MB200_EXP) && MB200_EXP == 5  // experiment: 2 warps per sub-partition
-    if (group >= 2) mt = 0;
-#endif
-#if defined(MB200_EXP) && MB200_EXP == 6  // experiment: 1 warp per sub-partition
-    if (group >= 1) mt = 0;
-#endif
+                                      row0, w, lane, 1 + group, cta_threads)
     if (mt == 2) MB200_GROUP(2);
     else if (mt == 1) MB200_GROUP(1);
 #undef MB200_GROUP
@@ -456,11 +509,10 @@ static int dispatch_dmma_dim(const double* q_in, const double* p_in, double* q_o
 
 // Returns MB200_ERR_UNSUPPORTED when the shape is outside this kernel's domain (the caller
 // then uses the general-dimension kernel).
-static int leapfrog_dmma_dispatch(const double* q_in, const double* p_in, double* q_out,
-                                  double* p_out, const int32_t* dir, int64_t n, int dim,
-                                  double eps, int n_steps, const double* minv, const ModelArgs& m,
-                                  double* h_out, int32_t* status, int32_t* n_done,
-                                  cudaStream_t st) {
+int leapfrog_dmma_dispatch(const double* q_in, const double* p_in, double* q_out, double* p_out,
+                           const int32_t* dir, int64_t n, int dim, double eps, int n_steps,
+                           const double* minv, const ModelArgs& m, double* h_out, int32_t* status,
+                           int32_t* n_done, cudaStream_t st) {
   if (dim > 128 || (dim & 1) || dim < 8) return MB200_ERR_UNSUPPORTED;
   if (!(eps != 0.0) || !isfinite(eps)) return MB200_ERR_UNSUPPORTED;  // eps*A formulation
   if ((reinterpret_cast<uintptr_t>(minv) & 15) != 0) return MB200_ERR_UNSUPPORTED;

@@ -28,15 +28,23 @@ struct StdGaussianTarget {
   __device__ __forceinline__ double nld_pair(int, double q0, double q1, const double*) const {
     return 0.5 * (q0 * q0 + q1 * q1);
   }
-  // fused momentum kick p += mh * grad (mh = -step/2): per-row scalar prepared once, then one
-  // fused multiply-add per coordinate (used by the tensor-core kernel)
-  __device__ __forceinline__ double kick_scalar(const double*, double mh) const { return mh; }
-  __device__ __forceinline__ void kick_pair(int, double q0, double q1, const double*, double mh,
-                                            double, double& p0, double& p1) const {
-    p0 = fma(mh, q0, p0);
-    p1 = fma(mh, q1, p1);
-  }
+  // ---- tile interface of the tensor-core kernel (leapfrog_dmma.cuh), see the note below
+  static constexpr bool TILE_SUM = false, ROW_SCALAR = false, LINEAR = true, COORD0 = false;
+  __device__ __forceinline__ double row_scalar(double) const { return 1.0; }
+  __device__ __forceinline__ double kick_coef(double mh, double) const { return mh; }
+  __device__ __forceinline__ double grad0(double q0, double, double) const { return q0; }
+  __device__ __forceinline__ void kick_pair_nl(double, double, double, double&, double&) const {}
 };
+
+// Tile interface (tensor-core kernel).  The kernel owns coordinates in aligned pairs and applies
+// the momentum kick p += mh * grad l(q) (mh = -step/2) with as few fp64 instructions as possible:
+//   LINEAR      grad_i = rs * q_i for every coordinate (but possibly coordinate 0): the kick is
+//               one FMA per coordinate with the per-chain coefficient kick_coef(mh, rs);
+//               otherwise kick_pair_nl(mh, x, y, p0, p1) applies the pair's kick itself
+//   ROW_SCALAR  rs = row_scalar(q[0]) is evaluated once per chain by the owner of coordinate 0
+//   TILE_SUM    S = sum over coordinates of q_i^2 (coordinate 0 excluded when COORD0) is
+//               reduced per chain
+//   COORD0      coordinate 0's gradient is grad0(q[0], S, rs) instead of the generic form
 
 // v = q[0], x = q[1:]:  l = v^2/18 + (D-1) v/2 + exp(-v) |x|^2 / 2
 struct NealFunnelTarget {
@@ -63,24 +71,17 @@ struct NealFunnelTarget {
     if (i != 0) return 0.0;
     return q0 * q0 / 18.0 + 0.5 * (dim - 1) * q0 + 0.5 * red[1] * red[0];
   }
-  // grad = exp(-v) * x for every coordinate but the first: fold exp(-v) into the kick scalar
-  __device__ __forceinline__ double kick_scalar(const double* red, double mh) const {
-    return mh * red[1];
+  // ---- tile interface of the tensor-core kernel: grad_i = exp(-v) x_i for i >= 1;
+  // grad_0 = v/9 + (D-1)/2 - exp(-v) |x|^2 / 2, with v/9 as a multiplication by the rounded
+  // reciprocal and the sum as two FMAs (the fp64 division is a ~15-deep dependent chain on the
+  // critical path of a 4-warp group; differs from grad_pair's `q0 / 9.0` by at most 1 ulp)
+  static constexpr bool TILE_SUM = true, ROW_SCALAR = true, LINEAR = true, COORD0 = true;
+  __device__ __forceinline__ double row_scalar(double v) const { return exp(-v); }
+  __device__ __forceinline__ double kick_coef(double mh, double rs) const { return mh * rs; }
+  __device__ __forceinline__ double grad0(double v, double xx, double rs) const {
+    return fma(-0.5 * rs, xx, fma(v, 1.0 / 9.0, 0.5 * (dim - 1)));
   }
-  __device__ __forceinline__ void kick_pair(int i, double q0, double q1, const double* red,
-                                            double mh, double mhe, double& p0, double& p1) const {
-    if (i == 0) {
-      // v/9 as a multiplication by the rounded reciprocal and the sum as two FMAs: the fp64
-      // division is a ~15-deep dependent chain that sits on the critical path of the whole
-      // 4-warp group in the tensor-core kernel (profiles/r01_notes.md); differs from
-      // grad_pair's `q0 / 9.0` by at most 1 ulp.
-      const double g0 = fma(-0.5 * red[1], red[0], fma(q0, 1.0 / 9.0, 0.5 * (dim - 1)));
-      p0 = fma(mh, g0, p0);
-    } else {
-      p0 = fma(mhe, q0, p0);
-    }
-    p1 = fma(mhe, q1, p1);
-  }
+  __device__ __forceinline__ void kick_pair_nl(double, double, double, double&, double&) const {}
 };
 
 // pairs (x, y) = (q[2k], q[2k+1]):  l = sum x^2/8 + (y - b x^2)^2 / 2
@@ -99,11 +100,15 @@ struct BananaTarget {
     const double r = y - b * x * x;
     return x * x / 8.0 + 0.5 * r * r;
   }
-  __device__ __forceinline__ double kick_scalar(const double*, double mh) const { return mh; }
-  __device__ __forceinline__ void kick_pair(int i, double x, double y, const double* red,
-                                            double mh, double, double& p0, double& p1) const {
+  // ---- tile interface of the tensor-core kernel: the gradient is not linear in q
+  static constexpr bool TILE_SUM = false, ROW_SCALAR = false, LINEAR = false, COORD0 = false;
+  __device__ __forceinline__ double row_scalar(double) const { return 1.0; }
+  __device__ __forceinline__ double kick_coef(double mh, double) const { return mh; }
+  __device__ __forceinline__ double grad0(double q0, double, double) const { return q0; }
+  __device__ __forceinline__ void kick_pair_nl(double mh, double x, double y, double& p0,
+                                               double& p1) const {
     double g0, g1;
-    grad_pair(i, x, y, red, g0, g1);
+    grad_pair(0, x, y, nullptr, g0, g1);
     p0 = fma(mh, g0, p0);
     p1 = fma(mh, g1, p1);
   }
