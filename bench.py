@@ -4,11 +4,21 @@
     python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K --warmup W   # CPU reference arm
 
-Workload (BASELINE.json configs[1], "C1"): dense-mass Euclidean leapfrog on Neal's funnel,
-D = 128, 8192 chains per GPU, step size 0.01.  One bench "step" = one launch of
+Headline workload (BASELINE.json configs[1], "C1"): dense-mass Euclidean leapfrog on Neal's
+funnel, D = 128, 8192 chains per GPU, step size 0.01.  One bench "step" = one launch of
 ``LEAPFROG_PER_LAUNCH`` fused leapfrog steps over the whole batch (the trajectory loop of
 ``transitions.py:289-291``).  Metric: aggregate leapfrog steps / s = chains x leapfrog steps /
 time.  Prints ONE JSON line (rank 0).
+
+The same line carries, under ``"workloads"``, the other GPU configurations of BASELINE.json
+(C2 SoftAbs implicit leapfrog, C3 constrained leapfrog on the torus, C4 dense Riemannian D = 512,
+8192 chains per GPU -- 65 536 over 8 GPUs), each with its own CUDA-event time, roofline entry
+and (at N = 1) a CPU baseline from the same worker pool, and under ``"strong_scaling"`` the C1
+launch with the 8192 chains divided over the N ranks.
+
+CPU arm: the UNMODIFIED reference (``mici``, imported from ``/root/reference/src`` or from the
+copy ``oracle/build_ref.sh`` places under ``oracle/_ref``) stepping chains in a process pool with
+one worker per usable core (``oracle/ref_baseline.py``).
 """
 
 from __future__ import annotations
@@ -30,13 +40,24 @@ WORKLOAD = "C1: dense-mass Euclidean leapfrog, Neal's funnel D=128, 8192 chains 
 N_CHAINS = 8192
 DIM = 128
 LEAPFROG_PER_LAUNCH = 50
-FP64_PEAK_TFLOPS = 37.1  # measured DMMA peak on this pool's B200 (profiles/r01_fp64_peak.txt)
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel at this
-# workload, from the `ncu --set full` capture summarised in
-# profiles/r01_c1_dmma_v3_ncu_summary.txt (16 970 496 B read, 0 B written: the outputs are still
-# in L2 when the kernel ends).  Algorithmic bytes per launch: 8192 x 4096 B = 33.5 MB.
-NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH = 16970496
 HBM_FALLBACK_GBS = 6650.0
+# FP64 peaks of this pool's B200 measured with profiles/tools/fp64_peak.cu
+# (profiles/r01_fp64_peak.txt; = 148 SMs x 64 FMA/clk x 1.965 GHz); not in MEASURED_PEAKS.json.
+FP64_DMMA_PEAK_TFLOPS = 37.1
+FP64_DFMA_PEAK_TFLOPS = 34.1
+FP64_PEAK_SOURCE = "constant: profiles/r01_fp64_peak.txt (builder-measured microbenchmark)"
+
+# The other GPU configurations of BASELINE.json.  `launch`: leapfrog steps fused per launch;
+# `reps`: timed launches; `cpu`: (chains per worker, steps, seconds) of the CPU sample.
+WORKLOADS = {
+    "C2": dict(cfg="C2", kwargs={}, launch=2, reps=5, cpu=(2, 2, 4.0),
+               label="C2: SoftAbs Riemannian implicit leapfrog, banana D=64, 2048 chains"),
+    "C3": dict(cfg="C3", kwargs={}, launch=50, reps=10, cpu=(8, 50, 3.0),
+               label="C3: constrained leapfrog (RATTLE + Newton), torus D=3 C=1, 4096 chains"),
+    "C4": dict(cfg="C4", kwargs={"n_chains": 8192}, launch=1, reps=3, cpu=(1, 1, 5.0),
+               label="C4: dense Riemannian (rank-1 registry metric, Sherman-Morrison policy) "
+                     "implicit leapfrog, quadratic D=512, 8192 chains per GPU"),
+}
 
 
 def parse_args():
@@ -47,6 +68,8 @@ def parse_args():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--leapfrog-per-launch", type=int, default=LEAPFROG_PER_LAUNCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true",
+                    help="headline workload only (skip C2 / C3 / C4 and strong scaling)")
     return ap.parse_args()
 
 
@@ -57,6 +80,16 @@ def measured_hbm_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:  # noqa: BLE001
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(name):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture of this
+    workload (profiles/r02_traffic.json, written by profiles/tools/ncu_traffic.py), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return json.load(f).get(name)
+    except Exception:  # noqa: BLE001
+        return None
 
 
 class ClockSampler:
@@ -121,42 +154,78 @@ class ClockSampler:
         }
 
 
-def cpu_baseline(kind_note=""):
-    from oracle import cpu_baseline as cb
+# ------------------------------------------------------------------------------- CPU arm
 
-    cores = os.cpu_count() or 1
-    res = cb.run("C1", {"n_chains": N_CHAINS, "dim": DIM}, chains_per_worker=8,
-                 n_steps=LEAPFROG_PER_LAUNCH, reps=150, n_workers=cores)
+
+def _cpu_entry(res):
     return {
         "value": res["value"],
         "unit": UNIT,
         "cores": res["cores"],
-        "kind": "port",
-        "sample": res["sample"] + kind_note,
+        "kind": res["kind"],
+        "sample": res["sample"],
+        "per_core": res["per_core"],
+        "probe_per_core": res["probe_per_core"],
+        "starved": res["starved"],
+        "failed_chains": res["failed_chains"],
         "seconds": res["seconds"],
     }
 
 
+def cpu_baselines(names, leapfrog_per_launch):
+    """CPU samples of C1 and of the workloads in `names` from ONE worker pool (before CUDA is
+    initialised in this process)."""
+    from oracle import ref_baseline as rb
+
+    pool = rb.Pool()
+    out = {}
+    try:
+        out["C1"] = _cpu_entry(rb.run("C1", {"dim": DIM}, 4, leapfrog_per_launch, 10.0, pool=pool))
+        for name in names:
+            w = WORKLOADS[name]
+            kw = {k: v for k, v in w["kwargs"].items() if k != "n_chains"}
+            cpw, ns, budget = w["cpu"]
+            out[name] = _cpu_entry(rb.run(w["cfg"], kw, cpw, ns, budget, pool=pool))
+    finally:
+        pool.close()
+    return out
+
+
 def run_reference(args, rank, world):
-    """Reference arm: the reference's CPU algorithm (oracle port; the Python reference cannot
-    travel to the GPU box) on all host cores, bounded sample per step."""
+    """Reference arm: the reference's own CPU implementation of the path on all usable host
+    cores; every bench step is a bounded sample (1.5 s) of the C1 workload."""
     if rank != 0:
         return
-    from oracle import cpu_baseline as cb
+    from oracle import ref_baseline as rb
 
-    cores = os.cpu_count() or 1
-    pool = cb.Pool(cores)
-    vals = []
-    for i in range(args.warmup + args.steps):
-        if i == args.warmup:
-            t0 = time.perf_counter()
-        res = cb.run("C1", {"n_chains": N_CHAINS, "dim": DIM}, chains_per_worker=8,
-                     n_steps=args.leapfrog_per_launch, reps=10, pool=pool)
-        if i >= args.warmup:
-            vals.append(res["value"])
-    wall = time.perf_counter() - t0
-    pool.close()
+    pool = rb.Pool()
+    vals, res = [], None
+    t0 = time.perf_counter()
+    try:
+        for i in range(args.warmup + args.steps):
+            if i == args.warmup:
+                t0 = time.perf_counter()
+            res = rb.run("C1", {"dim": DIM}, 4, args.leapfrog_per_launch, 1.5, pool=pool,
+                         probe=(i == 0))
+            if i == 0:
+                probe = res["probe_per_core"]
+            if i >= args.warmup:
+                vals.append(res["value"])
+        wall = time.perf_counter() - t0
+        extra = {}
+        if not args.no_workloads:
+            for name, w in WORKLOADS.items():
+                kw = {k: v for k, v in w["kwargs"].items() if k != "n_chains"}
+                cpw, ns, budget = w["cpu"]
+                extra[name] = _cpu_entry(rb.run(w["cfg"], kw, cpw, ns, budget, pool=pool))
+    finally:
+        pool.close()
     value = sum(vals) / len(vals)
+    cores = res["cores"]
+    cpu = {"value": value, "unit": UNIT, "cores": cores, "kind": res["kind"],
+           "sample": res["sample"] + f"; mean of {args.steps} samples",
+           "per_core": value / cores, "probe_per_core": probe,
+           "starved": bool(probe and value / cores < 0.5 * probe)}
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -171,19 +240,130 @@ def run_reference(args, rank, world):
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "leapfrog_steps_per_launch": args.leapfrog_per_launch,
-                   "integrator": "LeapfrogIntegrator", "metric": "dense"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": res["sample"]},
+        "config": {"workload": WORKLOAD},
+        "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "workloads": extra,
     }
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------- CUDA arm
+
+
+def time_launches(torch, fn, reps, flush=None):
+    """Per-launch CUDA-event times (ms) of `fn`, L2 optionally flushed between launches."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(reps)]
+    out = None
+    for i, (a, b) in enumerate(ev):
+        if flush is not None:
+            flush.fill_(float(i))
+        a.record()
+        out = fn()
+        b.record()
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in ev], out
+
+
+def run_workload(name, torch, dist, dev, rank, world, flush, hbm_peak):
+    """One of the non-headline configurations on this rank; returns a dict (rank 0) with
+    aggregate throughput (max launch time over ranks) and the roofline entry."""
+    from mici_b200 import engine, problems
+
+    w = WORKLOADS[name]
+    kw = dict(w["kwargs"])
+    base_seed = {"C2": 2, "C3": 3, "C4": 4}[w["cfg"]]
+    prob = problems.make_problem(w["cfg"], seed=problems.BASE_SEED + base_seed + 1000 * rank, **kw)
+    integ = engine.build_integrator(prob)
+    state = engine.build_state(prob, dev)
+    n, dim = state.pos.shape
+    L = w["launch"]
+    integ.step_n(state, L)  # warm-up
+    integ.step_n(state, L)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    times, out = time_launches(torch, lambda: integ.step_n(state, L), w["reps"], flush)
+    t = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device=dev)
+    done = out.n_done.sum().to(torch.float64).reshape(1)
+    ok = (out.status == 0).sum().to(torch.float64).reshape(1)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(done)
+        dist.all_reduce(ok)
+    ms = float(t.item())
+    steps_done = float(done.item())
+    value = steps_done / (ms * 1e-3)
+    iters = None
+    if out.solver_iters is not None:
+        it = out.solver_iters.to(torch.float64)
+        iters = it.mean(0).tolist() if it.ndim > 1 else float(it.mean().item())
+    b_alg = prob.algorithmic_bytes_per_chain_step
+    res = {
+        "workload": w["label"],
+        "value": value,
+        "unit": UNIT,
+        "ms_per_launch": ms,
+        "leapfrog_steps_per_launch": L,
+        "chains_per_gpu": n,
+        "n_gpus": world,
+        "dim": dim,
+        "ok_fraction": float(ok.item()) / (n * world),
+        "mean_solver_iters_last_step": iters,
+    }
+    hbm_gbs = value / world * b_alg / 1e9
+    if name == "C2":
+        # metric builds (eigendecompositions) per step: _step_a + every iteration of the two
+        # position fixed points + _step_b_adj; quadratic-form gradients: every iteration of the
+        # two momentum fixed points + 1.  F_alg = builds * 9 D^3 + quad * 2 D^3 (SURVEY 8(d)).
+        builds = iters[1] + iters[2] + 2.0
+        quads = iters[0] + iters[3] + 1.0
+        f_alg = builds * 9.0 * dim**3 + quads * 2.0 * dim**3
+        tf = value / world * f_alg / 1e12
+        res["roofline"] = {
+            "bound": "fp64 (scalar pipe: Jacobi eigensolver)", "achieved": tf,
+            "peak": FP64_DFMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_DFMA_PEAK_TFLOPS,
+            "peak_source": FP64_PEAK_SOURCE, "traffic": ncu_traffic(name),
+            "flops_per_chain_step": f_alg, "metric_builds_per_step": builds,
+            "formula": "builds*9*D^3 + quad_grads*2*D^3, builds = it_c_rev + it_c + 2",
+            "hbm_frac": hbm_gbs / hbm_peak,
+            "kernel": "implicit_leapfrog_kernel<BananaRTarget, SoftAbsMetric>",
+        }
+    elif name == "C3":
+        res["roofline"] = {
+            "bound": "latency / issue (B_alg = 96 B per chain-step)", "achieved": hbm_gbs,
+            "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
+            "traffic": ncu_traffic(name),
+            "kernel": "constrained_leapfrog_kernel<TorusTarget, 1>",
+            "newton_iterations_per_step": iters,
+        }
+    elif name == "C4":
+        # the Sherman-Morrison policy never factorises: per metric build 2 D^2 (B^-1 q), per
+        # M^-1 v 2 D^2, per target gradient 2 D^2; counted from the iteration counts
+        builds = iters[1] + iters[2] + 2.0
+        quads = iters[0] + iters[3] + 1.0
+        matvecs = 2.0 * builds + quads + 2.0  # build + M^-1 p per build; M^-1 p per quad; 2 grads
+        f_exec = matvecs * 2.0 * dim**2
+        f_ref = builds * dim**3 / 3.0 + matvecs * 2.0 * dim**2
+        tf = value / world * f_exec / 1e12
+        res["roofline"] = {
+            "bound": "fp64 (L2-resident mat-vecs against the shared B^-1, P)", "achieved": tf,
+            "peak": FP64_DFMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_DFMA_PEAK_TFLOPS,
+            "peak_source": FP64_PEAK_SOURCE, "traffic": ncu_traffic(name),
+            "flops_per_chain_step_executed": f_exec,
+            "flops_per_chain_step_reference_algorithm": f_ref,
+            "metric_builds_per_step": builds, "hbm_frac": hbm_gbs / hbm_peak,
+            "kernel": "implicit_leapfrog_kernel<QuadraticRTarget, Rank1WoodburyMetric>",
+        }
+    return res
+
+
 def run_cuda(args, rank, local_rank, world):
     cpu = None
+    extra_names = [] if args.no_workloads else list(WORKLOADS)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline()  # before CUDA is initialised in this process
+        cpu = cpu_baselines(extra_names, args.leapfrog_per_launch)  # before CUDA is initialised
 
     import numpy as np
     import torch
@@ -257,21 +437,59 @@ def run_cuda(args, rank, local_rank, world):
         integ.step_n_host(pos_h, mom_h, L, out_pos=pos_o, out_mom=mom_o, out_status=st_o,
                           device=dev, n_chunks=8)
 
-    for _ in range(args.warmup):
-        e2e_step()
-    sync_all()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e1.record()
-    sync_all()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e2e_ms.item())
-    _ = time.perf_counter() - t0
+    def timed_e2e(fn):
+        for _ in range(args.warmup):
+            fn()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        sync_all()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms = torch.tensor([max(e0.elapsed_time(e1), wall_ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    e2e_ms = timed_e2e(e2e_step)
+
+    # the same call with PAGEABLE NumPy-backed inputs and outputs (what the reference's
+    # ChainState holds, states.py:160-305): no pre-pinned buffers anywhere
+    pos_p, mom_p = torch.from_numpy(np.array(prob.pos)), torch.from_numpy(np.array(prob.mom))
+
+    def e2e_pageable_step():
+        integ.step_n_host(pos_p, mom_p, L, device=dev, n_chunks=8)
+
+    e2e_pageable_ms = timed_e2e(e2e_pageable_step)
+
+    # ---------------- the other configurations and strong scaling
+    hbm_peak, peak_src = measured_hbm_peak()
+    workloads = {}
+    strong = None
+    if not args.no_workloads:
+        names = extra_names if world == 1 else ["C4"]  # C2 / C3 are 1-GPU configurations
+        for name in names:
+            res = run_workload(name, torch, dist, dev, rank, world, flush, hbm_peak)
+            if cpu is not None and name in cpu:
+                res["cpu_baseline"] = cpu[name]
+            workloads[name] = res
+        # strong scaling: the 8192 chains of C1 divided over the ranks
+        n_s = N_CHAINS // world
+        sprob = problems.make_problem("C1", n_chains=N_CHAINS, dim=DIM,
+                                      seed=problems.BASE_SEED + 1)
+        sstate = engine.build_state(sprob, dev, chains=slice(rank * n_s, (rank + 1) * n_s))
+        integ.step_n(sstate, L)
+        sync_all()
+        st_times, _ = time_launches(torch, lambda: integ.step_n(sstate, L), 10, flush)
+        st_ms = torch.tensor([sum(st_times) / len(st_times)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(st_ms, op=dist.ReduceOp.MAX)
+        strong = {"total_chains": n_s * world, "chains_per_gpu": n_s,
+                  "ms_per_launch": float(st_ms.item()),
+                  "value": n_s * world * L / (float(st_ms.item()) * 1e-3), "unit": UNIT}
 
     # ---------------- write-out: the one collective (outside the timed step path)
     if world > 1:
@@ -287,11 +505,12 @@ def run_cuda(args, rank, local_rank, world):
     chain_steps_per_launch = n * L
     value = world * chain_steps_per_launch * args.steps / (total_ms * 1e-3)
     e2e_value = world * chain_steps_per_launch * args.steps / (e2e_ms * 1e-3)
+    e2e_pageable = world * chain_steps_per_launch * args.steps / (e2e_pageable_ms * 1e-3)
     b_alg = prob.algorithmic_bytes_per_chain_step  # 32 * D = 4096 B
     avg_launch_s = (sum(times_ms) / len(times_ms)) * 1e-3
-    hbm_peak, peak_src = measured_hbm_peak()
     achieved_gbs = b_alg * chain_steps_per_launch / avg_launch_s / 1e9
     flops = (2.0 * dim * dim) * chain_steps_per_launch / avg_launch_s
+    n_launches = args.steps + (sum(w["reps"] for k, w in WORKLOADS.items() if k in workloads))
     line = {
         "metric": METRIC,
         "value": value,
@@ -324,25 +543,32 @@ def run_cuda(args, rank, local_rank, world):
             "peak": hbm_peak,
             "unit": "GB/s",
             "frac": achieved_gbs / hbm_peak,
-            "traffic": NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH if (n, dim) == (8192, 128) else None,
+            "traffic": ncu_traffic("C1") if (n, dim) == (8192, 128) else None,
+            "traffic_source": "profiles/r02_traffic.json (ncu --set full capture of this command)",
             "peak_source": peak_src,
             "kernel": "leapfrog_dmma_kernel<NealFunnelTarget,128>",
             "algorithmic_bytes_per_chain_step": b_alg,
             "fp64_tflops": flops / 1e12,
-            "fp64_peak_tflops": FP64_PEAK_TFLOPS,
-            "fp64_frac": flops / 1e12 / FP64_PEAK_TFLOPS,
+            "fp64_peak_tflops": FP64_DMMA_PEAK_TFLOPS,
+            "fp64_peak_source": FP64_PEAK_SOURCE,
+            "fp64_frac": flops / 1e12 / FP64_DMMA_PEAK_TFLOPS,
         },
         "e2e": {
             "value": e2e_value,
             "unit": UNIT,
             "h2d_bytes_per_step": int(2 * n * dim * 8),
             "d2h_bytes_per_step": int(2 * n * dim * 8 + n * 4),
+            "buffers": "pinned host tensors in and out",
+            "pageable": {"value": e2e_pageable, "unit": UNIT,
+                         "buffers": "pageable NumPy-backed tensors in, fresh pageable out"},
         },
-        "gpu_launches": args.steps,
+        "gpu_launches": n_launches,
         "clocks": clocks.summary(),
+        "workloads": workloads,
+        "strong_scaling": strong,
     }
     if cpu is not None:
-        line["cpu_baseline"] = cpu
+        line["cpu_baseline"] = cpu["C1"]
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

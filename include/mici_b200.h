@@ -260,6 +260,15 @@ int mb200_sample_momentum_riemannian(const double* pos, const double* normals, d
                                      int32_t* status, void* stream);
 
 /*
+ * RiemannianMetricSystem.dh2_dmom / System.dh_dmom (systems.py:1398-1399, 202-207): the velocity
+ * M(q)^-1 p of every chain, read by the no-U-turn criteria (transitions.py:434-435, 472-473).
+ * status 3 (and NaN velocities) where M(q) cannot be built.
+ */
+int mb200_dh_dmom_riemannian(const double* pos, const double* mom, double* vel_out,
+                             int64_t n_chains, int32_t dim, const mb200_model* model,
+                             int32_t* status, void* stream);
+
+/*
  * "Next" row N3 (and the random-length transition of N1): explicit leapfrog / symmetric
  * composition with PER-CHAIN step sizes and, optionally, per-chain trajectory lengths.
  *   step_sizes         [n_chains] device array -- during warm-up every chain carries its own

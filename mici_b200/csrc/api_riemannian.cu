@@ -100,6 +100,21 @@ static int launch_sample_momentum(const double* q, const double* z, double* p_ou
   return check_launch("riemannian_sample_momentum_kernel");
 }
 
+template <class Target, template <class> class MetricT>
+static int launch_velocity(const double* q, const double* p, double* vel, int64_t n, int dim,
+                           const ModelArgs& m, int32_t* status, cudaStream_t st) {
+  auto kern = riemannian_velocity_kernel<Target, MetricT>;
+  const int n_mats = MetricT<Target>::N_MATS;
+  const size_t smem = rm_smem_doubles(dim, n_mats) * sizeof(double);
+  if (smem > 227 * 1024) return fail(MB200_ERR_UNSUPPORTED, "dim %d too large", dim);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(MB200_ERR_CUDA, "smem attr: %s", cudaGetErrorString(e));
+  int64_t blocks = (int64_t)num_sms() * 2;
+  if (blocks > n) blocks = n;
+  kern<<<(unsigned)blocks, RM_THREADS, smem, st>>>(q, p, vel, n, dim, m, status, n_mats);
+  return check_launch("riemannian_velocity_kernel");
+}
+
 }  // namespace mb200
 
 using namespace mb200;
@@ -248,6 +263,41 @@ int mb200_implicit_riemannian_per_chain(
                                             0.0, max_n_steps, model, fp_solver, fp_convergence_tol,
                                             fp_divergence_tol, fp_max_iters, reverse_check_tol,
                                             h_out, status, n_done, fp_iters, nullptr, 0, stream);
+}
+
+int mb200_dh_dmom_riemannian(const double* pos, const double* mom, double* vel_out,
+                             int64_t n_chains, int32_t dim, const mb200_model* model,
+                             int32_t* status, void* stream) {
+  if (n_chains == 0 && dim >= 1) return 0;
+  if (!pos || !mom || !vel_out || !model) return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
+  if (n_chains < 0 || dim < 1) return fail(MB200_ERR_INVALID_ARG, "bad sizes");
+  const DeviceScope device_scope(pos);
+  const ModelArgs m = to_args(model);
+  cudaStream_t st = (cudaStream_t)stream;
+#define MB200_ARGS pos, mom, vel_out, n_chains, dim, m, status, st
+  if (m.rmetric_id == MB200_RMETRIC_SOFTABS) {
+    if (m.target_id == MB200_TARGET_BANANA) return launch_velocity<BananaRTarget, SoftAbsMetric>(MB200_ARGS);
+    return fail(MB200_ERR_UNSUPPORTED, "target %d has no device Hessian", m.target_id);
+  }
+  if (m.rmetric_id == MB200_RMETRIC_RANK1) {
+    if (!m.maux) return fail(MB200_ERR_INVALID_ARG, "rank-1 metric needs its base matrix");
+    const bool fits = rm_smem_doubles(dim, 1) * sizeof(double) <= 227 * 1024;
+    const bool woodbury = !fits || m.mp[2] != 0.0;
+    switch (m.target_id) {
+      case MB200_TARGET_QUADRATIC:
+        return woodbury ? launch_velocity<QuadraticRTarget, Rank1WoodburyMetric>(MB200_ARGS)
+                        : launch_velocity<QuadraticRTarget, Rank1DenseMetric>(MB200_ARGS);
+      case MB200_TARGET_STD_GAUSSIAN:
+        return woodbury ? launch_velocity<StdGaussianRTarget, Rank1WoodburyMetric>(MB200_ARGS)
+                        : launch_velocity<StdGaussianRTarget, Rank1DenseMetric>(MB200_ARGS);
+      case MB200_TARGET_BANANA:
+        return woodbury ? launch_velocity<BananaRTarget, Rank1WoodburyMetric>(MB200_ARGS)
+                        : launch_velocity<BananaRTarget, Rank1DenseMetric>(MB200_ARGS);
+      default: return fail(MB200_ERR_UNSUPPORTED, "target %d not available", m.target_id);
+    }
+  }
+#undef MB200_ARGS
+  return fail(MB200_ERR_INVALID_ARG, "unknown rmetric_id %d", m.rmetric_id);
 }
 
 }  // extern "C"

@@ -64,15 +64,17 @@ constexpr int DMMA_TILES_PER_CTA = 7;
 #ifndef MB200_DMMA_GROUPS
 #define MB200_DMMA_GROUPS 4
 #endif
-// groups of 4 warps; the 7 row tiles are dealt 2,2,2,1 (4 groups), 2,2,1,1,1 (5), 2,1,1,1,1,1 (6)
-// or 1 each (7): more groups = more warps per sub-partition to cover each other's serial
-// phases, at fewer registers per thread and less B-fragment reuse
+// groups of 4 warps (one per SM sub-partition); the 7 row tiles are dealt as evenly as possible:
+// 2,2,2,1 for 4 groups, 4,3 for 2 groups
 constexpr int DMMA_GROUPS = MB200_DMMA_GROUPS;
-__host__ __device__ constexpr int dmma_tile_start(int g) {
-  // first tile of group g: groups [0, 7 - G) own two tiles, the rest one
-  return g <= 7 - DMMA_GROUPS ? 2 * g : 2 * (7 - DMMA_GROUPS) + (g - (7 - DMMA_GROUPS));
+__host__ __device__ constexpr int dmma_tile_count(int g) {
+  return DMMA_TILES_PER_CTA / DMMA_GROUPS + (g < DMMA_TILES_PER_CTA % DMMA_GROUPS ? 1 : 0);
 }
-__host__ __device__ constexpr int dmma_tile_count(int g) { return g < 7 - DMMA_GROUPS ? 2 : 1; }
+__host__ __device__ constexpr int dmma_tile_start(int g) {
+  return g * (DMMA_TILES_PER_CTA / DMMA_GROUPS) +
+         (g < DMMA_TILES_PER_CTA % DMMA_GROUPS ? g : DMMA_TILES_PER_CTA % DMMA_GROUPS);
+}
+constexpr int DMMA_MAX_MT = (DMMA_TILES_PER_CTA + DMMA_GROUPS - 1) / DMMA_GROUPS;
 constexpr int DMMA_THREADS = 32 * 4 * DMMA_GROUPS;
 constexpr int DMMA_ROWS_PER_CTA = 8 * DMMA_TILES_PER_CTA;  // 56 chains
 
@@ -468,7 +470,9 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   leapfrog_dmma_group<Target, DP, MT>(sm, target, q_in, p_in, q_out, p_out, dir, n_chains,    \
                                       dim, step_size, n_steps, h_out, status, n_done, chain0, \
                                       row0, w, lane, 1 + group, cta_threads)
-    if (mt == 2) MB200_GROUP(2);
+    if (DMMA_MAX_MT >= 4 && mt == 4) MB200_GROUP(4);
+    else if (DMMA_MAX_MT >= 3 && mt == 3) MB200_GROUP(3);
+    else if (mt == 2) MB200_GROUP(2);
     else if (mt == 1) MB200_GROUP(1);
 #undef MB200_GROUP
     __syncthreads();  // next block of chains reuses sm.P / sm.part

@@ -1266,4 +1266,35 @@ __global__ void __launch_bounds__(RM_THREADS)
   }
 }
 
+// vel = M(q)^-1 p for every chain: RiemannianMetricSystem.dh2_dmom / dh_dmom (systems.py:1398-1399,
+// 202-207), read by the no-U-turn criteria (transitions.py:434-435, 472-473).
+template <class Target, template <class> class MetricT>
+__global__ void __launch_bounds__(RM_THREADS)
+    riemannian_velocity_kernel(const double* __restrict__ q_in, const double* __restrict__ p_in,
+                               double* __restrict__ vel_out, int64_t n_chains, int dim,
+                               ModelArgs model, int32_t* __restrict__ status, int n_mats) {
+  extern __shared__ double smem[];
+  Blk blk;
+  blk.tid = threadIdx.x, blk.nthr = blockDim.x, blk.lane = threadIdx.x & 31;
+  blk.warp = threadIdx.x >> 5, blk.nwarp = blockDim.x >> 5;
+  RmWork w;
+  rm_carve(w, smem, dim, n_mats, blk);
+  const Target target(model, dim);
+  MetricT<Target> metric(target, model);
+  for (int64_t ch = blockIdx.x; ch < n_chains; ch += gridDim.x) {
+    __syncthreads();
+    for (int i = blk.tid; i < dim; i += blk.nthr) {
+      w.q[i] = q_in[(size_t)ch * dim + i];
+      w.p[i] = p_in[(size_t)ch * dim + i];
+    }
+    __syncthreads();
+    metric.reset();
+    const int st = metric.build(blk, w, w.q) != 0 ? MB200_STATUS_LINALG : MB200_STATUS_OK;
+    if (st == MB200_STATUS_OK) metric.inv_matvec(blk, w, w.p, w.v1);
+    for (int i = blk.tid; i < dim; i += blk.nthr)
+      vel_out[(size_t)ch * dim + i] = (st == MB200_STATUS_OK) ? w.v1[i] : nan("");
+    if (blk.tid == 0 && status != nullptr) status[ch] = st;
+  }
+}
+
 }  // namespace mb200

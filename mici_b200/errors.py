@@ -60,9 +60,30 @@ STATUS_TO_ERROR = {
 }
 
 
+_DUAL = {}
+
+
+def compatible(exc):
+    """``exc`` itself, or -- when the reference package was imported AFTER this module, so that
+    the classes above are this package's own -- a subclass of both ``exc`` and the reference's
+    class of the same name: ``except mici.errors.IntegratorError`` in reference code
+    (transitions.py:292, 670; adapters.py:338) and ``except mici_b200.errors.IntegratorError``
+    both catch it."""
+    import sys  # noqa: PLC0415
+
+    ref_mod = sys.modules.get("mici.errors")
+    ref = getattr(ref_mod, exc.__name__, None) if ref_mod is not None else None
+    if ref is None or issubclass(exc, ref):
+        return exc
+    key = (exc, ref)
+    if key not in _DUAL:
+        _DUAL[key] = type(exc.__name__, (exc, ref), {})
+    return _DUAL[key]
+
+
 def raise_for_status(code: int, what: str = "integrator step") -> None:
     """Raise the reference exception matching a per-chain status code (single-chain shim)."""
     if code == STATUS_OK:
         return
-    exc = STATUS_TO_ERROR.get(int(code), IntegratorError)
+    exc = compatible(STATUS_TO_ERROR.get(int(code), IntegratorError))
     raise exc(f"{what} failed with status {int(code)} ({exc.__name__}).")

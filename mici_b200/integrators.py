@@ -25,7 +25,7 @@ from abc import ABC, abstractmethod
 import torch
 
 from . import _lib
-from .errors import AdaptationError, raise_for_status
+from .errors import AdaptationError, compatible, raise_for_status
 from .solvers import (
     maximum_norm,
     solve_fixed_point_direct,
@@ -76,7 +76,7 @@ class Integrator(ABC):
                 "Integrator `step_size` is `None`. This value should only be used if a "
                 "step size adapter is being used to set the step size."
             )
-            raise AdaptationError(msg)
+            raise compatible(AdaptationError)(msg)
         pos, mom, d, single = _batched(state)
         n, dim = pos.shape
         dev = pos.device

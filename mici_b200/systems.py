@@ -249,7 +249,7 @@ class EuclideanMetricSystem(TractableFlowSystem):
         _lib.check(rc, "mb200_euclidean_eval")
         if single:
             out = {k: v[0] for k, v in out.items()}
-        return out
+        return {k: _like_input(state.pos, v) for k, v in out.items()}  # NumPy in -> NumPy out
 
     def neg_log_dens(self, state):
         return self._eval(state, nld=True)["nld"]
@@ -270,6 +270,8 @@ class EuclideanMetricSystem(TractableFlowSystem):
         return self._eval(state, vel=True)["vel"]
 
     def dh2_dpos(self, state):
+        if isinstance(state.pos, np.ndarray):
+            return np.zeros_like(state.pos)
         return torch.zeros_like(state.pos)
 
     def dh_dpos(self, state):
@@ -306,7 +308,10 @@ class EuclideanMetricSystem(TractableFlowSystem):
         from .transitions import _normals  # noqa: PLC0415
 
         pos = state.pos if state.pos.ndim == 2 else state.pos[None]
-        z = _normals(rng, tuple(pos.shape), pos.device).contiguous()
+        # NumPy-held states (the reference's own ChainState storage): device work on the current
+        # CUDA device, NumPy back out
+        dev = torch.device("cuda") if isinstance(pos, np.ndarray) else pos.device
+        z = _normals(rng, tuple(pos.shape), dev).contiguous()
         m = self._metric
         if m.kind != METRIC_IDENTITY:
             n, dim = z.shape
@@ -324,7 +329,7 @@ class EuclideanMetricSystem(TractableFlowSystem):
             )
             _lib.check(rc, "mb200_euclidean_eval")
             z = out
-        return z if state.pos.ndim == 2 else z[0]
+        return _like_input(state.pos, z if state.pos.ndim == 2 else z[0])
 
 
 class GaussianEuclideanMetricSystem(EuclideanMetricSystem):
@@ -507,6 +512,26 @@ class RiemannianMetricSystem(System):
         )
         _lib.check(rc, "mb200_hamiltonian_riemannian")
         return _like_input(state.pos, h[0] if single else h)
+
+    def dh2_dmom(self, state):
+        """``M(q)^-1 p`` (systems.py:1398-1399); not cached, as in the reference."""
+        from .errors import LinAlgError  # noqa: PLC0415
+
+        pos, mom, _, single = _batched(state)
+        n, dim = pos.shape
+        dev = pos.device
+        vel = torch.empty((n, dim), dtype=torch.float64, device=dev)
+        status = torch.empty(n, dtype=torch.int32, device=dev)
+        model = self._model(dev)
+        rc = _lib.load().mb200_dh_dmom_riemannian(
+            _lib.ptr(pos.contiguous()), _lib.ptr(mom.contiguous()), _lib.ptr(vel), n, dim,
+            ctypes.byref(model), _lib.ptr(status), _lib.current_stream_ptr(dev),
+        )
+        _lib.check(rc, "mb200_dh_dmom_riemannian")
+        if bool((status != 0).any()):
+            bad = int((status != 0).sum())
+            raise LinAlgError(f"metric factorisation failed for {bad} of {n} chains")
+        return _like_input(state.pos, vel[0] if single else vel)
 
     def sample_momentum(self, state, rng):
         """``metric(state).sqrt @ N(0, I)`` (systems.py:1401-1402): the factor of M(q) is built

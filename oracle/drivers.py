@@ -17,7 +17,15 @@ import numpy as np
 from . import mici_oracle as mo
 from . import targets as tg
 
-REFERENCE_SRC = "/root/reference/src"
+# The unmodified reference: the read-only checkout in the build container, else the verbatim copy
+# that oracle/build_ref.sh places under oracle/_ref/ (git-ignored; travels to the GPU box).
+_REF_CANDIDATES = (
+    "/root/reference/src",
+    os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref"),
+)
+REFERENCE_SRC = next(
+    (d for d in _REF_CANDIDATES if os.path.isdir(os.path.join(d, "mici"))), _REF_CANDIDATES[0]
+)
 
 
 def build_target(problem):
@@ -134,7 +142,7 @@ def reference_available():
 
 
 def import_reference():
-    """Import the unmodified reference package from /root/reference/src (read-only)."""
+    """Import the unmodified reference package (``REFERENCE_SRC``, never written to)."""
     if not reference_available():
         raise ImportError("reference not present on this machine")
     sys.dont_write_bytecode = True
