@@ -167,6 +167,8 @@ def _cpu_entry(res):
         "per_core": res["per_core"],
         "probe_per_core": res["probe_per_core"],
         "starved": res["starved"],
+        "schedulable_cpus": res["schedulable_cpus"],
+        "cgroup_cpu_quota": res["cgroup_cpu_quota"],
         "failed_chains": res["failed_chains"],
         "seconds": res["seconds"],
     }
@@ -225,7 +227,9 @@ def run_reference(args, rank, world):
     cpu = {"value": value, "unit": UNIT, "cores": cores, "kind": res["kind"],
            "sample": res["sample"] + f"; mean of {args.steps} samples",
            "per_core": value / cores, "probe_per_core": probe,
-           "starved": bool(probe and value / cores < 0.5 * probe)}
+           "starved": bool(probe and value / cores < 0.5 * probe),
+           "schedulable_cpus": res["schedulable_cpus"],
+           "cgroup_cpu_quota": res["cgroup_cpu_quota"]}
     line = {
         "impl": "reference",
         "metric": METRIC,

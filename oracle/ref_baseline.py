@@ -21,11 +21,36 @@ import os
 import time
 
 
-def usable_cores():
+def cgroup_cpu_quota():
+    """CPUs this container may use according to its cgroup (v2 ``cpu.max`` / v1 cfs quota), or
+    None when unlimited.  A box can show 128 schedulable CPUs and still be capped at 16."""
     try:
-        return len(os.sched_getaffinity(0))
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            return max(1, int(int(quota) / int(period) + 0.5))
+    except (OSError, ValueError):
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+            quota = int(f.read())
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+            period = int(f.read())
+        if quota > 0:
+            return max(1, int(quota / period + 0.5))
+    except (OSError, ValueError):
+        pass
+    return None
+
+
+def usable_cores():
+    """Worker count: the CPUs this process may be scheduled on, capped by the cgroup quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
     except AttributeError:  # pragma: no cover - non-Linux
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    quota = cgroup_cpu_quota()
+    return n if quota is None else max(1, min(n, quota))
 
 
 def _worker(args):
@@ -146,6 +171,8 @@ def run(cfg, kwargs, chains_per_worker, n_steps, budget_s, pool=None, n_workers=
         "seconds": slowest,
         "failed_chains": sum(r[2] for r in res),
         "kind": "reference" if use_reference else "port",
+        "schedulable_cpus": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None,
+        "cgroup_cpu_quota": cgroup_cpu_quota(),
         "sample": (
             f"{n} workers x {chains_per_worker} chains x {n_steps} leapfrog steps, repeated for "
             f"{budget_s:g} s, of {cfg} ("
