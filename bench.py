@@ -255,6 +255,38 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------- CUDA arm
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads (and therefore its pinned buffers' first touch and its copy
+    submission) to the CPUs of the NUMA node the GPU hangs off.  At N = 8 the end-to-end path is
+    eight processes pushing cudaMemcpyAsync traffic through the host at once; crossing the
+    socket interconnect costs bandwidth.  Returns a short description, or None if unavailable."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # nvml prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        base = f"/sys/bus/pci/devices/{bus}"
+        with open(base + "/local_cpulist") as f:
+            spec = f.read().strip()
+        with open(base + "/numa_node") as f:
+            node = int(f.read())
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def time_launches(torch, fn, reps, flush=None):
     """Per-launch CUDA-event times (ms) of `fn`, L2 optionally flushed between launches."""
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -377,6 +409,7 @@ def run_cuda(args, rank, local_rank, world):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -565,6 +598,7 @@ def run_cuda(args, rank, local_rank, world):
             "buffers": "pinned host tensors in and out",
             "pageable": {"value": e2e_pageable, "unit": UNIT,
                          "buffers": "pageable NumPy-backed tensors in, fresh pageable out"},
+            "host_binding": numa,
         },
         "gpu_launches": n_launches,
         "clocks": clocks.summary(),

@@ -52,6 +52,17 @@ class Adapter(ABC):
         """Whether the adapter only needs local information (adapters.py:115-124)."""
 
 
+def _any_rank(flag, device, group=None):
+    """``flag`` OR-ed over the ranks of ``group`` (one tiny all-reduce), so that a failure seen by
+    one rank's chains raises on EVERY rank instead of leaving the others waiting in the next
+    collective (``finalize``)."""
+    if group is False or not (dist.is_available() and dist.is_initialized()):
+        return bool(flag)
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return bool(t.item())
+
+
 def _all_ranks(tensor, group=None):
     """List of ``tensor`` from every rank (just ``[tensor]`` without a process group, or with
     ``group=False``: adapt on this rank's chains only)."""
@@ -102,7 +113,10 @@ class DualAveragingStepSizeAdapter(Adapter):
 
     def __init__(self, adapt_stat_target=0.8, adapt_stat_func=None, log_step_size_reg_target=None,
                  log_step_size_reg_coefficient=0.05, iter_decay_coeff=0.75, iter_offset=10,
-                 max_init_step_size_iters=100, log_step_size_reducer=None):
+                 max_init_step_size_iters=100, log_step_size_reducer=None, group=None):
+        # `group`: process group whose ranks share the chains (None = default group when
+        # torch.distributed is initialised; False = this rank alone)
+        self.group = group
         self.adapt_stat_target = adapt_stat_target
         self.adapt_stat_func = default_adapt_stat_func if adapt_stat_func is None else adapt_stat_func
         self.log_step_size_reg_target = log_step_size_reg_target
@@ -138,7 +152,7 @@ class DualAveragingStepSizeAdapter(Adapter):
         n = init_state.pos.shape[0]
         dev = init_state.pos.device
         h_init = system.h(init_state)
-        if bool(torch.isnan(h_init).any()):
+        if _any_rank(bool(torch.isnan(h_init).any()), dev, self.group):
             raise AdaptationError("Hamiltonian evaluating to NaN at initial state.")
         eps = torch.ones(n, dtype=torch.float64, device=dev)
         too_big = torch.zeros(n, dtype=torch.bool, device=dev)
@@ -161,11 +175,12 @@ class DualAveragingStepSizeAdapter(Adapter):
             eps = torch.where(still, torch.where(flag, eps / 2, eps * 2), eps)
             too_big = torch.where(active, flag, too_big)
             active = still
-            if not bool(active.any()):
+            # every rank runs the same number of search iterations (the slowest chain anywhere)
+            if not _any_rank(bool(active.any()), dev, self.group):
                 integrator.step_size = eps
                 return eps
         integrator.step_size = eps
-        bad = eps[active]
+        bad = eps[active] if bool(active.any()) else eps
         msg = (
             f"Could not find reasonable initial step size in {self.max_init_step_size_iters} "
             f"iterations for {int(active.sum())} chains (final step sizes between "

@@ -57,6 +57,8 @@ def write_chain_data(memmap_path, traces, statistics, first_chain_index=0):
     of this rank's first chain when chains are sharded over ranks."""
     from .traces import write_chain_traces  # noqa: PLC0415
 
+    if not traces and not statistics:
+        return {}, {}
     n = next(iter(traces.values())).shape[0] if traces else next(iter(statistics.values())).shape[0]
     indices = range(first_chain_index, first_chain_index + n)
     paths = write_chain_traces(memmap_path, "trace", traces, indices) if traces else {}

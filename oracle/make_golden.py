@@ -31,7 +31,7 @@ CASES = {
     "c1_funnel_dense_d24": ("C1", {"n_chains": 16, "dim": 24}, (1, 20), {}),
     "c1_funnel_diag": ("C1", {"n_chains": 16, "dim": 40, "metric_kind": "diagonal"}, (1, 20), {}),
     "c1_funnel_identity": ("C1", {"n_chains": 16, "dim": 7, "metric_kind": "identity"}, (1, 20), {}),
-    "c2_softabs_banana": ("C2", {"n_chains": 16}, (1, 5), {}),
+    "c2_softabs_banana": ("C2", {"n_chains": 16}, (1, 5, 20), {}),
     "c2_softabs_banana_d8": ("C2", {"n_chains": 32, "dim": 8}, (1, 5, 20), {}),
     "c3_torus": ("C3", {"n_chains": 64}, (1, 5, 20), {}),
     "c3_torus_inner3": ("C3", {"n_chains": 32}, (1, 5), {"n_inner_step": 3}),
@@ -55,7 +55,7 @@ CASES = {
     "s1_sphere_diag_d70_inner2": ("S1", {"n_chains": 8, "dim": 70, "metric_kind": "diagonal"}, (1, 5), {"n_inner_step": 2}),
     "s1_sphere_identity_d5": ("S1", {"n_chains": 16, "dim": 5, "metric_kind": "identity"}, (1, 20), {}),
     "c4_dense_riemannian_d64": ("C4", {"n_chains": 8, "dim": 64}, (1, 5), {}),
-    "c4_dense_riemannian_d512": ("C4", {"n_chains": 2, "dim": 512}, (1,), {}),
+    "c4_dense_riemannian_d512": ("C4", {"n_chains": 8, "dim": 512}, (1, 5), {}),
 }
 
 # failure-path fixtures: step sizes chosen so that some chains raise IntegratorError
@@ -292,8 +292,22 @@ def adapt_cases():
                  step_size_trace=o["step_size_trace"], **r)
 
 
-def main():
+def main(argv=None):
+    """No arguments: regenerate every fixture.  With arguments: only the named step fixtures
+    (keys of CASES / FAILURE_CASES)."""
+    import sys  # noqa: PLC0415
+
+    names = list(sys.argv[1:] if argv is None else argv)
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    if names:
+        for name in names:
+            if name in CASES:
+                cfg, kwargs, steps, ov = CASES[name]
+                generate_case(name, cfg, kwargs, steps, ov)
+            else:
+                cfg, kwargs, eps, steps, ov = FAILURE_CASES[name]
+                generate_case(name, cfg, kwargs, steps, ov, step_size=eps)
+        return
     hmc_cases()
     nuts_cases()
     adapt_cases()
