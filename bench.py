@@ -54,9 +54,17 @@ WORKLOADS = {
                label="C2: SoftAbs Riemannian implicit leapfrog, banana D=64, 2048 chains"),
     "C3": dict(cfg="C3", kwargs={}, launch=50, reps=10, cpu=(8, 50, 3.0),
                label="C3: constrained leapfrog (RATTLE + Newton), torus D=3 C=1, 4096 chains"),
-    "C4": dict(cfg="C4", kwargs={"n_chains": 8192}, launch=1, reps=3, cpu=(1, 1, 5.0),
-               label="C4: dense Riemannian (rank-1 registry metric, Sherman-Morrison policy) "
-                     "implicit leapfrog, quadratic D=512, 8192 chains per GPU"),
+    "C4": dict(cfg="C4", kwargs={"n_chains": 8192}, launch=1, reps=2, cpu=(1, 1, 5.0),
+               label="C4: dense Riemannian implicit leapfrog, quadratic D=512, 8192 chains per "
+                     "GPU; metric B + c q q^T factorised per chain (blocked DMMA Cholesky, "
+                     "explicit inverse: the reference's algorithm)"),
+    "C4_low_rank": dict(cfg="C4", kwargs={"n_chains": 8192}, launch=1, reps=3, cpu=None,
+                        metric_overrides={"force_low_rank_form": True},
+                        label="C4 with the OPTIONAL Sherman-Morrison policy for the rank-1 "
+                              "registry metric (O(D^2) per metric, no factorisation)"),
+    "C5": dict(cfg="C5", kwargs={"n_chains": 8192}, launch=1, reps=2, cpu=(1, 1, 5.0),
+               label="C5: as C4 with the full-rank metric B + c (q q^T) o S (no low-rank "
+                     "shortcut exists), D=512, 8192 chains per GPU"),
 }
 
 
@@ -186,6 +194,8 @@ def cpu_baselines(names, leapfrog_per_launch):
         for name in names:
             w = WORKLOADS[name]
             kw = {k: v for k, v in w["kwargs"].items() if k != "n_chains"}
+            if w["cpu"] is None:
+                continue
             cpw, ns, budget = w["cpu"]
             out[name] = _cpu_entry(rb.run(w["cfg"], kw, cpw, ns, budget, pool=pool))
     finally:
@@ -217,6 +227,8 @@ def run_reference(args, rank, world):
         extra = {}
         if not args.no_workloads:
             for name, w in WORKLOADS.items():
+                if w["cpu"] is None:
+                    continue
                 kw = {k: v for k, v in w["kwargs"].items() if k != "n_chains"}
                 cpw, ns, budget = w["cpu"]
                 extra[name] = _cpu_entry(rb.run(w["cfg"], kw, cpw, ns, budget, pool=pool))
@@ -309,8 +321,10 @@ def run_workload(name, torch, dist, dev, rank, world, flush, hbm_peak):
 
     w = WORKLOADS[name]
     kw = dict(w["kwargs"])
-    base_seed = {"C2": 2, "C3": 3, "C4": 4}[w["cfg"]]
+    base_seed = {"C2": 2, "C3": 3, "C4": 4, "C5": 7}[w["cfg"]]
     prob = problems.make_problem(w["cfg"], seed=problems.BASE_SEED + base_seed + 1000 * rank, **kw)
+    if w.get("metric_overrides"):
+        prob.metric_params = dict(prob.metric_params, **w["metric_overrides"])
     integ = engine.build_integrator(prob)
     state = engine.build_state(prob, dev)
     n, dim = state.pos.shape
@@ -374,7 +388,26 @@ def run_workload(name, torch, dist, dev, rank, world, flush, hbm_peak):
             "kernel": "constrained_leapfrog_kernel<TorusTarget, 1>",
             "newton_iterations_per_step": iters,
         }
-    elif name == "C4":
+    elif name in ("C4", "C5"):
+        # per metric build: Cholesky D^3/3 (+ fill); per position fixed-point iteration one
+        # M^-1 p = two triangular solves 2 D^2; two explicit inverses per step (the two _step_a
+        # kicks need grad_log_abs_det = M^-1): L^-1 (D^3/3) and X^T X (D^3/3); per momentum
+        # fixed-point iteration one M^-1 p and the model's VJP (2 D^2)
+        builds = iters[1] + iters[2] + 2.0
+        quads = iters[0] + iters[3] + 1.0
+        f_exec = (builds * (dim**3 / 3.0 + 2.0 * dim**2) + 2.0 * (2.0 * dim**3 / 3.0)
+                  + quads * 4.0 * dim**2 + 2.0 * 2.0 * dim**2)
+        tf = value / world * f_exec / 1e12
+        res["roofline"] = {
+            "bound": "fp64 tensor pipe (DMMA: blocked Cholesky, L^-1, X^T X)", "achieved": tf,
+            "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_DMMA_PEAK_TFLOPS,
+            "peak_source": FP64_PEAK_SOURCE, "traffic": ncu_traffic(name),
+            "flops_per_chain_step": f_exec, "metric_builds_per_step": builds,
+            "formula": "builds*(D^3/3 + 2 D^2) + 2*(2 D^3/3) + quad_grads*4 D^2 + 4 D^2",
+            "hbm_frac": hbm_gbs / hbm_peak,
+            "kernel": "implicit_leapfrog_kernel<QuadraticRTarget, GlobalDenseMetricT<...>>",
+        }
+    elif name == "C4_low_rank":
         # the Sherman-Morrison policy never factorises: per metric build 2 D^2 (B^-1 q), per
         # M^-1 v 2 D^2, per target gradient 2 D^2; counted from the iteration counts
         builds = iters[1] + iters[2] + 2.0
@@ -507,7 +540,8 @@ def run_cuda(args, rank, local_rank, world):
     workloads = {}
     strong = None
     if not args.no_workloads:
-        names = extra_names if world == 1 else ["C4"]  # C2 / C3 are 1-GPU configurations
+        # C2 / C3 are 1-GPU configurations; C4 is the 8-GPU one (65 536 chains over 8 GPUs)
+        names = extra_names if world == 1 else ["C4", "C4_low_rank"]
         for name in names:
             res = run_workload(name, torch, dist, dev, rank, world, flush, hbm_peak)
             if cpu is not None and name in cpu:

@@ -63,7 +63,8 @@ extern "C" {
 
 /* position-dependent metrics of Riemannian systems */
 #define MB200_RMETRIC_SOFTABS 0 /* SoftAbs of target Hessian (matrices.py:1631-1685); params: softabs_coeff */
-#define MB200_RMETRIC_RANK1 1   /* dense M(q) = B + c q q^T;  aux: [B | B^-1] (2*dim*dim), params: c, log|B|, force_woodbury */
+#define MB200_RMETRIC_RANK1 1   /* dense M(q) = B + c q q^T;  aux: [B | B^-1] (2*dim*dim), params: c, log|B|, force_woodbury, generic_rank1_vjp */
+#define MB200_RMETRIC_HADAMARD 2 /* dense M(q) = B + c (q q^T) o S (full rank); aux: [B | S] (2*dim*dim), params: c, -, -, generic_rank1_vjp */
 
 /* fixed-point solvers fused into the implicit integrators (solvers.py:47-94, 97-154) */
 #define MB200_FP_SOLVER_DIRECT 0
@@ -226,6 +227,17 @@ int mb200_composition_euclidean(const double* pos_in, const double* mom_in, doub
  */
 int mb200_selftest_eigh(const double* matrices, int64_t n_matrices, int32_t dim, int32_t warm_from,
                         double* eigval, double* eigvec, int32_t* status, void* stream);
+
+/*
+ * Diagnostic: the blocked DMMA factorisation of the global-workspace dense metric policy
+ * (csrc/dense_global.cuh) on arbitrary SPD matrices [n_matrices*dim*dim], one CTA per matrix:
+ * lower Cholesky factor, explicit inverse, solution of M x = rhs and log|M| -- the operations of
+ * DensePositiveDefiniteMatrix (matrices.py:1161-1188, 982-984) that tests compare with
+ * numpy.linalg.  status 3 where the factorisation fails.
+ */
+int mb200_selftest_dense_factor(const double* matrices, const double* rhs, int64_t n_matrices,
+                                int32_t dim, double* chol_out, double* inv_out, double* sol_out,
+                                double* logdet_out, int32_t* status, void* stream);
 
 /*
  * "Next" row N4: n_steps implicit-midpoint steps on a Riemannian-metric system.

@@ -85,6 +85,7 @@ SIGNATURES = {
     "mb200_project_onto_cotangent_space": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _MP, _P]),
     "mb200_sample_momentum_riemannian": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _MP, _P, _P]),
     "mb200_dh_dmom_riemannian": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _MP, _P, _P]),
+    "mb200_selftest_dense_factor": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P]),
     "mb200_leapfrog_euclidean_per_chain": (
         ctypes.c_int,
         [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _I32, _I32, _P, _I32, _I32, _P, _MP, _P, _P, _P, _P],

@@ -86,4 +86,16 @@ int leapfrog_dmma_dispatch(const double* q_in, const double* p_in, double* q_out
                            const double* minv, const ModelArgs& m, double* h_out, int32_t* status,
                            int32_t* n_done, cudaStream_t st);
 
+// implemented in api_dense.cu (global-workspace dense metric policy, dense_global.cuh)
+int64_t dense_global_workspace_bytes(int64_t n_chains, int dim);
+bool dense_global_supported(int dim);
+int dense_global_implicit(const double* q_in, const double* p_in, double* q_out, double* p_out,
+                          const int32_t* dir, int64_t n, int dim, double eps, int n_steps,
+                          const ModelArgs& m, double fp_tol, double fp_div, int fp_max,
+                          double rev_tol, double* h_out, int32_t* status, int32_t* n_done,
+                          int32_t* fp_iters, cudaStream_t st, int midpoint, int fp_solver, void* ws,
+                          int64_t ws_bytes);
+int dense_global_vector(const double* q, const double* v, double* out, int64_t n, int dim,
+                        const ModelArgs& m, int32_t* status, cudaStream_t st, int velocity);
+
 }  // namespace mb200

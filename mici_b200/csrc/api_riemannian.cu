@@ -34,15 +34,31 @@ static int launch_implicit(const double* q_in, const double* p_in, double* q_out
   return check_launch("implicit_leapfrog_kernel");
 }
 
+// Dense metrics whose factor does not fit in shared memory (and every Hadamard metric) run through
+// the global-workspace policy (api_dense.cu); the rank-1 metric keeps its Sherman-Morrison form
+// as an OPTIONAL policy (rmetric_params[2] != 0) and for targets the dense policy is not
+// compiled for.
+static bool wants_global_dense(const ModelArgs& m, int dim) {
+  if (m.rmetric_id == MB200_RMETRIC_HADAMARD) return true;
+  if (m.rmetric_id != MB200_RMETRIC_RANK1) return false;
+  const bool fits = rm_smem_doubles(dim, 1) * sizeof(double) <= 227 * 1024;
+  return !fits && m.mp[2] == 0.0 && m.target_id == MB200_TARGET_QUADRATIC &&
+         dense_global_supported(dim);
+}
+
 static int implicit_dispatch(const double* q_in, const double* p_in, double* q_out, double* p_out,
                              const int32_t* dir, int64_t n, int dim, double eps, int n_steps,
                              const ModelArgs& m, double fp_tol, double fp_div, int fp_max,
                              double rev_tol, double* h_out, int32_t* status, int32_t* n_done,
                              int32_t* fp_iters, cudaStream_t st, int midpoint = 0,
-                             int fp_solver = 0) {
+                             int fp_solver = 0, void* ws = nullptr, int64_t ws_bytes = 0) {
   if (fp_solver != MB200_FP_SOLVER_DIRECT && fp_solver != MB200_FP_SOLVER_STEFFENSEN)
     return fail(MB200_ERR_INVALID_ARG, "unknown fixed-point solver %d", fp_solver);
   const DeviceScope device_scope(q_in);
+  if (wants_global_dense(m, dim))
+    return dense_global_implicit(q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, m, fp_tol,
+                                 fp_div, fp_max, rev_tol, h_out, status, n_done, fp_iters, st,
+                                 midpoint, fp_solver, ws, ws_bytes);
 #define MB200_ARGS                                                                           \
   q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, m, fp_tol, fp_div, fp_max, rev_tol,   \
       h_out, status, n_done, fp_iters, st, midpoint, fp_solver
@@ -65,6 +81,8 @@ static int implicit_dispatch(const double* q_in, const double* p_in, double* q_o
       return fail(MB200_ERR_INVALID_ARG, "banana target needs even dim");
     // per-chain Cholesky factor in shared memory when it fits (or when forced), else the
     // Sherman-Morrison form that never materialises M(q); mp[2] != 0 forces the latter
+    // (dimensions beyond shared memory reach this point only with the Sherman-Morrison policy
+    // forced or for targets the global-workspace dense policy is not compiled for)
     const bool fits = rm_smem_doubles(dim, 1) * sizeof(double) <= 227 * 1024;
     const bool woodbury = !fits || m.mp[2] != 0.0;
     switch (m.target_id) {
@@ -128,8 +146,6 @@ int mb200_implicit_leapfrog_riemannian(
     double fp_divergence_tol, int32_t fp_max_iters, double reverse_check_tol, double* h_out,
     int32_t* status, int32_t* n_done, int32_t* fp_iters, void* workspace, int64_t workspace_bytes,
     void* stream) {
-  (void)workspace;
-  (void)workspace_bytes;
   if (n_chains == 0 && dim >= 1) return 0;
   if (!pos_in || !mom_in || !pos_out || !mom_out || !model)
     return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
@@ -139,18 +155,22 @@ int mb200_implicit_leapfrog_riemannian(
   return implicit_dispatch(pos_in, mom_in, pos_out, mom_out, dir, n_chains, dim, step_size,
                            n_steps, to_args(model), fp_convergence_tol, fp_divergence_tol,
                            fp_max_iters, reverse_check_tol, h_out, status, n_done, fp_iters,
-                           (cudaStream_t)stream, 0, fp_solver);
+                           (cudaStream_t)stream, 0, fp_solver, workspace, workspace_bytes);
 }
 
-// every per-chain buffer of the implicit kernels lives in shared memory for the supported sizes
-int64_t mb200_implicit_workspace_bytes(int64_t, int32_t, const mb200_model*) { return 0; }
+// Per-chain buffers live in shared memory except for the global-workspace dense metric policy
+// (D x D matrices per resident CTA).  A caller that passes less (or NULL) still works: the
+// library then takes the scratch from the stream-ordered allocator for the duration of the call.
+int64_t mb200_implicit_workspace_bytes(int64_t n_chains, int32_t dim, const mb200_model* model) {
+  if (!model || n_chains <= 0 || dim < 1) return 0;
+  const ModelArgs m = to_args(model);
+  return wants_global_dense(m, dim) ? dense_global_workspace_bytes(n_chains, dim) : 0;
+}
 
 int mb200_hamiltonian_riemannian(const double* pos, const double* mom, int64_t n_chains,
                                  int32_t dim, const mb200_model* model, double* h_out,
                                  int32_t* status, void* workspace, int64_t workspace_bytes,
                                  void* stream) {
-  (void)workspace;
-  (void)workspace_bytes;
   if (n_chains == 0 && dim >= 1) return 0;
   if (!pos || !mom || !model || !h_out) return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
   if (n_chains < 0 || dim < 1) return fail(MB200_ERR_INVALID_ARG, "bad sizes");
@@ -158,7 +178,8 @@ int mb200_hamiltonian_riemannian(const double* pos, const double* mom, int64_t n
   // zero steps: state written back unchanged in place, h evaluated
   return implicit_dispatch(pos, mom, const_cast<double*>(pos), const_cast<double*>(mom), nullptr,
                            n_chains, dim, 0.0, 0, to_args(model), 1e-9, 1e10, 100, 2e-8, h_out,
-                           status, nullptr, nullptr, (cudaStream_t)stream);
+                           status, nullptr, nullptr, (cudaStream_t)stream, 0, 0, workspace,
+                           workspace_bytes);
 }
 
 int mb200_selftest_fixed_point(int32_t func_id, int32_t fp_solver, const double* x0,
@@ -224,6 +245,8 @@ int mb200_sample_momentum_riemannian(const double* pos, const double* normals, d
   const ModelArgs m = to_args(model);
   cudaStream_t st = (cudaStream_t)stream;
 #define MB200_ARGS pos, normals, mom_out, n_chains, dim, m, status, st
+  if (wants_global_dense(m, dim))
+    return dense_global_vector(pos, normals, mom_out, n_chains, dim, m, status, st, 0);
   if (m.rmetric_id == MB200_RMETRIC_SOFTABS) {
     if (m.target_id == MB200_TARGET_BANANA) return launch_sample_momentum<BananaRTarget, SoftAbsMetric>(MB200_ARGS);
     return fail(MB200_ERR_UNSUPPORTED, "target %d has no device Hessian", m.target_id);
@@ -275,6 +298,8 @@ int mb200_dh_dmom_riemannian(const double* pos, const double* mom, double* vel_o
   const ModelArgs m = to_args(model);
   cudaStream_t st = (cudaStream_t)stream;
 #define MB200_ARGS pos, mom, vel_out, n_chains, dim, m, status, st
+  if (wants_global_dense(m, dim))
+    return dense_global_vector(pos, mom, vel_out, n_chains, dim, m, status, st, 1);
   if (m.rmetric_id == MB200_RMETRIC_SOFTABS) {
     if (m.target_id == MB200_TARGET_BANANA) return launch_velocity<BananaRTarget, SoftAbsMetric>(MB200_ARGS);
     return fail(MB200_ERR_UNSUPPORTED, "target %d has no device Hessian", m.target_id);

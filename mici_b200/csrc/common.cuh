@@ -45,6 +45,10 @@ struct ModelArgs {
   // constrained kernels (device arrays [n_chains] or NULL), set by the *_per_chain entry points
   const double* step_sizes;
   const int32_t* n_steps_pc;
+  // per-CTA global scratch of the global-workspace dense metric policy (dense_global.cuh):
+  // CTA b owns [workspace + b * ws_stride, + ws_stride) doubles
+  double* workspace;
+  size_t ws_stride;
 };
 
 // Splitting schedule of a symmetric composition integrator (integrators.py:176-378): flow i is

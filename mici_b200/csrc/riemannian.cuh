@@ -172,13 +172,25 @@ struct RmWork {
   double *z0, *z1, *z2, *zb, *zp;  // [2*dim] implicit midpoint: iterates, base, previous (q, p)
   double *rc, *rs;  // rotation cos / sin [dim/2 + 1]
   int *top, *bot;   // round-robin index arrays [dim/2 + 1]
+  double* extra;    // shared memory beyond the carved vectors (global-dense policy: panel buffers)
 };
+
+// shared-memory doubles the global-workspace dense policy (dense_global.cuh) needs beyond the
+// vectors: the panel [(np - 32) x 36], the diagonal block and its inverse [32 x 36] each
+__host__ __device__ inline int dg_padded_dim(int dim) { return (dim + 31) & ~31; }
+__host__ __device__ inline size_t dg_smem_doubles(int dim) {
+  const int np = dg_padded_dim(dim);
+  return (size_t)(np > 32 ? np - 32 : 32) * 36 + 2 * 32 * 36;
+}
+constexpr int RM_NMATS_GLOBAL = -1;  // n_mats code: compact vector set + dg_smem_doubles()
 
 // n_mats: per-chain D x D matrices kept in shared memory (SoftAbs 2, or 3 with warm-started
 // eigensolves; dense Cholesky 1; Sherman-Morrison 0)
 __host__ __device__ inline size_t rm_smem_doubles(int dim, int n_mats) {
   const int ld = dim + 1;
   const int dpad = (dim + 1) & ~1;
+  if (n_mats == RM_NMATS_GLOBAL)  // q p qs ps x0 x1 x2 base v1 v2 v3 ev + scratch + panel buffers
+    return (size_t)12 * dpad + 40 + dg_smem_doubles(dim);
   size_t n = (size_t)dim * ld * n_mats;
   n += (size_t)16 * dpad;      // vectors (Vn counts double: NEED <= 2)
   n += (size_t)dpad;           // second half of Vn
@@ -194,6 +206,23 @@ __device__ inline void rm_carve(RmWork& w, double* s, int dim, int n_mats, Blk& 
   const int dpad = (dim + 1) & ~1;
   w.dim = dim;
   w.ld = ld;
+  if (n_mats == RM_NMATS_GLOBAL) {
+    w.M1 = w.M2 = w.M3 = nullptr;
+    double** cv[] = {&w.q, &w.p, &w.qs, &w.ps, &w.x0, &w.x1, &w.x2, &w.base, &w.v1, &w.v2, &w.v3,
+                     &w.ev};
+    for (auto v : cv) {
+      *v = s;
+      s += dpad;
+    }
+    w.lam = w.sa = w.gsa = w.Vn = nullptr;
+    w.z0 = w.z1 = w.z2 = w.zb = w.zp = nullptr;
+    w.rc = w.rs = nullptr;
+    w.top = w.bot = nullptr;
+    blk.red = s;
+    s += 40;
+    w.extra = s;
+    return;
+  }
   w.M1 = n_mats >= 1 ? s : nullptr;
   if (n_mats >= 1) s += (size_t)dim * ld;
   w.M2 = n_mats >= 2 ? s : nullptr;
@@ -226,6 +255,7 @@ __device__ inline void rm_carve(RmWork& w, double* s, int dim, int n_mats, Blk& 
   w.bot = w.top + (dpad / 2 + 2);
   s += dpad / 2 + 2;
   blk.red = s;
+  w.extra = s + 40;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -436,7 +466,7 @@ __device__ inline void smem_matmul(const Blk& k, int n, int ld, const double* X,
 // Diagnostic kernel: K3 on arbitrary dense symmetric matrices (one CTA per matrix).  With
 // `warm_from` >= 0 the solve of matrix i is warm-started from the eigenvectors of matrix
 // `warm_from` (exercising the V^T H V path used between fixed-point iterates).
-__global__ void __launch_bounds__(RM_THREADS)
+static __global__ void __launch_bounds__(RM_THREADS)
     eigh_selftest_kernel(const double* __restrict__ mats, int64_t n_mats, int dim, int warm_from,
                          double* __restrict__ eigval, double* __restrict__ eigvec,
                          int32_t* __restrict__ status) {
@@ -917,7 +947,7 @@ __device__ inline int fixed_point_steffensen(const Blk& k, int dim, double* xa, 
 // Diagnostic kernel: K4 on the reference's own known-answer problems
 // (reference tests/test_solvers.py:25-47): 0 babylonian (y/x + x)/2, 1 ratio (x+y)/(x+1),
 // 2 cosine, 3 doubling 2x, 4 quadratic 1 + x^2.  One CTA per problem instance.
-__global__ void __launch_bounds__(64)
+static __global__ void __launch_bounds__(64)
     fixed_point_selftest_kernel(int func_id, int solver, const double* __restrict__ x0,
                                 const double* __restrict__ y, int64_t n, int dim, double tol,
                                 double div_tol, int max_iters, double* __restrict__ x_out,

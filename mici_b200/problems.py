@@ -207,6 +207,32 @@ def c4_dense_riemannian(n_chains=8192, dim=512, seed=BASE_SEED + 4, coeff=0.1,
     )
 
 
+def c5_dense_hadamard(n_chains=8192, dim=512, seed=BASE_SEED + 7, coeff=0.1,
+                      integrator="implicit_leapfrog"):
+    """C4's system with a metric that has NO low-rank structure: M(q) = B + c (q q^T) o S.  The
+    quadratic target and the SPD matrices are generated like C4's; the metric can only be handled
+    by the generic dense path (per-chain Cholesky + explicit inverse + dense VJP)."""
+    rng = np.random.default_rng(seed)
+    g = rng.standard_normal((dim, dim))
+    prec = np.identity(dim) + 0.1 * (g @ g.T) / dim
+    base = dense_spd_metric(rng, dim)
+    scale = dense_spd_metric(rng, dim)
+    pos = 0.5 * rng.standard_normal((n_chains, dim))
+    mom = rng.standard_normal((n_chains, dim)) @ np.linalg.cholesky(base).T
+    return Problem(
+        name="C5",
+        integrator=integrator,
+        system="dense_riemannian",
+        target="quadratic",
+        target_params={"prec": prec},
+        step_size=0.05,
+        pos=pos,
+        mom=mom,
+        metric_model="hadamard",
+        metric_params={"base": base, "scale": scale, "coeff": coeff},
+    )
+
+
 def sphere_constrained(n_chains=64, dim=10, seed=BASE_SEED + 5, metric_kind="dense"):
     """Extra parity case for K6 beyond C3: unit sphere in R^dim, tilted Gaussian density,
     optional diagonal / dense metric (exercises the general-dimension constrained path)."""
@@ -253,6 +279,7 @@ CONFIGS = {
     "C2": c2_softabs_banana,
     "C3": c3_torus,
     "C4": c4_dense_riemannian,
+    "C5": c5_dense_hadamard,
     "S1": sphere_constrained,
     "G1": g1_gaussian_split,
 }

@@ -23,7 +23,7 @@ import torch
 
 from . import _lib
 from .errors import LinAlgError
-from .targets import RMETRIC_SOFTABS, Rank1Metric, Target
+from .targets import RMETRIC_SOFTABS, HadamardMetric, Rank1Metric, Target
 
 METRIC_IDENTITY, METRIC_DIAGONAL, METRIC_DENSE = 0, 1, 2
 
@@ -563,14 +563,20 @@ class RiemannianMetricSystem(System):
 
 
 class DenseRiemannianMetricSystem(RiemannianMetricSystem):
-    """Dense position-dependent metric (systems.py:1710-1760): ``metric_func`` is a
-    ``mici_b200.targets.Rank1Metric`` model (M(q) = B + c q q^T)."""
+    """Dense position-dependent metric (systems.py:1710-1760): ``metric_func`` is a registered
+    metric model -- ``mici_b200.targets.Rank1Metric`` (M(q) = B + c q q^T) or
+    ``mici_b200.targets.HadamardMetric`` (M(q) = B + c (q q^T) o S, full rank).  Each chain's
+    metric is factorised (Cholesky), inverted explicitly and differentiated through the model's
+    VJP as the reference does (matrices.py:1161-1188, systems.py:1381-1399): in shared memory
+    for D <= 160, in a per-CTA global workspace with DMMA-blocked routines beyond
+    (csrc/dense_global.cuh)."""
 
     def __init__(self, neg_log_dens, metric_func, *, vjp_metric_func=None,
                  grad_neg_log_dens=None, backend=None):
         super().__init__(neg_log_dens, grad_neg_log_dens=grad_neg_log_dens, backend=backend)
-        if not isinstance(metric_func, Rank1Metric):
-            raise TypeError("`metric_func` must be a registered metric model (Rank1Metric).")
+        if not isinstance(metric_func, (Rank1Metric, HadamardMetric)):
+            raise TypeError("`metric_func` must be a registered metric model "
+                            "(Rank1Metric or HadamardMetric).")
         if vjp_metric_func is not None:
             raise ValueError("The metric VJP is fused into the kernels.")
         self.metric_model = metric_func

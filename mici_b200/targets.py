@@ -20,6 +20,7 @@ TARGET_SPHERE = 5
 
 RMETRIC_SOFTABS = 0
 RMETRIC_RANK1 = 1
+RMETRIC_HADAMARD = 2
 
 
 class Target:
@@ -110,7 +111,13 @@ class Rank1Metric:
     rmetric_id = RMETRIC_RANK1
     name = "rank1"
 
-    def __init__(self, base, coeff, force_low_rank_form=False):
+    def __init__(self, base, coeff, force_low_rank_form=False, generic_rank1_vjp=False):
+        """``force_low_rank_form``: evaluate the metric through the Sherman-Morrison identities
+        against the shared explicit ``B^-1`` (O(D^2) per metric, never factorises) instead of the
+        reference's per-chain Cholesky path -- an OPTIONAL policy; by default the metric is
+        factorised per chain exactly as a generic dense metric.  ``generic_rank1_vjp``: form
+        ``-(M^-1 p)(M^-1 p)^T`` explicitly and hand it to the dense VJP (matrices.py:1179-1181)
+        instead of using the model's rank-one VJP."""
         base = np.ascontiguousarray(base, dtype=np.float64)
         # shared explicit inverse and log-determinant of B, built once on the host the way the
         # reference builds a fixed dense metric's inverse (matrices.py:1161-1188, 982-984)
@@ -125,13 +132,32 @@ class Rank1Metric:
             float(coeff),
             float(2.0 * np.log(np.abs(chol.diagonal())).sum()),
             1.0 if force_low_rank_form else 0.0,
+            1.0 if generic_rank1_vjp else 0.0,
         )
+
+
+class HadamardMetric:
+    """Position-dependent dense metric M(q) = B + c (q q^T) o S, B and S symmetric positive
+    definite: a full-rank perturbation of B (Schur product theorem keeps it SPD), so only the
+    generic dense path -- per-chain Cholesky, explicit inverse, dense VJP -- applies."""
+
+    rmetric_id = RMETRIC_HADAMARD
+    name = "hadamard"
+
+    def __init__(self, base, scale, coeff, generic_rank1_vjp=False):
+        base = np.ascontiguousarray(base, dtype=np.float64)
+        scale = np.ascontiguousarray(scale, dtype=np.float64)
+        if base.shape != scale.shape or base.ndim != 2 or base.shape[0] != base.shape[1]:
+            raise ValueError("`base` and `scale` must be square matrices of the same shape.")
+        self.base, self.scale = base, scale
+        self.aux = np.ascontiguousarray(np.concatenate([base.ravel(), scale.ravel()]))
+        self.params = (float(coeff), 0.0, 0.0, 1.0 if generic_rank1_vjp else 0.0)
 
 
 REGISTRY = {
     cls.name: cls for cls in (StdGaussian, NealFunnel, Banana, Quadratic, Torus, Sphere)
 }
-METRIC_REGISTRY = {"rank1": Rank1Metric}
+METRIC_REGISTRY = {"rank1": Rank1Metric, "hadamard": HadamardMetric}
 
 
 def make_target(name, **params):

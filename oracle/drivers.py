@@ -47,7 +47,11 @@ def build_target(problem):
 
 def build_metric_model(problem):
     if problem.metric_model == "rank1":
-        return tg.Rank1Metric(**problem.metric_params)
+        return tg.Rank1Metric(**{k: v for k, v in problem.metric_params.items()
+                                 if k in ("base", "coeff")})
+    if problem.metric_model == "hadamard":
+        return tg.HadamardMetric(**{k: v for k, v in problem.metric_params.items()
+                                    if k in ("base", "scale", "coeff")})
     if problem.metric_model is None:
         return None
     raise KeyError(problem.metric_model)

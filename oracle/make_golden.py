@@ -56,6 +56,10 @@ CASES = {
     "s1_sphere_identity_d5": ("S1", {"n_chains": 16, "dim": 5, "metric_kind": "identity"}, (1, 20), {}),
     "c4_dense_riemannian_d64": ("C4", {"n_chains": 8, "dim": 64}, (1, 5), {}),
     "c4_dense_riemannian_d512": ("C4", {"n_chains": 8, "dim": 512}, (1, 5), {}),
+    # full-rank position-dependent metric M(q) = B + c (q q^T) o S: generic dense path only
+    "c5_hadamard_d24": ("C5", {"n_chains": 8, "dim": 24}, (1, 5, 20), {}),
+    "c5_hadamard_d100": ("C5", {"n_chains": 6, "dim": 100}, (1, 5), {}),
+    "c5_hadamard_d512": ("C5", {"n_chains": 8, "dim": 512}, (1, 5), {}),
 }
 
 # failure-path fixtures: step sizes chosen so that some chains raise IntegratorError

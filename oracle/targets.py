@@ -142,6 +142,28 @@ class Rank1Metric:
         return lambda v: c * ((v + v.T) @ q)
 
 
+class HadamardMetric:
+    """Position-dependent dense metric M(q) = B + c (q q^T) o S with B, S symmetric positive
+    definite (``o`` = elementwise product).  M(q) is SPD by the Schur product theorem and, unlike
+    the rank-1 model, is a full-rank perturbation of B: no low-rank identity applies, the
+    reference's Cholesky / explicit-inverse path (matrices.py:1161-1188) is the only way through.
+    dM_ij/dq_k = c S_ij (d_ik q_j + d_jk q_i), so vjp(V)_k = c sum_j (V_kj + V_jk) S_kj q_j."""
+
+    name = "hadamard"
+
+    def __init__(self, base, scale, coeff):
+        self.base = np.asarray(base)
+        self.scale = np.asarray(scale)
+        self.coeff = float(coeff)
+
+    def metric_func(self, q):
+        return self.base + self.coeff * (np.outer(q, q) * self.scale)
+
+    def vjp_metric_func(self, q):
+        c, s = self.coeff, self.scale
+        return lambda v: c * (((v + v.T) * s) @ q)
+
+
 class Torus:
     """Density on a torus embedded in R^3 (config C3; reference README.md:315-337).
 

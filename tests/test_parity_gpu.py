@@ -428,11 +428,75 @@ def test_riemannian_sample_momentum_matches_oracle(cfg, kwargs):
 
 
 def test_riemannian_sample_momentum_unavailable_in_low_rank_form():
+    """The OPTIONAL Sherman-Morrison policy has no Cholesky factor of M(q); the default dense
+    policy at D = 512 (global-workspace blocked Cholesky) samples like the oracle."""
     problem = problems.make_problem("C4", n_chains=4, dim=512)
+    problem.metric_params = dict(problem.metric_params, force_low_rank_form=True)
     system = engine.build_system(problem)
     state = engine.build_state(problem, DEV)
     with pytest.raises(RuntimeError, match="does not fit"):
         system.sample_momentum(state, np.random.default_rng(0))
+
+
+@pytest.mark.parametrize("cfg,kwargs", [
+    ("C4", {"n_chains": 4, "dim": 512}),
+    ("C5", {"n_chains": 5, "dim": 200}),
+])
+def test_global_dense_metric_momentum_velocity_and_energy_match_oracle(cfg, kwargs):
+    """sqrt(M) z, M^-1 p and h through the global-workspace dense policy (D > 160)."""
+    problem = problems.make_problem(cfg, **kwargs)
+    system = engine.build_system(problem)
+    state = engine.build_state(problem, DEV)
+    _, h_fn, osys = dr.oracle_step_fn(problem)
+    rngs = [np.random.default_rng([7, i]) for i in range(problem.n_chains)]
+    got = system.sample_momentum(state, rngs).cpu().numpy()
+    want = np.stack([osys.metric(problem.pos[i]).sqrt_matvec(
+        np.random.default_rng([7, i]).normal(size=problem.dim)) for i in range(problem.n_chains)])
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-11)
+    vel = system.dh_dmom(state).cpu().numpy()
+    want_v = np.stack([osys.metric(problem.pos[i]).inv_matvec(problem.mom[i])
+                       for i in range(problem.n_chains)])
+    np.testing.assert_allclose(vel, want_v, rtol=1e-9, atol=1e-11)
+    h = system.h(state).cpu().numpy()
+    want_h = np.array([h_fn(problem.pos[i], problem.mom[i]) for i in range(problem.n_chains)])
+    np.testing.assert_allclose(h, want_h, rtol=1e-10)
+
+
+@pytest.mark.parametrize("dim", [5, 32, 33, 64, 100, 200, 512])
+def test_blocked_dmma_cholesky_inverse_and_solve_match_numpy(dim):
+    """csrc/dense_global.cuh on random SPD matrices: L, M^-1, M^-1 b and log|M| vs numpy.linalg
+    (the arithmetic of DensePositiveDefiniteMatrix, matrices.py:1161-1188, 982-984)."""
+    import ctypes
+
+    from mici_b200 import _lib
+
+    rng = np.random.default_rng(dim)
+    n_mats = 6
+    a = rng.standard_normal((n_mats, dim, dim))
+    mats = a @ a.transpose(0, 2, 1) / dim + np.identity(dim)
+    mats[-1] = mats[-1] - 3.0 * np.identity(dim)  # not positive definite: status 3
+    rhs = rng.standard_normal((n_mats, dim))
+    d_m = torch.as_tensor(mats, device=DEV).contiguous()
+    d_b = torch.as_tensor(rhs, device=DEV).contiguous()
+    chol = torch.zeros_like(d_m)
+    inv = torch.zeros_like(d_m)
+    sol = torch.zeros_like(d_b)
+    logdet = torch.zeros(n_mats, dtype=torch.float64, device=DEV)
+    status = torch.full((n_mats,), -1, dtype=torch.int32, device=DEV)
+    rc = _lib.load().mb200_selftest_dense_factor(
+        _lib.ptr(d_m), _lib.ptr(d_b), n_mats, dim, _lib.ptr(chol), _lib.ptr(inv), _lib.ptr(sol),
+        _lib.ptr(logdet), _lib.ptr(status), _lib.current_stream_ptr(torch.device(DEV)))
+    _lib.check(rc, "mb200_selftest_dense_factor")
+    torch.cuda.synchronize()
+    st = status.cpu().numpy()
+    assert list(st[:-1]) == [0] * (n_mats - 1) and st[-1] == 3
+    for i in range(n_mats - 1):
+        want_l = np.linalg.cholesky(mats[i])
+        np.testing.assert_allclose(chol[i].cpu().numpy(), want_l, rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(inv[i].cpu().numpy(), np.linalg.inv(mats[i]), rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(sol[i].cpu().numpy(), np.linalg.solve(mats[i], rhs[i]),
+                                   rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(float(logdet[i]), np.linalg.slogdet(mats[i])[1], rtol=1e-12)
 
 
 ADAPT_NAMES = ["adapt_c1_dualavg_variance", "adapt_c1_dualavg_covariance", "adapt_c0_dualavg_min",
