@@ -158,35 +158,62 @@ __device__ __forceinline__ void dg_zero(double (&acc)[4][4][2]) {
     for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = 0.0, acc[mt][nt][1] = 0.0;
 }
 
+// Factor the 32 x 32 diagonal block at `Akk` (row stride np) and invert the factor: one warp, one
+// row per lane.  Publishes L_kk to the workspace (strict upper part zeroed) and W_kk = L_kk^-1 to
+// g.wblk (shared, for the panel product) and g.W (workspace, for the triangular solves).
+__device__ __forceinline__ int dg_factor_diag(DgWork& g, int kb, int lane) {
+  const int np = g.np;
+  double* Akk = g.L + (size_t)(kb * DG_NB) * np + kb * DG_NB;
+  double rowv[32], w[32];
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const double2 v = *reinterpret_cast<const double2*>(&Akk[(size_t)lane * np + j]);
+    rowv[j] = v.x, rowv[j + 1] = v.y;
+  }
+  const int ok = warp_chol32(rowv, lane) ? 1 : 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) w[j] = 0.0;
+  warp_trinv32(rowv, w, lane);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    Akk[(size_t)lane * np + j] = j <= lane ? rowv[j] : 0.0;
+    g.wblk[j * DG_LDP + lane] = w[j];  // W[j][lane]
+    g.W[(size_t)kb * DG_NB * DG_NB + j * DG_NB + lane] = w[j];
+  }
+  return ok;
+}
+
+// tile index t of the lower-triangular enumeration (0,0), (1,0), (1,1), (2,0), ... -> (bi, bj)
+__device__ __forceinline__ void dg_tile_decode(int t, int& bi, int& bj) {
+  bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+  while (bi * (bi + 1) / 2 > t) --bi;
+  while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+  bj = t - bi * (bi + 1) / 2;
+}
+
 // In-place blocked Cholesky of the SPD matrix in g.L (lower triangle referenced; on return the
 // lower triangle holds L, the strict upper triangle of the diagonal blocks is zero, blocks above
 // the diagonal are untouched) and W_kk = L_kk^-1 in g.W.  Returns false on a failed pivot
 // (-> LinAlgError "Cholesky factorisation failed", matrices.py:1170-1172).
-__device__ inline bool dg_cholesky(const Blk& k, DgWork& g) {
+//
+// Per 32-column panel: [panel product L_ik = A_ik W^T] -> barrier -> [trailing update, tiles
+// handed out through a shared counter; warp 0 takes the tile of the NEXT diagonal block first and
+// factors / inverts it while the other warps finish the update (look-ahead: the serial 32 x 32
+// factorisation leaves the critical path)] -> barrier.  A warp prefetches the C tile of its next
+// work item while the tensor pipe works on the current one.
+__device__ __noinline__ bool dg_cholesky(const Blk& k, DgWork& g) {
   const int np = g.np, lane = k.lane, r = lane >> 2, c = lane & 3;
+  int* counter = reinterpret_cast<int*>(g.dblk);  // shared work counter (+ failure flag)
+  if (k.tid == 0) counter[0] = 0, counter[1] = 1;
+  __syncthreads();
+  if (k.warp == 0) {
+    const int ok = dg_factor_diag(g, 0, lane);
+    if (lane == 0) counter[1] = ok;
+  }
+  __syncthreads();
   for (int kb = 0; kb < g.nblk; ++kb) {
+    if (counter[1] == 0) return false;  // uniform: written before the last barrier
     const int d0 = kb * DG_NB;
-    double* Akk = g.L + (size_t)d0 * np + d0;
-    // ---- diagonal block: factor and invert (warp 0), publish to shared memory and the workspace
-    int ok = 1;
-    if (k.warp == 0) {
-      double rowv[32], w[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) rowv[j] = Akk[(size_t)lane * np + j];
-      ok = warp_chol32(rowv, lane) ? 1 : 0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) w[j] = 0.0;
-      warp_trinv32(rowv, w, lane);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const double v = j <= lane ? rowv[j] : 0.0;
-        Akk[(size_t)lane * np + j] = v;
-        g.dblk[lane * DG_LDP + j] = v;
-        g.wblk[j * DG_LDP + lane] = w[j];                       // W[j][lane]
-        g.W[(size_t)kb * DG_NB * DG_NB + j * DG_NB + lane] = w[j];
-      }
-    }
-    if (__syncthreads_and(ok) == 0) return false;
     const int m = np - d0 - DG_NB;  // rows below the diagonal block
     if (m == 0) break;
     // ---- panel: raw A[d0+32 .., d0 .. d0+32) into shared memory
@@ -196,6 +223,7 @@ __device__ inline bool dg_cholesky(const Blk& k, DgWork& g) {
       const double2 v = *reinterpret_cast<const double2*>(Ap + (size_t)row * np + 2 * c2);
       *reinterpret_cast<double2*>(&g.panel[row * DG_LDP + 2 * c2]) = v;
     }
+    if (k.tid == 0) counter[0] = 1;  // tile 0 is reserved for warp 0
     __syncthreads();
     // L_ik = A_ik W^T, one 32-row block per warp, in place (a warp touches only its own rows)
     for (int ib = k.warp; ib < m / DG_NB; ib += k.nwarp) {
@@ -215,38 +243,98 @@ __device__ inline bool dg_cholesky(const Blk& k, DgWork& g) {
         }
     }
     __syncthreads();
-    // ---- trailing update: A_ij -= L_ik L_jk^T, block pairs i >= j dealt round-robin to the warps
-    const int rb = m / DG_NB;
-    int cnt = 0;
-    for (int bi = 0; bi < rb; ++bi)
-      for (int bj = 0; bj <= bi; ++bj, ++cnt) {
-        if (cnt % k.nwarp != k.warp) continue;
-        double acc[4][4][2];
-        dg_zero(acc);
-        dg_tile_abt(acc, g.panel + (size_t)bi * DG_NB * DG_LDP, DG_LDP,
-                    g.panel + (size_t)bj * DG_NB * DG_LDP, DG_LDP, 8, r, c);
-        double* Cij = g.L + (size_t)(d0 + DG_NB + bi * DG_NB) * np + d0 + DG_NB + bj * DG_NB;
+    // ---- trailing update: A_ij -= L_ik L_jk^T over the block pairs i >= j
+    const int rb = m / DG_NB, ntiles = rb * (rb + 1) / 2;
+    double* C0 = g.L + (size_t)(d0 + DG_NB) * np + d0 + DG_NB;
+    auto tile_ptr = [&](int t, int& bi, int& bj) {
+      dg_tile_decode(t, bi, bj);
+      return C0 + (size_t)(bi * DG_NB) * np + bj * DG_NB;
+    };
+    auto next_tile = [&]() {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(&counter[0], 1);
+      return __shfl_sync(FULL_MASK, t, 0);
+    };
+    double cur[4][4][2], nxt[4][4][2];
+    auto load_tile = [&](const double* Cij, double (&dst)[4][4][2]) {
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+      for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) {
-            double2* ptr = reinterpret_cast<double2*>(&Cij[(size_t)(8 * mt + r) * np + 8 * nt + 2 * c]);
-            double2 v = *ptr;
-            v.x -= acc[mt][nt][0];
-            v.y -= acc[mt][nt][1];
-            *ptr = v;
-          }
+        for (int nt = 0; nt < 4; ++nt) {
+          const double2 v =
+              *reinterpret_cast<const double2*>(&Cij[(size_t)(8 * mt + r) * np + 8 * nt + 2 * c]);
+          dst[mt][nt][0] = v.x, dst[mt][nt][1] = v.y;
+        }
+    };
+    int t = (k.warp == 0) ? 0 : next_tile();
+    int bi = 0, bj = 0;
+    double* Cij = nullptr;
+    if (t < ntiles) {
+      Cij = tile_ptr(t, bi, bj);
+      load_tile(Cij, cur);
+    }
+    while (t < ntiles) {
+      const bool diag_next = (k.warp == 0 && t == 0);
+      // look-ahead: warp 0 goes straight to the next diagonal block after tile 0
+      const int tn = diag_next ? ntiles : next_tile();
+      int bin = 0, bjn = 0;
+      double* Cn = nullptr;
+      if (tn < ntiles) {
+        Cn = tile_ptr(tn, bin, bjn);
+        load_tile(Cn, nxt);
       }
+      // cur -= L_i L_j^T: the A fragments enter negated
+      {
+        const double* A = g.panel + (size_t)bi * DG_NB * DG_LDP;
+        const double* B = g.panel + (size_t)bj * DG_NB * DG_LDP;
+        for (int ks = 0; ks < 8; ++ks) {
+          double a[4], b[4];
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) {
+            a[tt] = -A[(8 * tt + r) * DG_LDP + 4 * ks + c];
+            b[tt] = B[(8 * tt + r) * DG_LDP + 4 * ks + c];
+          }
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) dg_dmma(cur[mt][nt][0], cur[mt][nt][1], a[mt], b[nt]);
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+          *reinterpret_cast<double2*>(&Cij[(size_t)(8 * mt + r) * np + 8 * nt + 2 * c]) =
+              make_double2(cur[mt][nt][0], cur[mt][nt][1]);
+      if (diag_next) {
+        __syncwarp();  // the tile written above is the next diagonal block: visible to all lanes
+        const int ok = dg_factor_diag(g, kb + 1, lane);
+        if (lane == 0 && !ok) counter[1] = 0;
+        __syncwarp();
+        // then help with whatever tiles are left
+        t = next_tile();
+        if (t < ntiles) {
+          Cij = tile_ptr(t, bi, bj);
+          load_tile(Cij, cur);
+        }
+        continue;
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) cur[mt][nt][0] = nxt[mt][nt][0], cur[mt][nt][1] = nxt[mt][nt][1];
+      t = tn, bi = bin, bj = bjn, Cij = Cn;
+    }
     __syncthreads();
   }
-  return true;
+  return counter[1] != 0;
 }
 
 // x = L^-1 b (forward) then x = L^-T x (backward) with the stored diagonal-block inverses; b, x in
 // shared memory (x may alias b), `tmp` a shared scratch vector of np doubles is NOT needed: the
 // right-hand side is updated in place.  Only entries < g.n are meaningful (padding rows are the
 // identity).
-__device__ inline void dg_solve(const Blk& k, const DgWork& g, const double* b, double* x,
+__device__ __noinline__ void dg_solve(const Blk& k, const DgWork& g, const double* b, double* x,
                                 bool forward, bool backward) {
   const int np = g.np, n = g.n;
   for (int i = k.tid; i < n; i += k.nthr) x[i] = b[i];
@@ -255,14 +343,22 @@ __device__ inline void dg_solve(const Blk& k, const DgWork& g, const double* b, 
   if (forward) {
     for (int kb = 0; kb < g.nblk; ++kb) {
       const int d0 = kb * DG_NB;
-      if (k.warp == 0) {  // y = W_kk x_kb
-        const double* Wk = g.W + (size_t)kb * DG_NB * DG_NB + (size_t)k.lane * DG_NB;
+      // y = W_kk x_kb: 8 threads per row (4 columns each), reduced with shuffles
+      {
+        const int row = k.tid >> 3, part = k.tid & 7;
+        const double* Wk = g.W + (size_t)kb * DG_NB * DG_NB + (size_t)row * DG_NB + 4 * part;
         double s = 0.0;
-        for (int j = 0; j <= k.lane; ++j) {
-          const int gj = d0 + j;
-          s = fma(Wk[j], gj < n ? x[gj] : 0.0, s);
+        if (k.tid < 8 * DG_NB) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int gj = d0 + 4 * part + j;
+            s = fma(Wk[j], gj < n ? x[gj] : 0.0, s);
+          }
         }
-        y[k.lane] = s;
+        s += __shfl_xor_sync(FULL_MASK, s, 1);
+        s += __shfl_xor_sync(FULL_MASK, s, 2);
+        s += __shfl_xor_sync(FULL_MASK, s, 4);
+        if (k.tid < 8 * DG_NB && part == 0) y[row] = s;
       }
       __syncthreads();
       if (k.tid < DG_NB && d0 + k.tid < n) x[d0 + k.tid] = y[k.tid];
@@ -280,14 +376,22 @@ __device__ inline void dg_solve(const Blk& k, const DgWork& g, const double* b, 
   if (backward) {
     for (int kb = g.nblk - 1; kb >= 0; --kb) {
       const int d0 = kb * DG_NB;
-      if (k.warp == 0) {  // y = W_kk^T x_kb
-        const double* Wk = g.W + (size_t)kb * DG_NB * DG_NB;
+      // y = W_kk^T x_kb: 8 threads per output entry (4 rows of W each), reduced with shuffles
+      {
+        const int col = k.tid >> 3, part = k.tid & 7;
+        const double* Wk = g.W + (size_t)kb * DG_NB * DG_NB + col;
         double s = 0.0;
-        for (int j = k.lane; j < DG_NB; ++j) {
-          const int gj = d0 + j;
-          s = fma(Wk[(size_t)j * DG_NB + k.lane], gj < n ? x[gj] : 0.0, s);
+        if (k.tid < 8 * DG_NB) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int jj = 4 * part + j, gj = d0 + jj;
+            s = fma(Wk[(size_t)jj * DG_NB], gj < n ? x[gj] : 0.0, s);
+          }
         }
-        y[k.lane] = s;
+        s += __shfl_xor_sync(FULL_MASK, s, 1);
+        s += __shfl_xor_sync(FULL_MASK, s, 2);
+        s += __shfl_xor_sync(FULL_MASK, s, 4);
+        if (k.tid < 8 * DG_NB && part == 0) y[col] = s;
       }
       __syncthreads();
       if (k.tid < DG_NB && d0 + k.tid < n) x[d0 + k.tid] = y[k.tid];
@@ -305,7 +409,7 @@ __device__ inline void dg_solve(const Blk& k, const DgWork& g, const double* b, 
 
 // Explicit inverse: X = L^-1 (block rows, X_ic = -W_ii sum_{c<=k<i} L_ik X_kc) then
 // M^-1 = X^T X; both matrices in the workspace, M^-1 stored full (symmetric).
-__device__ inline void dg_explicit_inverse(const Blk& k, DgWork& g) {
+__device__ __noinline__ void dg_explicit_inverse(const Blk& k, DgWork& g) {
   const int np = g.np, nb = g.nblk, lane = k.lane, r = lane >> 2, c = lane & 3;
   // ---- X = L^-1
   for (int i = 0; i < nb; ++i) {
@@ -472,6 +576,7 @@ template <class Target, class Model>
 struct GlobalDenseMetricT {
   static constexpr bool SOFTABS = false;
   static constexpr int N_MATS = RM_NMATS_GLOBAL;
+  static constexpr int MIN_BLOCKS = 1;  // ~200 KB of shared memory per CTA: one CTA per SM
   const Target& t;
   Model model;
   DgWork g;
@@ -491,16 +596,20 @@ struct GlobalDenseMetricT {
     have_inv = false;
     const int n = g.n, np = g.np;
     bool bad = false;
-    for (int idx = k.tid; idx < np * np; idx += k.nthr) {
-      const int i = idx / np, j = idx - i * np;
-      double v;
-      if (i < n && j < n) {
-        v = model.entry(q, i, j);
-        if (!isfinite(v)) bad = true;
-      } else {
-        v = (i == j) ? 1.0 : 0.0;  // identity padding
+    // lower triangle only (the factorisation never reads above the diagonal blocks): one row
+    // per warp, lanes along the row
+    for (int i = k.warp; i < np; i += k.nwarp) {
+      const int jmax = (i | 31) + 1;  // through the end of the row's diagonal block
+      for (int j = k.lane; j < jmax; j += 32) {
+        double v;
+        if (i < n && j < n) {
+          v = model.entry(q, i, j);
+          if (!isfinite(v)) bad = true;
+        } else {
+          v = (i == j) ? 1.0 : 0.0;  // identity padding
+        }
+        g.L[(size_t)i * np + j] = v;
       }
-      g.L[idx] = v;
     }
     if (block_any(k, bad)) return MB200_STATUS_LINALG;  // "Array is not finite" (:211-215)
     if (!dg_cholesky(k, g)) return MB200_STATUS_LINALG;
