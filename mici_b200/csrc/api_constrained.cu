@@ -82,6 +82,20 @@ int mb200_constrained_leapfrog_euclidean(
       if (dim <= 128) return launch_constrained<SphereTarget, 2>(MB200_ARGS);
       if (dim <= 256) return launch_constrained<SphereTarget, 4>(MB200_ARGS);
       return fail(MB200_ERR_UNSUPPORTED, "sphere target: dim %d > 256 not supported", dim);
+    case MB200_TARGET_MULTI_SPHERE: {
+      const int nc = (int)m.tp[0];
+      if ((nc != 2 && nc != 4 && nc != 8) || dim % nc != 0 || dim > 128)
+        return fail(MB200_ERR_UNSUPPORTED,
+                    "multi-sphere target: n_constr must be 2, 4 or 8, dim a multiple <= 128");
+      if (dim <= 64) {
+        if (nc == 2) return launch_constrained<MultiSphereTarget<2>, 1>(MB200_ARGS);
+        if (nc == 4) return launch_constrained<MultiSphereTarget<4>, 1>(MB200_ARGS);
+        return launch_constrained<MultiSphereTarget<8>, 1>(MB200_ARGS);
+      }
+      if (nc == 2) return launch_constrained<MultiSphereTarget<2>, 2>(MB200_ARGS);
+      if (nc == 4) return launch_constrained<MultiSphereTarget<4>, 2>(MB200_ARGS);
+      return launch_constrained<MultiSphereTarget<8>, 2>(MB200_ARGS);
+    }
     default:
       return fail(MB200_ERR_UNSUPPORTED, "target %d defines no constraint", m.target_id);
   }
@@ -111,6 +125,20 @@ int mb200_project_onto_cotangent_space(const double* pos, const double* mom_in, 
       if (dim <= 128) return launch_project<SphereTarget, 2>(MB200_ARGS);
       if (dim <= 256) return launch_project<SphereTarget, 4>(MB200_ARGS);
       return fail(MB200_ERR_UNSUPPORTED, "sphere target: dim %d > 256 not supported", dim);
+    case MB200_TARGET_MULTI_SPHERE: {
+      const int nc = (int)m.tp[0];
+      if ((nc != 2 && nc != 4 && nc != 8) || dim % nc != 0 || dim > 128)
+        return fail(MB200_ERR_UNSUPPORTED,
+                    "multi-sphere target: n_constr must be 2, 4 or 8, dim a multiple <= 128");
+      if (dim <= 64) {
+        if (nc == 2) return launch_project<MultiSphereTarget<2>, 1>(MB200_ARGS);
+        if (nc == 4) return launch_project<MultiSphereTarget<4>, 1>(MB200_ARGS);
+        return launch_project<MultiSphereTarget<8>, 1>(MB200_ARGS);
+      }
+      if (nc == 2) return launch_project<MultiSphereTarget<2>, 2>(MB200_ARGS);
+      if (nc == 4) return launch_project<MultiSphereTarget<4>, 2>(MB200_ARGS);
+      return launch_project<MultiSphereTarget<8>, 2>(MB200_ARGS);
+    }
     default:
       return fail(MB200_ERR_UNSUPPORTED, "target %d defines no constraint", m.target_id);
   }

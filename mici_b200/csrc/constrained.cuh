@@ -95,6 +95,29 @@ struct TorusTarget {
     if (lane == 0) J[0][0] = f * x, J[0][1] = f * y;
     if (lane == 1) J[0][0] = 2.0 * z;
   }
+
+  // out_j = sum_{k,i} m[k][i] d^2 c_k / dq_i dq_j (matrix-Hessian product, systems.py:964-975):
+  // with f = 2 (rho - R) / rho and g = 2 R / rho^3 the Hessian of c is
+  // [[f + g x^2, g x y, 0], [g x y, f + g y^2, 0], [0, 0, 2]]
+  template <int NV>
+  __device__ __forceinline__ void mhp(int lane, int, const double (&q)[NV],
+                                      const double (&m)[NC][NV], double (&out)[NV]) const {
+    double x, y, z;
+    gather(q, x, y, z);
+    const double mx = __shfl_sync(FULL_MASK, m[0][0], 0);
+    const double my = __shfl_sync(FULL_MASK, m[0][1], 0);
+    const double mz = __shfl_sync(FULL_MASK, m[0][0], 1);
+    const double rho = sqrt(x * x + y * y);
+    const double f = 2.0 * (rho - R) / rho;
+    const double g = 2.0 * R / (rho * rho * rho);
+#pragma unroll
+    for (int e = 0; e < NV; ++e) out[e] = 0.0;
+    if (lane == 0) {
+      out[0] = mx * (f + g * x * x) + my * (g * x * y);
+      out[1] = mx * (g * x * y) + my * (f + g * y * y);
+    }
+    if (lane == 1) out[0] = 2.0 * mz;
+  }
 };
 
 // Unit sphere in R^D: l = |q|^2/2 + q[0];  c = |q|^2 - 1.
@@ -131,6 +154,73 @@ struct SphereTarget {
     c[0] = warp_sum(s) - 1.0;
 #pragma unroll
     for (int e = 0; e < NV; ++e) J[0][e] = 2.0 * q[e];
+  }
+
+  template <int NV>
+  __device__ __forceinline__ void mhp(int, int, const double (&)[NV], const double (&m)[NC][NV],
+                                      double (&out)[NV]) const {
+#pragma unroll
+    for (int e = 0; e < NV; ++e) out[e] = 2.0 * m[0][e];  // Hessian of c is 2 I
+  }
+};
+
+// NCON unit spheres: consecutive blocks of dim / NCON coordinates, c_k = |q_block_k|^2 - 1;
+// l = |q|^2/2 + q[0].  With a dense metric the Gram matrix is a full NCON x NCON matrix.
+template <int NCON>
+struct MultiSphereTarget {
+  static constexpr int NC = NCON;
+  int block;
+  __device__ MultiSphereTarget(const ModelArgs&, int dim) : block(dim / NCON) {}
+
+  template <int NV>
+  __device__ __forceinline__ void grad(int lane, int dim, const double (&q)[NV],
+                                       double (&g)[NV]) const {
+#pragma unroll
+    for (int e = 0; e < NV; ++e) {
+      const int i = 2 * lane + 64 * (e >> 1) + (e & 1);
+      g[e] = (i < dim) ? q[e] : 0.0;
+      if (i == 0) g[e] += 1.0;
+    }
+  }
+
+  template <int NV>
+  __device__ __forceinline__ double nld(int, int, const double (&q)[NV]) const {
+    double s = 0.0;
+#pragma unroll
+    for (int e = 0; e < NV; ++e) s = fma(q[e], q[e], s);
+    s = warp_sum(s);
+    return 0.5 * s + __shfl_sync(FULL_MASK, q[0], 0);
+  }
+
+  template <int NV>
+  __device__ __forceinline__ void constr_jacob(int lane, int dim, const double (&q)[NV],
+                                               double (&c)[NC], double (&J)[NC][NV]) const {
+#pragma unroll
+    for (int a = 0; a < NC; ++a) {
+      double s = 0.0;
+#pragma unroll
+      for (int e = 0; e < NV; ++e) {
+        const int i = 2 * lane + 64 * (e >> 1) + (e & 1);
+        const bool mine = i < dim && i / block == a;
+        J[a][e] = mine ? 2.0 * q[e] : 0.0;
+        if (mine) s = fma(q[e], q[e], s);
+      }
+      c[a] = warp_sum(s) - 1.0;
+    }
+  }
+
+  template <int NV>
+  __device__ __forceinline__ void mhp(int lane, int dim, const double (&)[NV],
+                                      const double (&m)[NC][NV], double (&out)[NV]) const {
+#pragma unroll
+    for (int e = 0; e < NV; ++e) {
+      const int i = 2 * lane + 64 * (e >> 1) + (e & 1);
+      double v = 0.0;
+#pragma unroll
+      for (int a = 0; a < NC; ++a)
+        if (i < dim && i / block == a) v = 2.0 * m[a][e];
+      out[e] = v;
+    }
   }
 };
 
@@ -191,6 +281,42 @@ __device__ __forceinline__ void spd_inverse_apply(const double (&G)[C][C], const
       s = fma(a, u[j], s);
     }
     x[i] = s;
+  }
+}
+
+// Ginv = explicit inverse of the SPD matrix G (as spd_inverse_apply builds it) and
+// half_logdet = sum log L_ii = log det G / 2 (DensePositiveDefiniteMatrix.log_abs_det / 2,
+// matrices.py:982-984, systems.py:836-838)
+template <int C>
+__device__ __forceinline__ void spd_inverse_logdet(const double (&G)[C][C], double (&Ginv)[C][C],
+                                                   double& half_logdet) {
+  half_logdet = 0.0;
+#pragma unroll
+  for (int b = 0; b < C; ++b) {
+    double u[C], x[C];
+#pragma unroll
+    for (int a = 0; a < C; ++a) u[a] = (a == b) ? 1.0 : 0.0;
+    spd_inverse_apply<C>(G, u, x);
+#pragma unroll
+    for (int a = 0; a < C; ++a) Ginv[a][b] = x[a];
+  }
+  // Cholesky diagonal again (cheap for C <= 8)
+  double L[C][C];
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    double d = G[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+    d = sqrt(d);
+    L[j][j] = d;
+    half_logdet += log(fabs(d));
+#pragma unroll
+    for (int i = j + 1; i < C; ++i) {
+      double t = G[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
+      L[i][j] = t / d;
+    }
   }
 }
 
@@ -277,6 +403,36 @@ struct ConstrainedOps {
 #pragma unroll
     for (int e = 0; e < NV; ++e) m = nanmax(m, fabs(a[e]));
     return warp_nanmax(m);
+  }
+
+  // dh1_dpos (systems.py:858-861): grad l, plus -- for a density given with respect to the
+  // Lebesgue measure (dens_wrt_hausdorff=False) -- grad_log_det_sqrt_gram =
+  // mhp_constr(inv_gram @ J @ M^-1) (systems.py:1024-1031).  Returns log det gram / 2 in *ldsg.
+  __device__ __forceinline__ void dh1(const double (&q)[NV], double (&g)[NV], bool lebesgue,
+                                      double* ldsg = nullptr) const {
+    t.grad(lane, dim, q, g);
+    if (!lebesgue) return;
+    double c[C], J[C][NV], W[C][NV], G[C][C], Ginv[C][C], m[C][NV], extra[NV], hl;
+    t.constr_jacob(lane, dim, q, c, J);
+    inv_metric_rows(J, W);  // rows of J M^-1 (M symmetric)
+#pragma unroll
+    for (int a = 0; a < C; ++a)
+#pragma unroll
+      for (int b = 0; b < C; ++b) G[a][b] = dot(J[a], W[b]);
+    spd_inverse_logdet<C>(G, Ginv, hl);
+#pragma unroll
+    for (int a = 0; a < C; ++a)
+#pragma unroll
+      for (int e = 0; e < NV; ++e) {
+        double v = 0.0;
+#pragma unroll
+        for (int b = 0; b < C; ++b) v = fma(Ginv[a][b], W[b][e], v);
+        m[a][e] = v;
+      }
+    t.mhp(lane, dim, q, m, extra);
+#pragma unroll
+    for (int e = 0; e < NV; ++e) g[e] = __dadd_rn(g[e], extra[e]);
+    if (ldsg != nullptr) *ldsg = hl;
   }
 
   // p <- p - J^T (J M^-1 J^T)^-1 J M^-1 p     (systems.py:863-873)
@@ -561,7 +717,8 @@ __global__ void __launch_bounds__(128)
       }
       q[2 * k] = q0, q[2 * k + 1] = q1, p[2 * k] = p0, p[2 * k + 1] = p1;
     }
-    target.grad(lane, dim, q, g);
+    const bool lebesgue = model.tp[MB200_MAX_PARAMS - 1] != 0.0;  // dens_wrt_hausdorff=False
+    ops.dh1(q, g, lebesgue);
     int st = MB200_STATUS_OK, done = 0, iters = 0;
     const double dt_inner = dt / n_inner;
     for (int s = 0; s < ns && st == MB200_STATUS_OK; ++s) {
@@ -599,7 +756,7 @@ __global__ void __launch_bounds__(128)
       }
       if (st == MB200_STATUS_OK) {
         // _step_a(dt/2)
-        target.grad(lane, dim, q, g);
+        ops.dh1(q, g, lebesgue);
 #pragma unroll
         for (int e = 0; e < NV; ++e) p[e] = __dsub_rn(p[e], __dmul_rn(0.5 * dt, g[e]));
         ops.project(p, q);
@@ -627,7 +784,12 @@ __global__ void __launch_bounds__(128)
       double v[NV];
       ops.inv_metric_vec(p, v);
       const double kin = ConstrainedOps<Target, KP>::dot(p, v);
-      const double l = target.nld(lane, dim, q);
+      double l = target.nld(lane, dim, q);
+      if (lebesgue) {  // h1 = l + log det gram / 2 (systems.py:853-856)
+        double gtmp[NV], ldsg = 0.0;
+        ops.dh1(q, gtmp, true, &ldsg);
+        l += ldsg;
+      }
       if (lane == 0) h_out[ch] = l + 0.5 * kin;
     }
     if (lane == 0) {

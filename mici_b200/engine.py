@@ -15,7 +15,9 @@ def build_system(problem):
     if problem.system == "gaussian_euclidean":
         return systems.GaussianEuclideanMetricSystem(target, metric=problem.metric)
     if problem.system == "constrained_euclidean":
-        return systems.DenseConstrainedEuclideanMetricSystem(target, target, metric=problem.metric)
+        return systems.DenseConstrainedEuclideanMetricSystem(
+            target, target, metric=problem.metric,
+            dens_wrt_hausdorff=problem.system_kwargs.get("dens_wrt_hausdorff", True))
     if problem.system == "softabs_riemannian":
         return systems.SoftAbsRiemannianMetricSystem(target, **problem.system_kwargs)
     if problem.system == "dense_riemannian":

@@ -154,7 +154,8 @@ def c2_softabs_banana(n_chains=2048, dim=64, seed=BASE_SEED + 2, integrator="imp
     )
 
 
-def c3_torus(n_chains=4096, seed=BASE_SEED + 3, R=1.0, r=0.5, alpha=0.9):
+def c3_torus(n_chains=4096, seed=BASE_SEED + 3, R=1.0, r=0.5, alpha=0.9,
+             dens_wrt_hausdorff=True):
     rng = np.random.default_rng(seed)
     theta, phi = rng.uniform(0, 2 * np.pi, size=(2, n_chains))
     pos = np.stack(
@@ -182,6 +183,7 @@ def c3_torus(n_chains=4096, seed=BASE_SEED + 3, R=1.0, r=0.5, alpha=0.9):
         pos=pos,
         mom=mom,
         integrator_kwargs={"n_inner_step": 1},
+        system_kwargs={"dens_wrt_hausdorff": dens_wrt_hausdorff},
     )
 
 
@@ -233,7 +235,8 @@ def c5_dense_hadamard(n_chains=8192, dim=512, seed=BASE_SEED + 7, coeff=0.1,
     )
 
 
-def sphere_constrained(n_chains=64, dim=10, seed=BASE_SEED + 5, metric_kind="dense"):
+def sphere_constrained(n_chains=64, dim=10, seed=BASE_SEED + 5, metric_kind="dense",
+                       dens_wrt_hausdorff=True):
     """Extra parity case for K6 beyond C3: unit sphere in R^dim, tilted Gaussian density,
     optional diagonal / dense metric (exercises the general-dimension constrained path)."""
     rng = np.random.default_rng(seed)
@@ -270,6 +273,48 @@ def sphere_constrained(n_chains=64, dim=10, seed=BASE_SEED + 5, metric_kind="den
         mom=mom,
         metric=metric,
         integrator_kwargs={"n_inner_step": 1},
+        system_kwargs={"dens_wrt_hausdorff": dens_wrt_hausdorff},
+    )
+
+
+def multi_sphere_constrained(n_chains=32, dim=16, n_constr=4, seed=BASE_SEED + 8,
+                             metric_kind="dense", dens_wrt_hausdorff=True):
+    """Extra parity case for K6 with SEVERAL constraints (C = n_constr <= 8): consecutive blocks
+    of dim / n_constr coordinates each on their unit sphere; with a dense metric the Gram matrix
+    and the Newton residual Jacobian are full C x C matrices."""
+    rng = np.random.default_rng(seed)
+    block = dim // n_constr
+    pos = rng.standard_normal((n_chains, n_constr, block))
+    pos /= np.linalg.norm(pos, axis=2, keepdims=True)
+    pos = pos.reshape(n_chains, dim)
+    mom = rng.standard_normal((n_chains, dim))
+    if metric_kind == "dense":
+        metric = dense_spd_metric(rng, dim)
+        minv = np.linalg.inv(metric)
+    elif metric_kind == "diagonal":
+        metric = rng.uniform(0.5, 2.0, dim)
+        minv = np.diag(1.0 / metric)
+    else:
+        metric = None
+        minv = np.identity(dim)
+    for i in range(n_chains):  # p -= J^T (J M^-1 J^T)^-1 J M^-1 p
+        jac = np.zeros((n_constr, dim))
+        for k in range(n_constr):
+            jac[k, k * block:(k + 1) * block] = 2.0 * pos[i, k * block:(k + 1) * block]
+        gram = jac @ minv @ jac.T
+        mom[i] -= jac.T @ np.linalg.solve(gram, jac @ (minv @ mom[i]))
+    return Problem(
+        name="S2",
+        integrator="constrained_leapfrog",
+        system="constrained_euclidean",
+        target="multi_sphere",
+        target_params={"dim": dim, "n_constr": n_constr},
+        step_size=0.15,
+        pos=pos,
+        mom=mom,
+        metric=metric,
+        integrator_kwargs={"n_inner_step": 1},
+        system_kwargs={"dens_wrt_hausdorff": dens_wrt_hausdorff},
     )
 
 
@@ -281,6 +326,7 @@ CONFIGS = {
     "C4": c4_dense_riemannian,
     "C5": c5_dense_hadamard,
     "S1": sphere_constrained,
+    "S2": multi_sphere_constrained,
     "G1": g1_gaussian_split,
 }
 

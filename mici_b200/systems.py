@@ -186,6 +186,9 @@ class System:
         m.n_target_params = len(t.params)
         for i, v in enumerate(t.params):
             m.target_params[i] = v
+        if not getattr(self, "dens_wrt_hausdorff", True):
+            # constrained systems: density given with respect to the Lebesgue measure
+            m.target_params[_lib.MAX_PARAMS - 1] = 1.0
         aux = self._aux_device("target_aux", t.aux, device)
         m.target_aux = None if aux is None else aux.data_ptr()
         m.rmetric_id = self._rmetric_id
@@ -409,7 +412,10 @@ class ConstrainedEuclideanMetricSystem(ConstrainedTractableFlowSystem, Euclidean
     """Euclidean system subject to holonomic constraints (systems.py:619-873).
 
     ``constr`` must be the same ``Target`` instance as ``neg_log_dens`` (constrained targets
-    carry their constraint function); ``dens_wrt_hausdorff`` must be ``True``.
+    carry their constraint function).  ``dens_wrt_hausdorff=False``: the target density is given
+    with respect to the Lebesgue measure and ``h1`` / ``dh1_dpos`` carry ``log det gram / 2`` and
+    its gradient through the constraint's matrix-Hessian product (systems.py:853-861, 1024-1031),
+    fused into the kernels.
     """
 
     def __init__(self, neg_log_dens, constr=None, *, metric=None, dens_wrt_hausdorff=True,
@@ -422,9 +428,7 @@ class ConstrainedEuclideanMetricSystem(ConstrainedTractableFlowSystem, Euclidean
             raise ValueError("The constraint Jacobian is fused into the kernels.")
         if neg_log_dens.n_constr < 1:
             raise ValueError(f"Target {neg_log_dens!r} defines no constraint function.")
-        if not dens_wrt_hausdorff:
-            raise NotImplementedError("Only `dens_wrt_hausdorff=True` is implemented.")
-        self.dens_wrt_hausdorff = dens_wrt_hausdorff
+        self.dens_wrt_hausdorff = bool(dens_wrt_hausdorff)
 
     def h(self, state):
         """``l(q) + p.M^-1 p/2`` (``dens_wrt_hausdorff=True``: systems.py:842-851, 187-196),
@@ -477,7 +481,7 @@ class DenseConstrainedEuclideanMetricSystem(ConstrainedEuclideanMetricSystem):
     def __init__(self, neg_log_dens, constr=None, *, metric=None, dens_wrt_hausdorff=True,
                  grad_neg_log_dens=None, jacob_constr=None, mhp_constr=None, backend=None):
         if mhp_constr is not None:
-            raise ValueError("`mhp_constr` is only used with `dens_wrt_hausdorff=False`.")
+            raise ValueError("The constraint's matrix-Hessian product is fused into the kernels.")
         super().__init__(neg_log_dens, constr, metric=metric,
                          dens_wrt_hausdorff=dens_wrt_hausdorff,
                          grad_neg_log_dens=grad_neg_log_dens, jacob_constr=jacob_constr,

@@ -17,6 +17,7 @@ TARGET_BANANA = 2
 TARGET_QUADRATIC = 3
 TARGET_TORUS = 4
 TARGET_SPHERE = 5
+TARGET_MULTI_SPHERE = 6
 
 RMETRIC_SOFTABS = 0
 RMETRIC_RANK1 = 1
@@ -47,6 +48,20 @@ class StdGaussian(Target):
 
     def __init__(self, dim):
         super().__init__(dim)
+
+
+class MultiSphere(Target):
+    """``n_constr`` (2, 4 or 8) unit spheres on consecutive blocks of ``dim / n_constr``
+    coordinates, c_k(q) = |q_block_k|^2 - 1; l = |q|^2/2 + q[0]."""
+
+    target_id = TARGET_MULTI_SPHERE
+    name = "multi_sphere"
+
+    def __init__(self, dim, n_constr):
+        if n_constr not in (2, 4, 8) or dim % n_constr:
+            raise ValueError("n_constr must be 2, 4 or 8 and divide dim.")
+        self.n_constr = n_constr
+        super().__init__(dim, (float(n_constr),))
 
 
 class NealFunnel(Target):
@@ -155,7 +170,8 @@ class HadamardMetric:
 
 
 REGISTRY = {
-    cls.name: cls for cls in (StdGaussian, NealFunnel, Banana, Quadratic, Torus, Sphere)
+    cls.name: cls
+    for cls in (StdGaussian, NealFunnel, Banana, Quadratic, Torus, Sphere, MultiSphere)
 }
 METRIC_REGISTRY = {"rank1": Rank1Metric, "hadamard": HadamardMetric}
 

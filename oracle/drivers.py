@@ -42,6 +42,8 @@ def build_target(problem):
         return tg.Torus(**kw)
     if name == "sphere":
         return tg.Sphere(**kw)
+    if name == "multi_sphere":
+        return tg.MultiSphere(**kw)
     raise KeyError(name)
 
 
@@ -111,7 +113,9 @@ def oracle_step_fn(problem, counts=None, **overrides):
 
         return step, system.h, system
     if problem.integrator == "constrained_leapfrog":
-        system = mo.ConstrainedSystem(target, problem.metric)
+        system = mo.ConstrainedSystem(
+            target, problem.metric,
+            dens_wrt_hausdorff=problem.system_kwargs.get("dens_wrt_hausdorff", True))
 
         def step(q, p, d):
             return mo.constrained_leapfrog_step(q, p, d * eps, system, counts=counts, **ikw)
@@ -199,9 +203,10 @@ def build_reference(problem, **overrides):
             neg_log_dens=target.neg_log_dens,
             constr=target.constr,
             metric=problem.metric,
-            dens_wrt_hausdorff=True,
+            dens_wrt_hausdorff=problem.system_kwargs.get("dens_wrt_hausdorff", True),
             grad_neg_log_dens=target.grad_neg_log_dens,
             jacob_constr=target.jacob_constr,
+            mhp_constr=target.mhp_constr,
         )
     else:
         raise KeyError(problem.system)

@@ -54,6 +54,16 @@ CASES = {
     "s1_sphere_dense_d10": ("S1", {"n_chains": 32, "dim": 10}, (1, 5, 20), {}),
     "s1_sphere_diag_d70_inner2": ("S1", {"n_chains": 8, "dim": 70, "metric_kind": "diagonal"}, (1, 5), {"n_inner_step": 2}),
     "s1_sphere_identity_d5": ("S1", {"n_chains": 16, "dim": 5, "metric_kind": "identity"}, (1, 20), {}),
+    # density with respect to the Lebesgue measure (dens_wrt_hausdorff=False): h1 carries
+    # log det gram / 2, dh1_dpos the constraint's matrix-Hessian product
+    "c3_torus_lebesgue": ("C3", {"n_chains": 32, "dens_wrt_hausdorff": False}, (1, 5, 20), {}),
+    "s1_sphere_dense_d10_lebesgue": ("S1", {"n_chains": 16, "dim": 10, "dens_wrt_hausdorff": False}, (1, 5, 20), {}),
+    # several constraints: full C x C Gram / residual-Jacobian matrices (C = 2, 4, 8)
+    "s2_multi_sphere_c2_identity_d12": ("S2", {"n_chains": 16, "dim": 12, "n_constr": 2, "metric_kind": "identity"}, (1, 5, 20), {}),
+    "s2_multi_sphere_c4_dense_d16": ("S2", {"n_chains": 16, "dim": 16, "n_constr": 4}, (1, 5, 20), {}),
+    "s2_multi_sphere_c8_dense_d32_lebesgue": ("S2", {"n_chains": 12, "dim": 32, "n_constr": 8, "dens_wrt_hausdorff": False}, (1, 5), {}),
+    "s2_multi_sphere_c4_diag_d72_inner2": ("S2", {"n_chains": 8, "dim": 72, "n_constr": 4, "metric_kind": "diagonal"}, (1, 5), {"n_inner_step": 2}),
+    "s2_multi_sphere_c8_quasi_newton_d16": ("S2", {"n_chains": 12, "dim": 16, "n_constr": 8}, (1, 5), {"projection_solver": "quasi_newton"}),
     "c4_dense_riemannian_d64": ("C4", {"n_chains": 8, "dim": 64}, (1, 5), {}),
     "c4_dense_riemannian_d512": ("C4", {"n_chains": 8, "dim": 512}, (1, 5), {}),
     # full-rank position-dependent metric M(q) = B + c (q q^T) o S: generic dense path only

@@ -579,13 +579,44 @@ def implicit_midpoint_step(q, p, time_step, system, reverse_check_tol=2e-8,
 
 
 class ConstrainedSystem:
-    """``DenseConstrainedEuclideanMetricSystem`` with ``dens_wrt_hausdorff=True``
-    (systems.py:786-873, 1006-1022)."""
+    """``DenseConstrainedEuclideanMetricSystem`` (systems.py:786-873, 1006-1031).  With
+    ``dens_wrt_hausdorff=False`` the target density is given with respect to the Lebesgue measure
+    of the ambient space and ``h1`` carries the correction ``log det gram / 2`` (:853-861)."""
 
-    def __init__(self, target, metric=None):
+    def __init__(self, target, metric=None, dens_wrt_hausdorff=True):
         self.target = target
         self.metric = coerce_metric(metric)
+        self.dens_wrt_hausdorff = dens_wrt_hausdorff
         self.n_constr_evals = 0
+
+    def gram(self, q):
+        jac = self.jacob_constr(q)
+        return jac @ self.inv_metric_mat(jac.T)  # systems.py:1013-1016
+
+    def h1(self, q):
+        if self.dens_wrt_hausdorff:
+            return self.target.neg_log_dens(q)
+        # log_det_sqrt_gram = 0.5 * DensePositiveDefiniteMatrix.log_abs_det (:836-838, 982-984)
+        chol = np.linalg.cholesky(self.gram(q))
+        return self.target.neg_log_dens(q) + 0.5 * (2 * np.log(np.abs(chol.diagonal())).sum())
+
+    def dh1_dpos(self, q):
+        if self.dens_wrt_hausdorff:
+            return self.target.grad_neg_log_dens(q)
+        # grad_log_det_sqrt_gram (:1024-1031): mhp_constr(inv_gram @ jac @ metric.inv)
+        jac = self.jacob_constr(q)
+        inv_gram = dense_spd_inverse(jac @ self.inv_metric_mat(jac.T))
+        m = (inv_gram @ jac) @ self.inv_metric_full()
+        return self.target.grad_neg_log_dens(q) + self.target.mhp_constr(q)(m)
+
+    def inv_metric_full(self):
+        """``metric.inv`` as the right operand of ``matrix @ metric.inv``."""
+        m = self.metric
+        if m.kind == "identity":
+            return np.identity(self.jacob_constr_dim)
+        if m.kind == "diagonal":
+            return np.diag(m.inv_diagonal)
+        return m.inv_array
 
     def constr(self, q):
         self.n_constr_evals += 1
@@ -604,7 +635,11 @@ class ConstrainedSystem:
         return m.inv_array @ a
 
     def h(self, q, p):
-        return self.target.neg_log_dens(q) + 0.5 * (p @ self.inv_metric_mat(p))
+        return self.h1(q) + 0.5 * (p @ self.inv_metric_mat(p))
+
+    @property
+    def jacob_constr_dim(self):
+        return self.target.dim
 
     def project_onto_cotangent_space(self, mom, q):
         """systems.py:863-873: p -= J^T (gram^-1 (J (M^-1 p))), gram = J M^-1 J^T as a
@@ -786,7 +821,7 @@ def constrained_leapfrog_step(
 
     try:
         # _step_a(dt/2) :947-949
-        p = p - (0.5 * time_step) * tgt.grad_neg_log_dens(q)
+        p = p - (0.5 * time_step) * system.dh1_dpos(q)
         p = system.project_onto_cotangent_space(p, q)
         # _step_b(dt) :951-979
         dt_inner = time_step / n_inner_step
@@ -799,7 +834,7 @@ def constrained_leapfrog_step(
             if rev_diff > reverse_check_tol:
                 raise OracleIntegratorError(STATUS_NON_REVERSIBLE, f"rev diff {rev_diff}")
         # _step_a(dt/2)
-        p = p - (0.5 * time_step) * tgt.grad_neg_log_dens(q)
+        p = p - (0.5 * time_step) * system.dh1_dpos(q)
         p = system.project_onto_cotangent_space(p, q)
     except (ValueError, _LinAlgError) as e:
         raise OracleIntegratorError(STATUS_LINALG, str(e)) from e

@@ -225,6 +225,21 @@ class Torus:
         f = 2.0 * (rho - self.R) / rho
         return np.array([[f * x, f * y, 2.0 * z]])
 
+    def hess_constr(self, q):
+        """Second derivatives of c = (rho - R)^2 + z^2 - r^2: with f = 2 (rho - R) / rho,
+        d/dx (f x) = f + x df/dx, df/dx = 2 R x / rho^3."""
+        x, y, z = q
+        rho = np.sqrt(x * x + y * y)
+        f = 2.0 * (rho - self.R) / rho
+        g = 2.0 * self.R / rho**3
+        return np.array([[[f + g * x * x, g * x * y, 0.0],
+                          [g * x * y, f + g * y * y, 0.0],
+                          [0.0, 0.0, 2.0]]])
+
+    def mhp_constr(self, q):
+        hess = self.hess_constr(q)
+        return lambda m: np.sum(m[:, :, None] * hess, axis=(0, 1))
+
 
 class Sphere:
     """Unit-sphere constraint c(q) = |q|^2 - 1 with Gaussian-tilted density (any D)."""
@@ -248,3 +263,50 @@ class Sphere:
 
     def jacob_constr(self, q):
         return 2.0 * q[None, :]
+
+    def mhp_constr(self, q):  # hess[0] = 2 I
+        return lambda m: 2.0 * m[0]
+
+
+class MultiSphere:
+    """``n_constr`` unit spheres: the coordinates are split into ``n_constr`` consecutive blocks
+    of ``dim / n_constr`` and every block is constrained to its unit sphere,
+    c_k(q) = |q_block_k|^2 - 1; tilted Gaussian density as ``Sphere``.  With a dense metric the
+    Gram matrix J M^-1 J^T is a full ``n_constr x n_constr`` matrix (exercises the general C x C
+    Cholesky / LU paths of the constrained integrator, C up to 8)."""
+
+    name = "multi_sphere"
+
+    def __init__(self, dim, n_constr):
+        if dim % n_constr != 0:
+            raise ValueError("dim must be a multiple of n_constr")
+        self.dim, self.n_constr = dim, n_constr
+        self.block = dim // n_constr
+
+    def neg_log_dens(self, q):
+        return 0.5 * (q @ q) + q[0]
+
+    def grad_neg_log_dens(self, q):
+        g = q.copy()
+        g[0] += 1.0
+        return g
+
+    def constr(self, q):
+        return (q.reshape(self.n_constr, self.block) ** 2).sum(-1) - 1.0
+
+    def jacob_constr(self, q):
+        jac = np.zeros((self.n_constr, self.dim))
+        for k in range(self.n_constr):
+            sl = slice(k * self.block, (k + 1) * self.block)
+            jac[k, sl] = 2.0 * q[sl]
+        return jac
+
+    def mhp_constr(self, q):  # hess[k] = 2 I on block k
+        def mhp(m):
+            out = np.empty(self.dim)
+            for k in range(self.n_constr):
+                sl = slice(k * self.block, (k + 1) * self.block)
+                out[sl] = 2.0 * m[k, sl]
+            return out
+
+        return mhp
