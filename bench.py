@@ -52,6 +52,10 @@ FP64_PEAK_SOURCE = "constant: profiles/r01_fp64_peak.txt (builder-measured micro
 WORKLOADS = {
     "C2": dict(cfg="C2", kwargs={}, launch=2, reps=5, cpu=(2, 2, 4.0),
                label="C2: SoftAbs Riemannian implicit leapfrog, banana D=64, 2048 chains"),
+    "C2_dense_hessian": dict(cfg="C6", kwargs={}, launch=2, reps=3, cpu=(2, 2, 4.0),
+                             label="C2 with a DENSE Hessian: SoftAbs implicit leapfrog on the "
+                                   "quartic target |q|^2/2 + sum_m (a_m.q)^4/4, D=64, 2048 "
+                                   "chains (the banana's Hessian is 2x2 block diagonal)"),
     "C3": dict(cfg="C3", kwargs={}, launch=50, reps=10, cpu=(8, 50, 3.0),
                label="C3: constrained leapfrog (RATTLE + Newton), torus D=3 C=1, 4096 chains"),
     "C4": dict(cfg="C4", kwargs={"n_chains": 8192}, launch=1, reps=2, cpu=(1, 1, 5.0),
@@ -321,7 +325,7 @@ def run_workload(name, torch, dist, dev, rank, world, flush, hbm_peak):
 
     w = WORKLOADS[name]
     kw = dict(w["kwargs"])
-    base_seed = {"C2": 2, "C3": 3, "C4": 4, "C5": 7}[w["cfg"]]
+    base_seed = {"C2": 2, "C3": 3, "C4": 4, "C5": 7, "C6": 9}[w["cfg"]]
     prob = problems.make_problem(w["cfg"], seed=problems.BASE_SEED + base_seed + 1000 * rank, **kw)
     if w.get("metric_overrides"):
         prob.metric_params = dict(prob.metric_params, **w["metric_overrides"])
@@ -363,7 +367,7 @@ def run_workload(name, torch, dist, dev, rank, world, flush, hbm_peak):
         "mean_solver_iters_last_step": iters,
     }
     hbm_gbs = value / world * b_alg / 1e9
-    if name == "C2":
+    if name in ("C2", "C2_dense_hessian"):
         # metric builds (eigendecompositions) per step: _step_a + every iteration of the two
         # position fixed points + _step_b_adj; quadratic-form gradients: every iteration of the
         # two momentum fixed points + 1.  F_alg = builds * 9 D^3 + quad * 2 D^3.
@@ -378,7 +382,8 @@ def run_workload(name, torch, dist, dev, rank, world, flush, hbm_peak):
             "flops_per_chain_step": f_alg, "metric_builds_per_step": builds,
             "formula": "builds*9*D^3 + quad_grads*2*D^3, builds = it_c_rev + it_c + 2",
             "hbm_frac": hbm_gbs / hbm_peak,
-            "kernel": "implicit_leapfrog_kernel<BananaRTarget, SoftAbsMetric>",
+            "kernel": "implicit_leapfrog_kernel<%s, SoftAbsMetric>"
+                      % ("BananaRTarget" if name == "C2" else "QuarticRTarget"),
         }
     elif name == "C3":
         res["roofline"] = {

@@ -61,6 +61,7 @@ extern "C" {
 #define MB200_TARGET_TORUS 4        /* density on torus (README:315-337) params: R, r, alpha */
 #define MB200_TARGET_SPHERE 5       /* tilted density on unit sphere    params: -            */
 #define MB200_TARGET_MULTI_SPHERE 6 /* n_constr unit spheres on consecutive blocks  params: n_constr (2, 4 or 8) */
+#define MB200_TARGET_QUARTIC 7      /* l = |q|^2/2 + gamma/4 sum_m (a_m.q)^4   params: gamma; aux: A [dim*dim] (dense Hessian; SoftAbs systems) */
 /* constrained targets: target_params[MB200_MAX_PARAMS - 1] != 0 means the density is given with
  * respect to the Lebesgue measure (dens_wrt_hausdorff=False, systems.py:853-861): h1 and dh1_dpos
  * carry log det gram / 2 and its gradient (systems.py:1024-1031) */

@@ -15,6 +15,7 @@ static int launch_implicit(const double* q_in, const double* p_in, double* q_out
   int n_mats = MetricT<Target>::N_MATS;
   // SoftAbs: a third matrix enables warm-started eigensolves; use it when two CTAs still fit
   if (MetricT<Target>::SOFTABS && rm_smem_doubles(dim, 3) * sizeof(double) <= 113 * 1024) n_mats = 3;
+  if (MetricT<Target>::SOFTABS && Target::DENSE_MTP) n_mats = 3;  // the third holds Z = A U
   const size_t smem = rm_smem_doubles(dim, n_mats) * sizeof(double);
   if (smem > 227 * 1024)
     return fail(MB200_ERR_UNSUPPORTED,
@@ -68,6 +69,13 @@ static int implicit_dispatch(const double* q_in, const double* p_in, double* q_o
       case MB200_TARGET_BANANA:
         if (dim & 1) return fail(MB200_ERR_INVALID_ARG, "banana target needs even dim");
         return launch_implicit<BananaRTarget, SoftAbsMetric>(MB200_ARGS);
+      case MB200_TARGET_QUARTIC:
+        if (!m.taux) return fail(MB200_ERR_INVALID_ARG, "quartic target needs its directions");
+        if (midpoint)
+          return fail(MB200_ERR_UNSUPPORTED, "implicit midpoint: quartic target not available");
+        if (rm_smem_doubles(dim, 3) * sizeof(double) > 227 * 1024)
+          return fail(MB200_ERR_UNSUPPORTED, "quartic target: dim %d too large (three matrices)", dim);
+        return launch_implicit<QuarticRTarget, SoftAbsMetric>(MB200_ARGS);
       default:
         return fail(MB200_ERR_UNSUPPORTED, "target %d has no device Hessian / MTP (SoftAbs metric)",
                     m.target_id);
@@ -249,6 +257,7 @@ int mb200_sample_momentum_riemannian(const double* pos, const double* normals, d
     return dense_global_vector(pos, normals, mom_out, n_chains, dim, m, status, st, 0);
   if (m.rmetric_id == MB200_RMETRIC_SOFTABS) {
     if (m.target_id == MB200_TARGET_BANANA) return launch_sample_momentum<BananaRTarget, SoftAbsMetric>(MB200_ARGS);
+    if (m.target_id == MB200_TARGET_QUARTIC) return launch_sample_momentum<QuarticRTarget, SoftAbsMetric>(MB200_ARGS);
     return fail(MB200_ERR_UNSUPPORTED, "target %d has no device Hessian", m.target_id);
   }
   if (m.rmetric_id == MB200_RMETRIC_RANK1) {
@@ -302,6 +311,7 @@ int mb200_dh_dmom_riemannian(const double* pos, const double* mom, double* vel_o
     return dense_global_vector(pos, mom, vel_out, n_chains, dim, m, status, st, 1);
   if (m.rmetric_id == MB200_RMETRIC_SOFTABS) {
     if (m.target_id == MB200_TARGET_BANANA) return launch_velocity<BananaRTarget, SoftAbsMetric>(MB200_ARGS);
+    if (m.target_id == MB200_TARGET_QUARTIC) return launch_velocity<QuarticRTarget, SoftAbsMetric>(MB200_ARGS);
     return fail(MB200_ERR_UNSUPPORTED, "target %d has no device Hessian", m.target_id);
   }
   if (m.rmetric_id == MB200_RMETRIC_RANK1) {

@@ -63,6 +63,8 @@ __device__ __forceinline__ bool block_any(const Blk&, bool flag) {
 // ---------------------------------------------------------------------------------------------
 
 struct BananaRTarget {
+  static constexpr bool DENSE_MTP = false;
+  __device__ void attach(double*) const {}
   static constexpr bool HAS_HESSIAN = true;
   static constexpr int NEED = 2;  // entries of a D x D gradient matrix needed per row by mtp
   double b;
@@ -116,6 +118,8 @@ struct BananaRTarget {
 };
 
 struct QuadraticRTarget {
+  static constexpr bool DENSE_MTP = false;
+  __device__ void attach(double*) const {}
   static constexpr bool HAS_HESSIAN = false;
   static constexpr int NEED = 1;
   const double* P;
@@ -145,6 +149,8 @@ struct QuadraticRTarget {
 };
 
 struct StdGaussianRTarget {
+  static constexpr bool DENSE_MTP = false;
+  __device__ void attach(double*) const {}
   static constexpr bool HAS_HESSIAN = false;
   static constexpr int NEED = 1;
   int dim;
@@ -160,6 +166,165 @@ struct StdGaussianRTarget {
   __device__ void hess(const Blk&, const double*, double*, int) const {}
   __device__ __forceinline__ int need_col(int, int) const { return -1; }
   __device__ void mtp_entries(const Blk&, const double*, const double*, double*) const {}
+};
+
+// l(q) = |q|^2/2 + (gamma/4) sum_m (a_m . q)^4, A = directions [D x D] in global memory (shared
+// by all chains, L2-resident).  Dense Hessian I + 3 gamma A^T diag(s^2) A, s = A q; the
+// matrix-Tressian product mtp(V)_k = 6 gamma sum_m s_m (a_m^T V a_m) a_mk needs the whole of V:
+// the SoftAbs policy hands this target the factors of V instead of entries (DENSE_MTP):
+//   V = U diag(d) U^T           ->  a_m^T V a_m = sum_i d_i Z_mi^2,          Z = A U
+//   V = -U ((e e^T) o J) U^T    ->  a_m^T V a_m = -(z_m o e)^T J (z_m o e)
+struct QuarticRTarget {
+  static constexpr bool DENSE_MTP = true;
+  static constexpr bool HAS_HESSIAN = true;
+  static constexpr int NEED = 1;
+  const double* A;
+  double gamma;
+  int dim;
+  mutable double* sbuf;  // [dim] shared scratch for s = A q (attached after the carve)
+  __device__ QuarticRTarget(const ModelArgs& m, int d)
+      : A(m.taux), gamma(m.tp[0]), dim(d), sbuf(nullptr) {}
+  __device__ void attach(double* scratch) const { sbuf = scratch; }
+
+  // s = A q into sbuf (one warp per direction)
+  __device__ void project(const Blk& k, const double* q) const {
+    for (int m = k.warp; m < dim; m += k.nwarp) {
+      double t = 0.0;
+      for (int j = k.lane; j < dim; j += 32) t = fma(A[(size_t)m * dim + j], q[j], t);
+      t = warp_sum(t);
+      if (k.lane == 0) sbuf[m] = t;
+    }
+    __syncthreads();
+  }
+  // out_k = base_k + coef * sum_m A_mk w_m  (coalesced over k)
+  __device__ void back_project(const Blk& k, const double* wv, double coef, const double* base,
+                               double* out) const {
+    for (int i = k.tid; i < dim; i += k.nthr) {
+      double t = 0.0;
+      for (int m = 0; m < dim; ++m) t = fma(A[(size_t)m * dim + i], wv[m], t);
+      out[i] = (base != nullptr ? base[i] : 0.0) + coef * t;
+    }
+    __syncthreads();
+  }
+  __device__ double nld(const Blk& k, const double* q) const {
+    project(k, q);
+    double t = 0.0;
+    for (int i = k.tid; i < dim; i += k.nthr) {
+      const double s2 = sbuf[i] * sbuf[i];
+      t += 0.5 * (q[i] * q[i]) + 0.25 * gamma * (s2 * s2);
+    }
+    return block_sum(k, t);
+  }
+  __device__ void grad(const Blk& k, const double* q, double* g) const {
+    project(k, q);
+    for (int i = k.tid; i < dim; i += k.nthr) sbuf[i] = sbuf[i] * sbuf[i] * sbuf[i];
+    __syncthreads();
+    back_project(k, sbuf, gamma, q, g);
+  }
+  // H = I + 3 gamma A^T diag(s^2) A, 4x4 register tiles
+  __device__ void hess(const Blk& k, const double* q, double* H, int ld) const {
+    project(k, q);
+    for (int i = k.tid; i < dim; i += k.nthr) sbuf[i] = 3.0 * gamma * (sbuf[i] * sbuf[i]);
+    __syncthreads();
+    const int tn = (dim + 3) / 4;
+    for (int t = k.tid; t < tn * tn; t += k.nthr) {
+      const int i0 = 4 * (t / tn), j0 = 4 * (t % tn);
+      double acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+      for (int m = 0; m < dim; ++m) {
+        const double* row = A + (size_t)m * dim;
+        const double wm = sbuf[m];
+        double x[4], y[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          x[a] = (i0 + a < dim) ? wm * row[i0 + a] : 0.0;
+          y[a] = (j0 + a < dim) ? row[j0 + a] : 0.0;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fma(x[a], y[b], acc[a][b]);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (i0 + a < dim && j0 + b < dim)
+            H[(i0 + a) * ld + j0 + b] = acc[a][b] + ((i0 + a == j0 + b) ? 1.0 : 0.0);
+    }
+    __syncthreads();
+  }
+  __device__ __forceinline__ int need_col(int, int) const { return -1; }
+  __device__ void mtp_entries(const Blk&, const double*, const double*, double*) const {}
+
+  // Z = A U (directions in the eigenbasis), Z [dim x dim] stride ld in shared memory
+  __device__ void eigen_directions(const Blk& k, const double* U, int ld, double* Z) const {
+    const int tn = (dim + 3) / 4;
+    for (int t = k.tid; t < tn * tn; t += k.nthr) {
+      const int m0 = 4 * (t / tn), j0 = 4 * (t % tn);
+      double acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+      for (int i = 0; i < dim; ++i) {
+        double x[4], y[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          x[a] = (m0 + a < dim) ? A[(size_t)(m0 + a) * dim + i] : 0.0;
+          y[a] = (j0 + a < dim) ? U[i * ld + j0 + a] : 0.0;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fma(x[a], y[b], acc[a][b]);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (m0 + a < dim && j0 + b < dim) Z[(m0 + a) * ld + j0 + b] = acc[a][b];
+    }
+    __syncthreads();
+  }
+  // out = mtp(U diag(d) U^T): t_m = sum_i d_i Z_mi^2
+  __device__ void mtp_diag(const Blk& k, const double* q, const double* Z, int ld, const double* d,
+                           double* tm, double* out) const {
+    project(k, q);
+    for (int m = k.warp; m < dim; m += k.nwarp) {
+      double t = 0.0;
+      for (int i = k.lane; i < dim; i += 32) t = fma(d[i] * Z[m * ld + i], Z[m * ld + i], t);
+      t = warp_sum(t);
+      if (k.lane == 0) tm[m] = sbuf[m] * t;
+    }
+    __syncthreads();
+    back_project(k, tm, 6.0 * gamma, nullptr, out);
+  }
+  // out = mtp(-U ((e e^T) o J) U^T): t_m = -(z_m o e)^T J (z_m o e); one warp per direction,
+  // y = z_m o e staged per warp in `ybuf` [nwarp * dim]
+  __device__ void mtp_quad(const Blk& k, const double* q, const double* Z, int ld, const double* e,
+                           const double* J, int ldj, double* ybuf, double* tm, double* out) const {
+    project(k, q);
+    double* y = ybuf + (size_t)k.warp * dim;
+    for (int m = k.warp; m < dim; m += k.nwarp) {
+      for (int i = k.lane; i < dim; i += 32) y[i] = Z[m * ld + i] * e[i];
+      __syncwarp();
+      double t = 0.0;
+      for (int j = k.lane; j < dim; j += 32) {
+        double u = 0.0;
+        for (int i = 0; i < dim; ++i) u = fma(y[i], J[i * ldj + j], u);
+        t = fma(u, y[j], t);
+      }
+      t = warp_sum(t);
+      if (k.lane == 0) tm[m] = -(sbuf[m] * t);
+      __syncwarp();
+    }
+    __syncthreads();
+    back_project(k, tm, 6.0 * gamma, nullptr, out);
+  }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -425,9 +590,59 @@ __device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U
 
 // C = op(X) * Y for n x n shared-memory matrices (stride ld), op = transpose if XT.  4x4 register
 // tiles, one per thread.  C must not alias X or Y.
+__device__ __forceinline__ void rm_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+// The same product on the FP64 tensor pipe (DMMA m8n8k4) for n a multiple of 32: one 16 x 32
+// output tile per warp and pass, operands read from shared memory as fragments (A by rows, or by
+// columns for X^T; B by rows).
+template <bool XT>
+__device__ inline void smem_matmul_dmma(const Blk& k, int n, int ld, const double* X,
+                                        const double* Y, double* C) {
+  const int r = k.lane >> 2, c = k.lane & 3;
+  const int tr = n / 16, tc = n / 32;
+  for (int t = k.warp; t < tr * tc; t += k.nwarp) {
+    const int i0 = 16 * (t / tc), j0 = 32 * (t % tc);
+    double acc[2][4][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = 0.0, acc[mt][nt][1] = 0.0;
+#pragma unroll 4
+    for (int ks = 0; ks < n / 4; ++ks) {
+      double a[2], b[4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+        a[mt] = XT ? X[(4 * ks + c) * ld + i0 + 8 * mt + r] : X[(i0 + 8 * mt + r) * ld + 4 * ks + c];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) b[nt] = Y[(4 * ks + c) * ld + j0 + 8 * nt + r];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) rm_dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        C[(i0 + 8 * mt + r) * ld + j0 + 8 * nt + 2 * c] = acc[mt][nt][0];
+        C[(i0 + 8 * mt + r) * ld + j0 + 8 * nt + 2 * c + 1] = acc[mt][nt][1];
+      }
+  }
+  __syncthreads();
+}
+
 template <bool XT>
 __device__ inline void smem_matmul(const Blk& k, int n, int ld, const double* X, const double* Y,
                                    double* C) {
+  if ((n & 31) == 0) {
+    smem_matmul_dmma<XT>(k, n, ld, X, Y, C);
+    return;
+  }
   const int tn = (n + 3) / 4;
   for (int t = k.tid; t < tn * tn; t += k.nthr) {
     const int i0 = 4 * (t / tn), j0 = 4 * (t % tn);
@@ -580,9 +795,10 @@ struct SoftAbsMetric {
   bool have_j;     // divided-difference matrix J built in w.M2 for the current metric?
   bool j_finite;   // ... and all of its entries are finite
   bool have_prev;  // w.M1 holds the eigenvectors of the previous build (warm start available)
+  bool have_z;     // DENSE_MTP targets: Z = A U of the current metric is in w.M3
 
   __device__ SoftAbsMetric(const Target& tt, const ModelArgs& m)
-      : t(tt), alpha(m.mp[0]), have_j(false), j_finite(false), have_prev(false) {}
+      : t(tt), alpha(m.mp[0]), have_j(false), j_finite(false), have_prev(false), have_z(false) {}
   // forget the previous eigenvectors (start of every integrator step: bounds the loss of
   // orthogonality from accumulating rotations over many warm-started solves)
   __device__ void reset() { have_prev = false; }
@@ -590,6 +806,7 @@ struct SoftAbsMetric {
   // returns 0, or MB200_STATUS_LINALG (eigh failure) / -1 (ValueError: non-positive eigenvalues)
   __device__ int build(const Blk& k, RmWork& w, const double* q) {
     have_j = false;
+    have_z = false;  // w.M3 is the warm start's scratch during the build
     t.hess(k, q, w.M2, w.ld);
     __syncthreads();
     // Warm start: successive fixed-point iterates move q only slightly, so the previous
@@ -667,8 +884,18 @@ struct SoftAbsMetric {
     return true;
   }
   // out = vjp(grad_log_abs_det), grad_log_abs_det = U diag(gs/s) U^T   (:1673-1676)
-  __device__ void vjp_grad_log_abs_det(const Blk& k, RmWork& w, const double* q, double* out) const {
+  __device__ void vjp_grad_log_abs_det(const Blk& k, RmWork& w, const double* q, double* out) {
     const int n = w.dim, ld = w.ld;
+    if constexpr (Target::DENSE_MTP) {
+      if (!have_z) {
+        t.eigen_directions(k, w.M1, ld, w.M3);
+        have_z = true;
+      }
+      for (int i = k.tid; i < n; i += k.nthr) w.ev[i] = w.gsa[i] / w.sa[i];
+      __syncthreads();
+      t.mtp_diag(k, q, w.M3, ld, w.ev, w.Vn + (size_t)k.nwarp * n, out);
+      return;
+    }
     for (int idx = k.tid; idx < n * Target::NEED; idx += k.nthr) {
       const int a = idx / Target::NEED, j = idx - a * Target::NEED;
       const int b = t.need_col(a, j);
@@ -703,6 +930,16 @@ struct SoftAbsMetric {
       w.ev[j] = s / w.sa[j];
     }
     __syncthreads();
+    if constexpr (Target::DENSE_MTP) {
+      if (!have_z) {
+        t.eigen_directions(k, w.M1, ld, w.M3);
+        have_z = true;
+      }
+      // per-warp staging rows and the per-direction results live in Vn (2 dpad doubles) and the
+      // z buffers that follow it (unused by the leapfrog integrator): (nwarp + 1) dim <= 12 dpad
+      t.mtp_quad(k, q, w.M3, ld, w.ev, w.M2, ld, w.Vn, w.Vn + (size_t)k.nwarp * n, out);
+      return;
+    }
     // one warp per row a: t_j = sum_i (U_ai e_i) J_ij, then V(a,b) = -sum_j t_j e_j U_bj
     double* trow = w.v3;  // reused per warp below via registers; v3 holds (U_a o e) of the row
     (void)trow;
@@ -1223,6 +1460,8 @@ __global__ void __launch_bounds__(RM_THREADS, MetricT<Target>::MIN_BLOCKS)
   RmWork w;
   rm_carve(w, smem, dim, n_mats, blk);
   const Target target(model, dim);
+  // scratch of DENSE_MTP targets: [dim] doubles behind the staging rows in the Vn / z region
+  target.attach(w.Vn != nullptr ? w.Vn + (size_t)(blk.nwarp + 1) * dim : nullptr);
   MetricT<Target> metric(target, model);
   ImplicitLeapfrog<Target, MetricT<Target>> integ{blk,    w,      target,  metric,
                                                   fp_tol, fp_div, rev_tol, fp_max, fp_solver};
@@ -1284,6 +1523,8 @@ __global__ void __launch_bounds__(RM_THREADS, MetricT<Target>::MIN_BLOCKS)
   RmWork w;
   rm_carve(w, smem, dim, n_mats, blk);
   const Target target(model, dim);
+  // scratch of DENSE_MTP targets: [dim] doubles behind the staging rows in the Vn / z region
+  target.attach(w.Vn != nullptr ? w.Vn + (size_t)(blk.nwarp + 1) * dim : nullptr);
   MetricT<Target> metric(target, model);
   for (int64_t ch = blockIdx.x; ch < n_chains; ch += gridDim.x) {
     __syncthreads();
@@ -1315,6 +1556,8 @@ __global__ void __launch_bounds__(RM_THREADS, MetricT<Target>::MIN_BLOCKS)
   RmWork w;
   rm_carve(w, smem, dim, n_mats, blk);
   const Target target(model, dim);
+  // scratch of DENSE_MTP targets: [dim] doubles behind the staging rows in the Vn / z region
+  target.attach(w.Vn != nullptr ? w.Vn + (size_t)(blk.nwarp + 1) * dim : nullptr);
   MetricT<Target> metric(target, model);
   for (int64_t ch = blockIdx.x; ch < n_chains; ch += gridDim.x) {
     __syncthreads();

@@ -154,6 +154,27 @@ def c2_softabs_banana(n_chains=2048, dim=64, seed=BASE_SEED + 2, integrator="imp
     )
 
 
+def c6_softabs_quartic(n_chains=2048, dim=64, seed=BASE_SEED + 9, gamma=1.0,
+                       integrator="implicit_leapfrog"):
+    """C2's system (SoftAbs metric, implicit leapfrog) on a target with a DENSE Hessian:
+    l = |q|^2/2 + (gamma/4) sum_m (a_m . q)^4 with D random directions.  The banana of C2 has a
+    2 x 2 block-diagonal Hessian that a Jacobi eigensolver diagonalises in one round; this target
+    needs every rotation of every sweep."""
+    rng = np.random.default_rng(seed)
+    directions = rng.standard_normal((dim, dim)) / np.sqrt(dim)
+    return Problem(
+        name="C6",
+        integrator=integrator,
+        system="softabs_riemannian",
+        target="quartic",
+        target_params={"directions": directions, "gamma": gamma},
+        step_size=0.1,
+        pos=0.5 * rng.standard_normal((n_chains, dim)),
+        mom=rng.standard_normal((n_chains, dim)),
+        system_kwargs={"softabs_coeff": 1.0},
+    )
+
+
 def c3_torus(n_chains=4096, seed=BASE_SEED + 3, R=1.0, r=0.5, alpha=0.9,
              dens_wrt_hausdorff=True):
     rng = np.random.default_rng(seed)
@@ -325,6 +346,7 @@ CONFIGS = {
     "C3": c3_torus,
     "C4": c4_dense_riemannian,
     "C5": c5_dense_hadamard,
+    "C6": c6_softabs_quartic,
     "S1": sphere_constrained,
     "S2": multi_sphere_constrained,
     "G1": g1_gaussian_split,

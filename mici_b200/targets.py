@@ -18,6 +18,7 @@ TARGET_QUADRATIC = 3
 TARGET_TORUS = 4
 TARGET_SPHERE = 5
 TARGET_MULTI_SPHERE = 6
+TARGET_QUARTIC = 7
 
 RMETRIC_SOFTABS = 0
 RMETRIC_RANK1 = 1
@@ -97,6 +98,20 @@ class Quadratic(Target):
         super().__init__(prec.shape[0], (), prec)
 
 
+class Quartic(Target):
+    """l(q) = |q|^2/2 + (gamma/4) sum_m (a_m . q)^4 with ``directions`` A [D x D]: dense Hessian
+    and third-derivative tensor (SoftAbs systems)."""
+
+    target_id = TARGET_QUARTIC
+    name = "quartic"
+
+    def __init__(self, directions, gamma=1.0):
+        a = np.ascontiguousarray(directions, dtype=np.float64)
+        if a.ndim != 2 or a.shape[0] != a.shape[1]:
+            raise ValueError("`directions` must be a square matrix (D directions in R^D).")
+        super().__init__(a.shape[1], (float(gamma),), a)
+
+
 class Torus(Target):
     """Density on a torus in R^3 with constraint c(q) = (rho - R)^2 + z^2 - r^2
     (reference README.md:315-337)."""
@@ -171,7 +186,7 @@ class HadamardMetric:
 
 REGISTRY = {
     cls.name: cls
-    for cls in (StdGaussian, NealFunnel, Banana, Quadratic, Torus, Sphere, MultiSphere)
+    for cls in (StdGaussian, NealFunnel, Banana, Quadratic, Quartic, Torus, Sphere, MultiSphere)
 }
 METRIC_REGISTRY = {"rank1": Rank1Metric, "hadamard": HadamardMetric}
 

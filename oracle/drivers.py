@@ -38,6 +38,8 @@ def build_target(problem):
         return tg.Banana(**kw)
     if name == "quadratic":
         return tg.Quadratic(**kw)
+    if name == "quartic":
+        return tg.Quartic(**kw)
     if name == "torus":
         return tg.Torus(**kw)
     if name == "sphere":

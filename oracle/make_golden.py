@@ -33,6 +33,9 @@ CASES = {
     "c1_funnel_identity": ("C1", {"n_chains": 16, "dim": 7, "metric_kind": "identity"}, (1, 20), {}),
     "c2_softabs_banana": ("C2", {"n_chains": 16}, (1, 5, 20), {}),
     "c2_softabs_banana_d8": ("C2", {"n_chains": 32, "dim": 8}, (1, 5, 20), {}),
+    # SoftAbs on a target with a DENSE Hessian and third-derivative tensor
+    "c6_softabs_quartic_d12": ("C6", {"n_chains": 16, "dim": 12}, (1, 5, 20), {}),
+    "c6_softabs_quartic_d64": ("C6", {"n_chains": 12, "dim": 64}, (1, 5), {}),
     "c3_torus": ("C3", {"n_chains": 64}, (1, 5, 20), {}),
     "c3_torus_inner3": ("C3", {"n_chains": 32}, (1, 5), {"n_inner_step": 3}),
     # GaussianEuclideanMetricSystem (exact h2 flow in the eigenbasis of the metric)

@@ -109,6 +109,36 @@ class Banana:
         return mtp
 
 
+class Quartic:
+    """l(q) = |q|^2 / 2 + (gamma / 4) sum_m (a_m . q)^4 with dense directions A [M x D]: the
+    Hessian I + 3 gamma A^T diag((A q)^2) A and the third-derivative tensor are DENSE (no block
+    structure for a SoftAbs eigensolver to exploit); mtp(V) = 6 gamma A^T ((A q) o diag(A V A^T))."""
+
+    name = "quartic"
+
+    def __init__(self, directions, gamma=1.0):
+        self.a = np.asarray(directions)
+        self.gamma = float(gamma)
+        self.dim = self.a.shape[1]
+
+    def neg_log_dens(self, q):
+        s = self.a @ q
+        return 0.5 * (q @ q) + 0.25 * self.gamma * np.sum(s**4)
+
+    def grad_neg_log_dens(self, q):
+        s = self.a @ q
+        return q + self.gamma * (self.a.T @ s**3)
+
+    def hess_neg_log_dens(self, q):
+        s = self.a @ q
+        return np.identity(self.dim) + 3.0 * self.gamma * ((self.a.T * s**2) @ self.a)
+
+    def mtp_neg_log_dens(self, q):
+        s = self.a @ q
+        a, gamma = self.a, self.gamma
+        return lambda m: 6.0 * gamma * (a.T @ (s * np.einsum("mi,ij,mj->m", a, m, a)))
+
+
 class Quadratic:
     """l(q) = 0.5 q^T P q with dense SPD P (config C4)."""
 

@@ -11,6 +11,7 @@ SPECS = {  # config -> (problem kwargs, leapfrog steps per launch, reps)
     "C3": ({}, 50, 10),
     "C4": ({"n_chains": 8192}, 1, 3),
     "C4small": ({"n_chains": 2048, "dim": 64}, 2, 5),
+    "C6": ({}, 2, 5),
 }
 for name in (sys.argv[1:] or ["C0", "C2", "C3", "C4"]):
     kw, L, reps = SPECS[name]

@@ -180,3 +180,38 @@ def test_numpy_chain_state_in_numpy_out():
     assert isinstance(out, ForeignState) and out.dir == -1
     ref2 = dr.oracle_run(problem, 1, dirs=-np.ones(5, dtype=np.int32))
     np.testing.assert_allclose(out.pos, ref2["pos"][2], rtol=RTOL, atol=ATOL)
+
+
+def test_trace_write_out_from_device_buffers_reference_file_layout(tmp_path):
+    """Row N2 on the GPU: per-iteration traces of a batched HMC run live in device buffers
+    ``[n_iter, n_chains, ...]`` and are written as the reference's per-chain memory-mappable
+    ``{prefix}_{index}_{key}.npy`` files (samplers.py:104-138); reading them back the way
+    ``interop.convert_to_inference_data`` does (interop.py:54-96: ``np.load(..., mmap_mode)``)
+    returns the traced positions."""
+    from mici_b200 import traces, transitions
+
+    prob = problems.make_problem("C1", n_chains=24, dim=16)
+    integ = engine.build_integrator(prob)
+    state = engine.build_state(prob, "cuda:0")
+    n_iter = 5
+    buf = traces.TraceBuffer(n_iter, prob.n_chains, (prob.dim,), device="cuda:0")
+    hbuf = traces.TraceBuffer(n_iter, prob.n_chains, (), device="cuda:0")
+    gen = torch.Generator(device="cuda:0")
+    gen.manual_seed(3)
+    mom_tr = transitions.IndependentMomentumTransition(integ.system)
+    int_tr = transitions.MetropolisStaticIntegrationTransition(integ.system, integ, n_step=4)
+    for _ in range(n_iter):
+        state, _ = mom_tr.sample(state, gen)
+        state, stats = int_tr.sample(state, gen)
+        buf.append(state.pos)
+        hbuf.append(integ.system.h(state))
+    gathered = traces.gather_traces({"pos": buf.data, "hamiltonian": hbuf.data}, prob.n_chains)
+    paths = traces.write_chain_traces(tmp_path, "trace", gathered)
+    assert len(paths["pos"]) == prob.n_chains
+    assert paths["pos"][3].name == "trace_3_pos.npy"
+    for i in (0, 7, 23):
+        mm = np.load(paths["pos"][i], mmap_mode="r")
+        assert mm.shape == (n_iter, prob.dim)
+        np.testing.assert_array_equal(np.asarray(mm), buf.data[:, i].cpu().numpy())
+        hm = np.load(paths["hamiltonian"][i], mmap_mode="r")
+        np.testing.assert_array_equal(np.asarray(hm), hbuf.data[:, i].cpu().numpy())
