@@ -252,21 +252,37 @@ __global__ void __launch_bounds__(KP == 2 ? 384 : 256)
       __syncwarp();
       N::ld(tree + (dirn == 1 ? PQ : NQ) * DP, lane, q[0]);
       N::ld(tree + (dirn == 1 ? PP : NP) * DP, lane, p[0]);
+      N::ld(tree + (dirn == 1 ? PVEL : NVEL) * DP, lane, v[0]);
       K::grad(target, dim, lane, q[0], g);
+      // ONE mat-vec per leaf: with u = M^-1 grad l(q) the velocity follows the momentum's half
+      // kicks by linearity, v = M^-1 p:  v -= (dt/2) u.  (The reference applies M^-1 to p twice
+      // per step -- for the drift and for dh_dmom of the new state; the two forms agree to
+      // rounding.)
+      double gu[1][NV], u[1][NV];
+#pragma unroll
+      for (int e = 0; e < NV; ++e) gu[0][e] = g[e];
+      MB200_NUTS_MATVEC(gu, u);
       bool terminate = false;
       double w_cur = 0.0, h_cur = 0.0;
       const int n_leaves = 1 << depth;
       for (int k = 1; k <= n_leaves; ++k) {
         // LeapfrogIntegrator._step (integrators.py:170-173), two separately rounded half kicks
 #pragma unroll
-        for (int e = 0; e < NV; ++e) p[0][e] = __dsub_rn(p[0][e], __dmul_rn(0.5 * dt, g[e]));
-        MB200_NUTS_MATVEC(p, v);
+        for (int e = 0; e < NV; ++e) {
+          p[0][e] = __dsub_rn(p[0][e], __dmul_rn(0.5 * dt, g[e]));
+          v[0][e] = __dsub_rn(v[0][e], __dmul_rn(0.5 * dt, u[0][e]));
+        }
 #pragma unroll
         for (int e = 0; e < NV; ++e) q[0][e] = __dadd_rn(q[0][e], __dmul_rn(dt, v[0][e]));
         K::grad(target, dim, lane, q[0], g);
 #pragma unroll
-        for (int e = 0; e < NV; ++e) p[0][e] = __dsub_rn(p[0][e], __dmul_rn(0.5 * dt, g[e]));
-        MB200_NUTS_MATVEC(p, v);
+        for (int e = 0; e < NV; ++e) gu[0][e] = g[e];
+        MB200_NUTS_MATVEC(gu, u);
+#pragma unroll
+        for (int e = 0; e < NV; ++e) {
+          p[0][e] = __dsub_rn(p[0][e], __dmul_rn(0.5 * dt, g[e]));
+          v[0][e] = __dsub_rn(v[0][e], __dmul_rn(0.5 * dt, u[0][e]));
+        }
         double h = energy();
         if (h != h) h = INFINITY;  // transitions.py:626
         w_cur = leaf_weight(h);
