@@ -247,6 +247,15 @@ __device__ __forceinline__ void leapfrog_dmma_group(
   auto drift = [&](double (&acc)[MT][NT][2]) {
     const double2* a_base = reinterpret_cast<const double2*>(&sm.P[(row0 + r) * LDA + 2 * c]);
     const double2* b_base = reinterpret_cast<const double2*>(&sm.A[(col0 + r) * LDA + 2 * c]);
+    // a single row tile gives a warp only NT independent accumulator chains (DMMA latency ~ 10
+    // issue slots): the two halves of every k-pair then go to separate accumulator sets that are
+    // added at the end (same products, summed in a different order)
+    constexpr bool KSPLIT = (MT == 1);
+    double acc2[KSPLIT ? NT : 1][2];
+    if (KSPLIT) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc2[nt][0] = 0.0, acc2[nt][1] = 0.0;
+    }
 #pragma unroll 4
     for (int j = 0; j < KS / 2; ++j) {
       double2 a[MT], b[NT];
@@ -261,7 +270,14 @@ __device__ __forceinline__ void leapfrog_dmma_group(
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, b[nt].y);
+        for (int nt = 0; nt < NT; ++nt) {
+          if (KSPLIT) dmma_m8n8k4(acc2[nt][0], acc2[nt][1], a[mt].y, b[nt].y);
+          else dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, b[nt].y);
+        }
+    }
+    if (KSPLIT) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[0][nt][0] += acc2[nt][0], acc[0][nt][1] += acc2[nt][1];
     }
   };
 
@@ -367,7 +383,8 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
                          const int32_t* __restrict__ dir, int64_t n_chains, int dim,
                          double step_size, int n_steps, const double* __restrict__ minv,
                          ModelArgs model, double* __restrict__ h_out,
-                         int32_t* __restrict__ status, int32_t* __restrict__ n_done) {
+                         int32_t* __restrict__ status, int32_t* __restrict__ n_done,
+                         int tiles_per_cta) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   DmmaSmem<DP>& sm = *reinterpret_cast<DmmaSmem<DP>*>(smem_raw);
   constexpr int LDA = DmmaSmem<DP>::LDA;
@@ -411,9 +428,9 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   }
   // pull this CTA's first block of state rows towards L2 while A is in flight
   {
-    const int64_t chain0 = (int64_t)blockIdx.x * DMMA_ROWS_PER_CTA;
+    const int64_t chain0 = (int64_t)blockIdx.x * (8 * tiles_per_cta);
     const int64_t left = n_chains - chain0;
-    const int64_t rows = left < DMMA_ROWS_PER_CTA ? left : DMMA_ROWS_PER_CTA;
+    const int64_t rows = left < 8 * tiles_per_cta ? left : 8 * tiles_per_cta;
     const int64_t lines = (rows * dim * 8 + 127) / 128;
     for (int64_t i = tid; i < 2 * lines; i += blockDim.x) {
       const double* base = (i < lines ? q_in : p_in) + (size_t)chain0 * dim;
@@ -456,16 +473,19 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   __syncthreads();
   MB200_K1_MARK(3);
 
-  for (int64_t blk = blockIdx.x; blk * DMMA_ROWS_PER_CTA < n_chains; blk += gridDim.x) {
-    const int64_t chain0 = blk * DMMA_ROWS_PER_CTA;
+  // A CTA owns `tiles_per_cta` (<= 7) row tiles of 8 chains per pass -- 7 when the batch fills
+  // the GPU (56 chains per SM), fewer for small batches so that the tiles spread over all SMs
+  // (strong scaling: 1024 chains -> 128 CTAs of one tile instead of 19 CTAs of seven).  The
+  // tiles of a pass are dealt to the 4 groups as evenly as possible (7 -> 2,2,2,1; 4 -> 1,1,1,1).
+  const int rows_per_cta = 8 * tiles_per_cta;
+  for (int64_t blk = blockIdx.x; blk * rows_per_cta < n_chains; blk += gridDim.x) {
+    const int64_t chain0 = blk * rows_per_cta;
     const int64_t left = n_chains - chain0;
-    const int tiles = (int)((left >= DMMA_ROWS_PER_CTA) ? DMMA_TILES_PER_CTA : (left + 7) / 8);
-    const int row0 = 8 * dmma_tile_start(group);
-    int active_groups = 0;
-    for (int g = 0; g < DMMA_GROUPS; ++g) active_groups += tiles > dmma_tile_start(g);
-    const int cta_threads = 128 * active_groups;
-    int mt = tiles - dmma_tile_start(group);
-    mt = mt > dmma_tile_count(group) ? dmma_tile_count(group) : mt;
+    const int tiles = (int)((left >= rows_per_cta) ? tiles_per_cta : (left + 7) / 8);
+    const int base = tiles / DMMA_GROUPS, rem = tiles % DMMA_GROUPS;
+    const int mt = base + (group < rem ? 1 : 0);
+    const int row0 = 8 * (group * base + (group < rem ? group : rem));
+    const int cta_threads = 128 * (tiles < DMMA_GROUPS ? tiles : DMMA_GROUPS);
 #define MB200_GROUP(MT)                                                                       \
   leapfrog_dmma_group<Target, DP, MT>(sm, target, q_in, p_in, q_out, p_out, dir, n_chains,    \
                                       dim, step_size, n_steps, h_out, status, n_done, chain0, \
@@ -489,10 +509,13 @@ static int launch_dmma(const double* q_in, const double* p_in, double* q_out, do
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
       cudaSuccess)
     return MB200_ERR_CUDA;
-  int64_t blocks = (n + DMMA_ROWS_PER_CTA - 1) / DMMA_ROWS_PER_CTA;
-  if (blocks > sms) blocks = sms;  // persistent: CTAs loop over blocks of 56 chains
+  const int64_t total_tiles = (n + 7) / 8;
+  int64_t tpc = (total_tiles + sms - 1) / sms;  // tiles per CTA and pass
+  if (tpc > DMMA_TILES_PER_CTA) tpc = DMMA_TILES_PER_CTA;
+  int64_t blocks = (total_tiles + tpc - 1) / tpc;
+  if (blocks > sms) blocks = sms;  // persistent: CTAs loop over passes of tpc tiles
   kern<<<(unsigned)blocks, DMMA_THREADS, smem, st>>>(q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps,
-                                            minv, m, h_out, status, n_done);
+                                            minv, m, h_out, status, n_done, (int)tpc);
   return 0;
 }
 
