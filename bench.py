@@ -303,11 +303,15 @@ def bind_to_gpu_numa_node(index):
     return None
 
 
-def time_launches(torch, fn, reps, flush=None):
-    """Per-launch CUDA-event times (ms) of `fn`, L2 optionally flushed between launches."""
+def time_launches(torch, fn, reps, flush=None, park_ms=0.0):
+    """Per-launch CUDA-event times (ms) of `fn`, L2 optionally flushed between launches.  With
+    `park_ms` the GPU is held busy while the host enqueues all launches, so that the event pairs
+    of sub-millisecond kernels contain device time only (no host launch gaps)."""
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(reps)]
     out = None
+    if park_ms > 0.0:
+        torch.cuda._sleep(int(park_ms * 1e-3 * 1.9e9))
     for i, (a, b) in enumerate(ev):
         if flush is not None:
             flush.fill_(float(i))
@@ -338,7 +342,8 @@ def run_workload(name, torch, dist, dev, rank, world, flush, hbm_peak):
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-    times, out = time_launches(torch, lambda: integ.step_n(state, L), w["reps"], flush)
+    times, out = time_launches(torch, lambda: integ.step_n(state, L), w["reps"], flush,
+                               park_ms=10.0 if name == "C3" else 0.0)
     t = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device=dev)
     done = out.n_done.sum().to(torch.float64).reshape(1)
     ok = (out.status == 0).sum().to(torch.float64).reshape(1)
@@ -559,7 +564,8 @@ def run_cuda(args, rank, local_rank, world):
         sstate = engine.build_state(sprob, dev, chains=slice(rank * n_s, (rank + 1) * n_s))
         integ.step_n(sstate, L)
         sync_all()
-        st_times, _ = time_launches(torch, lambda: integ.step_n(sstate, L), 10, flush)
+        st_times, _ = time_launches(torch, lambda: integ.step_n(sstate, L), 10, flush,
+                                    park_ms=20.0)
         st_ms = torch.tensor([sum(st_times) / len(st_times)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(st_ms, op=dist.ReduceOp.MAX)

@@ -378,6 +378,10 @@ class GaussianEuclideanMetricSystem(EuclideanMetricSystem):
             return m._dev[key]
         key = ("rot", str(device), float(step_size), tuple(float(c) for c in drift_coefficients))
         if key not in m._dev:
+            # keep only the rotations of the most recent step sizes (adaptation visits many)
+            stale = [k for k in m._dev if isinstance(k, tuple) and k and k[0] == "rot"]
+            for k in stale[:-3]:
+                del m._dev[k]
             eigval, u = self._eig()
             omega = 1.0 / eigval**0.5
             mats = []
