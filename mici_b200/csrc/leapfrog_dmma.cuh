@@ -448,6 +448,9 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
     }
   }
   MB200_K1_MARK(1);
+  // every thread polls the mbarrier below: its initialisation by warp 0 (and the zero-fill
+  // above) must be visible first
+  __syncthreads();
   // wait for the bytes to land (phase 0), then scale the staged metric: sm.A = eps * A
   {
     uint32_t done = 0;
@@ -461,7 +464,6 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
     }
   }
   MB200_K1_MARK(2);
-  __syncthreads();  // the zero-fill above is complete as well
 #pragma unroll 4
   for (int idx = tid; idx < DP * (DP / 2); idx += blockDim.x) {
     const int row = idx / (DP / 2), c2 = idx - row * (DP / 2);
