@@ -402,6 +402,56 @@ int mb200_nuts_euclidean(const double* pos_in, const double* mom_in, double* pos
  * at least mb200_host_scratch_bytes(n_chains, dim) bytes owned by the caller and must not be
  * shared by concurrent calls.  synchronize != 0: wait for all streams before returning.
  */
+/*
+ * Dynamic transitions for ANY integrator / system pair (constrained, implicit, compositions):
+ * the tree bookkeeping of DynamicIntegrationTransition (transitions.py:528-581, 610-770) as
+ * device kernels around batched integrator steps.  The caller advances all chains in lock-step:
+ *   begin(initial pos, mom, dh_dmom, h)
+ *   for depth in 0 .. max_tree_depth-1:
+ *     start(depth) -> per-chain direction, edge state, active mask      [stop if none active]
+ *     for k in 1 .. 2^depth:  one batched Integrator.step of the edge state with those
+ *       directions, system.h and system.dh_dmom of the result, then leaf(k, 2^depth, ...)
+ *     finish(depth)
+ *   end() -> returned state and statistics
+ * `status` of a leaf is the integrator's per-chain status: != 0 terminates that chain's tree and
+ * sets convergence_error / non_reversible_step (transitions.py:670-676).  Uniform variates are
+ * consumed per chain in the reference's order, as in mb200_nuts_euclidean.  workspace:
+ * mb200_nuts_workspace_bytes(); chain_state: mb200_nuts_generic_state_bytes().  flags_out bits:
+ * 0 diverging, 1 convergence_error, 2 non_reversible_step, 3 ran out of uniform variates.
+ */
+typedef struct mb200_nuts_options {
+  int32_t max_tree_depth;
+  int32_t slice_variant;
+  int32_t euclidean_criterion;
+  int32_t extra_subtree_checks;
+  double max_delta_h;
+  const double* uniforms;   /* [n_chains * n_uniforms] */
+  int32_t n_uniforms;
+} mb200_nuts_options;
+
+int64_t mb200_nuts_generic_state_bytes(int64_t n_chains);
+int mb200_nuts_generic_begin(const double* pos, const double* mom, const double* vel,
+                             const double* h, int64_t n_chains, int32_t dim,
+                             const mb200_nuts_options* options, void* workspace,
+                             int64_t workspace_bytes, void* chain_state, int64_t chain_state_bytes,
+                             void* stream);
+int mb200_nuts_generic_start(int64_t n_chains, int32_t dim, int32_t depth,
+                             const mb200_nuts_options* options, void* workspace, void* chain_state,
+                             double* pos_edge, double* mom_edge, int32_t* dir_out, int32_t* active,
+                             void* stream);
+int mb200_nuts_generic_leaf(const double* pos, const double* mom, const double* vel,
+                            const double* h, const int32_t* status, int64_t n_chains, int32_t dim,
+                            int32_t k, int32_t n_leaves, const mb200_nuts_options* options,
+                            void* workspace, void* chain_state, int32_t* active, void* stream);
+int mb200_nuts_generic_finish(int64_t n_chains, int32_t dim, int32_t depth,
+                              const mb200_nuts_options* options, void* workspace, void* chain_state,
+                              void* stream);
+int mb200_nuts_generic_end(int64_t n_chains, int32_t dim, const mb200_nuts_options* options,
+                           void* workspace, void* chain_state, double* pos_out, double* mom_out,
+                           double* h_out, int32_t* n_step, double* av_metrop_accept_prob,
+                           double* reject_prob, int32_t* tree_depth, int32_t* flags_out,
+                           int32_t* n_uniforms_used, int32_t* dir_out, void* stream);
+
 int64_t mb200_host_scratch_bytes(int64_t n_chains, int32_t dim);
 int mb200_leapfrog_euclidean_host(const double* pos_in, const double* mom_in, double* pos_out,
                                   double* mom_out, const int32_t* dir, int64_t n_chains,

@@ -25,6 +25,20 @@ c_double_p = ctypes.c_void_p  # device pointers travel as integers
 c_int32_p = ctypes.c_void_p
 
 
+class NutsOptions(ctypes.Structure):
+    """``struct mb200_nuts_options``."""
+
+    _fields_ = [
+        ("max_tree_depth", ctypes.c_int32),
+        ("slice_variant", ctypes.c_int32),
+        ("euclidean_criterion", ctypes.c_int32),
+        ("extra_subtree_checks", ctypes.c_int32),
+        ("max_delta_h", ctypes.c_double),
+        ("uniforms", ctypes.c_void_p),
+        ("n_uniforms", ctypes.c_int32),
+    ]
+
+
 class Model(ctypes.Structure):
     """``struct mb200_model``."""
 
@@ -42,6 +56,7 @@ class Model(ctypes.Structure):
 
 _I64, _I32, _F64, _P = ctypes.c_int64, ctypes.c_int32, ctypes.c_double, ctypes.c_void_p
 _MP = ctypes.POINTER(Model)
+_NP = ctypes.POINTER(NutsOptions)
 
 # symbol -> (restype, argtypes): every symbol declared in include/mici_b200.h
 SIGNATURES = {
@@ -86,6 +101,16 @@ SIGNATURES = {
     "mb200_sample_momentum_riemannian": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _MP, _P, _P]),
     "mb200_dh_dmom_riemannian": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _MP, _P, _P]),
     "mb200_selftest_dense_factor": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P]),
+    "mb200_nuts_generic_state_bytes": (ctypes.c_int64, [_I64]),
+    "mb200_nuts_generic_begin": (
+        ctypes.c_int, [_P, _P, _P, _P, _I64, _I32, _NP, _P, _I64, _P, _I64, _P]),
+    "mb200_nuts_generic_start": (
+        ctypes.c_int, [_I64, _I32, _I32, _NP, _P, _P, _P, _P, _P, _P, _P]),
+    "mb200_nuts_generic_leaf": (
+        ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _NP, _P, _P, _P, _P]),
+    "mb200_nuts_generic_finish": (ctypes.c_int, [_I64, _I32, _I32, _NP, _P, _P, _P]),
+    "mb200_nuts_generic_end": (
+        ctypes.c_int, [_I64, _I32, _NP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mb200_leapfrog_euclidean_per_chain": (
         ctypes.c_int,
         [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _I32, _I32, _P, _I32, _I32, _P, _MP, _P, _P, _P, _P],

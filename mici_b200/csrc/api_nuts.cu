@@ -2,6 +2,7 @@
 // Host-side argument checking and kernel dispatch only; all arithmetic is in the .cuh kernels.
 #include "api_common.cuh"
 #include "nuts.cuh"
+#include "nuts_generic.cuh"
 #include "transitions.cuh"
 
 namespace mb200 {
@@ -152,6 +153,151 @@ int mb200_nuts_euclidean(const double* pos_in, const double* mom_in, double* pos
                   m.target_id);
   }
 #undef MB200_ARGS
+}
+
+// ---------------------------------------------------------------- generic dynamic transitions
+namespace {
+
+mb200::NutsGenArgs gen_args(const mb200_nuts_options* o) {
+  mb200::NutsGenArgs a;
+  a.max_depth = o->max_tree_depth;
+  a.slice = o->slice_variant;
+  a.euclid = o->euclidean_criterion;
+  a.extra = o->extra_subtree_checks;
+  a.max_delta_h = o->max_delta_h;
+  a.uniforms = o->uniforms;
+  a.n_uniforms = o->n_uniforms;
+  return a;
+}
+
+int gen_check(int64_t n, int32_t dim, const mb200_nuts_options* o, const void* ws, const void* cs) {
+  if (!o || !ws || !cs || !o->uniforms) return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
+  if (n < 0 || dim < 1 || dim > 1024) return fail(MB200_ERR_INVALID_ARG, "bad sizes");
+  if (o->max_tree_depth < 1 || o->max_tree_depth > NUTS_MAX_DEPTH || o->n_uniforms < 1)
+    return fail(MB200_ERR_INVALID_ARG, "max_tree_depth must be in [1, %d]", NUTS_MAX_DEPTH);
+  return 0;
+}
+
+unsigned gen_blocks(int64_t n) {
+  const int64_t cap = (int64_t)num_sms() * 8;
+  int64_t b = (n + 3) / 4;
+  return (unsigned)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+
+#define MB200_KP_DISPATCH(CALL)                 \
+  do {                                          \
+    if (dim <= 64) { CALL(1); }                 \
+    else if (dim <= 128) { CALL(2); }           \
+    else if (dim <= 256) { CALL(4); }           \
+    else if (dim <= 512) { CALL(8); }           \
+    else { CALL(16); }                          \
+  } while (0)
+
+int64_t mb200_nuts_generic_state_bytes(int64_t n_chains) {
+  return n_chains < 0 ? -1 : n_chains * (int64_t)sizeof(NutsGenState);
+}
+
+int mb200_nuts_generic_begin(const double* pos, const double* mom, const double* vel,
+                             const double* h, int64_t n_chains, int32_t dim,
+                             const mb200_nuts_options* options, void* workspace,
+                             int64_t workspace_bytes, void* chain_state, int64_t chain_state_bytes,
+                             void* stream) {
+  if (n_chains == 0) return 0;
+  if (!pos || !mom || !vel || !h) return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
+  if (int rc = gen_check(n_chains, dim, options, workspace, chain_state)) return rc;
+  if (workspace_bytes < mb200_nuts_workspace_bytes(n_chains, dim, options->max_tree_depth) ||
+      chain_state_bytes < mb200_nuts_generic_state_bytes(n_chains))
+    return fail(MB200_ERR_INVALID_ARG, "workspace / chain state too small");
+  const DeviceScope device_scope(pos);
+  const NutsGenArgs a = gen_args(options);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(KP)                                                                              \
+  nuts_generic_begin_kernel<KP><<<gen_blocks(n_chains), 128, 0, st>>>(                        \
+      pos, mom, vel, h, n_chains, dim, a, (double*)workspace, (NutsGenState*)chain_state)
+  MB200_KP_DISPATCH(CALL);
+#undef CALL
+  return check_launch("nuts_generic_begin_kernel");
+}
+
+int mb200_nuts_generic_start(int64_t n_chains, int32_t dim, int32_t depth,
+                             const mb200_nuts_options* options, void* workspace, void* chain_state,
+                             double* pos_edge, double* mom_edge, int32_t* dir_out, int32_t* active,
+                             void* stream) {
+  if (n_chains == 0) return 0;
+  if (!pos_edge || !mom_edge || !dir_out || !active)
+    return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
+  if (int rc = gen_check(n_chains, dim, options, workspace, chain_state)) return rc;
+  const DeviceScope device_scope(pos_edge);
+  const NutsGenArgs a = gen_args(options);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(KP)                                                                           \
+  nuts_generic_start_kernel<KP><<<gen_blocks(n_chains), 128, 0, st>>>(                     \
+      n_chains, dim, depth, a, (double*)workspace, (NutsGenState*)chain_state, pos_edge,   \
+      mom_edge, dir_out, active)
+  MB200_KP_DISPATCH(CALL);
+#undef CALL
+  return check_launch("nuts_generic_start_kernel");
+}
+
+int mb200_nuts_generic_leaf(const double* pos, const double* mom, const double* vel,
+                            const double* h, const int32_t* status, int64_t n_chains, int32_t dim,
+                            int32_t k, int32_t n_leaves, const mb200_nuts_options* options,
+                            void* workspace, void* chain_state, int32_t* active, void* stream) {
+  if (n_chains == 0) return 0;
+  if (!pos || !mom || !vel || !h || !status || !active)
+    return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
+  if (int rc = gen_check(n_chains, dim, options, workspace, chain_state)) return rc;
+  const DeviceScope device_scope(pos);
+  const NutsGenArgs a = gen_args(options);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(KP)                                                                              \
+  nuts_generic_leaf_kernel<KP><<<gen_blocks(n_chains), 128, 0, st>>>(                         \
+      pos, mom, vel, h, status, n_chains, dim, k, n_leaves, a, (double*)workspace,            \
+      (NutsGenState*)chain_state, active)
+  MB200_KP_DISPATCH(CALL);
+#undef CALL
+  return check_launch("nuts_generic_leaf_kernel");
+}
+
+int mb200_nuts_generic_finish(int64_t n_chains, int32_t dim, int32_t depth,
+                              const mb200_nuts_options* options, void* workspace, void* chain_state,
+                              void* stream) {
+  if (n_chains == 0) return 0;
+  if (int rc = gen_check(n_chains, dim, options, workspace, chain_state)) return rc;
+  const DeviceScope device_scope(workspace);
+  const NutsGenArgs a = gen_args(options);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(KP)                                                                  \
+  nuts_generic_finish_kernel<KP><<<gen_blocks(n_chains), 128, 0, st>>>(           \
+      n_chains, dim, depth, a, (double*)workspace, (NutsGenState*)chain_state)
+  MB200_KP_DISPATCH(CALL);
+#undef CALL
+  return check_launch("nuts_generic_finish_kernel");
+}
+
+int mb200_nuts_generic_end(int64_t n_chains, int32_t dim, const mb200_nuts_options* options,
+                           void* workspace, void* chain_state, double* pos_out, double* mom_out,
+                           double* h_out, int32_t* n_step, double* av_metrop_accept_prob,
+                           double* reject_prob, int32_t* tree_depth, int32_t* flags_out,
+                           int32_t* n_uniforms_used, int32_t* dir_out, void* stream) {
+  if (n_chains == 0) return 0;
+  if (!pos_out || !mom_out || !h_out || !n_step || !av_metrop_accept_prob || !reject_prob ||
+      !tree_depth || !flags_out || !n_uniforms_used || !dir_out)
+    return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
+  if (int rc = gen_check(n_chains, dim, options, workspace, chain_state)) return rc;
+  const DeviceScope device_scope(pos_out);
+  const NutsGenArgs a = gen_args(options);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(KP)                                                                               \
+  nuts_generic_end_kernel<KP><<<gen_blocks(n_chains), 128, 0, st>>>(                           \
+      n_chains, dim, a, (const double*)workspace, (const NutsGenState*)chain_state, pos_out,    \
+      mom_out, h_out, n_step, av_metrop_accept_prob, reject_prob, tree_depth, flags_out,       \
+      n_uniforms_used, dir_out)
+  MB200_KP_DISPATCH(CALL);
+#undef CALL
+  return check_launch("nuts_generic_end_kernel");
 }
 
 }  // extern "C"

@@ -242,7 +242,11 @@ class EuclideanMetricSystem(TractableFlowSystem):
             out["vel"] = torch.empty_like(pos)
         if kin:
             out["kin"] = torch.empty(n, dtype=torch.float64, device=dev)
-        model = self._model(dev)
+        if nld or grad:
+            model = self._model(dev)
+        else:  # M^-1 p and p.M^-1 p do not involve the target (constrained targets have no
+            model = _lib.Model()  # Euclidean-eval functor): neutral model
+            model.target_id = 0
         rc = lib.mb200_euclidean_eval(
             _lib.ptr(pos), _lib.ptr(mom), n, dim, self._metric.kind,
             _lib.ptr(self._metric.inv_device(dev)), ctypes.byref(model),

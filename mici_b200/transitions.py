@@ -207,11 +207,18 @@ def riemannian_no_u_turn_criterion(system, state_1, state_2, sum_mom):
 
 
 class DynamicIntegrationTransition:
-    """Dynamic-length integration transition (NUTS) for all chains in ONE launch
-    (transitions.py:487-770): every chain builds its own binary trajectory tree inside
-    ``mb200_nuts_euclidean`` (one warp per chain).  Same constructor as the reference; use the
-    ``Multinomial...`` / ``Slice...`` subclasses.  Available for ``LeapfrogIntegrator`` on an
-    ``EuclideanMetricSystem`` (shared or per-chain step size).
+    """Dynamic-length integration transition (NUTS) for all chains (transitions.py:487-770).
+    Same constructor as the reference; use the ``Multinomial...`` / ``Slice...`` subclasses.
+
+    * ``LeapfrogIntegrator`` on an ``EuclideanMetricSystem`` (shared or per-chain step size):
+      every chain builds its own binary trajectory tree inside ``mb200_nuts_euclidean`` (one warp
+      per chain, ONE launch per transition).
+    * Any other integrator / system (``ConstrainedLeapfrogIntegrator``,
+      ``ImplicitLeapfrogIntegrator``, compositions ...): the chains grow their trees in lock-step,
+      one batched ``integrator.step`` per leaf, with the tree bookkeeping (weights, binary-counter
+      merges, no-U-turn tests, progressive sampling) in the ``mb200_nuts_generic_*`` kernels; a
+      failed step terminates that chain's tree and sets ``convergence_error`` /
+      ``non_reversible_step`` as transitions.py:670-676 does.
 
     Random numbers: the kernel consumes, per chain, exactly the uniform variates the reference
     draws from that chain's generator, in the same order.  With a sequence of per-chain NumPy
@@ -238,11 +245,13 @@ class DynamicIntegrationTransition:
         if termination_criterion not in (euclidean_no_u_turn_criterion,
                                          riemannian_no_u_turn_criterion):
             raise ValueError("Only the two no-U-turn criteria of this module are fused.")
-        if type(integrator) is not LeapfrogIntegrator or not isinstance(
-                system, EuclideanMetricSystem) or isinstance(
-                system, (ConstrainedEuclideanMetricSystem, GaussianEuclideanMetricSystem)):
-            raise NotImplementedError(
-                "Dynamic transitions are fused for LeapfrogIntegrator on EuclideanMetricSystem.")
+        # LeapfrogIntegrator on a plain EuclideanMetricSystem: whole transitions in ONE launch
+        # (mb200_nuts_euclidean).  Every other pair (constrained, implicit, compositions,
+        # Gaussian splitting): lock-step leaves through the integrator's own kernels with the
+        # tree bookkeeping in the mb200_nuts_generic_* kernels.
+        self._fused = type(integrator) is LeapfrogIntegrator and isinstance(
+            system, EuclideanMetricSystem) and not isinstance(
+            system, (ConstrainedEuclideanMetricSystem, GaussianEuclideanMetricSystem))
         self.system = system
         self.integrator = integrator
         self.max_tree_depth = int(max_tree_depth)
@@ -260,6 +269,8 @@ class DynamicIntegrationTransition:
 
         if self.integrator.step_size is None:
             raise AdaptationError("Integrator `step_size` is `None`.")
+        if not self._fused:
+            return self._sample_generic(state, rng)
         pos, mom = state.pos.contiguous(), state.mom.contiguous()
         n, dim = pos.shape
         dev = pos.device
@@ -325,6 +336,113 @@ class DynamicIntegrationTransition:
             "step_size": _step_size_stat(eps, n, dev),
         }
         return new, stats
+
+    def _sample_generic(self, state, rng):
+        """Lock-step dynamic transition through the integrator's own step kernels."""
+        pos, mom = state.pos.contiguous(), state.mom.contiguous()
+        n, dim = pos.shape
+        dev = pos.device
+        n_uni = self.n_uniforms
+        saved = None
+        if isinstance(rng, torch.Generator):
+            uni = torch.rand((n, n_uni), dtype=torch.float64, device=dev, generator=rng)
+        elif isinstance(rng, Sequence):
+            saved = [g.bit_generator.state for g in rng]
+            uni = torch.as_tensor(np.stack([g.uniform(size=n_uni) for g in rng]), device=dev)
+        else:
+            uni = torch.as_tensor(rng.uniform(size=(n, n_uni)), device=dev)
+        lib = _lib.load()
+        system, integ = self.system, self.integrator
+        ws_bytes = int(lib.mb200_nuts_workspace_bytes(n, dim, self.max_tree_depth))
+        cs_bytes = int(lib.mb200_nuts_generic_state_bytes(n))
+        if ws_bytes < 0:
+            raise ValueError("unsupported dim / max_tree_depth for the dynamic transition")
+        ws = system._dev.get(("nuts_ws", str(dev)))
+        if ws is None or ws.numel() < ws_bytes:
+            ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
+            system._dev[("nuts_ws", str(dev))] = ws
+        cs = torch.empty(max(cs_bytes, 8), dtype=torch.uint8, device=dev)
+        opts = _lib.NutsOptions()
+        opts.max_tree_depth = self.max_tree_depth
+        opts.slice_variant = 1 if self._slice else 0
+        opts.euclidean_criterion = (
+            1 if self.termination_criterion is euclidean_no_u_turn_criterion else 0)
+        opts.extra_subtree_checks = 1 if self.do_extra_subtree_checks else 0
+        opts.max_delta_h = self.max_delta_h
+        opts.uniforms = uni.data_ptr()
+        opts.n_uniforms = n_uni
+        o = ctypes.byref(opts)
+        stream = _lib.current_stream_ptr(dev)
+        f64 = {"dtype": torch.float64, "device": dev}
+        i32 = {"dtype": torch.int32, "device": dev}
+        init = ChainState(pos=pos, mom=mom, dir=1)
+        h0 = system.h(init).contiguous()
+        v0 = system.dh_dmom(init).contiguous()
+        _lib.check(lib.mb200_nuts_generic_begin(
+            _lib.ptr(pos), _lib.ptr(mom), _lib.ptr(v0), _lib.ptr(h0), n, dim, o, _lib.ptr(ws),
+            ws.numel(), _lib.ptr(cs), cs.numel(), stream), "mb200_nuts_generic_begin")
+        q_edge, p_edge = torch.empty_like(pos), torch.empty_like(mom)
+        dirs, active = torch.empty(n, **i32), torch.empty(n, **i32)
+        for depth in range(self.max_tree_depth):
+            _lib.check(lib.mb200_nuts_generic_start(
+                n, dim, depth, o, _lib.ptr(ws), _lib.ptr(cs), _lib.ptr(q_edge), _lib.ptr(p_edge),
+                _lib.ptr(dirs), _lib.ptr(active), stream), "mb200_nuts_generic_start")
+            if not bool(active.any()):
+                break
+            cur = ChainState(pos=q_edge, mom=p_edge, dir=dirs)
+            n_leaves = 2**depth
+            for k in range(1, n_leaves + 1):
+                new = integ.step_n(cur, 1, return_h=True)
+                vel = system.dh_dmom(_quiet(new)).contiguous()
+                _lib.check(lib.mb200_nuts_generic_leaf(
+                    _lib.ptr(new.pos), _lib.ptr(new.mom), _lib.ptr(vel), _lib.ptr(new.h),
+                    _lib.ptr(new.status), n, dim, k, n_leaves, o, _lib.ptr(ws), _lib.ptr(cs),
+                    _lib.ptr(active), stream), "mb200_nuts_generic_leaf")
+                cur = ChainState(pos=new.pos, mom=new.mom, dir=dirs)
+                # every chain's doubling may have terminated early: look now and then
+                if k < n_leaves and (k & 7) == 0 and not bool(active.any()):
+                    break
+            _lib.check(lib.mb200_nuts_generic_finish(
+                n, dim, depth, o, _lib.ptr(ws), _lib.ptr(cs), stream), "mb200_nuts_generic_finish")
+        pos_out, mom_out = torch.empty_like(pos), torch.empty_like(mom)
+        h, av, rej = torch.empty(n, **f64), torch.empty(n, **f64), torch.empty(n, **f64)
+        n_step, tdepth, flags = torch.empty(n, **i32), torch.empty(n, **i32), torch.empty(n, **i32)
+        used, dir_out = torch.empty(n, **i32), torch.empty(n, **i32)
+        _lib.check(lib.mb200_nuts_generic_end(
+            n, dim, o, _lib.ptr(ws), _lib.ptr(cs), _lib.ptr(pos_out), _lib.ptr(mom_out),
+            _lib.ptr(h), _lib.ptr(n_step), _lib.ptr(av), _lib.ptr(rej), _lib.ptr(tdepth),
+            _lib.ptr(flags), _lib.ptr(used), _lib.ptr(dir_out), stream), "mb200_nuts_generic_end")
+        if saved is not None:
+            for g, st, k in zip(rng, saved, used.cpu().tolist()):
+                g.bit_generator.state = st
+                if k:
+                    g.uniform(size=k)
+        if bool(((flags >> 3) & 1).any()):
+            raise RuntimeError("dynamic transition ran out of uniform variates")
+        diverging = (flags & 1).bool()
+        conv = ((flags >> 1) & 1).bool()
+        nonrev = ((flags >> 2) & 1).bool()
+        failed = diverging | conv | nonrev
+        new = ChainState(pos=pos_out, mom=mom_out, dir=dir_out)
+        new.h = h
+        stats = {
+            "n_step": n_step.to(torch.int64),
+            "accept_stat": torch.where(failed, torch.zeros_like(av), av),
+            "av_metrop_accept_prob": av,
+            "reject_prob": rej,
+            "tree_depth": tdepth.to(torch.int64),
+            "diverging": diverging,
+            "convergence_error": conv,
+            "non_reversible_step": nonrev,
+            "step_size": _step_size_stat(integ.step_size, n, dev),
+        }
+        return new, stats
+
+
+def _quiet(state):
+    """A state whose ``dh_dmom`` is wanted for every chain although some chains may hold a
+    failed step's (finite, pre-step) state: plain (pos, mom) copy without auxiliary slots."""
+    return ChainState(pos=state.pos, mom=state.mom, dir=1)
 
 
 class MultinomialDynamicIntegrationTransition(DynamicIntegrationTransition):

@@ -506,7 +506,9 @@ ADAPT_NAMES = ["adapt_c1_dualavg_variance", "adapt_c1_dualavg_covariance", "adap
                "adapt_c0_variance_first", "adapt_c3_torus_dualavg", "adapt_c2_softabs_d6_dualavg",
                "adapt_nuts_c0_dualavg", "adapt_nuts_c1_dualavg_variance"]
 NUTS_NAMES = ["nuts_c1_multinomial_d10", "nuts_c1_slice_euclidean_d16",
-              "nuts_c0_depth4_no_extra_checks", "nuts_c1_diag_divergent", "nuts_c1_identity_d70"]
+              "nuts_c0_depth4_no_extra_checks", "nuts_c1_diag_divergent", "nuts_c1_identity_d70",
+              # constrained / implicit integrators: lock-step leaves + mb200_nuts_generic_* kernels
+              "nuts_c3_torus_constrained", "nuts_c2_softabs_d4_implicit"]
 
 
 def _dynamic_transition(integ, opts):
@@ -767,8 +769,10 @@ def test_dynamic_transition_matches_reference_fixture(name):
         integ.system, integ, state, rngs, 0, n_iter,
         integration_transition=_dynamic_transition(integ, opts))
     torch.cuda.synchronize()
-    for k in ("n_step", "tree_depth", "diverging"):
-        np.testing.assert_array_equal(stats[k].cpu().numpy().astype(np.float64), g[k], err_msg=k)
+    for k in ("n_step", "tree_depth", "diverging", "convergence_error", "non_reversible_step"):
+        if k in g:
+            np.testing.assert_array_equal(stats[k].cpu().numpy().astype(np.float64), g[k],
+                                          err_msg=k)
     np.testing.assert_array_equal(final.dir.cpu().numpy(), g["dir"][-1])
     np.testing.assert_allclose(trace.cpu().numpy(), g["pos"], rtol=1e-8, atol=1e-10)
     for k in ("av_metrop_accept_prob", "accept_stat", "reject_prob"):
@@ -790,6 +794,36 @@ def test_dynamic_transition_matches_reference_fixture(name):
                 q, _, _ = mo.nuts_transition(q, sample_mom(q, g_ref), g_ref.uniform, step, h_fn,
                                              vel, **opts)
         assert rngs[i].uniform() == g_ref.uniform()
+
+
+@pytest.mark.parametrize("cfg,kwargs,eps,opts", [
+    ("C1", {"n_chains": 24, "dim": 16}, 0.15, {}),
+    ("C1", {"n_chains": 16, "dim": 70, "metric_kind": "diagonal"}, 0.2,
+     {"variant": "slice", "criterion": "euclidean", "max_tree_depth": 6}),
+])
+def test_generic_dynamic_transition_equals_fused_kernel(cfg, kwargs, eps, opts):
+    """The lock-step generic path (batched steps + bookkeeping kernels) and the fused one-launch
+    kernel are two implementations of the same transition: identical discrete outcomes and
+    uniform consumption, states equal to rounding, on a Euclidean system where both apply."""
+    problem = problems.make_problem(cfg, **kwargs)
+    problem.step_size = eps
+    integ = engine.build_integrator(problem)
+    state = engine.build_state(problem, DEV)
+    out = []
+    for fused in (True, False):
+        tr = _dynamic_transition(integ, opts)
+        tr._fused = fused
+        rngs = [np.random.default_rng([91, i]) for i in range(problem.n_chains)]
+        st = state
+        for _ in range(3):
+            st, stats = tr.sample(st, rngs)
+        out.append((st, stats, [r.uniform() for r in rngs]))
+    (a, sa, ua), (b, sb, ub) = out
+    for k in ("n_step", "tree_depth", "diverging"):
+        assert torch.equal(sa[k], sb[k]), k
+    assert ua == ub
+    assert torch.equal(a.dir, b.dir)
+    np.testing.assert_allclose(b.pos.cpu().numpy(), a.pos.cpu().numpy(), rtol=1e-9, atol=1e-11)
 
 
 def test_dynamic_transition_full_size_device_rng():
