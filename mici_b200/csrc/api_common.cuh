@@ -80,6 +80,29 @@ struct DeviceScope {
   }
 };
 
+// Workspace: caller-provided when large enough, else a stream-ordered allocation that is freed
+// (stream-ordered) right after the launch -- entry points without a workspace parameter
+// (momentum refresh, velocity, per-chain variants) use the latter.
+struct DgScratch {
+  double* ptr = nullptr;
+  bool owned = false;
+  cudaStream_t st;
+  DgScratch(void* user, int64_t user_bytes, size_t need, cudaStream_t s) : st(s) {
+    if (need == 0) return;
+    if (user != nullptr && user_bytes >= (int64_t)need &&
+        (reinterpret_cast<uintptr_t>(user) & 15) == 0) {
+      ptr = static_cast<double*>(user);
+    } else if (cudaMallocAsync(reinterpret_cast<void**>(&ptr), need, s) == cudaSuccess) {
+      owned = true;
+    } else {
+      ptr = nullptr;
+    }
+  }
+  ~DgScratch() {
+    if (owned && ptr != nullptr) cudaFreeAsync(ptr, st);
+  }
+};
+
 // implemented in api_dmma.cu (tensor-core leapfrog); MB200_ERR_UNSUPPORTED = outside its domain
 int leapfrog_dmma_dispatch(const double* q_in, const double* p_in, double* q_out, double* p_out,
                            const int32_t* dir, int64_t n, int dim, double eps, int n_steps,

@@ -7,28 +7,6 @@
 
 namespace mb200 {
 
-// Workspace: caller-provided when large enough, else a stream-ordered allocation that is freed
-// (stream-ordered) right after the launch -- entry points without a workspace parameter
-// (momentum refresh, velocity, per-chain variants) use the latter.
-struct DgScratch {
-  double* ptr = nullptr;
-  bool owned = false;
-  cudaStream_t st;
-  DgScratch(void* user, int64_t user_bytes, size_t need, cudaStream_t s) : st(s) {
-    if (user != nullptr && user_bytes >= (int64_t)need &&
-        (reinterpret_cast<uintptr_t>(user) & 15) == 0) {
-      ptr = static_cast<double*>(user);
-    } else if (cudaMallocAsync(reinterpret_cast<void**>(&ptr), need, s) == cudaSuccess) {
-      owned = true;
-    } else {
-      ptr = nullptr;
-    }
-  }
-  ~DgScratch() {
-    if (owned && ptr != nullptr) cudaFreeAsync(ptr, st);
-  }
-};
-
 static int dg_blocks(int64_t n) {
   const int64_t cap = (int64_t)num_sms();  // one CTA per SM (its shared memory is ~200 KB)
   return (int)(n < cap ? n : cap);

@@ -16,20 +16,37 @@ static int launch_implicit(const double* q_in, const double* p_in, double* q_out
   // SoftAbs: a third matrix enables warm-started eigensolves; use it when two CTAs still fit
   if (MetricT<Target>::SOFTABS && rm_smem_doubles(dim, 3) * sizeof(double) <= 113 * 1024) n_mats = 3;
   if (MetricT<Target>::SOFTABS && Target::DENSE_MTP) n_mats = 3;  // the third holds Z = A U
-  const size_t smem = rm_smem_doubles(dim, n_mats) * sizeof(double);
-  if (smem > 227 * 1024)
-    return fail(MB200_ERR_UNSUPPORTED,
-                "dim %d: per-chain metric (%zu bytes) exceeds shared memory; not supported yet",
-                dim, smem);
+  size_t smem = rm_smem_doubles(dim, n_mats) * sizeof(double);
+  bool in_ws = false;
+  if (smem > 227 * 1024) {
+    // SoftAbs beyond shared memory: the same kernels with the matrices in a per-CTA global
+    // workspace (L2-resident operands: slower, but the reference has no dimension limit)
+    if (!MetricT<Target>::SOFTABS)
+      return fail(MB200_ERR_UNSUPPORTED,
+                  "dim %d: per-chain metric (%zu bytes) exceeds shared memory", dim, smem);
+    n_mats = RM_NMATS_IN_WORKSPACE + 3;
+    smem = rm_smem_doubles(dim, n_mats) * sizeof(double);
+    in_ws = true;
+    if (smem > 227 * 1024) return fail(MB200_ERR_UNSUPPORTED, "dim %d too large", dim);
+  }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(MB200_ERR_CUDA, "smem attr: %s", cudaGetErrorString(e));
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RM_THREADS, smem);
   if (per_sm < 1) per_sm = 1;
+  if (in_ws && per_sm > 2) per_sm = 2;
   int64_t blocks = (int64_t)num_sms() * per_sm;
   if (blocks > n) blocks = n;
+  ModelArgs margs = m;
+  const size_t per_cta = 3 * ((((size_t)dim * (dim + 1)) + 1) & ~(size_t)1);
+  DgScratch scratch(nullptr, 0, in_ws ? per_cta * blocks * sizeof(double) : 0, st);
+  if (in_ws) {
+    if (scratch.ptr == nullptr) return fail(MB200_ERR_CUDA, "SoftAbs workspace allocation failed");
+    margs.workspace = scratch.ptr;
+    margs.ws_stride = per_cta;
+  }
   kern<<<(unsigned)blocks, RM_THREADS, smem, st>>>(q_in, p_in, q_out, p_out, dir, n, dim, eps,
-                                                   n_steps, m, fp_tol, fp_div, fp_max, rev_tol,
+                                                   n_steps, margs, fp_tol, fp_div, fp_max, rev_tol,
                                                    h_out, status, n_done, fp_iters, n_mats,
                                                    midpoint, fp_solver);
   return check_launch("implicit_leapfrog_kernel");
@@ -73,8 +90,6 @@ static int implicit_dispatch(const double* q_in, const double* p_in, double* q_o
         if (!m.taux) return fail(MB200_ERR_INVALID_ARG, "quartic target needs its directions");
         if (midpoint)
           return fail(MB200_ERR_UNSUPPORTED, "implicit midpoint: quartic target not available");
-        if (rm_smem_doubles(dim, 3) * sizeof(double) > 227 * 1024)
-          return fail(MB200_ERR_UNSUPPORTED, "quartic target: dim %d too large (three matrices)", dim);
         return launch_implicit<QuarticRTarget, SoftAbsMetric>(MB200_ARGS);
       default:
         return fail(MB200_ERR_UNSUPPORTED, "target %d has no device Hessian / MTP (SoftAbs metric)",
@@ -115,14 +130,29 @@ template <class Target, template <class> class MetricT>
 static int launch_sample_momentum(const double* q, const double* z, double* p_out, int64_t n,
                                   int dim, const ModelArgs& m, int32_t* status, cudaStream_t st) {
   auto kern = riemannian_sample_momentum_kernel<Target, MetricT>;
-  const int n_mats = MetricT<Target>::N_MATS;
-  const size_t smem = rm_smem_doubles(dim, n_mats) * sizeof(double);
-  if (smem > 227 * 1024) return fail(MB200_ERR_UNSUPPORTED, "dim %d too large", dim);
+  int n_mats = MetricT<Target>::N_MATS;
+  size_t smem = rm_smem_doubles(dim, n_mats) * sizeof(double);
+  bool in_ws = false;
+  if (smem > 227 * 1024) {
+    if (!MetricT<Target>::SOFTABS) return fail(MB200_ERR_UNSUPPORTED, "dim %d too large", dim);
+    n_mats = RM_NMATS_IN_WORKSPACE + 3;
+    smem = rm_smem_doubles(dim, n_mats) * sizeof(double);
+    in_ws = true;
+    if (smem > 227 * 1024) return fail(MB200_ERR_UNSUPPORTED, "dim %d too large", dim);
+  }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(MB200_ERR_CUDA, "smem attr: %s", cudaGetErrorString(e));
   int64_t blocks = (int64_t)num_sms() * 2;
   if (blocks > n) blocks = n;
-  kern<<<(unsigned)blocks, RM_THREADS, smem, st>>>(q, z, p_out, n, dim, m, status, n_mats);
+  ModelArgs margs = m;
+  const size_t per_cta = 3 * ((((size_t)dim * (dim + 1)) + 1) & ~(size_t)1);
+  DgScratch scratch(nullptr, 0, in_ws ? per_cta * blocks * sizeof(double) : 0, st);
+  if (in_ws) {
+    if (scratch.ptr == nullptr) return fail(MB200_ERR_CUDA, "SoftAbs workspace allocation failed");
+    margs.workspace = scratch.ptr;
+    margs.ws_stride = per_cta;
+  }
+  kern<<<(unsigned)blocks, RM_THREADS, smem, st>>>(q, z, p_out, n, dim, margs, status, n_mats);
   return check_launch("riemannian_sample_momentum_kernel");
 }
 
@@ -130,14 +160,29 @@ template <class Target, template <class> class MetricT>
 static int launch_velocity(const double* q, const double* p, double* vel, int64_t n, int dim,
                            const ModelArgs& m, int32_t* status, cudaStream_t st) {
   auto kern = riemannian_velocity_kernel<Target, MetricT>;
-  const int n_mats = MetricT<Target>::N_MATS;
-  const size_t smem = rm_smem_doubles(dim, n_mats) * sizeof(double);
-  if (smem > 227 * 1024) return fail(MB200_ERR_UNSUPPORTED, "dim %d too large", dim);
+  int n_mats = MetricT<Target>::N_MATS;
+  size_t smem = rm_smem_doubles(dim, n_mats) * sizeof(double);
+  bool in_ws = false;
+  if (smem > 227 * 1024) {
+    if (!MetricT<Target>::SOFTABS) return fail(MB200_ERR_UNSUPPORTED, "dim %d too large", dim);
+    n_mats = RM_NMATS_IN_WORKSPACE + 3;
+    smem = rm_smem_doubles(dim, n_mats) * sizeof(double);
+    in_ws = true;
+    if (smem > 227 * 1024) return fail(MB200_ERR_UNSUPPORTED, "dim %d too large", dim);
+  }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(MB200_ERR_CUDA, "smem attr: %s", cudaGetErrorString(e));
   int64_t blocks = (int64_t)num_sms() * 2;
   if (blocks > n) blocks = n;
-  kern<<<(unsigned)blocks, RM_THREADS, smem, st>>>(q, p, vel, n, dim, m, status, n_mats);
+  ModelArgs margs = m;
+  const size_t per_cta = 3 * ((((size_t)dim * (dim + 1)) + 1) & ~(size_t)1);
+  DgScratch scratch(nullptr, 0, in_ws ? per_cta * blocks * sizeof(double) : 0, st);
+  if (in_ws) {
+    if (scratch.ptr == nullptr) return fail(MB200_ERR_CUDA, "SoftAbs workspace allocation failed");
+    margs.workspace = scratch.ptr;
+    margs.ws_stride = per_cta;
+  }
+  kern<<<(unsigned)blocks, RM_THREADS, smem, st>>>(q, p, vel, n, dim, margs, status, n_mats);
   return check_launch("riemannian_velocity_kernel");
 }
 

@@ -348,6 +348,11 @@ __host__ __device__ inline size_t dg_smem_doubles(int dim) {
   return (size_t)(np > 32 ? np - 32 : 32) * 36 + 2 * 32 * 36;
 }
 constexpr int RM_NMATS_GLOBAL = -1;  // n_mats code: compact vector set + dg_smem_doubles()
+// n_mats code RM_NMATS_IN_WORKSPACE + k: the k per-chain D x D matrices of the shared-memory
+// policies (SoftAbs: eigenvectors, work / divided-difference matrix, warm-start matrix) live in
+// the per-CTA GLOBAL workspace instead (dimensions whose matrices exceed 227 KB: SoftAbs at
+// D > ~100); the algorithms are unchanged, the operands are simply L2-resident
+constexpr int RM_NMATS_IN_WORKSPACE = 100;
 
 // n_mats: per-chain D x D matrices kept in shared memory (SoftAbs 2, or 3 with warm-started
 // eigensolves; dense Cholesky 1; Sherman-Morrison 0)
@@ -356,6 +361,7 @@ __host__ __device__ inline size_t rm_smem_doubles(int dim, int n_mats) {
   const int dpad = (dim + 1) & ~1;
   if (n_mats == RM_NMATS_GLOBAL)  // q p qs ps x0 x1 x2 base v1 v2 v3 ev + scratch + panel buffers
     return (size_t)12 * dpad + 40 + dg_smem_doubles(dim);
+  if (n_mats >= RM_NMATS_IN_WORKSPACE) n_mats = 0;  // matrices in the global workspace
   size_t n = (size_t)dim * ld * n_mats;
   n += (size_t)16 * dpad;      // vectors (Vn counts double: NEED <= 2)
   n += (size_t)dpad;           // second half of Vn
@@ -366,7 +372,8 @@ __host__ __device__ inline size_t rm_smem_doubles(int dim, int n_mats) {
   return n;
 }
 
-__device__ inline void rm_carve(RmWork& w, double* s, int dim, int n_mats, Blk& blk) {
+__device__ inline void rm_carve(RmWork& w, double* s, int dim, int n_mats, Blk& blk,
+                                double* gmats = nullptr) {
   const int ld = dim + 1;
   const int dpad = (dim + 1) & ~1;
   w.dim = dim;
@@ -388,12 +395,21 @@ __device__ inline void rm_carve(RmWork& w, double* s, int dim, int n_mats, Blk& 
     w.extra = s;
     return;
   }
-  w.M1 = n_mats >= 1 ? s : nullptr;
-  if (n_mats >= 1) s += (size_t)dim * ld;
-  w.M2 = n_mats >= 2 ? s : nullptr;
-  if (n_mats >= 2) s += (size_t)dim * ld;
-  w.M3 = n_mats >= 3 ? s : nullptr;
-  if (n_mats >= 3) s += (size_t)dim * ld;
+  if (n_mats >= RM_NMATS_IN_WORKSPACE) {
+    const int km = n_mats - RM_NMATS_IN_WORKSPACE;
+    const size_t sq = ((size_t)dim * ld + 1) & ~(size_t)1;
+    w.M1 = km >= 1 ? gmats : nullptr;
+    w.M2 = km >= 2 ? gmats + sq : nullptr;
+    w.M3 = km >= 3 ? gmats + 2 * sq : nullptr;
+    n_mats = 0;
+  } else {
+    w.M1 = n_mats >= 1 ? s : nullptr;
+    if (n_mats >= 1) s += (size_t)dim * ld;
+    w.M2 = n_mats >= 2 ? s : nullptr;
+    if (n_mats >= 2) s += (size_t)dim * ld;
+    w.M3 = n_mats >= 3 ? s : nullptr;
+    if (n_mats >= 3) s += (size_t)dim * ld;
+  }
   double** vecs[] = {&w.q, &w.p, &w.qs, &w.ps, &w.x0, &w.x1, &w.x2, &w.base, &w.v1,
                      &w.v2, &w.v3, &w.lam, &w.sa, &w.gsa, &w.ev};
   for (auto v : vecs) {
@@ -1458,7 +1474,9 @@ __global__ void __launch_bounds__(RM_THREADS, MetricT<Target>::MIN_BLOCKS)
   blk.warp = threadIdx.x >> 5;
   blk.nwarp = blockDim.x >> 5;
   RmWork w;
-  rm_carve(w, smem, dim, n_mats, blk);
+  rm_carve(w, smem, dim, n_mats, blk,
+           model.workspace != nullptr ? model.workspace + (size_t)blockIdx.x * model.ws_stride
+                                      : nullptr);
   const Target target(model, dim);
   // scratch of DENSE_MTP targets: [dim] doubles behind the staging rows in the Vn / z region
   target.attach(w.Vn != nullptr ? w.Vn + (size_t)(blk.nwarp + 1) * dim : nullptr);
@@ -1521,7 +1539,9 @@ __global__ void __launch_bounds__(RM_THREADS, MetricT<Target>::MIN_BLOCKS)
   blk.tid = threadIdx.x, blk.nthr = blockDim.x, blk.lane = threadIdx.x & 31;
   blk.warp = threadIdx.x >> 5, blk.nwarp = blockDim.x >> 5;
   RmWork w;
-  rm_carve(w, smem, dim, n_mats, blk);
+  rm_carve(w, smem, dim, n_mats, blk,
+           model.workspace != nullptr ? model.workspace + (size_t)blockIdx.x * model.ws_stride
+                                      : nullptr);
   const Target target(model, dim);
   // scratch of DENSE_MTP targets: [dim] doubles behind the staging rows in the Vn / z region
   target.attach(w.Vn != nullptr ? w.Vn + (size_t)(blk.nwarp + 1) * dim : nullptr);
@@ -1554,7 +1574,9 @@ __global__ void __launch_bounds__(RM_THREADS, MetricT<Target>::MIN_BLOCKS)
   blk.tid = threadIdx.x, blk.nthr = blockDim.x, blk.lane = threadIdx.x & 31;
   blk.warp = threadIdx.x >> 5, blk.nwarp = blockDim.x >> 5;
   RmWork w;
-  rm_carve(w, smem, dim, n_mats, blk);
+  rm_carve(w, smem, dim, n_mats, blk,
+           model.workspace != nullptr ? model.workspace + (size_t)blockIdx.x * model.ws_stride
+                                      : nullptr);
   const Target target(model, dim);
   // scratch of DENSE_MTP targets: [dim] doubles behind the staging rows in the Vn / z region
   target.attach(w.Vn != nullptr ? w.Vn + (size_t)(blk.nwarp + 1) * dim : nullptr);

@@ -33,6 +33,9 @@ CASES = {
     "c1_funnel_identity": ("C1", {"n_chains": 16, "dim": 7, "metric_kind": "identity"}, (1, 20), {}),
     "c2_softabs_banana": ("C2", {"n_chains": 16}, (1, 5, 20), {}),
     "c2_softabs_banana_d8": ("C2", {"n_chains": 32, "dim": 8}, (1, 5, 20), {}),
+    # beyond shared memory: the SoftAbs matrices live in the per-CTA global workspace
+    "c2_softabs_banana_d128": ("C2", {"n_chains": 6, "dim": 128}, (1, 3), {}),
+    "c6_softabs_quartic_d160": ("C6", {"n_chains": 4, "dim": 160}, (1, 2), {}),
     # SoftAbs on a target with a DENSE Hessian and third-derivative tensor
     "c6_softabs_quartic_d12": ("C6", {"n_chains": 16, "dim": 12}, (1, 5, 20), {}),
     "c6_softabs_quartic_d64": ("C6", {"n_chains": 12, "dim": 64}, (1, 5), {}),
