@@ -35,7 +35,7 @@ static int dg_launch_implicit(const double* q_in, const double* p_in, double* q_
   if (scratch.ptr == nullptr) return fail(MB200_ERR_CUDA, "dense metric workspace allocation failed");
   m.workspace = scratch.ptr;
   m.ws_stride = dg_workspace_doubles(dim);
-  kern<<<(unsigned)blocks, RM_THREADS, smem, st>>>(q_in, p_in, q_out, p_out, dir, n, dim, eps,
+  kern<<<(unsigned)blocks, DG_THREADS, smem, st>>>(q_in, p_in, q_out, p_out, dir, n, dim, eps,
                                                    n_steps, m, fp_tol, fp_div, fp_max, rev_tol,
                                                    h_out, status, n_done, fp_iters,
                                                    RM_NMATS_GLOBAL, 0, fp_solver);
@@ -81,12 +81,12 @@ static int dg_launch_vec(const double* q, const double* v, double* out, int64_t 
     auto kern = riemannian_velocity_kernel<Target, MetricT>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(MB200_ERR_CUDA, "smem attr: %s", cudaGetErrorString(e));
-    kern<<<(unsigned)blocks, RM_THREADS, smem, st>>>(q, v, out, n, dim, m, status, RM_NMATS_GLOBAL);
+    kern<<<(unsigned)blocks, DG_THREADS, smem, st>>>(q, v, out, n, dim, m, status, RM_NMATS_GLOBAL);
   } else {
     auto kern = riemannian_sample_momentum_kernel<Target, MetricT>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(MB200_ERR_CUDA, "smem attr: %s", cudaGetErrorString(e));
-    kern<<<(unsigned)blocks, RM_THREADS, smem, st>>>(q, v, out, n, dim, m, status, RM_NMATS_GLOBAL);
+    kern<<<(unsigned)blocks, DG_THREADS, smem, st>>>(q, v, out, n, dim, m, status, RM_NMATS_GLOBAL);
   }
   return check_launch("riemannian vector kernel (global dense metric)");
 }
@@ -136,7 +136,7 @@ int mb200_selftest_dense_factor(const double* matrices, const double* rhs, int64
   memset(&m, 0, sizeof(m));
   m.workspace = scratch.ptr;
   m.ws_stride = dg_workspace_doubles(dim);
-  dense_global_selftest_kernel<<<(unsigned)blocks, RM_THREADS, smem, st>>>(
+  dense_global_selftest_kernel<<<(unsigned)blocks, DG_THREADS, smem, st>>>(
       matrices, rhs, n_matrices, dim, m, chol_out, inv_out, sol_out, logdet_out, status);
   return check_launch("dense_global_selftest_kernel");
 }

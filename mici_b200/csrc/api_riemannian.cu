@@ -32,7 +32,7 @@ static int launch_implicit(const double* q_in, const double* p_in, double* q_out
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(MB200_ERR_CUDA, "smem attr: %s", cudaGetErrorString(e));
   int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RM_THREADS, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MetricT<Target>::THREADS, smem);
   if (per_sm < 1) per_sm = 1;
   if (in_ws && per_sm > 2) per_sm = 2;
   int64_t blocks = (int64_t)num_sms() * per_sm;

@@ -30,6 +30,7 @@
 
 namespace mb200 {
 
+constexpr int DG_THREADS = 256;
 constexpr int DG_NB = 32;
 constexpr int DG_LDP = 36;  // shared-memory row stride (doubles): rows shift by 32 B mod 128 B
 
@@ -68,14 +69,18 @@ __device__ inline void dg_attach(DgWork& g, const RmWork& w, const ModelArgs& m)
 
 // Cholesky factor of a 32 x 32 SPD block held one row per lane (rowv[c] valid for c <= lane);
 // entries above the diagonal end up undefined.  Returns false on a non-positive / non-finite pivot.
-__device__ __forceinline__ bool warp_chol32(double (&rowv)[32], int lane) {
+__device__ __forceinline__ bool warp_chol32(double (&rowv)[32], double (&rdiag)[32], int lane) {
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const double d = __shfl_sync(FULL_MASK, rowv[j], j);
     if (!(d > 0.0) || isinf(d)) ok = false;  // warp-uniform
-    const double l = sqrt(d);
-    const double x = (lane == j) ? l : rowv[j] / l;
+    // this warp is the critical path of every panel step: one reciprocal square root (and two
+    // multiplications) per column instead of a square root and a division
+    const double rs = rsqrt(d);
+    const double l = d * rs;
+    rdiag[j] = rs;  // 1 / L[j][j], reused by the inversion below
+    const double x = (lane == j) ? l : rowv[j] * rs;
     rowv[j] = x;
 #pragma unroll
     for (int c = j + 1; c < 32; ++c) {
@@ -87,14 +92,20 @@ __device__ __forceinline__ bool warp_chol32(double (&rowv)[32], int lane) {
 }
 
 // Inverse of the lower-triangular 32 x 32 factor held one row per lane: lane c returns column c of
-// W = L^-1 in w[i] (zero for i < c).
-__device__ __forceinline__ void warp_trinv32(const double (&rowv)[32], double (&w)[32], int lane) {
+// W = L^-1 in w[i] (zero for i < c).  rdiag[i] = 1 / L[i][i].
+__device__ __forceinline__ void warp_trinv32(const double (&rowv)[32], const double (&rdiag)[32],
+                                             double (&w)[32], int lane) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
-    double s = (lane == i) ? 1.0 : 0.0;
+    // two partial sums: halves the dependent chain of row i
+    double s0 = (lane == i) ? 1.0 : 0.0, s1 = 0.0;
 #pragma unroll
-    for (int k = 0; k < i; ++k) s -= __shfl_sync(FULL_MASK, rowv[k], i) * w[k];
-    w[i] = s / __shfl_sync(FULL_MASK, rowv[i], i);
+    for (int k = 0; k < i; ++k) {
+      const double lik = __shfl_sync(FULL_MASK, rowv[k], i);
+      if (k & 1) s1 -= lik * w[k];
+      else s0 -= lik * w[k];
+    }
+    w[i] = (s0 + s1) * rdiag[i];
   }
 }
 
@@ -164,16 +175,16 @@ __device__ __forceinline__ void dg_zero(double (&acc)[4][4][2]) {
 __device__ __forceinline__ int dg_factor_diag(DgWork& g, int kb, int lane) {
   const int np = g.np;
   double* Akk = g.L + (size_t)(kb * DG_NB) * np + kb * DG_NB;
-  double rowv[32], w[32];
+  double rowv[32], w[32], rdiag[32];
 #pragma unroll
   for (int j = 0; j < 32; j += 2) {
     const double2 v = *reinterpret_cast<const double2*>(&Akk[(size_t)lane * np + j]);
     rowv[j] = v.x, rowv[j + 1] = v.y;
   }
-  const int ok = warp_chol32(rowv, lane) ? 1 : 0;
+  const int ok = warp_chol32(rowv, rdiag, lane) ? 1 : 0;
 #pragma unroll
   for (int j = 0; j < 32; ++j) w[j] = 0.0;
-  warp_trinv32(rowv, w, lane);
+  warp_trinv32(rowv, rdiag, w, lane);
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     Akk[(size_t)lane * np + j] = j <= lane ? rowv[j] : 0.0;
@@ -199,8 +210,9 @@ __device__ __forceinline__ void dg_tile_decode(int t, int& bi, int& bj) {
 // Per 32-column panel: [panel product L_ik = A_ik W^T] -> barrier -> [trailing update, tiles
 // handed out through a shared counter; warp 0 takes the tile of the NEXT diagonal block first and
 // factors / inverts it while the other warps finish the update (look-ahead: the serial 32 x 32
-// factorisation leaves the critical path)] -> barrier.  A warp prefetches the C tile of its next
-// work item while the tensor pipe works on the current one.
+// factorisation leaves the critical path)] -> barrier.  8 warps with 255 registers: 16 warps
+// under a 128-register budget, and a register-prefetched next C tile, both measured slower
+// (the diagonal-block code spills).
 __device__ __noinline__ bool dg_cholesky(const Blk& k, DgWork& g) {
   const int np = g.np, lane = k.lane, r = lane >> 2, c = lane & 3;
   int* counter = reinterpret_cast<int*>(g.dblk);  // shared work counter (+ failure flag)
@@ -255,34 +267,19 @@ __device__ __noinline__ bool dg_cholesky(const Blk& k, DgWork& g) {
       if (lane == 0) t = atomicAdd(&counter[0], 1);
       return __shfl_sync(FULL_MASK, t, 0);
     };
-    double cur[4][4][2], nxt[4][4][2];
-    auto load_tile = [&](const double* Cij, double (&dst)[4][4][2]) {
+    double cur[4][4][2];
+    int t = (k.warp == 0) ? 0 : next_tile();
+    while (t < ntiles) {
+      int bi, bj;
+      double* Cij = tile_ptr(t, bi, bj);
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const double2 v =
               *reinterpret_cast<const double2*>(&Cij[(size_t)(8 * mt + r) * np + 8 * nt + 2 * c]);
-          dst[mt][nt][0] = v.x, dst[mt][nt][1] = v.y;
+          cur[mt][nt][0] = v.x, cur[mt][nt][1] = v.y;
         }
-    };
-    int t = (k.warp == 0) ? 0 : next_tile();
-    int bi = 0, bj = 0;
-    double* Cij = nullptr;
-    if (t < ntiles) {
-      Cij = tile_ptr(t, bi, bj);
-      load_tile(Cij, cur);
-    }
-    while (t < ntiles) {
-      const bool diag_next = (k.warp == 0 && t == 0);
-      // look-ahead: warp 0 goes straight to the next diagonal block after tile 0
-      const int tn = diag_next ? ntiles : next_tile();
-      int bin = 0, bjn = 0;
-      double* Cn = nullptr;
-      if (tn < ntiles) {
-        Cn = tile_ptr(tn, bin, bjn);
-        load_tile(Cn, nxt);
-      }
       // cur -= L_i L_j^T: the A fragments enter negated
       {
         const double* A = g.panel + (size_t)bi * DG_NB * DG_LDP;
@@ -306,24 +303,14 @@ __device__ __noinline__ bool dg_cholesky(const Blk& k, DgWork& g) {
         for (int nt = 0; nt < 4; ++nt)
           *reinterpret_cast<double2*>(&Cij[(size_t)(8 * mt + r) * np + 8 * nt + 2 * c]) =
               make_double2(cur[mt][nt][0], cur[mt][nt][1]);
-      if (diag_next) {
-        __syncwarp();  // the tile written above is the next diagonal block: visible to all lanes
+      if (k.warp == 0 && t == 0) {
+        // look-ahead: the tile just written is the next diagonal block
+        __syncwarp();
         const int ok = dg_factor_diag(g, kb + 1, lane);
         if (lane == 0 && !ok) counter[1] = 0;
         __syncwarp();
-        // then help with whatever tiles are left
-        t = next_tile();
-        if (t < ntiles) {
-          Cij = tile_ptr(t, bi, bj);
-          load_tile(Cij, cur);
-        }
-        continue;
       }
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) cur[mt][nt][0] = nxt[mt][nt][0], cur[mt][nt][1] = nxt[mt][nt][1];
-      t = tn, bi = bin, bj = bjn, Cij = Cn;
+      t = next_tile();
     }
     __syncthreads();
   }
@@ -577,6 +564,7 @@ struct GlobalDenseMetricT {
   static constexpr bool SOFTABS = false;
   static constexpr int N_MATS = RM_NMATS_GLOBAL;
   static constexpr int MIN_BLOCKS = 1;  // ~200 KB of shared memory per CTA: one CTA per SM
+  static constexpr int THREADS = DG_THREADS;
   const Target& t;
   Model model;
   DgWork g;
@@ -668,7 +656,7 @@ using GlobalDenseHadamard = GlobalDenseMetricT<Target, HadamardModel>;
 
 // Diagnostic kernel: factor / solve / invert arbitrary SPD matrices (one CTA per matrix) so that
 // the blocked routines can be checked against numpy.linalg directly (tests/test_parity_gpu.py).
-static __global__ void __launch_bounds__(RM_THREADS)
+static __global__ void __launch_bounds__(DG_THREADS)
     dense_global_selftest_kernel(const double* __restrict__ mats, const double* __restrict__ rhs,
                                  int64_t n_mats, int dim, ModelArgs margs,
                                  double* __restrict__ chol_out, double* __restrict__ inv_out,

@@ -806,6 +806,7 @@ struct SoftAbsMetric {
   // register budget: two CTAs per SM (<= 128 registers); stated explicitly because ptxas's own
   // choice flips with unrelated code changes (48 vs 80 registers measured 3.4x apart on C4)
   static constexpr int MIN_BLOCKS = 2;
+  static constexpr int THREADS = RM_THREADS;
   const Target& t;
   double alpha;
   bool have_j;     // divided-difference matrix J built in w.M2 for the current metric?
@@ -998,6 +999,7 @@ struct Rank1DenseMetric {
   static constexpr bool SOFTABS = false;
   static constexpr int N_MATS = 1;
   static constexpr int MIN_BLOCKS = 2;
+  static constexpr int THREADS = RM_THREADS;
   const Target& t;
   const double* B;
   double c;
@@ -1069,6 +1071,7 @@ struct Rank1WoodburyMetric {
   static constexpr bool SOFTABS = false;
   static constexpr int N_MATS = 0;
   static constexpr int MIN_BLOCKS = 2;
+  static constexpr int THREADS = RM_THREADS;
   const Target& t;
   const double* Binv;
   double c, logdet_b, denom;
@@ -1458,7 +1461,7 @@ struct ImplicitLeapfrog {
 };
 
 template <class Target, template <class> class MetricT>
-__global__ void __launch_bounds__(RM_THREADS, MetricT<Target>::MIN_BLOCKS)
+__global__ void __launch_bounds__(MetricT<Target>::THREADS, MetricT<Target>::MIN_BLOCKS)
     implicit_leapfrog_kernel(const double* q_in, const double* p_in, double* q_out, double* p_out,
                              const int32_t* __restrict__ dir, int64_t n_chains, int dim,
                              double step_size, int n_steps, ModelArgs model, double fp_tol,
@@ -1530,7 +1533,7 @@ __global__ void __launch_bounds__(RM_THREADS, MetricT<Target>::MIN_BLOCKS)
 
 // mom = sqrt(M(q)) z for every chain: RiemannianMetricSystem.sample_momentum (systems.py:1401-1402).
 template <class Target, template <class> class MetricT>
-__global__ void __launch_bounds__(RM_THREADS, MetricT<Target>::MIN_BLOCKS)
+__global__ void __launch_bounds__(MetricT<Target>::THREADS, MetricT<Target>::MIN_BLOCKS)
     riemannian_sample_momentum_kernel(const double* __restrict__ q_in, const double* __restrict__ z,
                                       double* __restrict__ p_out, int64_t n_chains, int dim,
                                       ModelArgs model, int32_t* __restrict__ status, int n_mats) {
@@ -1565,7 +1568,7 @@ __global__ void __launch_bounds__(RM_THREADS, MetricT<Target>::MIN_BLOCKS)
 // vel = M(q)^-1 p for every chain: RiemannianMetricSystem.dh2_dmom / dh_dmom (systems.py:1398-1399,
 // 202-207), read by the no-U-turn criteria (transitions.py:434-435, 472-473).
 template <class Target, template <class> class MetricT>
-__global__ void __launch_bounds__(RM_THREADS, MetricT<Target>::MIN_BLOCKS)
+__global__ void __launch_bounds__(MetricT<Target>::THREADS, MetricT<Target>::MIN_BLOCKS)
     riemannian_velocity_kernel(const double* __restrict__ q_in, const double* __restrict__ p_in,
                                double* __restrict__ vel_out, int64_t n_chains, int dim,
                                ModelArgs model, int32_t* __restrict__ status, int n_mats) {

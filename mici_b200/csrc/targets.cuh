@@ -15,6 +15,33 @@
 
 namespace mb200 {
 
+// exp(x) with a short dependent chain for the tensor-core kernel, where one lane's exp(-v) sits on
+// the critical path of a 4-warp group's update phase (removing it entirely is worth 1.5 % of the
+// C1 launch; profiles/r02_notes.md): x = k ln2 + r, |r| <= ln2/2, e^r by its degree-13 Taylor
+// polynomial in Estrin form (truncation 4e-18 relative; depth 4 after r instead of libm's 11-deep
+// Horner chain), scaled by 2^k through the exponent bits.  Agrees with libm's exp to ~2 ulp;
+// arguments outside [-700, 700] (or non-finite) take libm's exp.
+__device__ __forceinline__ double exp_short_chain(double x) {
+  if (!(fabs(x) < 700.0)) return exp(x);
+  const double t = fma(x, 1.4426950408889634, 6755399441055744.0);  // 2^52 + 2^51: rint in low bits
+  const double k = t - 6755399441055744.0;
+  double r = fma(k, -6.93147180369123816490e-01, x);   // ln2 high part
+  r = fma(k, -1.90821492927058770002e-10, r);          // ln2 low part
+  const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+  const double p0 = fma(r, 1.0, 1.0);
+  const double p1 = fma(r, 1.0 / 6.0, 0.5);
+  const double p2 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  const double p3 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
+  const double p4 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
+  const double p5 = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0);
+  const double p6 = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
+  const double q0 = fma(p1, r2, p0), q1 = fma(p3, r2, p2), q2 = fma(p5, r2, p4);
+  const double s0 = fma(q1, r4, q0), s1 = fma(p6, r4, q2);
+  const double e = fma(s1, r8, s0);
+  const long long bits = __double_as_longlong(e) + ((long long)k << 52);
+  return __longlong_as_double(bits);
+}
+
 struct StdGaussianTarget {
   static constexpr int NRED = 0;
   __device__ StdGaussianTarget(const ModelArgs&, int) {}
@@ -76,7 +103,7 @@ struct NealFunnelTarget {
   // reciprocal and the sum as two FMAs (the fp64 division is a ~15-deep dependent chain on the
   // critical path of a 4-warp group; differs from grad_pair's `q0 / 9.0` by at most 1 ulp)
   static constexpr bool TILE_SUM = true, ROW_SCALAR = true, LINEAR = true, COORD0 = true;
-  __device__ __forceinline__ double row_scalar(double v) const { return exp(-v); }
+  __device__ __forceinline__ double row_scalar(double v) const { return exp_short_chain(-v); }
   __device__ __forceinline__ double kick_coef(double mh, double rs) const { return mh * rs; }
   __device__ __forceinline__ double grad0(double v, double xx, double rs) const {
     return fma(-0.5 * rs, xx, fma(v, 1.0 / 9.0, 0.5 * (dim - 1)));
