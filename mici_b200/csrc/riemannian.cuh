@@ -957,6 +957,66 @@ struct SoftAbsMetric {
       t.mtp_quad(k, q, w.M3, ld, w.ev, w.M2, ld, w.Vn, w.Vn + (size_t)k.nwarp * n, out);
       return;
     }
+    // V = -U G U^T with G = diag(e) J diag(e).  When a third matrix is available and one pass of
+    // 16 x 32 DMMA tiles covers the product (D = 32, 64 with 8 warps), P = U G runs on the tensor
+    // pipe (this contraction was 30 % of the C2 step as scalar code) and only the NEED entries
+    // per row of V = -P U^T are formed.
+    if (w.M3 != nullptr && (n & 31) == 0 && (n / 16) * (n / 32) <= k.nwarp) {
+      for (int idx = k.tid; idx < n * n; idx += k.nthr) {
+        const int i = idx / n, j = idx - i * n;
+        w.M3[i * ld + j] = (w.ev[i] * w.M2[i * ld + j]) * w.ev[j];
+      }
+      __syncthreads();
+      {
+        const int r = k.lane >> 2, c = k.lane & 3;
+        const int tc = n / 32, tile = k.warp;
+        const bool active = tile < (n / 16) * tc;
+        const int i0 = 16 * (tile / tc), j0 = 32 * (tile % tc);
+        double acc[2][4][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = 0.0, acc[mt][nt][1] = 0.0;
+        if (active) {
+#pragma unroll 4
+          for (int ks = 0; ks < n / 4; ++ks) {
+            double a[2], b[4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) a[mt] = w.M1[(i0 + 8 * mt + r) * ld + 4 * ks + c];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) b[nt] = w.M3[(4 * ks + c) * ld + j0 + 8 * nt + r];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt) rm_dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+          }
+        }
+        __syncthreads();  // every warp has read G: P may overwrite it
+        if (active) {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              w.M3[(i0 + 8 * mt + r) * ld + j0 + 8 * nt + 2 * c] = acc[mt][nt][0];
+              w.M3[(i0 + 8 * mt + r) * ld + j0 + 8 * nt + 2 * c + 1] = acc[mt][nt][1];
+            }
+        }
+        __syncthreads();
+      }
+      for (int idx = k.warp; idx < n * Target::NEED; idx += k.nwarp) {
+        const int a = idx / Target::NEED, jn = idx - a * Target::NEED;
+        const int b = t.need_col(a, jn);
+        double sacc = 0.0;
+        if (b >= 0)
+          for (int j = k.lane; j < n; j += 32) sacc = fma(w.M3[a * ld + j], w.M1[b * ld + j], sacc);
+        sacc = warp_sum(sacc);
+        if (k.lane == 0) w.Vn[idx] = -sacc;
+      }
+      __syncthreads();
+      t.mtp_entries(k, q, w.Vn, out);
+      __syncthreads();
+      return;
+    }
     // one warp per row a: t_j = sum_i (U_ai e_i) J_ij, then V(a,b) = -sum_j t_j e_j U_bj
     double* trow = w.v3;  // reused per warp below via registers; v3 holds (U_a o e) of the row
     (void)trow;
