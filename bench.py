@@ -395,7 +395,7 @@ def run_workload(name, torch, dist, dev, rank, world, flush, hbm_peak):
             "bound": "latency / issue (B_alg = 96 B per chain-step)", "achieved": hbm_gbs,
             "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
             "traffic": ncu_traffic(name),
-            "kernel": "constrained_leapfrog_kernel<TorusTarget, 1>",
+            "kernel": "constrained_torus_thread_kernel (one thread per chain)",
             "newton_iterations_per_step": iters,
         }
     elif name in ("C4", "C5"):

@@ -836,4 +836,184 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K6t: the torus configuration (C3: D = 3, one constraint, identity metric, Newton projection,
+// density with respect to the Hausdorff measure) with ONE THREAD per chain.
+//
+// The warp-per-chain kernel above keeps 3 coordinates in 2 of a warp's 32 lanes and spends most of
+// its instructions on warp reductions of two values; with D = 3 the whole chain state fits in a
+// thread's registers and every reduction is a handful of scalar operations.  The arithmetic below
+// follows the warp kernel operation for operation (same fma / add association as its lane
+// layout produces: lane 0 holds x, y, lane 1 holds z), so both kernels agree bit for bit.
+// ---------------------------------------------------------------------------------------------
+struct Vec3 {
+  double x, y, z;
+};
+
+struct TorusThread {
+  double R, r, alpha;
+  __device__ __forceinline__ static double dot(const Vec3& a, const Vec3& b) {
+    const double s0 = fma(a.y, b.y, fma(a.x, b.x, 0.0));
+    const double s1 = fma(a.z, b.z, 0.0);
+    return s0 + s1;
+  }
+  __device__ __forceinline__ static double maxabs(const Vec3& a) {
+    const double m0 = nanmax(nanmax(0.0, fabs(a.x)), fabs(a.y));
+    const double m1 = nanmax(nanmax(0.0, fabs(a.z)), 0.0);
+    return nanmax(m0, m1);
+  }
+  __device__ __forceinline__ Vec3 grad(const Vec3& q) const {
+    const double x = q.x, y = q.y, z = q.z;
+    const double a = r / R;
+    const double rho2 = x * x + y * y;
+    const double rho = sqrt(rho2);
+    const double u = rho - R;
+    const double theta = atan2(y, x);
+    const double phi = atan2(z, u);
+    double s4, c4, sp, cp;
+    sincos(4.0 * theta, &s4, &c4);
+    sincos(phi, &sp, &cp);
+    const double d1 = 1.0 + a * cp;
+    const double d2 = 1.0 + alpha * s4 * cp;
+    const double dl_dphi = -a * sp / d1 + alpha * s4 * sp / d2;
+    const double dl_dth = -4.0 * alpha * c4 * cp / d2;
+    const double w = u * u + z * z;
+    const double dphi_du = -z / w;
+    const double dphi_dz = u / w;
+    Vec3 g;
+    g.x = dl_dth * (-y / rho2) + dl_dphi * dphi_du * (x / rho);
+    g.y = dl_dth * (x / rho2) + dl_dphi * dphi_du * (y / rho);
+    g.z = dl_dphi * dphi_dz;
+    return g;
+  }
+  __device__ __forceinline__ double nld(const Vec3& q) const {
+    const double rho = sqrt(q.x * q.x + q.y * q.y);
+    const double theta = atan2(q.y, q.x);
+    const double phi = atan2(q.z, rho - R);
+    return log1p(r * cos(phi) / R) - log1p(sin(4.0 * theta) * cos(phi) * alpha);
+  }
+  __device__ __forceinline__ void constr_jacob(const Vec3& q, double& c, Vec3& J) const {
+    const double rho = sqrt(q.x * q.x + q.y * q.y);
+    const double d = rho - R;
+    c = d * d + q.z * q.z - r * r;
+    const double f = 2.0 * d / rho;
+    J.x = f * q.x, J.y = f * q.y, J.z = 2.0 * q.z;
+  }
+  // p <- p - J^T (J J^T)^-1 J p  (identity metric; spd_inverse_apply<1> spelled out)
+  __device__ __forceinline__ void project(Vec3& p, const Vec3& q) const {
+    double c;
+    Vec3 J;
+    constr_jacob(q, c, J);
+    const double G = dot(J, J);
+    const double u = dot(J, p);
+    const double L = sqrt(G);
+    const double Li = 1.0 / L;
+    const double a = fma(Li, Li, 0.0);
+    const double w = fma(a, u, 0.0);
+    p.x = __dsub_rn(p.x, fma(J.x, w, 0.0));
+    p.y = __dsub_rn(p.y, fma(J.y, w, 0.0));
+    p.z = __dsub_rn(p.z, fma(J.z, w, 0.0));
+  }
+  // h2_flow then Newton retraction (solvers.py:346-469), as ConstrainedOps::retract_newton
+  __device__ __forceinline__ bool retract(Vec3& q, Vec3& p, const Vec3& q_prev, double dt,
+                                          double ctol, double ptol, double dtol, int max_iters,
+                                          int& iters) const {
+    q.x = __dadd_rn(q.x, __dmul_rn(dt, p.x));
+    q.y = __dadd_rn(q.y, __dmul_rn(dt, p.y));
+    q.z = __dadd_rn(q.z, __dmul_rn(dt, p.z));
+    Vec3 mu = {0.0, 0.0, 0.0}, Jp, S;
+    double cp;
+    constr_jacob(q_prev, cp, Jp);
+    const double adt = fabs(dt);
+    S.x = adt * Jp.x, S.y = adt * Jp.y, S.z = adt * Jp.z;
+    for (int i = 0; i < max_iters; ++i) {
+      double c;
+      Vec3 J;
+      constr_jacob(q, c, J);
+      const double err = nanmax(0.0, fabs(c));
+      const double Rm = dot(J, S);
+      const double xs = c / Rm;  // lu_solve<1>
+      Vec3 dmu, dpos;
+      dmu.x = fma(Jp.x, xs, 0.0), dmu.y = fma(Jp.y, xs, 0.0), dmu.z = fma(Jp.z, xs, 0.0);
+      dpos.x = fma(S.x, xs, 0.0), dpos.y = fma(S.y, xs, 0.0), dpos.z = fma(S.z, xs, 0.0);
+      ++iters;
+      if (err > dtol || err != err) return false;
+      if (err < ctol && maxabs(dpos) < ptol) {
+        const double sgn = (dt > 0.0) ? 1.0 : ((dt < 0.0) ? -1.0 : 0.0);
+        p.x = __dsub_rn(p.x, sgn * mu.x);
+        p.y = __dsub_rn(p.y, sgn * mu.y);
+        p.z = __dsub_rn(p.z, sgn * mu.z);
+        return true;
+      }
+      mu.x = __dadd_rn(mu.x, dmu.x), mu.y = __dadd_rn(mu.y, dmu.y), mu.z = __dadd_rn(mu.z, dmu.z);
+      q.x = __dsub_rn(q.x, dpos.x), q.y = __dsub_rn(q.y, dpos.y), q.z = __dsub_rn(q.z, dpos.z);
+    }
+    return false;
+  }
+};
+
+__global__ void __launch_bounds__(32)
+    constrained_torus_thread_kernel(const double* q_in, const double* p_in, double* q_out,
+                                    double* p_out, const int32_t* __restrict__ dir,
+                                    int64_t n_chains, double step_size, int n_steps, int n_inner,
+                                    ModelArgs model, double constraint_tol, double position_tol,
+                                    double divergence_tol, int max_iters, double rev_tol,
+                                    double* __restrict__ h_out, int32_t* __restrict__ status,
+                                    int32_t* __restrict__ n_done,
+                                    int32_t* __restrict__ newton_iters, int lanes) {
+  const TorusThread t{model.tp[0], model.tp[1], model.tp[2]};
+  if ((int)threadIdx.x >= lanes) return;
+  for (int64_t ch = (int64_t)blockIdx.x * lanes + threadIdx.x; ch < n_chains;
+       ch += (int64_t)gridDim.x * lanes) {
+    Vec3 q = {q_in[ch * 3], q_in[ch * 3 + 1], q_in[ch * 3 + 2]};
+    Vec3 p = {p_in[ch * 3], p_in[ch * 3 + 1], p_in[ch * 3 + 2]};
+    const double eps = model.step_sizes != nullptr ? model.step_sizes[ch] : step_size;
+    const double dt = (dir != nullptr) ? (double)dir[ch] * eps : eps;
+    const int ns = model.n_steps_pc != nullptr ? min(model.n_steps_pc[ch], n_steps) : n_steps;
+    Vec3 g = t.grad(q);
+    int st = MB200_STATUS_OK, done = 0, iters = 0;
+    const double dt_inner = dt / n_inner;
+    for (int s = 0; s < ns && st == MB200_STATUS_OK; ++s) {
+      const Vec3 qs = q, ps = p;
+      p.x = __dsub_rn(p.x, __dmul_rn(0.5 * dt, g.x));
+      p.y = __dsub_rn(p.y, __dmul_rn(0.5 * dt, g.y));
+      p.z = __dsub_rn(p.z, __dmul_rn(0.5 * dt, g.z));
+      t.project(p, q);
+      for (int i = 0; i < n_inner && st == MB200_STATUS_OK; ++i) {
+        const Vec3 qprev = q;
+        if (!t.retract(q, p, qprev, dt_inner, constraint_tol, position_tol, divergence_tol,
+                       max_iters, iters)) {
+          st = MB200_STATUS_CONVERGENCE;
+          break;
+        }
+        t.project(p, q);
+        Vec3 qb = q, pb = p;
+        if (!t.retract(qb, pb, q, -dt_inner, constraint_tol, position_tol, divergence_tol,
+                       max_iters, iters)) {
+          st = MB200_STATUS_CONVERGENCE;
+          break;
+        }
+        const Vec3 diff = {qb.x - qprev.x, qb.y - qprev.y, qb.z - qprev.z};
+        if (TorusThread::maxabs(diff) > rev_tol) st = MB200_STATUS_NON_REVERSIBLE;
+      }
+      if (st == MB200_STATUS_OK) {
+        g = t.grad(q);
+        p.x = __dsub_rn(p.x, __dmul_rn(0.5 * dt, g.x));
+        p.y = __dsub_rn(p.y, __dmul_rn(0.5 * dt, g.y));
+        p.z = __dsub_rn(p.z, __dmul_rn(0.5 * dt, g.z));
+        t.project(p, q);
+        ++done;
+      } else {
+        q = qs, p = ps;
+      }
+    }
+    q_out[ch * 3] = q.x, q_out[ch * 3 + 1] = q.y, q_out[ch * 3 + 2] = q.z;
+    p_out[ch * 3] = p.x, p_out[ch * 3 + 1] = p.y, p_out[ch * 3 + 2] = p.z;
+    if (h_out != nullptr) h_out[ch] = t.nld(q) + 0.5 * TorusThread::dot(p, p);
+    if (status != nullptr) status[ch] = st;
+    if (n_done != nullptr) n_done[ch] = done;
+    if (newton_iters != nullptr) newton_iters[ch] = iters;
+  }
+}
+
 }  // namespace mb200

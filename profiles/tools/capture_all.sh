@@ -16,7 +16,7 @@ cap() {  # name kernel-regex skip command...
 cap r02_c1_dmma leapfrog_dmma 3 python bench.py --no-cpu-baseline --no-workloads --steps 2 --warmup 1
 cap r02_c2_softabs implicit_leapfrog 0 python $T/run_cfg.py C2 1 1
 cap r02_c6_softabs_dense implicit_leapfrog 0 python $T/run_cfg.py C6 1 1 296
-cap r02_c3_constrained constrained_leapfrog 0 python $T/run_cfg.py C3 50 1
+cap r02_c3_constrained constrained_ 0 python $T/run_cfg.py C3 50 1
 cap r02_c4_dense implicit_leapfrog 0 python $T/run_cfg.py C4 1 1 148
 cap r02_nuts_c1 nuts_euclidean 0 python $T/run_nuts.py
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
