@@ -297,8 +297,10 @@ int mb200_dh_dmom_riemannian(const double* pos, const double* mom, double* vel_o
  *   coefficients       HOST array of n_flows composition coefficients or NULL for the leapfrog
  *                      schedule {0.5, 1, 0.5} (then n_flows / initial_h1_flow_step are ignored)
  * n_done[c] receives the number of steps chain c took.  Other arguments as
- * mb200_leapfrog_euclidean.  Runs on the general-dimension kernel (the tensor-core kernel
- * folds one shared step size into the staged metric).
+ * mb200_leapfrog_euclidean.  With a dense metric, the leapfrog schedule and one trajectory
+ * length (n_steps_per_chain == NULL) it runs on the tensor-core kernel, which then applies the
+ * step size on the momentum side (tile s = eps_c * dir * p against the unscaled metric);
+ * otherwise on the general-dimension kernel.
  */
 int mb200_leapfrog_euclidean_per_chain(const double* pos_in, const double* mom_in, double* pos_out,
                                        double* mom_out, const int32_t* dir, int64_t n_chains,

@@ -105,9 +105,9 @@ struct DgScratch {
 
 // implemented in api_dmma.cu (tensor-core leapfrog); MB200_ERR_UNSUPPORTED = outside its domain
 int leapfrog_dmma_dispatch(const double* q_in, const double* p_in, double* q_out, double* p_out,
-                           const int32_t* dir, int64_t n, int dim, double eps, int n_steps,
-                           const double* minv, const ModelArgs& m, double* h_out, int32_t* status,
-                           int32_t* n_done, cudaStream_t st);
+                           const int32_t* dir, const double* step_sizes, int64_t n, int dim,
+                           double eps, int n_steps, const double* minv, const ModelArgs& m,
+                           double* h_out, int32_t* status, int32_t* n_done, cudaStream_t st);
 
 // implemented in api_dense.cu (global-workspace dense metric policy, dense_global.cuh)
 int64_t dense_global_workspace_bytes(int64_t n_chains, int dim);

@@ -68,7 +68,6 @@ static int leapfrog_euclidean_impl(const double* q_in, const double* p_in, doubl
                                    int32_t* n_done, cudaStream_t st, bool allow_dmma,
                                    const FlowSchedule* schedule = nullptr) {
   const FlowSchedule sched = schedule ? *schedule : leapfrog_schedule();
-  if (schedule) allow_dmma = false;
   if (n == 0 && dim >= 1 && n_steps >= 0) return 0;  // empty batch: nothing to do
   if (!q_in || !p_in || !q_out || !p_out || !model)
     return fail(MB200_ERR_INVALID_ARG, "null pointer argument");
@@ -82,8 +81,8 @@ static int leapfrog_euclidean_impl(const double* q_in, const double* p_in, doubl
   if (m.target_id == MB200_TARGET_BANANA && (dim & 1))
     return fail(MB200_ERR_INVALID_ARG, "banana target needs even dim");
   if (allow_dmma && metric_kind == MB200_METRIC_DENSE && n_steps > 0) {
-    int rc = leapfrog_dmma_dispatch(q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, minv, m,
-                                    h_out, status, n_done, st);
+    int rc = leapfrog_dmma_dispatch(q_in, p_in, q_out, p_out, dir, sched.step_sizes, n, dim, eps,
+                                    n_steps, minv, m, h_out, status, n_done, st);
     if (rc == 0) return check_launch("leapfrog_dmma_kernel");
     if (rc != MB200_ERR_UNSUPPORTED) return fail(rc, "leapfrog_dmma launch failed");
   }
@@ -246,9 +245,11 @@ int mb200_leapfrog_euclidean_per_chain(const double* pos_in, const double* mom_i
   }
   s.step_sizes = step_sizes;
   s.n_steps = n_steps_per_chain;
+  // plain leapfrog with one trajectory length: the DMMA kernel takes the step sizes per chain
+  const bool dmma_ok = coefficients == nullptr && n_steps_per_chain == nullptr;
   return leapfrog_euclidean_impl(pos_in, mom_in, pos_out, mom_out, dir, n_chains, dim, 0.0,
                                  max_n_steps, metric_kind, metric_inv, model, h_out, status,
-                                 n_done, (cudaStream_t)stream, false, &s);
+                                 n_done, (cudaStream_t)stream, dmma_ok, &s);
 }
 
 int mb200_leapfrog_gaussian_euclidean(const double* pos_in, const double* mom_in, double* pos_out,

@@ -113,12 +113,19 @@ struct DmmaSmem {
 // zero under every registry target's kick), one FMA chain for the reduction, the per-chain scalar
 // (funnel: exp(-v)) published by its owner instead of being summed, own momenta pre-loaded
 // before the group barrier, two barriers per step.
-template <class Target, int DP, int MT>
+//
+// PC = true: per-chain step sizes (adaptive warm-up, adapters.py:40-235 per chain).  sm.A then holds
+// A unscaled (step_size = 1) and the momentum tile holds  s = eps_c * dir * p:
+//   kick:  s -= (eps_c^2 / 2) * grad l(q)      drift: q += s . A
+// -- the same two flows, with eps_c applied on the momentum side instead of the matrix side.
+template <class Target, int DP, int MT, bool PC>
 __device__ __forceinline__ void leapfrog_dmma_group(
     DmmaSmem<DP>& sm, const Target& target, const double* q_in, const double* p_in,
-    double* q_out, double* p_out, const int32_t* __restrict__ dir, int64_t n_chains, int dim,
+    double* q_out, double* p_out, const int32_t* __restrict__ dir,
+    const double* __restrict__ step_sizes, int64_t n_chains, int dim,
     double step_size, int n_steps, double* __restrict__ h_out, int32_t* __restrict__ status,
-    int32_t* __restrict__ n_done, int64_t chain0, int row0, int w, int lane, int bar_id, int cta_threads) {
+    int32_t* __restrict__ n_done, int64_t chain0, int row0, int w, int lane, int bar_id,
+    int cta_threads, bool vec2) {
   constexpr int LDA = DmmaSmem<DP>::LDA;
   constexpr int NT = DP / 32;  // 8-column tiles per warp
   constexpr int KS = DP / 4;   // k steps
@@ -130,7 +137,7 @@ __device__ __forceinline__ void leapfrog_dmma_group(
 
   // registers: positions of the slice in C-fragment layout (row 8mt + r, columns
   // col0 + 8nt + 2c + {0,1}); signed momenta live in sm.P with the same ownership
-  double q[MT][NT][2], sgn[MT];
+  double q[MT][NT][2], sgn[MT], mhr[PC ? MT : 1];
   bool live[MT];
   double2* pslot[MT];  // &sm.P[row][col0 + 2c]; + 4*nt double2 per column tile
   int row[MT];
@@ -141,14 +148,24 @@ __device__ __forceinline__ void leapfrog_dmma_group(
     const int64_t ch = chain0 + row[mt];
     live[mt] = ch < n_chains;
     sgn[mt] = (live[mt] && dir != nullptr && dir[ch] < 0) ? -1.0 : 1.0;
+    if (PC) {  // sgn becomes the load scale dir * eps_c
+      const double e = live[mt] ? step_sizes[ch] : 0.0;
+      sgn[mt] *= e;
+      mhr[mt] = -0.5 * (e * e);
+    }
     pslot[mt] = reinterpret_cast<double2*>(&sm.P[row[mt] * LDA + col0 + 2 * c]);
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       const int i = col0 + 8 * nt + 2 * c;
       double2 a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
-      if (live[mt] && i < dim) {  // dim is even on this path
-        a = *reinterpret_cast<const double2*>(q_in + (size_t)ch * dim + i);
-        b = *reinterpret_cast<const double2*>(p_in + (size_t)ch * dim + i);
+      if (live[mt] && i < dim) {
+        if (vec2) {  // even dim, 16-byte aligned state arrays
+          a = *reinterpret_cast<const double2*>(q_in + (size_t)ch * dim + i);
+          b = *reinterpret_cast<const double2*>(p_in + (size_t)ch * dim + i);
+        } else {
+          a.x = q_in[(size_t)ch * dim + i], b.x = p_in[(size_t)ch * dim + i];
+          if (i + 1 < dim) a.y = q_in[(size_t)ch * dim + i + 1], b.y = p_in[(size_t)ch * dim + i + 1];
+        }
       }
       q[mt][nt][0] = a.x, q[mt][nt][1] = a.y;
       pslot[mt][4 * nt] = make_double2(sgn[mt] * b.x, sgn[mt] * b.y);
@@ -203,12 +220,13 @@ __device__ __forceinline__ void leapfrog_dmma_group(
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       const double rs = Target::ROW_SCALAR ? sm.rscal[row[mt]] : 1.0;
-      const double coef = target.kick_coef(mh, rs);
+      const double mhm = PC ? mhr[PC ? mt : 0] : mh;
+      const double coef = target.kick_coef(mhm, rs);
       double c00 = coef, a00 = q[mt][0][0];
       if (Target::COORD0 && w == 0) {  // warp-uniform; only the owner lanes differ
         const double4 ps = *reinterpret_cast<const double4*>(&sm.psum[row[mt]][0]);
         const double g0 = target.grad0(q[mt][0][0], ((ps.x + ps.y) + ps.z) + ps.w, rs);
-        c00 = owner ? mh : coef;
+        c00 = owner ? mhm : coef;
         a00 = owner ? g0 : a00;
       }
 #pragma unroll
@@ -223,7 +241,7 @@ __device__ __forceinline__ void leapfrog_dmma_group(
         } else {
 #pragma unroll
           for (int k = 0; k < KICKS; ++k)
-            target.kick_pair_nl(mh, q[mt][nt][0], q[mt][nt][1], v.x, v.y);
+            target.kick_pair_nl(mhm, q[mt][nt][0], q[mt][nt][1], v.x, v.y);
         }
         pslot[mt][4 * nt] = v;
       }
@@ -309,11 +327,26 @@ __device__ __forceinline__ void leapfrog_dmma_group(
     for (int nt = 0; nt < NT; ++nt) {
       const int i = col0 + 8 * nt + 2 * c;
       if (i < dim) {
-        *reinterpret_cast<double2*>(q_out + (size_t)ch * dim + i) =
-            make_double2(q[mt][nt][0], q[mt][nt][1]);
         const double2 sv = pslot[mt][4 * nt];
-        *reinterpret_cast<double2*>(p_out + (size_t)ch * dim + i) =
-            make_double2(sgn[mt] * sv.x, sgn[mt] * sv.y);
+        double2 pv = make_double2(sgn[mt] * sv.x, sgn[mt] * sv.y);  // dir = +-1: exact
+        if (PC) {
+          // s = (dir eps_c) p  ->  p = s / (dir eps_c); a chain with eps_c = 0 has not moved
+          if (sgn[mt] != 0.0) {
+            pv = make_double2(sv.x / sgn[mt], sv.y / sgn[mt]);
+          } else {
+            pv.x = p_in[(size_t)ch * dim + i];
+            pv.y = (i + 1 < dim) ? p_in[(size_t)ch * dim + i + 1] : 0.0;
+          }
+        }
+        if (vec2) {
+          *reinterpret_cast<double2*>(q_out + (size_t)ch * dim + i) =
+              make_double2(q[mt][nt][0], q[mt][nt][1]);
+          *reinterpret_cast<double2*>(p_out + (size_t)ch * dim + i) = pv;
+        } else {
+          q_out[(size_t)ch * dim + i] = q[mt][nt][0], p_out[(size_t)ch * dim + i] = pv.x;
+          if (i + 1 < dim)
+            q_out[(size_t)ch * dim + i + 1] = q[mt][nt][1], p_out[(size_t)ch * dim + i + 1] = pv.y;
+        }
       }
     }
     if (w == 0 && c == 0) {
@@ -371,20 +404,26 @@ __device__ __forceinline__ void leapfrog_dmma_group(
         const double4 l4 = *reinterpret_cast<const double4*>(&sm.ex[1][row[mt]][0]);
         const double ks = ((k4.x + k4.y) + k4.z) + k4.w;
         const double ls = ((l4.x + l4.y) + l4.z) + l4.w;
-        h_out[chain0 + row[mt]] = ls + 0.5 * (ks / step_size);
+        if (PC) {  // ks = eps_c^2 p.A p  (p.A p itself is unavailable for eps_c = 0: NaN)
+          const double e = step_sizes[chain0 + row[mt]];
+          h_out[chain0 + row[mt]] = ls + 0.5 * (ks / (e * e));
+        } else {
+          h_out[chain0 + row[mt]] = ls + 0.5 * (ks / step_size);
+        }
       }
     }
   }
 }
 
-template <class Target, int DP>
+template <class Target, int DP, bool PC>
 __global__ void __launch_bounds__(DMMA_THREADS, 1)
     leapfrog_dmma_kernel(const double* q_in, const double* p_in, double* q_out, double* p_out,
-                         const int32_t* __restrict__ dir, int64_t n_chains, int dim,
+                         const int32_t* __restrict__ dir, const double* __restrict__ step_sizes,
+                         int64_t n_chains, int dim,
                          double step_size, int n_steps, const double* __restrict__ minv,
                          ModelArgs model, double* __restrict__ h_out,
                          int32_t* __restrict__ status, int32_t* __restrict__ n_done,
-                         int tiles_per_cta) {
+                         int tiles_per_cta, int vec2, int tma_rows) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   DmmaSmem<DP>& sm = *reinterpret_cast<DmmaSmem<DP>*>(smem_raw);
   constexpr int LDA = DmmaSmem<DP>::LDA;
@@ -403,7 +442,7 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   // ---- stage A = M^-1 into shared memory: one TMA bulk copy per row, one mbarrier.  Issued
   // first; everything below until the wait overlaps the copies.
   const uint32_t mbar = smem_u32(&sm.mbar);
-  if (warp == 0) {
+  if (tma_rows && warp == 0) {
     if (lane == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -438,6 +477,12 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
     }
   }
+  if (!tma_rows) {  // odd dim / unaligned matrix: rows are not 16-byte multiples, plain copies
+    for (int idx = tid; idx < dim * dim; idx += blockDim.x) {
+      const int row = idx / dim, col = idx - row * dim;
+      sm.A[row * LDA + col] = minv[idx];
+    }
+  }
   // zero the part of the padding that the fragment loads read (rows / columns in [dim, DP)) --
   // disjoint from the TMA destinations; sm.P needs none (every slot that is read is written by
   // the state load, phantom coordinates as zeros)
@@ -452,7 +497,7 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   // above) must be visible first
   __syncthreads();
   // wait for the bytes to land (phase 0), then scale the staged metric: sm.A = eps * A
-  {
+  if (tma_rows) {
     uint32_t done = 0;
     while (!done) {
       asm volatile(
@@ -464,6 +509,7 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
     }
   }
   MB200_K1_MARK(2);
+  if (!PC)  // per-chain step sizes: the matrix stays unscaled
 #pragma unroll 4
   for (int idx = tid; idx < DP * (DP / 2); idx += blockDim.x) {
     const int row = idx / (DP / 2), c2 = idx - row * (DP / 2);
@@ -489,9 +535,10 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
     const int row0 = 8 * (group * base + (group < rem ? group : rem));
     const int cta_threads = 128 * (tiles < DMMA_GROUPS ? tiles : DMMA_GROUPS);
 #define MB200_GROUP(MT)                                                                       \
-  leapfrog_dmma_group<Target, DP, MT>(sm, target, q_in, p_in, q_out, p_out, dir, n_chains,    \
-                                      dim, step_size, n_steps, h_out, status, n_done, chain0, \
-                                      row0, w, lane, 1 + group, cta_threads)
+  leapfrog_dmma_group<Target, DP, MT, PC>(sm, target, q_in, p_in, q_out, p_out, dir,          \
+                                          step_sizes, n_chains, dim, step_size, n_steps,      \
+                                          h_out, status, n_done, chain0, row0, w, lane,       \
+                                          1 + group, cta_threads, vec2 != 0)
     if (DMMA_MAX_MT >= 4 && mt == 4) MB200_GROUP(4);
     else if (DMMA_MAX_MT >= 3 && mt == 3) MB200_GROUP(3);
     else if (mt == 2) MB200_GROUP(2);
@@ -501,12 +548,13 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   }
 }
 
-template <class Target, int DP>
+template <class Target, int DP, bool PC>
 static int launch_dmma(const double* q_in, const double* p_in, double* q_out, double* p_out,
-                       const int32_t* dir, int64_t n, int dim, double eps, int n_steps,
+                       const int32_t* dir, const double* step_sizes, int64_t n, int dim,
+                       double eps, int n_steps,
                        const double* minv, const ModelArgs& m, double* h_out, int32_t* status,
                        int32_t* n_done, cudaStream_t st, int sms) {
-  auto kern = leapfrog_dmma_kernel<Target, DP>;
+  auto kern = leapfrog_dmma_kernel<Target, DP, PC>;
   const size_t smem = sizeof(DmmaSmem<DP>);
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
       cudaSuccess)
@@ -515,20 +563,31 @@ static int launch_dmma(const double* q_in, const double* p_in, double* q_out, do
   int64_t tpc = (total_tiles + sms - 1) / sms;  // tiles per CTA and pass
   if (tpc > DMMA_TILES_PER_CTA) tpc = DMMA_TILES_PER_CTA;
   int64_t blocks = (total_tiles + tpc - 1) / tpc;
-  if (blocks > sms) blocks = sms;  // persistent: CTAs loop over passes of tpc tiles
-  kern<<<(unsigned)blocks, DMMA_THREADS, smem, st>>>(q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps,
-                                            minv, m, h_out, status, n_done, (int)tpc);
+  if (blocks > sms) blocks = sms;
+  auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+  const int even = (dim & 1) == 0;
+  const int vec2 = even && al16(q_in) && al16(p_in) && al16(q_out) && al16(p_out);
+  const int tma_rows = even && al16(minv);  // persistent: CTAs loop over passes of tpc tiles
+  kern<<<(unsigned)blocks, DMMA_THREADS, smem, st>>>(q_in, p_in, q_out, p_out, dir, step_sizes, n,
+                                                     dim, PC ? 1.0 : eps, n_steps, minv, m, h_out,
+                                                     status, n_done, (int)tpc, vec2, tma_rows);
   return 0;
 }
 
 template <class Target>
 static int dispatch_dmma_dim(const double* q_in, const double* p_in, double* q_out, double* p_out,
-                             const int32_t* dir, int64_t n, int dim, double eps, int n_steps,
+                             const int32_t* dir, const double* step_sizes, int64_t n, int dim,
+                             double eps, int n_steps,
                              const double* minv, const ModelArgs& m, double* h_out,
                              int32_t* status, int32_t* n_done, cudaStream_t st, int sms) {
-#define MB200_DM(DP)                                                                           \
-  return launch_dmma<Target, DP>(q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, minv, m, \
-                                 h_out, status, n_done, st, sms)
+#define MB200_DM(DP)                                                                        \
+  return step_sizes != nullptr                                                              \
+             ? launch_dmma<Target, DP, true>(q_in, p_in, q_out, p_out, dir, step_sizes, n,  \
+                                             dim, eps, n_steps, minv, m, h_out, status,     \
+                                             n_done, st, sms)                               \
+             : launch_dmma<Target, DP, false>(q_in, p_in, q_out, p_out, dir, nullptr, n,    \
+                                              dim, eps, n_steps, minv, m, h_out, status,    \
+                                              n_done, st, sms)
   if (dim <= 32) MB200_DM(32);
   if (dim <= 64) MB200_DM(64);
   if (dim <= 96) MB200_DM(96);
@@ -539,17 +598,19 @@ static int dispatch_dmma_dim(const double* q_in, const double* p_in, double* q_o
 // Returns MB200_ERR_UNSUPPORTED when the shape is outside this kernel's domain (the caller
 // then uses the general-dimension kernel).
 int leapfrog_dmma_dispatch(const double* q_in, const double* p_in, double* q_out, double* p_out,
-                           const int32_t* dir, int64_t n, int dim, double eps, int n_steps,
+                           const int32_t* dir, const double* step_sizes, int64_t n, int dim,
+                           double eps, int n_steps,
                            const double* minv, const ModelArgs& m, double* h_out, int32_t* status,
                            int32_t* n_done, cudaStream_t st) {
-  if (dim > 128 || (dim & 1) || dim < 8) return MB200_ERR_UNSUPPORTED;
-  if (!(eps != 0.0) || !isfinite(eps)) return MB200_ERR_UNSUPPORTED;  // eps*A formulation
-  if ((reinterpret_cast<uintptr_t>(minv) & 15) != 0) return MB200_ERR_UNSUPPORTED;
+  if (dim > 128 || dim < 8) return MB200_ERR_UNSUPPORTED;
+  if (step_sizes == nullptr && (!(eps != 0.0) || !isfinite(eps)))
+    return MB200_ERR_UNSUPPORTED;  // eps*A formulation
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-#define MB200_ARGS \
-  q_in, p_in, q_out, p_out, dir, n, dim, eps, n_steps, minv, m, h_out, status, n_done, st, sms
+#define MB200_ARGS                                                                             \
+  q_in, p_in, q_out, p_out, dir, step_sizes, n, dim, eps, n_steps, minv, m, h_out, status, n_done, \
+      st, sms
   switch (m.target_id) {
     case MB200_TARGET_STD_GAUSSIAN: return dispatch_dmma_dim<StdGaussianTarget>(MB200_ARGS);
     case MB200_TARGET_NEAL_FUNNEL: return dispatch_dmma_dim<NealFunnelTarget>(MB200_ARGS);

@@ -71,7 +71,7 @@ int main(int argc, char** argv) {
     float best = 1e30f;
     for (int rep = 0; rep < 6; ++rep) {
       cudaEventRecord(e0);
-      int rc = leapfrog_dmma_dispatch(dq, dp, dqo, dpo, nullptr, n, dim, 0.01, steps, dm, m, with_h ? dh : nullptr, dst,
+      int rc = leapfrog_dmma_dispatch(dq, dp, dqo, dpo, nullptr, nullptr, n, dim, 0.01, steps, dm, m, with_h ? dh : nullptr, dst,
                                       dnd, 0);
       cudaEventRecord(e1);
       cudaEventSynchronize(e1);

@@ -635,6 +635,65 @@ def test_per_chain_step_sizes_and_lengths_match_individual_launches():
         assert torch.equal(got2.pos[c], ref.pos[0]) and torch.equal(got2.mom[c], ref.mom[0])
 
 
+@pytest.mark.parametrize("dim, n_chains", [(48, 37), (128, 70)])
+def test_per_chain_step_sizes_on_the_dmma_kernel(dim, n_chains):
+    """Per-chain step sizes with ONE trajectory length stay on the DMMA kernel (K1, momentum
+    tile scaled by eps_c): every chain equals the oracle's leapfrog with its own step size; a
+    chain with eps_c = 0 does not move."""
+    problem = problems.make_problem("C1", n_chains=n_chains, dim=dim)
+    integ = engine.build_integrator(problem)
+    state = engine.build_state(problem, DEV)
+    rng = np.random.default_rng(11)
+    eps = rng.uniform(0.005, 0.04, n_chains)
+    eps[3] = 0.0
+    dirs = torch.as_tensor(rng.choice([-1, 1], n_chains).astype(np.int32), device=DEV)
+    state.dir = dirs
+    integ.step_size = torch.as_tensor(eps, device=DEV)
+    got = integ.step_n(state, 6, return_h=True)
+    torch.cuda.synchronize()
+    assert int((got.status != 0).sum()) == 0
+    assert torch.equal(got.pos[3], state.pos[3]) and torch.equal(got.mom[3], state.mom[3])
+    from oracle import mici_oracle as mo
+
+    target, metric = dr.build_target(problem), mo.coerce_metric(problem.metric)
+    for c in range(n_chains):
+        q, p = mo.leapfrog_steps(problem.pos[c], problem.mom[c], float(dirs[c]) * eps[c], 6,
+                                 target, metric)
+        np.testing.assert_allclose(got.pos[c].cpu().numpy(), q, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(got.mom[c].cpu().numpy(), p, rtol=RTOL, atol=ATOL)
+        if c != 3:
+            assert float(got.h[c]) == pytest.approx(mo.euclidean_h(q, p, target, metric),
+                                                    rel=1e-10)
+
+
+@pytest.mark.parametrize("dim, offset", [(47, 0), (48, 1), (127, 1)])
+def test_dmma_kernel_odd_dim_and_unaligned_state(dim, offset):
+    """K1 with an odd dimension (phantom last coordinate, plain staging of the metric) and with
+    state arrays that are only 8-byte aligned (scalar loads / stores): equals the oracle."""
+    n_chains = 45
+    problem = problems.make_problem("C1", n_chains=n_chains, dim=dim)
+    integ = engine.build_integrator(problem)
+    state = engine.build_state(problem, DEV)
+    if offset:
+        for name in ("pos", "mom"):
+            buf = torch.empty(n_chains * dim + offset, dtype=torch.float64, device=DEV)
+            view = buf[offset:].view(n_chains, dim)
+            view.copy_(getattr(state, name))
+            setattr(state, name, view)
+        assert state.pos.data_ptr() % 16 == 8
+    got = integ.step_n(state, 5, return_h=True)
+    torch.cuda.synchronize()
+    from oracle import mici_oracle as mo
+
+    target, metric = dr.build_target(problem), mo.coerce_metric(problem.metric)
+    for c in range(0, n_chains, 4):
+        q, p = mo.leapfrog_steps(problem.pos[c], problem.mom[c], float(integ.step_size), 5,
+                                 target, metric)
+        np.testing.assert_allclose(got.pos[c].cpu().numpy(), q, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(got.mom[c].cpu().numpy(), p, rtol=RTOL, atol=ATOL)
+        assert float(got.h[c]) == pytest.approx(mo.euclidean_h(q, p, target, metric), rel=1e-10)
+
+
 def test_initial_step_size_search_matches_oracle():
     """DualAveragingStepSizeAdapter._find_and_set_init_step_size (adapters.py:285-352), all
     chains at once with per-chain halving / doubling."""
