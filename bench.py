@@ -358,6 +358,14 @@ def run_workload(name, torch, dist, dev, rank, world, flush, hbm_peak):
     if out.solver_iters is not None:
         it = out.solver_iters.to(torch.float64)
         iters = it.mean(0).tolist() if it.ndim > 1 else float(it.mean().item())
+    # what the kernels evaluated per leapfrog step, tallied by the kernels themselves
+    # (mb200_set_call_counters) in one more untimed launch on this rank
+    integ.count_calls()
+    cnt_out = integ.step_n(state, L)
+    torch.cuda.synchronize(dev)
+    cnt_steps = max(1.0, float(cnt_out.n_done.sum().item()))
+    counted = {k: v / cnt_steps for k, v in integ.call_count_totals().items()}
+    integ.count_calls(False)
     b_alg = prob.algorithmic_bytes_per_chain_step
     res = {
         "workload": w["label"],
@@ -370,14 +378,14 @@ def run_workload(name, torch, dist, dev, rank, world, flush, hbm_peak):
         "dim": dim,
         "ok_fraction": float(ok.item()) / (n * world),
         "mean_solver_iters_last_step": iters,
+        "kernel_counted_per_step": counted,
     }
     hbm_gbs = value / world * b_alg / 1e9
     if name in ("C2", "C2_dense_hessian"):
         # metric builds (eigendecompositions) per step: _step_a + every iteration of the two
         # position fixed points + _step_b_adj; quadratic-form gradients: every iteration of the
         # two momentum fixed points + 1.  F_alg = builds * 9 D^3 + quad * 2 D^3.
-        builds = iters[1] + iters[2] + 2.0
-        quads = iters[0] + iters[3] + 1.0
+        builds, quads = counted["metric"], counted["quad_form_vjp"]
         f_alg = builds * 9.0 * dim**3 + quads * 2.0 * dim**3
         tf = value / world * f_alg / 1e12
         res["roofline"] = {
@@ -385,7 +393,7 @@ def run_workload(name, torch, dist, dev, rank, world, flush, hbm_peak):
             "peak": FP64_DFMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_DFMA_PEAK_TFLOPS,
             "peak_source": FP64_PEAK_SOURCE, "traffic": ncu_traffic(name),
             "flops_per_chain_step": f_alg, "metric_builds_per_step": builds,
-            "formula": "builds*9*D^3 + quad_grads*2*D^3, builds = it_c_rev + it_c + 2",
+            "formula": "builds*9*D^3 + quad_grads*2*D^3; builds, quad_grads counted in the kernel",
             "hbm_frac": hbm_gbs / hbm_peak,
             "kernel": "implicit_leapfrog_kernel<%s, SoftAbsMetric>"
                       % ("BananaRTarget" if name == "C2" else "QuarticRTarget"),
@@ -403,8 +411,7 @@ def run_workload(name, torch, dist, dev, rank, world, flush, hbm_peak):
         # M^-1 p = two triangular solves 2 D^2; two explicit inverses per step (the two _step_a
         # kicks need grad_log_abs_det = M^-1): L^-1 (D^3/3) and X^T X (D^3/3); per momentum
         # fixed-point iteration one M^-1 p and the model's VJP (2 D^2)
-        builds = iters[1] + iters[2] + 2.0
-        quads = iters[0] + iters[3] + 1.0
+        builds, quads = counted["metric"], counted["quad_form_vjp"]
         f_exec = (builds * (dim**3 / 3.0 + 2.0 * dim**2) + 2.0 * (2.0 * dim**3 / 3.0)
                   + quads * 4.0 * dim**2 + 2.0 * 2.0 * dim**2)
         tf = value / world * f_exec / 1e12
@@ -420,8 +427,7 @@ def run_workload(name, torch, dist, dev, rank, world, flush, hbm_peak):
     elif name == "C4_low_rank":
         # the Sherman-Morrison policy never factorises: per metric build 2 D^2 (B^-1 q), per
         # M^-1 v 2 D^2, per target gradient 2 D^2; counted from the iteration counts
-        builds = iters[1] + iters[2] + 2.0
-        quads = iters[0] + iters[3] + 1.0
+        builds, quads = counted["metric"], counted["quad_form_vjp"]
         matvecs = 2.0 * builds + quads + 2.0  # build + M^-1 p per build; M^-1 p per quad; 2 grads
         f_exec = matvecs * 2.0 * dim**2
         f_ref = builds * dim**3 / 3.0 + matvecs * 2.0 * dim**2

@@ -97,6 +97,28 @@ int mb200_version(void);
 const char* mb200_last_error(void);
 
 /*
+ * Call counters -- the device-side counterpart of ChainState._call_counts (states.py:44-72,
+ * 160-300: every memoised system method bumps a counter that the samplers report).
+ * `counters` is a device array [n_chains][MB200_N_COUNTERS] of int32 (or NULL to switch the
+ * counting off).  Every later integrator launch issued FROM THE CALLING THREAD adds, per chain,
+ * what that chain evaluated during the launch (rejected step attempts included, the optional
+ * h_out energy evaluation excluded):
+ *   MB200_COUNT_GRAD          grad_neg_log_dens evaluations
+ *   MB200_COUNT_METRIC        Riemannian systems: metric builds (Cholesky factorisations /
+ *                             eigendecompositions); constrained systems: constraint-Jacobian
+ *                             evaluations; 0 otherwise
+ *   MB200_COUNT_QUAD_VJP      VJPs of the quadratic form p.M(q)^-1 p (Riemannian systems)
+ *   MB200_COUNT_SOLVER_ITERS  fixed-point / Newton iterations, summed over all steps
+ * The counts are accumulated (+=): zero the array to start a new tally.
+ */
+#define MB200_N_COUNTERS 4
+#define MB200_COUNT_GRAD 0
+#define MB200_COUNT_METRIC 1
+#define MB200_COUNT_QUAD_VJP 2
+#define MB200_COUNT_SOLVER_ITERS 3
+int mb200_set_call_counters(int32_t* counters);
+
+/*
  * n_steps explicit leapfrog steps on a Euclidean-metric system, fused gradient.
  * Replaces: LeapfrogIntegrator.step/_step (integrators.py:63-80, 170-173) +
  *           System.h1_flow/dh1_dpos/grad_neg_log_dens (systems.py:109-152) +

@@ -62,6 +62,7 @@ _NP = ctypes.POINTER(NutsOptions)
 SIGNATURES = {
     "mb200_version": (ctypes.c_int, []),
     "mb200_last_error": (ctypes.c_char_p, []),
+    "mb200_set_call_counters": (ctypes.c_int, [_P]),
     "mb200_leapfrog_euclidean": (
         ctypes.c_int,
         [_P, _P, _P, _P, _P, _I64, _I32, _F64, _I32, _I32, _P, _MP, _P, _P, _P, _P],

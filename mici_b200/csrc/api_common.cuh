@@ -30,6 +30,7 @@ inline int check_launch(const char* what) {
 // thread only (thread-local, scoped): the plain entry points stay re-entrant and unchanged.
 inline thread_local const double* tl_step_sizes = nullptr;
 inline thread_local const int32_t* tl_n_steps = nullptr;
+inline thread_local int32_t* tl_counters = nullptr;  // mb200_set_call_counters
 struct PerChainScope {
   PerChainScope(const double* eps, const int32_t* ns) { tl_step_sizes = eps, tl_n_steps = ns; }
   ~PerChainScope() { tl_step_sizes = nullptr, tl_n_steps = nullptr; }
@@ -40,6 +41,7 @@ inline ModelArgs to_args(const mb200_model* m) {
   memset(&a, 0, sizeof(a));
   a.step_sizes = tl_step_sizes;
   a.n_steps_pc = tl_n_steps;
+  a.counters = tl_counters;
   a.target_id = m->target_id;
   for (int i = 0; i < MB200_MAX_PARAMS; ++i) a.tp[i] = m->target_params[i];
   a.taux = m->target_aux;

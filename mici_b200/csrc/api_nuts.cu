@@ -70,6 +70,11 @@ int mb200_version(void) { return MB200_VERSION; }
 
 const char* mb200_last_error(void) { return g_err; }
 
+int mb200_set_call_counters(int32_t* counters) {
+  tl_counters = counters;
+  return 0;
+}
+
 
 int mb200_metropolis_select(double* pos, double* mom, const double* pos_prop,
                             const double* mom_prop, const double* h_init, const double* h_prop,

@@ -49,6 +49,8 @@ struct ModelArgs {
   // CTA b owns [workspace + b * ws_stride, + ws_stride) doubles
   double* workspace;
   size_t ws_stride;
+  // optional call counters [n_chains][MB200_N_COUNTERS] (mb200_set_call_counters) or NULL
+  int32_t* counters;
 };
 
 // Splitting schedule of a symmetric composition integrator (integrators.py:176-378): flow i is

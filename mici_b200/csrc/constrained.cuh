@@ -720,6 +720,9 @@ __global__ void __launch_bounds__(128)
     const bool lebesgue = model.tp[MB200_MAX_PARAMS - 1] != 0.0;  // dens_wrt_hausdorff=False
     ops.dh1(q, g, lebesgue);
     int st = MB200_STATUS_OK, done = 0, iters = 0;
+    // constraint-Jacobian evaluations: one per projection, one per retraction (at the previous
+    // position) plus one per Newton iteration, one per Lebesgue-density gradient
+    int n_proj = 0, n_retr = 0;
     const double dt_inner = dt / n_inner;
     for (int s = 0; s < ns && st == MB200_STATUS_OK; ++s) {
       double qs[NV], ps[NV];
@@ -729,17 +732,20 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
       for (int e = 0; e < NV; ++e) p[e] = __dsub_rn(p[e], __dmul_rn(0.5 * dt, g[e]));
       ops.project(p, q);
+      ++n_proj;
       // _step_b(dt)
       for (int i = 0; i < n_inner && st == MB200_STATUS_OK; ++i) {
         double qprev[NV];
 #pragma unroll
         for (int e = 0; e < NV; ++e) qprev[e] = q[e];
+        ++n_retr;
         if (!ops.retract(q, p, qprev, dt_inner, constraint_tol, position_tol, divergence_tol,
                          max_iters, iters)) {
           st = MB200_STATUS_CONVERGENCE;
           break;
         }
         ops.project(p, q);
+        ++n_proj, ++n_retr;
         double qb[NV], pb[NV];
 #pragma unroll
         for (int e = 0; e < NV; ++e) qb[e] = q[e], pb[e] = p[e];
@@ -760,6 +766,7 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
         for (int e = 0; e < NV; ++e) p[e] = __dsub_rn(p[e], __dmul_rn(0.5 * dt, g[e]));
         ops.project(p, q);
+        ++n_proj;
         ++done;
       } else {
 #pragma unroll
@@ -796,6 +803,12 @@ __global__ void __launch_bounds__(128)
       if (status != nullptr) status[ch] = st;
       if (n_done != nullptr) n_done[ch] = done;
       if (newton_iters != nullptr) newton_iters[ch] = iters;
+      if (model.counters != nullptr) {
+        int32_t* cnt = model.counters + ch * MB200_N_COUNTERS;
+        cnt[MB200_COUNT_GRAD] += 1 + done;
+        cnt[MB200_COUNT_METRIC] += n_proj + n_retr + iters + (lebesgue ? 1 + done : 0);
+        cnt[MB200_COUNT_SOLVER_ITERS] += iters;
+      }
     }
   }
 }
@@ -971,7 +984,7 @@ __global__ void __launch_bounds__(32)
     const double dt = (dir != nullptr) ? (double)dir[ch] * eps : eps;
     const int ns = model.n_steps_pc != nullptr ? min(model.n_steps_pc[ch], n_steps) : n_steps;
     Vec3 g = t.grad(q);
-    int st = MB200_STATUS_OK, done = 0, iters = 0;
+    int st = MB200_STATUS_OK, done = 0, iters = 0, n_proj = 0, n_retr = 0;
     const double dt_inner = dt / n_inner;
     for (int s = 0; s < ns && st == MB200_STATUS_OK; ++s) {
       const Vec3 qs = q, ps = p;
@@ -979,14 +992,17 @@ __global__ void __launch_bounds__(32)
       p.y = __dsub_rn(p.y, __dmul_rn(0.5 * dt, g.y));
       p.z = __dsub_rn(p.z, __dmul_rn(0.5 * dt, g.z));
       t.project(p, q);
+      ++n_proj;
       for (int i = 0; i < n_inner && st == MB200_STATUS_OK; ++i) {
         const Vec3 qprev = q;
+        ++n_retr;
         if (!t.retract(q, p, qprev, dt_inner, constraint_tol, position_tol, divergence_tol,
                        max_iters, iters)) {
           st = MB200_STATUS_CONVERGENCE;
           break;
         }
         t.project(p, q);
+        ++n_proj, ++n_retr;
         Vec3 qb = q, pb = p;
         if (!t.retract(qb, pb, q, -dt_inner, constraint_tol, position_tol, divergence_tol,
                        max_iters, iters)) {
@@ -1002,6 +1018,7 @@ __global__ void __launch_bounds__(32)
         p.y = __dsub_rn(p.y, __dmul_rn(0.5 * dt, g.y));
         p.z = __dsub_rn(p.z, __dmul_rn(0.5 * dt, g.z));
         t.project(p, q);
+        ++n_proj;
         ++done;
       } else {
         q = qs, p = ps;
@@ -1013,6 +1030,12 @@ __global__ void __launch_bounds__(32)
     if (status != nullptr) status[ch] = st;
     if (n_done != nullptr) n_done[ch] = done;
     if (newton_iters != nullptr) newton_iters[ch] = iters;
+    if (model.counters != nullptr) {
+      int32_t* cnt = model.counters + ch * MB200_N_COUNTERS;
+      cnt[MB200_COUNT_GRAD] += 1 + done;
+      cnt[MB200_COUNT_METRIC] += n_proj + n_retr + iters;
+      cnt[MB200_COUNT_SOLVER_ITERS] += iters;
+    }
   }
 }
 

@@ -125,7 +125,7 @@ __device__ __forceinline__ void leapfrog_dmma_group(
     const double* __restrict__ step_sizes, int64_t n_chains, int dim,
     double step_size, int n_steps, double* __restrict__ h_out, int32_t* __restrict__ status,
     int32_t* __restrict__ n_done, int64_t chain0, int row0, int w, int lane, int bar_id,
-    int cta_threads, bool vec2) {
+    int cta_threads, bool vec2, int32_t* __restrict__ counters) {
   constexpr int LDA = DmmaSmem<DP>::LDA;
   constexpr int NT = DP / 32;  // 8-column tiles per warp
   constexpr int KS = DP / 4;   // k steps
@@ -352,6 +352,7 @@ __device__ __forceinline__ void leapfrog_dmma_group(
     if (w == 0 && c == 0) {
       if (status != nullptr) status[ch] = MB200_STATUS_OK;
       if (n_done != nullptr) n_done[ch] = n_steps;
+      if (counters != nullptr) counters[ch * MB200_N_COUNTERS + MB200_COUNT_GRAD] += n_steps + 1;
     }
   }
 
@@ -538,7 +539,7 @@ __global__ void __launch_bounds__(DMMA_THREADS, 1)
   leapfrog_dmma_group<Target, DP, MT, PC>(sm, target, q_in, p_in, q_out, p_out, dir,          \
                                           step_sizes, n_chains, dim, step_size, n_steps,      \
                                           h_out, status, n_done, chain0, row0, w, lane,       \
-                                          1 + group, cta_threads, vec2 != 0)
+                                          1 + group, cta_threads, vec2 != 0, model.counters)
     if (DMMA_MAX_MT >= 4 && mt == 4) MB200_GROUP(4);
     else if (DMMA_MAX_MT >= 3 && mt == 3) MB200_GROUP(3);
     else if (mt == 2) MB200_GROUP(2);

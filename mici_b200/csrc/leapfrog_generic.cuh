@@ -244,6 +244,9 @@ __global__ void __launch_bounds__(128)
       if (lane == 0) {
         if (status != nullptr) status[ch] = MB200_STATUS_OK;
         if (n_done != nullptr) n_done[ch] = ns[c];
+        if (model.counters != nullptr)  // one gradient per position update + the initial one
+          model.counters[ch * MB200_N_COUNTERS + MB200_COUNT_GRAD] +=
+              1 + ns[c] * __popc(sched.drift_mask & ((1u << sched.n) - 1u));
       }
     }
   }

@@ -1325,6 +1325,22 @@ struct ImplicitLeapfrog {
   double fp_tol, fp_div, rev_tol;
   int fp_max;
   int fp_solver;  // MB200_FP_SOLVER_DIRECT / MB200_FP_SOLVER_STEFFENSEN
+  // call counters of the chain in flight (block-uniform; mb200_set_call_counters):
+  // gradients of l, metric builds (factorisations / eigendecompositions), VJPs of the
+  // quadratic form p.M^-1 p, fixed-point iterations
+  int n_grad = 0, n_build = 0, n_quad = 0, n_fp = 0;
+  __device__ __forceinline__ int build_(const double* q) {
+    ++n_build;
+    return m.build(k, w, q);
+  }
+  __device__ __forceinline__ void grad_(const double* q, double* g) {
+    ++n_grad;
+    t.grad(k, q, g);
+  }
+  __device__ __forceinline__ void quad_(const double* q, const double* p, double* out) {
+    ++n_quad;
+    m.vjp_grad_quad_inv(k, w, q, p, out);
+  }
 
   // K4 on this chain's buffers (see fixed_point_direct below)
   template <class F>
@@ -1337,7 +1353,7 @@ struct ImplicitLeapfrog {
 
   // dh1_dpos = grad l + vjp(grad_log_abs_det) / 2   (systems.py:1381-1385); metric of q current
   __device__ void kick_h1(double dt) {
-    t.grad(k, w.q, w.v1);
+    grad_(w.q, w.v1);
     m.vjp_grad_log_abs_det(k, w, w.q, w.v2);
     for (int i = k.tid; i < w.dim; i += k.nthr)
       w.p[i] = __dsub_rn(w.p[i], __dmul_rn(dt, __dadd_rn(w.v1[i], __dmul_rn(0.5, w.v2[i]))));
@@ -1351,7 +1367,7 @@ struct ImplicitLeapfrog {
     int it_b = 0, it_crev = 0, it_c = 0, it_brev = 0;
     // ---- _step_a (:493-494)
     m.reset();
-    st = m.build(k, w, w.q);
+    st = build_(w.q);
     if (st != 0) return MB200_STATUS_LINALG;
     kick_h1(dt);
     // ---- _step_b_fwd (:496-502): p = p0 - dt * dh2_dpos(q, p), metric fixed
@@ -1360,7 +1376,7 @@ struct ImplicitLeapfrog {
     double* sol;
     auto fb = [&](double sdt) {
       return [&, sdt](const double* xin, double* xout) {
-        m.vjp_grad_quad_inv(k, w, w.q, xin, w.v1);
+        quad_(w.q, xin, w.v1);
         for (int i = k.tid; i < n; i += k.nthr)
           xout[i] = __dsub_rn(w.base[i], __dmul_rn(sdt, __dmul_rn(0.5, w.v1[i])));
         __syncthreads();
@@ -1381,7 +1397,7 @@ struct ImplicitLeapfrog {
     // fixed point in q: x = base + sdt * M(x)^-1 p, new metric every iteration (:530-536)
     auto fc = [&](double sdt) {
       return [&, sdt](const double* xin, double* xout) {
-        const int bs = m.build(k, w, xin);
+        const int bs = build_(xin);
         if (bs != 0) return 1;
         m.inv_matvec(k, w, w.p, w.v1);
         for (int i = k.tid; i < n; i += k.nthr)
@@ -1410,11 +1426,11 @@ struct ImplicitLeapfrog {
     for (int i = k.tid; i < n; i += k.nthr) w.q[i] = sol[i];
     __syncthreads();
     // ---- _step_b_adj (:504-515): p -= dt * dh2_dpos(q, p) at the new metric, then reverse check
-    st = m.build(k, w, w.q);
+    st = build_(w.q);
     if (st != 0) return MB200_STATUS_LINALG;
     for (int i = k.tid; i < n; i += k.nthr) w.v3[i] = w.p[i];  // mom_init
     __syncthreads();
-    m.vjp_grad_quad_inv(k, w, w.q, w.p, w.v1);
+    quad_(w.q, w.p, w.v1);
     for (int i = k.tid; i < n; i += k.nthr)
       w.p[i] = __dsub_rn(w.p[i], __dmul_rn(dt, __dmul_rn(0.5, w.v1[i])));
     __syncthreads();
@@ -1439,11 +1455,11 @@ struct ImplicitLeapfrog {
   // (systems.py:198-207, 1381-1399).  Returns 0 or the metric-build failure.
   __device__ int hamiltonian_gradient(const double* q, const double* p, double* vel,
                                       double* force) {
-    if (m.build(k, w, q) != 0) return 1;
+    if (build_(q) != 0) return 1;
     m.inv_matvec(k, w, p, vel);
-    t.grad(k, q, w.v1);
+    grad_(q, w.v1);
     m.vjp_grad_log_abs_det(k, w, q, w.v2);
-    m.vjp_grad_quad_inv(k, w, q, p, w.v3);
+    quad_(q, p, w.v3);
     for (int i = k.tid; i < w.dim; i += k.nthr)
       force[i] = __dadd_rn(__dadd_rn(w.v1[i], __dmul_rn(0.5, w.v2[i])), __dmul_rn(0.5, w.v3[i]));
     __syncthreads();
@@ -1509,7 +1525,7 @@ struct ImplicitLeapfrog {
   // h = l(q) + log|M|/2 + p.M^-1 p/2   (systems.py:1375-1390); NaN if the metric cannot be built
   __device__ double hamiltonian() {
     m.reset();
-    if (m.build(k, w, w.q) != 0) return nan("");
+    if (m.build(k, w, w.q) != 0) return nan("");  // diagnostics: not counted
     m.inv_matvec(k, w, w.p, w.v1);
     double s = 0.0;
     for (int i = k.tid; i < w.dim; i += k.nthr) s = fma(w.p[i], w.v1[i], s);
@@ -1559,11 +1575,13 @@ __global__ void __launch_bounds__(MetricT<Target>::THREADS, MetricT<Target>::MIN
     const int ns = model.n_steps_pc != nullptr ? min(model.n_steps_pc[ch], n_steps) : n_steps;
     int st = MB200_STATUS_OK, done = 0;
     int it4[4] = {0, 0, 0, 0};
+    integ.n_grad = integ.n_build = integ.n_quad = integ.n_fp = 0;
     for (int s = 0; s < ns && st == MB200_STATUS_OK; ++s) {
       for (int i = blk.tid; i < dim; i += blk.nthr) w.qs[i] = w.q[i], w.ps[i] = w.p[i];
       __syncthreads();
       int it_step[4] = {0, 0, 0, 0};
       st = midpoint ? integ.midpoint_step(dt, it_step) : integ.step(dt, it_step);
+      integ.n_fp += it_step[0] + it_step[1] + it_step[2] + it_step[3];
       if (st == MB200_STATUS_OK) {
         ++done;
 #pragma unroll
@@ -1587,6 +1605,11 @@ __global__ void __launch_bounds__(MetricT<Target>::THREADS, MetricT<Target>::MIN
       if (n_done != nullptr) n_done[ch] = done;
       if (fp_iters != nullptr)
         for (int j = 0; j < 4; ++j) fp_iters[ch * 4 + j] = it4[j];
+      if (model.counters != nullptr) {  // the energy evaluation above is not counted
+        int32_t* c = model.counters + ch * MB200_N_COUNTERS;
+        c[MB200_COUNT_GRAD] += integ.n_grad, c[MB200_COUNT_METRIC] += integ.n_build;
+        c[MB200_COUNT_QUAD_VJP] += integ.n_quad, c[MB200_COUNT_SOLVER_ITERS] += integ.n_fp;
+      }
     }
   }
 }

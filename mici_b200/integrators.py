@@ -56,9 +56,30 @@ from .systems import (
 class Integrator(ABC):
     """Base class for integrators (integrators.py:30-89)."""
 
+    COUNTER_NAMES = ("grad_neg_log_dens", "metric", "quad_form_vjp", "solver_iters")
+
     def __init__(self, system, step_size=None):
         self.system = system
         self.step_size = step_size
+        self.call_counts = None  # int32 [n_chains, 4] device tensor once `count_calls()` is on
+        self._counting = False
+
+    def count_calls(self, enable=True):
+        """Switch the kernel-side call counters on / off (``mb200_set_call_counters``; the
+        per-chain counterpart of ``ChainState._call_counts``, states.py:44-72).  While on, every
+        ``step_n`` adds to ``self.call_counts[chain]``: gradient evaluations, metric builds
+        (Riemannian: factorisations / eigendecompositions; constrained: constraint-Jacobian
+        evaluations), quadratic-form VJPs and solver iterations (``COUNTER_NAMES`` order)."""
+        self._counting = bool(enable)
+        self.call_counts = None
+        return self
+
+    def call_count_totals(self):
+        """``{name: total over chains}`` of the counters gathered since ``count_calls()``."""
+        if self.call_counts is None:
+            return dict.fromkeys(self.COUNTER_NAMES, 0)
+        tot = self.call_counts.sum(0).tolist()
+        return dict(zip(self.COUNTER_NAMES, (int(v) for v in tot)))
 
     def step(self, state):
         """Perform a single integrator step from a supplied state; returns a new state."""
@@ -89,8 +110,17 @@ class Integrator(ABC):
         h = torch.empty(n, dtype=torch.float64, device=dev) if return_h else None
         if not isinstance(n_steps, torch.Tensor):
             n_steps = int(n_steps)
-        aux = self._launch(pos, mom, pos_out, mom_out, _dir_tensor(d, n, dev), n_steps, h,
-                           status, n_done)
+        if self._counting:
+            if self.call_counts is None or self.call_counts.shape[0] != n \
+                    or self.call_counts.device != dev:
+                self.call_counts = torch.zeros(n, 4, dtype=torch.int32, device=dev)
+            _lib.load().mb200_set_call_counters(_lib.ptr(self.call_counts))
+        try:
+            aux = self._launch(pos, mom, pos_out, mom_out, _dir_tensor(d, n, dev), n_steps, h,
+                               status, n_done)
+        finally:
+            if self._counting:
+                _lib.load().mb200_set_call_counters(None)
         new = _new_state_like(state, _like_input(state.pos, pos_out[0] if single else pos_out),
                               _like_input(state.pos, mom_out[0] if single else mom_out))
         if not isinstance(new, ChainState):  # foreign (reference) state object: no extra slots

@@ -215,3 +215,50 @@ def test_trace_write_out_from_device_buffers_reference_file_layout(tmp_path):
         np.testing.assert_array_equal(np.asarray(mm), buf.data[:, i].cpu().numpy())
         hm = np.load(paths["hamiltonian"][i], mmap_mode="r")
         np.testing.assert_array_equal(np.asarray(hm), hbuf.data[:, i].cpu().numpy())
+
+
+def test_kernel_side_call_counters():
+    """``mb200_set_call_counters``: per-chain tallies written by the kernels themselves."""
+    # K1 (tensor-core leapfrog): one gradient per step plus the initial one
+    prob = problems.make_problem("C1", n_chains=19, dim=32)
+    integ = engine.build_integrator(prob).count_calls()
+    state = engine.build_state(prob, DEV)
+    integ.step_n(state, 5)
+    integ.step_n(state, 2)
+    c = integ.call_counts.cpu().numpy()
+    assert (c[:, 0] == 6 + 3).all() and (c[:, 1:] == 0).all()
+    assert integ.call_count_totals()["grad_neg_log_dens"] == 19 * 9
+    # three-stage composition on the general kernel: one gradient per drift
+    prob = problems.make_problem("C1", n_chains=5, dim=20, integrator="bcss3")
+    integ = engine.build_integrator(prob).count_calls()
+    integ.step_n(engine.build_state(prob, DEV), 4)
+    got = integ.call_counts.cpu().numpy()[:, 0]
+    assert (got == 1 + 4 * 3).all()  # flows a b a b a b a: three drifts per step
+    # implicit leapfrog (SoftAbs): builds / VJPs follow the fixed-point iteration counts
+    prob = problems.make_problem("C2", n_chains=6, dim=8)
+    integ = engine.build_integrator(prob).count_calls()
+    out = integ.step_n(engine.build_state(prob, DEV), 1)
+    it = out.solver_iters.cpu().numpy()
+    c = integ.call_counts.cpu().numpy()
+    ok = out.status.cpu().numpy() == 0
+    assert ok.all()
+    np.testing.assert_array_equal(c[:, 3], it.sum(1))
+    np.testing.assert_array_equal(c[:, 1], it[:, 1] + it[:, 2] + 2)  # metric builds
+    np.testing.assert_array_equal(c[:, 2], it[:, 0] + it[:, 3] + 1)  # quadratic-form VJPs
+    np.testing.assert_array_equal(c[:, 0], 2)
+    # constrained leapfrog: 3 projections + 2 retractions per step, one Jacobian per Newton
+    # iteration; the thread-per-chain torus kernel and the warp kernel (sphere) count alike
+    for cfg, kw in (("C3", dict(n_chains=40)), ("S1", dict(n_chains=9, dim=10))):
+        prob = problems.make_problem(cfg, **kw)
+        integ = engine.build_integrator(prob).count_calls()
+        out = integ.step_n(engine.build_state(prob, DEV), 3)
+        assert int((out.status != 0).sum()) == 0
+        c = integ.call_counts.cpu().numpy()
+        it = out.solver_iters.cpu().numpy().reshape(-1)
+        np.testing.assert_array_equal(c[:, 3], it)
+        np.testing.assert_array_equal(c[:, 1], 5 * 3 + it)
+        np.testing.assert_array_equal(c[:, 0], 4)
+    # switched off again: later launches leave the tally alone
+    integ.count_calls(False)
+    integ.step_n(engine.build_state(prob, DEV), 1)
+    assert integ.call_counts is None

@@ -95,8 +95,8 @@ def test_system_rejects_python_callables_and_foreign_derivatives():
         systems.EuclideanMetricSystem(targets.StdGaussian(3), grad_neg_log_dens=lambda q: q)
     with pytest.raises(ValueError):
         systems.DenseConstrainedEuclideanMetricSystem(targets.StdGaussian(3))
-    with pytest.raises(NotImplementedError):
-        systems.DenseConstrainedEuclideanMetricSystem(targets.Torus(), dens_wrt_hausdorff=False)
+    # densities with respect to the Lebesgue measure are supported (systems.py:853-861)
+    systems.DenseConstrainedEuclideanMetricSystem(targets.Torus(), dens_wrt_hausdorff=False)
     with pytest.raises(ValueError):
         systems.SoftAbsRiemannianMetricSystem(targets.Banana(4), softabs_coeff=0.0)
 
@@ -289,21 +289,21 @@ def test_transition_constructors_validate_like_reference():
         transitions.MultinomialDynamicIntegrationTransition(system, integ, max_tree_depth=0)
     with pytest.raises(TypeError):
         transitions.DynamicIntegrationTransition(system, integ)
-    with pytest.raises(NotImplementedError):
-        transitions.SliceDynamicIntegrationTransition(
-            system, integrators.BCSSTwoStageIntegrator(system, 0.1))
+    # other integrators take the generic lock-step tree builder (nuts_generic.cuh)
+    tr2 = transitions.SliceDynamicIntegrationTransition(
+        system, integrators.BCSSTwoStageIntegrator(system, 0.1))
+    assert not tr2._fused
     tr = transitions.SliceDynamicIntegrationTransition(system, integ, max_tree_depth=5)
     assert tr.n_uniforms == 2 * 5 + 2**5 + 1
-    # systems the fused tree builder does not cover fail loudly at construction
+    # systems the fused tree builder does not cover run leaf by leaf through their integrator
     torus = targets.make_target("torus")
     csys = systems.DenseConstrainedEuclideanMetricSystem(torus, torus)
-    with pytest.raises(NotImplementedError):
-        transitions.MultinomialDynamicIntegrationTransition(
-            csys, integrators.ConstrainedLeapfrogIntegrator(csys, 0.1))
+    tr3 = transitions.MultinomialDynamicIntegrationTransition(
+        csys, integrators.ConstrainedLeapfrogIntegrator(csys, 0.1))
     gsys = systems.GaussianEuclideanMetricSystem(targets.StdGaussian(4))
-    with pytest.raises(NotImplementedError):
-        transitions.MultinomialDynamicIntegrationTransition(
-            gsys, integrators.LeapfrogIntegrator(gsys, 0.1))
+    tr4 = transitions.MultinomialDynamicIntegrationTransition(
+        gsys, integrators.LeapfrogIntegrator(gsys, 0.1))
+    assert not tr3._fused and not tr4._fused and tr._fused
 
 
 def test_sampler_front_ends_mirror_reference_signatures_and_defaults():
