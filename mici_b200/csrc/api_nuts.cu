@@ -2,10 +2,35 @@
 // Host-side argument checking and kernel dispatch only; all arithmetic is in the .cuh kernels.
 #include "api_common.cuh"
 #include "nuts.cuh"
+#include "nuts_dmma.cuh"
 #include "nuts_generic.cuh"
 #include "transitions.cuh"
 
 namespace mb200 {
+
+// Shared dense metric, dim <= 128: the chains of a CTA in lock-step, mat-vecs on the tensor pipe
+template <class Target, int KP, int WARPS>
+static int launch_nuts_dmma(const double* q_in, const double* p_in, double* q_out, double* p_out,
+                            int64_t n, int dim, double eps, const double* minv, const ModelArgs& m,
+                            const NutsArgs& a, double* ws, double* h_out, int32_t* n_step,
+                            double* av_accept, double* reject_prob, int32_t* depth,
+                            int32_t* diverging, int32_t* n_used, int32_t* dir_out,
+                            int32_t* status, cudaStream_t st) {
+  auto kern = nuts_dmma_kernel<Target, KP, WARPS>;
+  const size_t smem = NutsDmmaLayout<KP, WARPS>::smem_bytes();
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(MB200_ERR_CUDA, "smem attr: %s", cudaGetErrorString(e));
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t blocks = (n + WARPS - 1) / WARPS;
+  const int64_t cap = (int64_t)num_sms() * per_sm;
+  if (blocks > cap) blocks = cap;
+  kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(q_in, p_in, q_out, p_out, n, dim, eps, minv, m,
+                                                    a, ws, h_out, n_step, av_accept, reject_prob,
+                                                    depth, diverging, n_used, dir_out, status);
+  return check_launch("nuts_dmma_kernel");
+}
 
 template <class Target, int KP>
 static int launch_nuts(const double* q_in, const double* p_in, double* q_out, double* p_out,
@@ -14,6 +39,15 @@ static int launch_nuts(const double* q_in, const double* p_in, double* q_out, do
                        int32_t* n_step, double* av_accept, double* reject_prob, int32_t* depth,
                        int32_t* diverging, int32_t* n_used, int32_t* dir_out, int32_t* status,
                        cudaStream_t st) {
+  if constexpr (KP <= 2) {
+    // shared dense metric, dim <= 128: 8 chains per CTA in lock-step, mat-vecs on the tensor
+    // pipe (measured on C1, depth 6: 8 warps 205 M leapfrog steps/s, 16 warps 168 M -- register
+    // spills and a workspace working set beyond L2 --, free-running nuts_euclidean_kernel 95 M)
+    if (metric_kind == MB200_METRIC_DENSE && dim >= 8)
+      return launch_nuts_dmma<Target, KP, 8>(q_in, p_in, q_out, p_out, n, dim, eps, minv, m, a, ws,
+                                             h_out, n_step, av_accept, reject_prob, depth,
+                                             diverging, n_used, dir_out, status, st);
+  }
   auto kern = nuts_euclidean_kernel<Target, KP>;
   NutsArgs args = a;
   // dense metric that fits in shared memory next to the staging rows: the warps of a CTA share it
