@@ -9,15 +9,16 @@
 namespace mb200 {
 
 // Shared dense metric, dim <= 128: the chains of a CTA in lock-step, mat-vecs on the tensor pipe
-template <class Target, int KP, int WARPS>
+template <class Target, int KP, int GROUPS>
 static int launch_nuts_dmma(const double* q_in, const double* p_in, double* q_out, double* p_out,
                             int64_t n, int dim, double eps, const double* minv, const ModelArgs& m,
                             const NutsArgs& a, double* ws, double* h_out, int32_t* n_step,
                             double* av_accept, double* reject_prob, int32_t* depth,
                             int32_t* diverging, int32_t* n_used, int32_t* dir_out,
                             int32_t* status, cudaStream_t st) {
-  auto kern = nuts_dmma_kernel<Target, KP, WARPS>;
-  const size_t smem = NutsDmmaLayout<KP, WARPS>::smem_bytes();
+  auto kern = nuts_dmma_kernel<Target, KP, GROUPS>;
+  constexpr int WARPS = 8 * GROUPS;
+  const size_t smem = NutsDmmaLayout<KP, GROUPS>::smem_bytes();
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(MB200_ERR_CUDA, "smem attr: %s", cudaGetErrorString(e));
   int per_sm = 1;
@@ -40,13 +41,15 @@ static int launch_nuts(const double* q_in, const double* p_in, double* q_out, do
                        int32_t* diverging, int32_t* n_used, int32_t* dir_out, int32_t* status,
                        cudaStream_t st) {
   if constexpr (KP <= 2) {
-    // shared dense metric, dim <= 128: 8 chains per CTA in lock-step, mat-vecs on the tensor
-    // pipe (measured on C1, depth 6: 8 warps 205 M leapfrog steps/s, 16 warps 168 M -- register
-    // spills and a workspace working set beyond L2 --, free-running nuts_euclidean_kernel 95 M)
+    // shared dense metric, dim <= 128: groups of 8 chains in lock-step, mat-vecs on the tensor
+    // pipe.  Measured on C1 (depth 6; free-running nuts_euclidean_kernel: 95 M leapfrog steps/s):
+    // one group per CTA 205 M, two groups 172 M (register spills at the 128-register budget and
+    // a workspace working set beyond L2), 16 chains in one lock-step 168 M; at dim = 64 (depth 8)
+    // two groups 377 M, one group 300 M, free-running 215 M.
     if (metric_kind == MB200_METRIC_DENSE && dim >= 8)
-      return launch_nuts_dmma<Target, KP, 8>(q_in, p_in, q_out, p_out, n, dim, eps, minv, m, a, ws,
-                                             h_out, n_step, av_accept, reject_prob, depth,
-                                             diverging, n_used, dir_out, status, st);
+      return launch_nuts_dmma<Target, KP, (KP == 1 ? 2 : 1)>(
+          q_in, p_in, q_out, p_out, n, dim, eps, minv, m, a, ws, h_out, n_step, av_accept,
+          reject_prob, depth, diverging, n_used, dir_out, status, st);
   }
   auto kern = nuts_euclidean_kernel<Target, KP>;
   NutsArgs args = a;

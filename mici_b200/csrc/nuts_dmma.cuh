@@ -34,20 +34,36 @@ __device__ __forceinline__ void nuts_dmma(double& c0, double& c1, double a, doub
                : "d"(a), "d"(b));
 }
 
-template <int KP, int WARPS>
+// A CTA holds GROUPS independent lock-step groups of 8 warps (8 chains: one DMMA row tile) that
+// share the staged metric and synchronise among themselves only (named barriers): while one
+// group is in its tensor-pipe phase the other does its bookkeeping.
+template <int KP, int GROUPS>
 struct NutsDmmaLayout {
   static constexpr int DP = 64 * KP;
-  static constexpr int LDA = DP + 8;       // row stride: conflict-free 128-bit fragment loads
-  static constexpr int MT = WARPS / 8;     // row tiles of 8 chains
-  static constexpr int NTW = DP / (8 * WARPS);  // 8-column tiles of U per warp
-  static_assert(WARPS % 8 == 0 && NTW >= 1 && NTW * 8 * WARPS == DP, "tile shape");
+  static constexpr int LDA = DP + 8;   // row stride: conflict-free 128-bit fragment loads
+  static constexpr int WARPS = 8 * GROUPS;
+  static constexpr int NTW = DP / 64;  // 8-column tiles of U per warp (8 warps span DP columns)
   static constexpr size_t smem_bytes() {
     return (size_t)(DP * LDA + 2 * WARPS * LDA) * sizeof(double);
   }
 };
 
-template <class Target, int KP, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1)
+__device__ __forceinline__ void nuts_group_sync(int id, int nthreads) {
+  asm volatile("barrier.cta.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ bool nuts_group_any(int id, int nthreads, bool pred) {
+  uint32_t res;
+  asm volatile(
+      "{\n .reg .pred p, q;\n setp.ne.u32 q, %3, 0;\n"
+      " barrier.cta.red.or.pred p, %1, %2, q;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(res)
+      : "r"(id), "r"(nthreads), "r"((uint32_t)pred)
+      : "memory");
+  return res != 0;
+}
+
+template <class Target, int KP, int GROUPS>
+__global__ void __launch_bounds__(GROUPS * 256, 1)
     nuts_dmma_kernel(const double* __restrict__ q_in, const double* __restrict__ p_in,
                      double* __restrict__ q_out, double* __restrict__ p_out, int64_t n_chains,
                      int dim, double step_size, const double* __restrict__ minv, ModelArgs model,
@@ -58,15 +74,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
                      int32_t* __restrict__ dir_out, int32_t* __restrict__ status) {
   using N = Nuts<Target, KP>;
   using K = LeapfrogGeneric<Target, KP, 1>;
-  using L = NutsDmmaLayout<KP, WARPS>;
+  using L = NutsDmmaLayout<KP, GROUPS>;
   constexpr int NV = 2 * KP;
-  constexpr int DP = L::DP, LDA = L::LDA, MT = L::MT, NTW = L::NTW;
+  constexpr int DP = L::DP, LDA = L::LDA, WARPS = L::WARPS, NTW = L::NTW, MT = 1;
   extern __shared__ __align__(16) double smem[];
   double* sA = smem;                 // M^-1, zero padded to DP x DP
   double* sG = sA + DP * LDA;        // operands  [WARPS][LDA]
   double* sU = sG + WARPS * LDA;     // products  [WARPS][LDA]
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const int grp = warp >> 3, gw = warp & 7;  // lock-step group, warp (= chain row) within it
+  const int bar_id = 1 + grp;
   for (int idx = threadIdx.x; idx < DP * DP; idx += blockDim.x) {
     const int row = idx / DP, col = idx - row * DP;
     sA[row * LDA + col] = (row < dim && col < dim) ? minv[(size_t)row * dim + col] : 0.0;
@@ -81,15 +99,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
   const double2* u_row = reinterpret_cast<const double2*>(sU + warp * LDA) + lane;
   // fragment bases of phase B (row r of every row tile; column col0 + r of every column tile)
   const int fr = lane >> 2, fc = lane & 3;
-  const int col0 = warp * (8 * NTW);
-  const double2* a_base = reinterpret_cast<const double2*>(sG + fr * LDA + 2 * fc);
+  const int col0 = gw * (8 * NTW);
+  const double2* a_base = reinterpret_cast<const double2*>(sG + (8 * grp + fr) * LDA + 2 * fc);
   const double2* b_base = reinterpret_cast<const double2*>(sA + (col0 + fr) * LDA + 2 * fc);
 
   enum { PH_INIT = 0, PH_START = 1, PH_LEAF = 2 };
 
-  for (int64_t base = (int64_t)blockIdx.x * WARPS; base < n_chains;
+  for (int64_t base = ((int64_t)blockIdx.x * GROUPS + grp) * 8; base < n_chains;
        base += (int64_t)gridDim.x * WARPS) {
-    const int64_t ch = base + warp;
+    const int64_t ch = base + gw;
     bool alive = ch < n_chains;
     const int64_t chs = alive ? ch : 0;  // dead warps of a ragged last block touch nothing
     double* tree = workspace + (size_t)chs * ws_stride;
@@ -169,7 +187,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
           for (int kk = 0; kk < KP; ++kk) g_row[32 * kk] = make_double2(g[2 * kk], g[2 * kk + 1]);
         }
       }
-      if (!__syncthreads_or(alive ? 1 : 0)) break;
+      if (!nuts_group_any(bar_id, 256, alive)) break;
 
       // ---------------------------------------------------------------- B: U = G . M^-1
       {
@@ -198,10 +216,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
           for (int nt = 0; nt < NTW; ++nt)
-            *reinterpret_cast<double2*>(sU + (8 * mt + fr) * LDA + col0 + 8 * nt + 2 * fc) =
+            *reinterpret_cast<double2*>(sU + (8 * grp + fr) * LDA + col0 + 8 * nt + 2 * fc) =
                 make_double2(acc[mt][nt][0] + acc2[mt][nt][0], acc[mt][nt][1] + acc2[mt][nt][1]);
       }
-      __syncthreads();
+      nuts_group_sync(bar_id, 256);
 
       // ---------------------------------------------------------------- C: per-chain bookkeeping
       if (!alive) continue;

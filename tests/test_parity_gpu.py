@@ -249,6 +249,18 @@ def test_host_buffer_path_equals_device_path():
     torch.cuda.synchronize()
     assert torch.equal(pos, ref.pos.cpu()) and torch.equal(mom, ref.mom.cpu())
     assert torch.equal(status, ref.status.cpu())
+    # pageable (NumPy-backed) buffers -- what the reference's ChainState holds -- take the
+    # library's own staging pipeline (worker threads + pinned bounce buffers); mixed directions
+    pos_n, mom_n = np.array(problem.pos), np.array(problem.mom)
+    dirs = torch.as_tensor(np.where(np.arange(777) % 3 == 0, -1, 1).astype(np.int32))
+    state.dir = dirs.to(DEV)
+    ref = integ.step_n(state, 6)
+    for _ in range(2):  # the second call reuses the bounce buffer and the workers
+        pos, mom, status = integ.step_n_host(torch.from_numpy(pos_n), torch.from_numpy(mom_n), 6,
+                                             dir=dirs, device=DEV, n_chunks=5)
+        assert not pos.is_pinned()
+        assert torch.equal(pos, ref.pos.cpu()) and torch.equal(mom, ref.mom.cpu())
+        assert torch.equal(status, ref.status.cpu())
 
 
 @pytest.mark.parametrize("name", HMC_NAMES)
