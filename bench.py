@@ -444,6 +444,62 @@ def run_workload(name, torch, dist, dev, rank, world, flush, hbm_peak):
     return res
 
 
+def run_nuts(torch, dist, dev, rank, world):
+    """Row N4: whole dynamic-HMC (NUTS) transitions on C1 -- momentum refresh excluded, one
+    launch per transition for all chains (`nuts_dmma_kernel`: 8 chains per CTA in lock-step, the
+    mat-vec of every leaf on the tensor pipe).  Leapfrog steps inside the trees per second."""
+    from mici_b200 import engine, problems, transitions
+
+    out = {}
+    for depth in (6, 8):
+        prob = problems.make_problem("C1", n_chains=N_CHAINS, dim=DIM,
+                                     seed=problems.BASE_SEED + 11 + 1000 * rank)
+        prob.step_size = 0.01
+        integ = engine.build_integrator(prob)
+        state = engine.build_state(prob, dev)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(rank)
+        tr = transitions.MultinomialDynamicIntegrationTransition(integ.system, integ,
+                                                                 max_tree_depth=depth)
+        mom = transitions.IndependentMomentumTransition(integ.system)
+        for _ in range(2):
+            state, _ = mom.sample(state, gen)
+            state, st = tr.sample(state, gen)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        reps, ms, steps = 5, 0.0, 0.0
+        for _ in range(reps):
+            state, _ = mom.sample(state, gen)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            state, st = tr.sample(state, gen)
+            b.record()
+            torch.cuda.synchronize(dev)
+            ms += a.elapsed_time(b)
+            steps += float(st["n_step"].sum().item())
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        sdone = torch.tensor([steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(sdone)
+        out[f"max_tree_depth_{depth}"] = {
+            "value": float(sdone.item()) / (float(t.item()) * 1e-3), "unit": UNIT,
+            "ms_per_transition": float(t.item()) / reps,
+            "mean_leapfrog_steps_per_transition": float(sdone.item()) / reps / (N_CHAINS * world),
+            "mean_tree_depth": float(st["tree_depth"].double().mean().item()),
+            "accept_stat": float(st["accept_stat"].mean().item()),
+        }
+    return {
+        "workload": "N4: MultinomialDynamicIntegrationTransition (NUTS) on C1 (funnel D=128, dense "
+                    "metric, 8192 chains per GPU, step size 0.01), uniforms generated on device",
+        "kernel": "nuts_dmma_kernel<NealFunnelTarget, 2, 1>",
+        "chains_per_gpu": N_CHAINS, "n_gpus": world, "dim": DIM,
+        "value": out["max_tree_depth_6"]["value"], "unit": UNIT,
+        **out,
+    }
+
+
 def run_cuda(args, rank, local_rank, world):
     cpu = None
     extra_names = [] if args.no_workloads else list(WORKLOADS)
@@ -568,6 +624,7 @@ def run_cuda(args, rank, local_rank, world):
             if cpu is not None and name in cpu:
                 res["cpu_baseline"] = cpu[name]
             workloads[name] = res
+        workloads["N4_nuts_C1"] = run_nuts(torch, dist, dev, rank, world)
         # strong scaling: the 8192 chains of C1 divided over the ranks
         n_s = N_CHAINS // world
         sprob = problems.make_problem("C1", n_chains=N_CHAINS, dim=DIM,
@@ -604,6 +661,8 @@ def run_cuda(args, rank, local_rank, world):
     achieved_gbs = b_alg * chain_steps_per_launch / avg_launch_s / 1e9
     flops = (2.0 * dim * dim) * chain_steps_per_launch / avg_launch_s
     n_launches = args.steps + (sum(w["reps"] for k, w in WORKLOADS.items() if k in workloads))
+    if "N4_nuts_C1" in workloads:
+        n_launches += 10  # 5 timed transitions at each of the two depths
     line = {
         "metric": METRIC,
         "value": value,

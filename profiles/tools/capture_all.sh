@@ -18,7 +18,7 @@ cap r02_c2_softabs implicit_leapfrog 0 python $T/run_cfg.py C2 1 1
 cap r02_c6_softabs_dense implicit_leapfrog 0 python $T/run_cfg.py C6 1 1 296
 cap r02_c3_constrained constrained_ 0 python $T/run_cfg.py C3 50 1
 cap r02_c4_dense implicit_leapfrog 0 python $T/run_cfg.py C4 1 1 148
-cap r02_nuts_c1 nuts_euclidean 0 python $T/run_nuts.py
+cap r02_nuts_c1 nuts_dmma 1 python $T/run_nuts.py 8192 6 2
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file $O/r02_bench_launches.csv python bench.py --no-cpu-baseline --steps 2 --warmup 1 \
     > $O/ncu_launches.log 2>&1
