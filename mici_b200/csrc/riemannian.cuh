@@ -476,8 +476,25 @@ __device__ __forceinline__ void rr_pair(int np, int r, int t, int& p, int& q) {
 
 // `warm`: U already holds an orthogonal basis V and A holds V^T H V (nearly diagonal); the
 // rotations are accumulated onto V, so that on return U holds the eigenvectors of H.
-__device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U, bool warm = false) {
+// SH: A and U are known to live in shared memory.  RmWork's pointers reach this (non-inlined)
+// function through memory, so the compiler cannot see their address space and would emit generic
+// LD / ST for every access; the assumptions below turn them back into LDS / STS (measured: C2
+// 137 k -> 194 k steps/s, dense-Hessian C2 13.5 k -> 17.5 k).
+template <bool SH>
+__device__ inline bool jacobi_eigh_impl(const Blk& k, RmWork& w, double* A, double* U, bool warm) {
   const int n = w.dim, ld = w.ld;
+  double* const rc = w.rc;
+  double* const rs = w.rs;
+  int* const top = w.top;
+  int* const bot = w.bot;
+  __builtin_assume(__isShared(rc));
+  __builtin_assume(__isShared(rs));
+  __builtin_assume(__isShared(top));
+  __builtin_assume(__isShared(bot));
+  if (SH) {
+    __builtin_assume(__isShared(A));
+    __builtin_assume(__isShared(U));
+  }
   const int m = (n + 1) / 2;  // pairs per round (odd n: one index idles each round)
   const int np = 2 * m;       // padded player count; index n (if odd) is a bye
   if (!warm)
@@ -503,6 +520,7 @@ __device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U
   // look-ahead votes: two banks of [nwarp] ints in the reduction scratch (k.red[16..32) is unused
   // by block_sum / block_nanmax), alternated per pass so that no extra barrier protects them
   int* flag_banks = reinterpret_cast<int*>(k.red + 16);
+  __builtin_assume(__isShared(flag_banks));
   int pass = 0;
   for (int sweep = 0; sweep < RM_MAX_SWEEPS; ++sweep) {
     double off = 0.0;
@@ -535,10 +553,10 @@ __device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U
             }
           }
           if (k.warp == 0) {
-            w.rc[t] = c;
-            w.rs[t] = s;
-            w.top[t] = p;
-            w.bot[t] = q;
+            rc[t] = c;
+            rs[t] = s;
+            top[t] = p;
+            bot[t] = q;
           }
         }
       }
@@ -556,14 +574,14 @@ __device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U
       }
       // --- A <- R^T A R on 2x2 blocks (pair a rows, pair b cols), U <- U R
       for (int b = tx; b < m; b += 32) {
-        const int pb = w.top[b], qb = w.bot[b];
-        const double cb = w.rc[b], sb = w.rs[b];
+        const int pb = top[b], qb = bot[b];
+        const double cb = rc[b], sb = rs[b];
         const bool vb = qb < n;
         for (int a = ty; a < m; a += ny) {
-          const double sa = w.rs[a];
+          const double sa = rs[a];
           if (sa == 0.0 && sb == 0.0) continue;  // both rotations are the identity
-          const int pa = w.top[a], qa = w.bot[a];
-          const double ca = w.rc[a];
+          const int pa = top[a], qa = bot[a];
+          const double ca = rc[a];
           const bool va = qa < n;
           if (va && vb) {
             const double a00 = A[pa * ld + pb], a01 = A[pa * ld + qb];
@@ -602,6 +620,11 @@ __device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U
     if (offmax <= tol) return true;  // the sweep just done squares this again
   }
   return false;
+}
+
+__device__ inline bool jacobi_eigh(const Blk& k, RmWork& w, double* A, double* U, bool warm = false) {
+  return __isShared(A) ? jacobi_eigh_impl<true>(k, w, A, U, warm)
+                       : jacobi_eigh_impl<false>(k, w, A, U, warm);
 }
 
 // C = op(X) * Y for n x n shared-memory matrices (stride ld), op = transpose if XT.  4x4 register
