@@ -544,10 +544,29 @@ __device__ inline bool jacobi_eigh_impl(const Blk& k, RmWork& w, double* A, doub
             if (fabs(apq) > 1e-300 && fabs(apq) > 1e-18 * scale) {
               need = true;
               if (k.warp == 0) {
+                // t = sign(tau) / (|tau| + sqrt(1 + tau^2)), tau = (aqq - app) / (2 apq), written
+                // as t = sign * |b| / (|d| + sqrt(d^2 + b^2)) with d = aqq - app, b = 2 apq, and
+                // c = 1 / sqrt(1 + t^2) through rsqrt + one Newton step: ONE division and two
+                // rsqrt in the dependent chain instead of three divisions and two sqrt -- this
+                // chain is the serial part of every round (all other warps wait for it).  How
+                // well t annihilates a_pq only affects convergence; orthogonality needs
+                // c^2 + s^2 = 1, which the Newton step restores to rounding.
                 const double app = A[p * ld + p], aqq = A[q * ld + q];
-                const double tau = (aqq - app) / (2.0 * apq);
-                const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                c = 1.0 / sqrt(1.0 + tt * tt);
+                const double d = aqq - app, b2 = 2.0 * apq;
+                const double w2 = fma(d, d, b2 * b2);
+                double tt;
+                if (w2 < 1e300 && w2 > 1e-300) {
+                  const double h = w2 * rsqrt(w2);
+                  tt = fabs(b2) / (fabs(d) + h);
+                } else {  // out of range for the squared form: the textbook expression
+                  const double tau = d / b2;
+                  tt = 1.0 / (fabs(tau) + sqrt(1.0 + tau * tau));
+                }
+                if (d != 0.0 && (d < 0.0) != (b2 < 0.0)) tt = -tt;  // sign(tau); tau = 0 -> +1
+                const double x = fma(tt, tt, 1.0);
+                double r = rsqrt(x);
+                r = r * fma(-0.5 * x, r * r, 1.5);
+                c = r;
                 s = tt * c;
               }
             }
@@ -605,7 +624,20 @@ __device__ inline bool jacobi_eigh_impl(const Blk& k, RmWork& w, double* A, doub
           }
         }
         if (vb && sb != 0.0) {
-          for (int i = ty; i < n; i += ny) {
+          // four rows per pass: all loads before the stores (independent round trips)
+          int i = ty;
+          for (; i + 3 * ny < n; i += 4 * ny) {
+            double u0[4], u1[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              u0[e] = U[(i + e * ny) * ld + pb], u1[e] = U[(i + e * ny) * ld + qb];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              U[(i + e * ny) * ld + pb] = fma(cb, u0[e], -(sb * u1[e]));
+              U[(i + e * ny) * ld + qb] = fma(sb, u0[e], cb * u1[e]);
+            }
+          }
+          for (; i < n; i += ny) {
             const double u0 = U[i * ld + pb], u1 = U[i * ld + qb];
             U[i * ld + pb] = fma(cb, u0, -(sb * u1));
             U[i * ld + qb] = fma(sb, u0, cb * u1);
