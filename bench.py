@@ -516,6 +516,8 @@ def run_cuda(args, rank, local_rank, world):
     torch.cuda.set_device(dev)
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
+        # NCCL prints its version banner / debug lines to stdout: keep stdout for the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     L = args.leapfrog_per_launch
