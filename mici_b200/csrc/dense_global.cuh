@@ -213,7 +213,17 @@ __device__ __forceinline__ void dg_tile_decode(int t, int& bi, int& bj) {
 // factorisation leaves the critical path)] -> barrier.  8 warps with 255 registers: 16 warps
 // under a 128-register budget, and a register-prefetched next C tile, both measured slower
 // (the diagonal-block code spills).
-__device__ __noinline__ bool dg_cholesky(const Blk& k, DgWork& g) {
+// The routines below are not inlined: DgWork reaches them through memory, where the compiler
+// cannot see which of its pointers are shared and which global and would emit generic LD / ST for
+// all of them (riemannian.cuh: RM_SHARED / RM_GLOBAL).  They work on a local copy with the address
+// spaces stated.
+#define DG_LOCAL(g, g_in)                                        \
+  DgWork g = g_in;                                               \
+  RM_SHARED(g.panel), RM_SHARED(g.dblk), RM_SHARED(g.wblk);      \
+  RM_GLOBAL(g.L), RM_GLOBAL(g.X), RM_GLOBAL(g.Minv), RM_GLOBAL(g.W)
+
+__device__ __noinline__ bool dg_cholesky(const Blk& k, DgWork& g_in) {
+  DG_LOCAL(g, g_in);
   const int np = g.np, lane = k.lane, r = lane >> 2, c = lane & 3;
   int* counter = reinterpret_cast<int*>(g.dblk);  // shared work counter (+ failure flag)
   if (k.tid == 0) counter[0] = 0, counter[1] = 1;
@@ -321,8 +331,9 @@ __device__ __noinline__ bool dg_cholesky(const Blk& k, DgWork& g) {
 // shared memory (x may alias b), `tmp` a shared scratch vector of np doubles is NOT needed: the
 // right-hand side is updated in place.  Only entries < g.n are meaningful (padding rows are the
 // identity).
-__device__ __noinline__ void dg_solve(const Blk& k, const DgWork& g, const double* b, double* x,
+__device__ __noinline__ void dg_solve(const Blk& k, const DgWork& g_in, const double* b, double* x,
                                 bool forward, bool backward) {
+  DG_LOCAL(g, g_in);
   const int np = g.np, n = g.n;
   for (int i = k.tid; i < n; i += k.nthr) x[i] = b[i];
   __syncthreads();
@@ -396,7 +407,8 @@ __device__ __noinline__ void dg_solve(const Blk& k, const DgWork& g, const doubl
 
 // Explicit inverse: X = L^-1 (block rows, X_ic = -W_ii sum_{c<=k<i} L_ik X_kc) then
 // M^-1 = X^T X; both matrices in the workspace, M^-1 stored full (symmetric).
-__device__ __noinline__ void dg_explicit_inverse(const Blk& k, DgWork& g) {
+__device__ __noinline__ void dg_explicit_inverse(const Blk& k, DgWork& g_in) {
+  DG_LOCAL(g, g_in);
   const int np = g.np, nb = g.nblk, lane = k.lane, r = lane >> 2, c = lane & 3;
   // ---- X = L^-1
   for (int i = 0; i < nb; ++i) {

@@ -28,6 +28,12 @@ namespace mb200 {
 constexpr int RM_THREADS = 256;
 constexpr int RM_MAX_SWEEPS = 40;
 
+// Address-space statements for pointer VALUES whose origin the compiler cannot see (pointers that
+// reach a non-inlined function through a struct in memory would otherwise be dereferenced with
+// generic LD / ST instead of LDS / STS or LDG / STG).
+#define RM_SHARED(p) __builtin_assume(__isShared(p))
+#define RM_GLOBAL(p) __builtin_assume(__isGlobal(p))
+
 struct Blk {
   int tid, nthr, lane, warp, nwarp;
   double* red;  // [34] reduction scratch

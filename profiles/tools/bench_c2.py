@@ -3,6 +3,6 @@ sys.path.insert(0, "/root/repo")
 import torch, bench
 dev = torch.device("cuda:0")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for name in ("C2", "C2_dense_hessian"):
+for name in (sys.argv[1:] or ["C2", "C2_dense_hessian"]):
     r = bench.run_workload(name, torch, None, dev, 0, 1, flush, 6566.4)
     print(name, r["ms_per_launch"], r["value"])
