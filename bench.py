@@ -584,7 +584,7 @@ def run_cuda(args, rank, local_rank, world):
 
     def e2e_step():
         integ.step_n_host(pos_h, mom_h, L, out_pos=pos_o, out_mom=mom_o, out_status=st_o,
-                          device=dev, n_chunks=8)
+                          device=dev, n_chunks=6)
 
     def timed_e2e(fn):
         for _ in range(args.warmup):

