@@ -387,7 +387,9 @@ int mb200_implicit_riemannian_per_chain(
  * MultinomialDynamicIntegrationTransition (:773-809; slice_variant = 0) or
  * SliceDynamicIntegrationTransition (:812-858; slice_variant = 1) weights and the
  * riemannian_ (euclidean_criterion = 0, the reference's default) or euclidean_no_u_turn_criterion
- * (:405-470).  Every chain builds its own tree (one warp per chain).
+ * (:405-470).  Every chain builds its own tree (one warp per chain); with a shared dense metric
+ * and dim <= 128 the chains of a group of 8 advance leaf by leaf in lock-step and the product
+ * M^-1 grad l(q) of the group is one tensor-pipe (DMMA) tile product per leaf (nuts_dmma.cuh).
  *   uniforms   [n_chains x n_uniforms] device array of U[0,1) variates; chain c consumes
  *              uniforms[c][0 .. n_uniforms_used[c]) in the order the reference calls
  *              rng.uniform().  2 max_tree_depth + 2^max_tree_depth variates always suffice;
@@ -422,9 +424,14 @@ int mb200_nuts_euclidean(const double* pos_in, const double* mom_in, double* pos
  * device pointer.  The batch is cut into n_chunks row blocks aligned to the CTA granularity of
  * the kernel; block k is copied in, stepped and copied out on streams[k % n_streams], so that the
  * host->device copy of later blocks and the device->host copy of earlier blocks overlap the
- * kernels (chains are independent: chunking changes no result).  `scratch` is a device buffer of
- * at least mb200_host_scratch_bytes(n_chains, dim) bytes owned by the caller and must not be
+ * kernels (chains are independent: chunking changes results at most in the last bits -- the
+ * tensor-core kernel picks its accumulation split by launch size).  `scratch` is a device buffer
+ * of at least mb200_host_scratch_bytes(n_chains, dim) bytes owned by the caller and must not be
  * shared by concurrent calls.  synchronize != 0: wait for all streams before returning.
+ * PAGEABLE host buffers (plain NumPy arrays) are detected and staged by the library itself: a
+ * small pool of worker threads copies each row block through a pinned bounce buffer (grow-only,
+ * owned by the library), so that the host copies of one block overlap the DMA and the kernel of
+ * the others; such a call is always synchronous.
  */
 /*
  * Dynamic transitions for ANY integrator / system pair (constrained, implicit, compositions):
