@@ -32,7 +32,7 @@ class HostStager {
     if (bytes > cap_) {
       if (buf_) cudaFreeHost(buf_);
       buf_ = nullptr, cap_ = 0;
-      if (cudaHostAlloc(&buf_, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+      if (cudaHostAlloc(&buf_, bytes, cudaHostAllocPortable) != cudaSuccess) return nullptr;
       cap_ = bytes;
     }
     return buf_;

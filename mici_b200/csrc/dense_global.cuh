@@ -240,10 +240,20 @@ __device__ __noinline__ bool dg_cholesky(const Blk& k, DgWork& g_in) {
     if (m == 0) break;
     // ---- panel: raw A[d0+32 .., d0 .. d0+32) into shared memory
     const double* Ap = g.L + (size_t)(d0 + DG_NB) * np + d0;
-    for (int idx = k.tid; idx < m * 16; idx += k.nthr) {
-      const int row = idx >> 4, c2 = idx & 15;
-      const double2 v = *reinterpret_cast<const double2*>(Ap + (size_t)row * np + 2 * c2);
-      *reinterpret_cast<double2*>(&g.panel[row * DG_LDP + 2 * c2]) = v;
+    for (int idx0 = k.tid; idx0 < m * 16; idx0 += 4 * k.nthr) {  // four loads in flight
+      double2 v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int idx = idx0 + e * k.nthr;
+        if (idx < m * 16)
+          v[e] = *reinterpret_cast<const double2*>(Ap + (size_t)(idx >> 4) * np + 2 * (idx & 15));
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int idx = idx0 + e * k.nthr;
+        if (idx < m * 16)
+          *reinterpret_cast<double2*>(&g.panel[(idx >> 4) * DG_LDP + 2 * (idx & 15)]) = v[e];
+      }
     }
     if (k.tid == 0) counter[0] = 1;  // tile 0 is reserved for warp 0
     __syncthreads();
@@ -334,6 +344,7 @@ __device__ __noinline__ bool dg_cholesky(const Blk& k, DgWork& g_in) {
 __device__ __noinline__ void dg_solve(const Blk& k, const DgWork& g_in, const double* b, double* x,
                                 bool forward, bool backward) {
   DG_LOCAL(g, g_in);
+  RM_SHARED(b), RM_SHARED(x);  // every caller passes per-chain vectors of the shared workspace
   const int np = g.np, n = g.n;
   for (int i = k.tid; i < n; i += k.nthr) x[i] = b[i];
   __syncthreads();
@@ -360,13 +371,26 @@ __device__ __noinline__ void dg_solve(const Blk& k, const DgWork& g_in, const do
       }
       __syncthreads();
       if (k.tid < DG_NB && d0 + k.tid < n) x[d0 + k.tid] = y[k.tid];
-      // x_i -= L[i, kb-block] y for the rows below
-      for (int i = d0 + DG_NB + k.tid; i < n; i += k.nthr) {
-        const double* Li = g.L + (size_t)i * np + d0;
-        double s = 0.0;
-#pragma unroll 8
-        for (int j = 0; j < DG_NB; ++j) s = fma(Li[j], y[j], s);
-        x[i] -= s;
+      // x_i -= L[i, kb-block] y for the rows below: 8 threads per row (4 columns each: a row's 32
+      // entries are one 256-byte piece read by 8 neighbouring lanes), reduced with shuffles; the
+      // passes over row groups are independent loads (a thread per row was a chain of 32 loads)
+      {
+        const int part = k.tid & 7, rows_per_pass = k.nthr >> 3;
+        const double y0 = y[4 * part], y1 = y[4 * part + 1], y2 = y[4 * part + 2],
+                     y3 = y[4 * part + 3];
+#pragma unroll 2
+        for (int base = d0 + DG_NB; base < n; base += rows_per_pass) {
+          const int i = base + (k.tid >> 3);
+          double s = 0.0;
+          if (i < n) {
+            const double* Li = g.L + (size_t)i * np + d0 + 4 * part;
+            s = fma(Li[3], y3, fma(Li[2], y2, fma(Li[1], y1, Li[0] * y0)));
+          }
+          s += __shfl_xor_sync(FULL_MASK, s, 1);
+          s += __shfl_xor_sync(FULL_MASK, s, 2);
+          s += __shfl_xor_sync(FULL_MASK, s, 4);
+          if (i < n && part == 0) x[i] -= s;
+        }
       }
       __syncthreads();
     }
@@ -506,7 +530,9 @@ struct Rank1Model {
   int n;
   __device__ Rank1Model(const ModelArgs& m, int dim) : B(m.maux), c(m.mp[0]), n(dim) {}
   __device__ __forceinline__ double entry(const double* q, int i, int j) const {
-    return B[(size_t)i * n + j] + c * (q[i] * q[j]);
+    const double* const Bg = B;
+    RM_GLOBAL(Bg);
+    return Bg[(size_t)i * n + j] + c * (q[i] * q[j]);
   }
   // out = c (V + V^T) q for the symmetric V stored full with stride ld
   __device__ void vjp_dense(const Blk& k, const double* q, const double* V, int ld, double* out) const {
@@ -541,7 +567,10 @@ struct HadamardModel {
   __device__ HadamardModel(const ModelArgs& m, int dim)
       : B(m.maux), S(m.maux + (size_t)dim * dim), c(m.mp[0]), n(dim) {}
   __device__ __forceinline__ double entry(const double* q, int i, int j) const {
-    return B[(size_t)i * n + j] + c * ((q[i] * q[j]) * S[(size_t)i * n + j]);
+    const double* const Bg = B;
+    const double* const Sg = S;
+    RM_GLOBAL(Bg), RM_GLOBAL(Sg);
+    return Bg[(size_t)i * n + j] + c * ((q[i] * q[j]) * Sg[(size_t)i * n + j]);
   }
   __device__ void vjp_dense(const Blk& k, const double* q, const double* V, int ld, double* out) const {
     for (int i = k.warp; i < n; i += k.nwarp) {
@@ -598,17 +627,28 @@ struct GlobalDenseMetricT {
     bool bad = false;
     // lower triangle only (the factorisation never reads above the diagonal blocks): one row
     // per warp, lanes along the row
+    // (four entries per lane and pass: their loads of the model's matrices are independent
+    // round trips to L2 -- one at a time this fill was 12 % of a C4 step)
+    double* const Lg = g.L;
+    RM_GLOBAL(Lg);
     for (int i = k.warp; i < np; i += k.nwarp) {
       const int jmax = (i | 31) + 1;  // through the end of the row's diagonal block
-      for (int j = k.lane; j < jmax; j += 32) {
-        double v;
-        if (i < n && j < n) {
-          v = model.entry(q, i, j);
-          if (!isfinite(v)) bad = true;
-        } else {
-          v = (i == j) ? 1.0 : 0.0;  // identity padding
+      for (int j0 = k.lane; j0 < jmax; j0 += 128) {
+        double v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = j0 + 32 * e;
+          v[e] = (i == j) ? 1.0 : 0.0;  // identity padding
+          if (j < jmax && i < n && j < n) v[e] = model.entry(q, i, j);
         }
-        g.L[(size_t)i * np + j] = v;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = j0 + 32 * e;
+          if (j < jmax) {
+            if (i < n && j < n && !isfinite(v[e])) bad = true;
+            Lg[(size_t)i * np + j] = v[e];
+          }
+        }
       }
     }
     if (block_any(k, bad)) return MB200_STATUS_LINALG;  // "Array is not finite" (:211-215)
