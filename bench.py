@@ -496,6 +496,16 @@ def run_nuts(torch, dist, dev, rank, world):
         "kernel": "nuts_dmma_kernel<NealFunnelTarget, 2, 1>",
         "chains_per_gpu": N_CHAINS, "n_gpus": world, "dim": DIM,
         "value": out["max_tree_depth_6"]["value"], "unit": UNIT,
+        "roofline": {
+            "bound": "tensor (fp64 DMMA: one M^-1 grad product per leaf, 2 D^2 flop)",
+            "achieved": out["max_tree_depth_6"]["value"] / world * 2.0 * DIM * DIM / 1e12,
+            "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+            "frac": out["max_tree_depth_6"]["value"] / world * 2.0 * DIM * DIM / 1e12
+                    / FP64_DMMA_PEAK_TFLOPS,
+            "peak_source": FP64_PEAK_SOURCE, "traffic": ncu_traffic("nuts_c1"),
+            "formula": "leapfrog steps/s x 2 D^2 (the INIT / START products of a transition are "
+                       "not counted)",
+        },
         **out,
     }
 
