@@ -247,11 +247,7 @@ __device__ __forceinline__ void leapfrog_dmma_group(
       }
     }
     MB200_K1_TRACE(4);
-#if defined(K1_LOCKSTEP)
-    named_barrier_sync(8, cta_threads);
-#else
     named_barrier_sync(bar_id, 128);
-#endif
     MB200_K1_TRACE(5);
   };
   using K0 = std::integral_constant<int, 0>;

@@ -47,6 +47,43 @@ struct LeapfrogGeneric {
     }
   }
 
+  // the same gradient, also handing out the target's reduced sums at q (red[NRED + 1]) so that a
+  // caller which needs l(q) at the same position next (a NUTS leaf) does not reduce them again
+  static __device__ __forceinline__ void grad_keep(const Target& t, int dim, int lane,
+                                                   const double (&q)[NV], double (&g)[NV],
+                                                   double (&red)[Target::NRED + 1]) {
+#pragma unroll
+    for (int r = 0; r < Target::NRED + 1; ++r) red[r] = 0.0;
+    if (Target::NRED > 0) {
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        const int i = 2 * lane + 64 * k;
+        if (i < dim) t.accumulate(i, q[2 * k], q[2 * k + 1], red);
+      }
+#pragma unroll
+      for (int r = 0; r < Target::NRED; ++r) red[r] = warp_sum(red[r]);
+    }
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int i = 2 * lane + 64 * k;
+      t.grad_pair(i, q[2 * k], q[2 * k + 1], red, g[2 * k], g[2 * k + 1]);
+      if (i >= dim) g[2 * k] = 0.0;
+      if (i + 1 >= dim) g[2 * k + 1] = 0.0;
+    }
+  }
+  // l(q) from sums already reduced at this q (grad_keep)
+  static __device__ __forceinline__ double neg_log_dens_with(const Target& t, int dim, int lane,
+                                                             const double (&q)[NV],
+                                                             const double (&red)[Target::NRED + 1]) {
+    double l = 0.0;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int i = 2 * lane + 64 * k;
+      if (i < dim) l += t.nld_pair(i, q[2 * k], q[2 * k + 1], red);
+    }
+    return warp_sum(l);
+  }
+
   static __device__ __forceinline__ double neg_log_dens(const Target& t, int dim, int lane,
                                                         const double (&q)[NV]) {
     double red[Target::NRED + 1];

@@ -130,6 +130,9 @@ __global__ void __launch_bounds__(GROUPS * 256, 1)
     const double eps = (alive && a.step_sizes != nullptr) ? a.step_sizes[ch] : step_size;
 
     double q[1][NV], p[1][NV], v[1][NV], g[NV], u[NV];
+    double red_q[Target::NRED + 1];  // the target's reduced sums at the current q (leaf phases)
+#pragma unroll
+    for (int r = 0; r < Target::NRED + 1; ++r) red_q[r] = 0.0;
 #pragma unroll
     for (int e = 0; e < NV; ++e) {
       const int i = 2 * lane + 64 * (e >> 1) + (e & 1);
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(GROUPS * 256, 1)
 #pragma unroll
             for (int e = 0; e < NV; ++e) q[0][e] = __dadd_rn(q[0][e], __dmul_rn(dt, v[0][e]));
           }
-          K::grad(target, dim, lane, q[0], g);
+          K::grad_keep(target, dim, lane, q[0], g, red_q);
 #pragma unroll
           for (int kk = 0; kk < KP; ++kk) g_row[32 * kk] = make_double2(g[2 * kk], g[2 * kk + 1]);
         }
@@ -262,7 +265,15 @@ __global__ void __launch_bounds__(GROUPS * 256, 1)
         p[0][e] = __dsub_rn(p[0][e], __dmul_rn(0.5 * dt, g[e]));
         v[0][e] = __dsub_rn(v[0][e], __dmul_rn(0.5 * dt, u[e]));
       }
-      double h = energy();
+      // System.h at the new state; l(q) reuses the sums the gradient reduced at this q
+      double h;
+      {
+        double kin = 0.0;
+#pragma unroll
+        for (int e = 0; e < NV; ++e) kin = fma(p[0][e], v[0][e], kin);
+        kin = warp_sum(kin);
+        h = K::neg_log_dens_with(target, dim, lane, q[0], red_q) + 0.5 * kin;
+      }
       if (h != h) h = INFINITY;  // transitions.py:626
       w_cur = leaf_weight(h);
       h_cur = h;
