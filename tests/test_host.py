@@ -101,6 +101,18 @@ def test_system_rejects_python_callables_and_foreign_derivatives():
         systems.SoftAbsRiemannianMetricSystem(targets.Banana(4), softabs_coeff=0.0)
 
 
+def test_call_counter_api_defaults():
+    """``Integrator.count_calls`` (kernel-side counters): off by default, zero totals, chainable."""
+    from mici_b200 import integrators
+
+    eu = systems.EuclideanMetricSystem(targets.NealFunnel(8))
+    integ = integrators.LeapfrogIntegrator(eu, 0.1)
+    assert integ.call_counts is None and not integ._counting
+    assert integ.call_count_totals() == dict.fromkeys(integ.COUNTER_NAMES, 0)
+    assert integ.count_calls() is integ and integ._counting
+    assert integ.count_calls(False).call_counts is None
+
+
 def test_integrator_constructor_contracts():
     """integrators.py:52-80, 121-130, 438-446, 855-864: names, defaults, rejections."""
     eu = systems.EuclideanMetricSystem(targets.NealFunnel(8))
