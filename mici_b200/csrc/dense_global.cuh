@@ -378,7 +378,7 @@ __device__ __noinline__ void dg_solve(const Blk& k, const DgWork& g_in, const do
         const int part = k.tid & 7, rows_per_pass = k.nthr >> 3;
         const double y0 = y[4 * part], y1 = y[4 * part + 1], y2 = y[4 * part + 2],
                      y3 = y[4 * part + 3];
-#pragma unroll 2
+#pragma unroll 4
         for (int base = d0 + DG_NB; base < n; base += rows_per_pass) {
           const int i = base + (k.tid >> 3);
           double s = 0.0;
